@@ -1,0 +1,110 @@
+/* b200msm.h -- C ABI of the B200-native G1 multi-scalar-multiplication engine.
+ *
+ * Drop-in boundary for the MSM hot path of Manta-Network/zprize-wasm-msm (wasmcurves fork).
+ * Every entry point names the reference interface it replaces (paths relative to
+ * /root/reference/wasmcurves/).  The reference's "plugin API" is the WASM export table plus one
+ * linear memory; here pointers are 64-bit, every call returns a status, and an
+ * explicit context owns the GPU stream and scratch memory.
+ *
+ * Data formats are the reference's, byte for byte:
+ *   Fq element  : n8 bytes little-endian, Montgomery form a*R mod q, R = 2^(8*n8)   (src/build_f1m.js:30-43)
+ *                 n8 = 48 for BLS12-381, 32 for BN254 ("bn128")
+ *   affine point: x || y (2*n8 bytes); infinity = all zero                             (src/build_curve_jacobian_a0.js:55-77)
+ *   Jacobian    : x || y || z (3*n8 bytes), (X/Z^2, Y/Z^3); infinity: z == 0, written as (0, R mod q, 0)  (:124-150)
+ *   scalar      : scalar_size bytes, plain unsigned little-endian integer, NOT Montgomery, NOT required < r
+ *                                                                                       (src/build_multiexp.js:73-92)
+ * All `const void*` inputs and `void*` outputs may be HOST or DEVICE pointers (detected with
+ * cudaPointerGetAttributes); device buffers must be 16-byte aligned.  There is no CPU fallback:
+ * every compute entry point fails with B200MSM_E_CUDA when no usable GPU is present.
+ * A context is not re-entrant (like a WASM instance, src/build_multiexp.js:273); use one per host thread.
+ */
+#ifndef B200MSM_H
+#define B200MSM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200msm_ctx b200msm_ctx;
+
+enum { B200MSM_BLS12_381_G1 = 0,   /* src/bls12381/build_bls12381.js:16-125 */
+       B200MSM_BN254_G1 = 1 };     /* src/bn128/build_bn128.js:14-125       */
+
+enum { B200MSM_OK = 0, B200MSM_E_ARG = -1, B200MSM_E_CUDA = -2, B200MSM_E_NOMEM = -3, B200MSM_E_UNSUPPORTED = -4 };
+
+/* Per-call measurements (milliseconds, CUDA events on the context's stream) and plan parameters. */
+typedef struct b200msm_stats {
+  uint32_t n, window_bits, windows, buckets_per_window, tree_rounds, reserved;
+  uint64_t pairs;            /* non-zero (point, window) digits = bucket insertions                     */
+  uint64_t affine_adds;      /* batch-affine additions executed                                          */
+  float ms_total, ms_h2d, ms_digits_sort, ms_accumulate, ms_bucket_reduce, ms_window_combine, ms_d2h;
+} b200msm_stats;
+
+/* ---- life cycle.  device_id < 0 selects the current CUDA device. */
+int  b200msm_create(b200msm_ctx** out, int device_id);
+void b200msm_destroy(b200msm_ctx* ctx);
+const char* b200msm_strerror(int status);
+const char* b200msm_last_error(const b200msm_ctx* ctx);      /* detail string of the last failure */
+const char* b200msm_version(void);
+/* Run on an externally owned CUDA stream (cudaStream_t passed as void*), e.g. torch's current stream. */
+int  b200msm_set_stream(b200msm_ctx* ctx, void* cuda_stream);
+int  b200msm_synchronize(b200msm_ctx* ctx);
+
+/* ---- == g1m_multiexpAffine(pBases, pScalars, scalarSize, n, pr)          src/build_multiexp.js:251-371
+ *      == g1m_multiexp_multiExp / g1m_multiexpAffine_multiExp(pPoints, pScalars, numPoints, pResult)
+ *                                                                         src/build_multiexp_opt.js:1987-2110 (scalar_size = 32)
+ * out receives 3*n8 bytes: sum_i scalars[i] * bases[i] as a Jacobian Montgomery point; n == 0 -> canonical zero. */
+int b200msm_g1_multiexp_affine(b200msm_ctx* ctx, int curve, const void* bases, const void* scalars,
+                               uint32_t scalar_size, uint64_t n, void* out);
+
+/* ---- == g1m_multiexpAffine_chunk(pBases, pScalars, scalarSize, n, startBit, chunkSize, pr)
+ *                                                                         src/build_multiexp.js:96-249
+ * One window: sum_i digit_i * bases[i], digit_i = bits [start_bit, start_bit + chunk_bits) of scalar i clipped at
+ * the scalar end (src/build_multiexp.js:25-94), WITHOUT the 2^start_bit factor.  chunk_bits in [1, 32]. */
+int b200msm_g1_multiexp_affine_chunk(b200msm_ctx* ctx, int curve, const void* bases, const void* scalars,
+                                     uint32_t scalar_size, uint64_t n, uint32_t start_bit, uint32_t chunk_bits, void* out);
+
+/* ---- resident bases: upload once (pb.alloc + pb.set of pBases in the reference rig, benchmarks/multiexp.js:16-23),
+ *      then run any number of MSMs against them.  n in the MSM call may be <= the uploaded count. */
+int b200msm_upload_bases(b200msm_ctx* ctx, int curve, const void* bases, uint64_t n, uint64_t* handle);
+int b200msm_free_bases(b200msm_ctx* ctx, uint64_t handle);
+int b200msm_g1_multiexp_resident(b200msm_ctx* ctx, uint64_t handle, const void* scalars, uint32_t scalar_size,
+                                 uint64_t n, void* out, b200msm_stats* stats /* nullable */);
+
+/* ---- == g1m_normalize + f1m_fromMontgomery(x), f1m_fromMontgomery(y)   src/build_curve_jacobian_a0.js:940-973,
+ *      the comparison form of the reference's tests (test/batchAffine.js:1249-1254):
+ * count Jacobian Montgomery points -> count canonical affine points x || y as plain LE integers < q; infinity -> zeros. */
+int b200msm_g1_normalize(b200msm_ctx* ctx, int curve, const void* jac, uint64_t count, void* affine_canonical);
+
+/* ---- == repeated g1m_add (src/build_curve_jacobian_a0.js:541-658): out = sum of count Jacobian points.
+ * Used to merge the per-GPU partial results of a point-range-sharded MSM. */
+int b200msm_g1_sum(b200msm_ctx* ctx, int curve, const void* jac_points, uint64_t count, void* out);
+
+/* ---- synthetic inputs (benchmarks/multiexp.js:16-23 builds bases on the module itself):
+ * device_out[i] = k_i * G for i in [0, n), affine Montgomery, k_i = splitmix64(seed + first + i) (0 mapped to 1).
+ * device_out must be a device pointer with room for n * 2*n8 bytes. */
+int b200msm_g1_generate_bases(b200msm_ctx* ctx, int curve, uint64_t seed, uint64_t first, uint64_t n, void* device_out);
+
+/* ---- kernel-level parity hooks: r[i] = op(a[i], b[i]) on Montgomery Fq elements
+ * op: 0 f1m_mul  1 f1m_add  2 f1m_sub  3 f1m_square  4 f1m_inverse  5 f1m_toMontgomery  6 f1m_fromMontgomery  7 f1m_neg
+ * (src/build_f1m.js:71-105, 466-777, 779-1076, 1089-1122) */
+int b200msm_fq_op(b200msm_ctx* ctx, int curve, int op, const void* a, const void* b, void* r, uint64_t count);
+
+/* ---- measurement hooks: integer-multiply roofline denominator and field-multiply rate, measured on this GPU.
+ * imad_per_s: 32x32+64 multiply-adds per second (register-resident mad.wide.u32 loop, all SMs);
+ * fqmul_per_s: dependent Montgomery multiplications per second for the given curve. */
+int b200msm_probe_imad(b200msm_ctx* ctx, double* imad_per_s);
+int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s);
+
+/* ---- tuning knobs (never change results).  key: "window_bits" (0 = auto), "accumulate" (0 = auto, 1 = serial, 2 = batch-affine). */
+int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t value);
+
+/* ---- host-only: field constants as the engine uses them (q, R mod q, R^2 mod q as n8-byte LE; np32). No GPU needed. */
+int b200msm_constants(int curve, uint32_t* n8, uint8_t* q, uint8_t* r_mod_q, uint8_t* r2_mod_q, uint32_t* np32);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MSM_H */

@@ -1,0 +1,59 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/b200msm.h declares,
+its field constants match the reference's, and compute entry points fail loudly (no CPU fallback) without a GPU."""
+import ctypes, os, re
+import pytest
+import pyref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported():
+    import b200msm
+    hdr = open(os.path.join(ROOT, "include", "b200msm.h")).read()
+    declared = set(re.findall(r"\b(b200msm_\w+)\s*\(", hdr))
+    assert declared == set(b200msm.EXPORTS), declared ^ set(b200msm.EXPORTS)
+    for sym in declared:
+        assert hasattr(b200msm.lib, sym), sym
+
+
+def test_no_torch_types_in_abi():
+    hdr = open(os.path.join(ROOT, "include", "b200msm.h")).read()
+    assert "torch" not in hdr.lower().replace("torch's current stream", "") and "at::" not in hdr and "Tensor" not in hdr
+
+
+def test_constants_match_reference_fields():
+    """q, R mod q, R^2 mod q, -q^-1 mod 2^32 (build_bls12381.js:22, build_bn128.js:20, build_f1m.js:30-43,504)"""
+    import b200msm
+    for cid, cv in ((0, pyref.BLS12_381), (1, pyref.BN254)):
+        n8, q, one, r2, np32 = b200msm.constants(cid)
+        assert (n8, q, one, r2) == (cv.n8, cv.q, cv.R % cv.q, cv.R * cv.R % cv.q)
+        assert np32 == (-pow(cv.q, -1, 1 << 32)) % (1 << 32)
+
+
+def test_status_strings_and_version():
+    import b200msm
+    assert b200msm.strerror(0) == "ok"
+    assert "CUDA" in b200msm.strerror(b200msm._lib.E_CUDA)
+    assert b"b200msm" in b200msm.lib.b200msm_version()
+
+
+def test_fails_loudly_without_gpu():
+    import torch, b200msm
+    if torch.cuda.is_available(): pytest.skip("a GPU is present")
+    with pytest.raises(b200msm.B200MsmError) as ei:
+        b200msm.Engine()
+    assert ei.value.status == b200msm._lib.E_CUDA
+
+
+def test_product_path_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under the package or the C sources may reference it."""
+    pkg = os.path.join(ROOT, "zprize-wasm-msm_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cc")):
+                src = open(os.path.join(dp, f)).read()
+                for bad in ("import pyref", "import coracle", "import refwasm", "liboracle", "libref_", "oracle/"):
+                    if bad == "oracle/" and f.endswith((".cu", ".cuh")):
+                        # comments may cite oracle/msm_oracle.c for the shared input generator stream
+                        continue
+                    assert bad not in src, (f, bad)

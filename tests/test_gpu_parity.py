@@ -1,0 +1,200 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the oracles
+on the same seeded inputs -- bit-exact on canonical affine output (SURVEY.md 8c parity definition)."""
+import json, os, random
+import pytest
+import pyref, coracle, refwasm
+from util import curve, make_bases, make_scalars, oracle_msm, gen_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import b200msm
+    e = b200msm.Engine()
+    yield e
+    e.close()
+
+
+def msm(eng, cv, bases, scalars, ssz, n):
+    return eng.normalize(cv.cid, eng.multiexp_affine(cv.cid, bases, scalars, ssz, n))
+
+
+# ---------------------------------------------------------------- field kernels (build_f1m.js)
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+def test_fq_ops_bit_exact(eng, cname):
+    cv = curve(cname); rnd = random.Random(11)
+    edge = [0, 1, 2, cv.q - 1, cv.q - 2, (cv.q - 1) // 2, cv.R % cv.q, (cv.R * cv.R) % cv.q, (1 << (8 * cv.n8 - 3)) % cv.q]
+    xs = edge + [rnd.randrange(cv.q) for _ in range(3000)]
+    ys = list(reversed(edge)) + [rnd.randrange(cv.q) for _ in range(3000)]
+    a = b"".join(pyref.fe_bytes(cv, x) for x in xs); b = b"".join(pyref.fe_bytes(cv, y) for y in ys)
+    assert eng.fq_op(cv.cid, 0, a, b) == coracle.fe_mul(cv.cid, a, b)
+    assert eng.fq_op(cv.cid, 1, a, b) == coracle.fe_add(cv.cid, a, b)
+    assert eng.fq_op(cv.cid, 2, a, b) == coracle.fe_sub(cv.cid, a, b)
+    assert eng.fq_op(cv.cid, 3, a) == coracle.fe_mul(cv.cid, a, a)
+    assert eng.fq_op(cv.cid, 5, a) == coracle.fe_to_mont(cv.cid, a)
+    assert eng.fq_op(cv.cid, 6, a) == coracle.fe_from_mont(cv.cid, a)
+    assert eng.fq_op(cv.cid, 7, a) == coracle.fe_sub(cv.cid, bytes(len(a)), a)
+    small = a[:200 * cv.n8]
+    inv = coracle.fe_inv(cv.cid, small)
+    assert eng.fq_op(cv.cid, 4, small) == inv          # binary extended Euclid
+    assert eng.fq_op(cv.cid, 8, small) == inv          # Fermat
+
+
+# ---------------------------------------------------------------- synthetic bases generator
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+def test_generate_bases_matches_oracle(eng, cname):
+    import torch
+    cv = curve(cname); n = 300
+    d = torch.empty(n * 2 * cv.n8, dtype=torch.uint8, device="cuda")
+    eng.generate_bases(cv.cid, 0xB2000000, 5, n, d)
+    got = bytes(d.cpu().numpy())
+    exp = coracle.generate_bases(cv.cid, gen_bytes(cv), 0xB2000000, 5, n)
+    assert got == exp
+
+
+# ---------------------------------------------------------------- MSM vs oracle, both accumulate forms
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("n", [1, 2, 3, 10, 100, 1000, 5000])
+def test_msm_random_matches_oracle(eng, cname, mode, n):
+    cv = curve(cname)
+    eng.set_option("accumulate", mode)
+    try:
+        bases = make_bases(cv, n); sc = make_scalars(n, 1000 + n, "u256")
+        assert msm(eng, cv, bases, sc, 32, n) == oracle_msm(cv, bases, sc, 32, n)
+    finally:
+        eng.set_option("accumulate", 0)
+
+
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+@pytest.mark.parametrize("wb", [1, 2, 5, 9, 13, 16])
+def test_msm_window_widths(eng, cname, wb):
+    cv = curve(cname); n = 700
+    eng.set_option("window_bits", wb)
+    try:
+        bases = make_bases(cv, n, 77); sc = make_scalars(n, 5, "u256")
+        assert msm(eng, cv, bases, sc, 32, n) == oracle_msm(cv, bases, sc, 32, n)
+    finally:
+        eng.set_option("window_bits", 0)
+
+
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+def test_msm_edge_cases(eng, cname):
+    cv = curve(cname); n8 = cv.n8
+    zero = bytes(2 * n8)
+    # n = 0 -> canonical zero (build_multiexp.js:283-287)
+    assert msm(eng, cv, b"", b"", 32, 0) == zero
+    raw0 = eng.multiexp_affine(cv.cid, b"", b"", 32, 0)
+    assert raw0 == bytes(n8) + pyref.fe_bytes(cv, cv.R % cv.q) + bytes(n8)
+    n = 600
+    bases = make_bases(cv, n, 9)
+    for kind in ("small", "equal"):
+        sc = make_scalars(n, 3, kind)
+        assert msm(eng, cv, bases, sc, 32, n) == oracle_msm(cv, bases, sc, 32, n), kind
+    assert msm(eng, cv, bases, bytes(32 * n), 32, n) == zero                      # all-zero scalars
+    # scalars >= r, r - 1, 2^256 - 1 (scalars are plain integers, not reduced)
+    special = [cv.r - 1, cv.r, cv.r + 1, (1 << 256) - 1, 1 << 255, 1, 0, (1 << 128) - 1]
+    sc = b"".join(v.to_bytes(32, "little") for v in special)
+    b8 = bases[:len(special) * 2 * n8]
+    assert msm(eng, cv, b8, sc, 32, len(special)) == oracle_msm(cv, b8, sc, 32, len(special))
+    # duplicate points, P and -P, infinity inputs: exercises doubling / cancellation / skip paths of batch-affine
+    g = gen_bytes(cv); ng = pyref.affine_to_bytes(cv, pyref.neg(cv, cv.G))
+    pts = (g + g + ng + zero + g + ng + ng + zero) * 40
+    m = len(pts) // (2 * n8)
+    for seed, kind in ((1, "equal"), (2, "small"), (3, "u256")):
+        sc = make_scalars(m, seed, kind)
+        assert msm(eng, cv, pts, sc, 32, m) == oracle_msm(cv, pts, sc, 32, m), kind
+    # G*5 + (-G)*5 = 0
+    five = (5).to_bytes(32, "little")
+    assert msm(eng, cv, g + ng, five * 2, 32, 2) == zero
+
+
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+@pytest.mark.parametrize("ssz", [1, 4, 5, 16, 31])
+def test_msm_scalar_sizes(eng, cname, ssz):
+    cv = curve(cname); n = 300
+    bases = make_bases(cv, n, 21); rnd = random.Random(ssz)
+    sc = bytes(rnd.getrandbits(8) for _ in range(n * ssz))
+    assert msm(eng, cv, bases, sc, ssz, n) == oracle_msm(cv, bases, sc, ssz, n)
+
+
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+def test_chunk_api_matches_oracle(eng, cname):
+    """g1m_multiexpAffine_chunk (build_multiexp.js:96-249), incl. the clipped top window and Horner recombination."""
+    cv = curve(cname); n = 500
+    bases = make_bases(cv, n, 33); sc = make_scalars(n, 8, "u256")
+    for start, bits in ((0, 5), (13, 7), (250, 11), (100, 16), (255, 1), (248, 8)):
+        got = eng.normalize(cv.cid, eng.multiexp_affine_chunk(cv.cid, bases, sc, 32, n, start, bits))
+        exp = coracle.normalize(cv.cid, coracle.multiexp_affine_chunk(cv.cid, bases, sc, 32, n, start, bits))
+        assert got == exp, (start, bits)
+    # Horner over chunks == whole MSM (the caller-side combination, build_multiexp.js:319-369)
+    c = 13; acc = None
+    nch = (256 - 1) // c + 1
+    for k in reversed(range(nch)):
+        if acc is not None:
+            for _ in range(c): acc = pyref.add(cv, acc, acc)
+        ch = eng.normalize(cv.cid, eng.multiexp_affine_chunk(cv.cid, bases, sc, 32, n, k * c, c))
+        x = int.from_bytes(ch[:cv.n8], "little"); y = int.from_bytes(ch[cv.n8:], "little")
+        acc = pyref.add(cv, acc, None if (x == 0 and y == 0) else (x, y))
+    assert pyref.canonical_bytes(cv, acc) == oracle_msm(cv, bases, sc, 32, n)
+
+
+def test_reference_kat_through_protoboard(eng):
+    """The reference's end-to-end KAT (test/batchAffine.js:1177-1255), written the way the reference writes it."""
+    import b200msm
+    G = os.path.join(os.path.dirname(__file__), "golden")
+    v = json.load(open(os.path.join(G, "batchAffine.json")))["tests"]["multiExp is correct (case 1)."]["values"]
+    inputPoints = [int(x, 16) for x in v["inputPoints"]]; inputScalars = [int(x, 16) for x in v["inputScalars"]]
+    expectedOutput = [int(x, 16) for x in v["expectedOutput"]]
+    numPoints = 10; n8q = 48; n8r = 32
+    pb = b200msm.Protoboard("bls12381", engine=eng)
+    pRes = pb.alloc(n8q * 3); pPoints = pb.alloc(numPoints * n8q * 2); pScalars = pb.alloc(numPoints * n8r)
+    for i in range(numPoints):
+        pb.set(pPoints + 96 * i, inputPoints[i * 2], 48); pb.set(pPoints + 96 * i + 48, inputPoints[i * 2 + 1], 48)
+        pb.f1m_toMontgomery(pPoints + 96 * i, pPoints + 96 * i); pb.f1m_toMontgomery(pPoints + 96 * i + 48, pPoints + 96 * i + 48)
+    for i in range(numPoints):
+        pb.set(pScalars + n8r * i, inputScalars[i], n8r)
+    pb.g1m_multiexp_multiExp(pPoints, pScalars, numPoints, pRes)
+    pb.g1m_normalize(pRes, pRes)
+    pb.f1m_fromMontgomery(pRes, pRes); pb.f1m_fromMontgomery(pRes + 48, pRes + 48)
+    output = pb.get(pRes, 2, 48)
+    assert output[0] == expectedOutput[0] and output[1] == expectedOutput[1]
+
+
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+def test_bn128_style_multiexp(eng, cname):
+    """test/bn128.js:462-497: sum_{i=1..8} i * (i*G) = 204*G"""
+    cv = curve(cname)
+    P = [pyref.mul(cv, i, cv.G) for i in range(1, 9)]
+    bases = b"".join(pyref.affine_to_bytes(cv, p) for p in P); sc = b"".join(i.to_bytes(32, "little") for i in range(1, 9))
+    assert msm(eng, cv, bases, sc, 32, 8) == pyref.canonical_bytes(cv, pyref.mul(cv, 204, cv.G))
+
+
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+def test_msm_2_14_against_reference_wasm(eng, cname):
+    """BASELINE configs[0]: 2^14 points; checked against the reference's own WASM module run natively."""
+    cv = curve(cname); n = 1 << 14
+    bases = make_bases(cv, n, 0xB2000000 + 14); sc = make_scalars(n, 14, "u256")
+    got = msm(eng, cv, bases, sc, 32, n)
+    assert got == oracle_msm(cv, bases, sc, 32, n)
+    if refwasm.available(cname):
+        assert got == pyref.canonical_bytes(cv, refwasm.RefModule(cname).msm_affine(bases, sc, 32, n))
+
+
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+def test_sum_and_resident_api(eng, cname):
+    cv = curve(cname); n = 2000
+    bases = make_bases(cv, n, 5); sc = make_scalars(n, 6, "modr", cv.r)
+    h = eng.upload_bases(cv.cid, bases, n)
+    try:
+        full, st = eng.multiexp_resident(h, sc, 32, n, cv.cid, want_stats=True)
+        assert eng.normalize(cv.cid, full) == oracle_msm(cv, bases, sc, 32, n)
+        assert st["n"] == n and st["pairs"] > 0 and st["ms_total"] > 0
+        # point-range shards + g1m_add merge
+        half = n // 2
+        a = eng.multiexp_affine(cv.cid, bases[:half * 2 * cv.n8], sc[:half * 32], 32, half)
+        b = eng.multiexp_affine(cv.cid, bases[half * 2 * cv.n8:], sc[half * 32:], 32, n - half)
+        assert eng.normalize(cv.cid, eng.sum_points(cv.cid, a + b, 2)) == eng.normalize(cv.cid, full)
+    finally:
+        eng.free_bases(h)

@@ -1,0 +1,102 @@
+"""Engine: thin Python owner of one b200msm_ctx (one GPU, one stream).
+
+Inputs may be `bytes`/`bytearray`/numpy arrays (host) or torch CUDA tensors / raw integer device
+pointers (device); they are passed to the C ABI as plain pointers -- no torch types cross the boundary.
+"""
+import ctypes
+from . import _lib
+from ._lib import lib, B200MsmError, Stats, N8
+
+
+def _ptr(x):
+    """(pointer, keepalive) for bytes / bytearray / memoryview / numpy / torch tensor / int"""
+    if x is None: return None, None
+    if isinstance(x, int): return ctypes.c_void_p(x), None
+    if isinstance(x, (bytes, bytearray)):
+        buf = (ctypes.c_char * len(x)).from_buffer_copy(x) if isinstance(x, bytes) else (ctypes.c_char * len(x)).from_buffer(x)
+        return ctypes.cast(buf, ctypes.c_void_p), buf
+    if hasattr(x, "data_ptr"):  # torch tensor (host or device)
+        assert x.is_contiguous()
+        return ctypes.c_void_p(x.data_ptr()), x
+    if hasattr(x, "ctypes"):    # numpy
+        return ctypes.c_void_p(x.ctypes.data), x
+    raise TypeError("unsupported buffer type %r" % type(x))
+
+
+class Engine:
+    def __init__(self, device=-1):
+        self._ctx = ctypes.c_void_p()
+        rc = lib.b200msm_create(ctypes.byref(self._ctx), device)
+        if rc: raise B200MsmError(rc, "b200msm_create failed: is a B200 visible? (no CPU fallback)")
+
+    def close(self):
+        if self._ctx: lib.b200msm_destroy(self._ctx); self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+
+    def _ck(self, rc):
+        if rc: raise B200MsmError(rc, lib.b200msm_last_error(self._ctx).decode())
+
+    # ---- configuration
+    def set_stream(self, cuda_stream_handle): self._ck(lib.b200msm_set_stream(self._ctx, ctypes.c_void_p(cuda_stream_handle)))
+    def synchronize(self): self._ck(lib.b200msm_synchronize(self._ctx))
+    def set_option(self, key, value): self._ck(lib.b200msm_set_option(self._ctx, key.encode(), int(value)))
+
+    # ---- the reference entry points
+    def multiexp_affine(self, curve, bases, scalars, scalar_size, n, out=None):
+        """g1m_multiexpAffine: returns 3*n8 bytes (Jacobian Montgomery) unless `out` (host/device buffer) is given."""
+        pb, kb = _ptr(bases); ps, ks = _ptr(scalars)
+        if out is None:
+            o = ctypes.create_string_buffer(3 * N8[curve])
+            self._ck(lib.b200msm_g1_multiexp_affine(self._ctx, curve, pb, ps, scalar_size, n, o)); return o.raw
+        po, ko = _ptr(out)
+        self._ck(lib.b200msm_g1_multiexp_affine(self._ctx, curve, pb, ps, scalar_size, n, po)); return out
+
+    def multiexp_affine_chunk(self, curve, bases, scalars, scalar_size, n, start_bit, chunk_bits):
+        pb, kb = _ptr(bases); ps, ks = _ptr(scalars)
+        o = ctypes.create_string_buffer(3 * N8[curve])
+        self._ck(lib.b200msm_g1_multiexp_affine_chunk(self._ctx, curve, pb, ps, scalar_size, n, start_bit, chunk_bits, o)); return o.raw
+
+    def upload_bases(self, curve, bases, n):
+        pb, kb = _ptr(bases); h = ctypes.c_uint64()
+        self._ck(lib.b200msm_upload_bases(self._ctx, curve, pb, n, ctypes.byref(h))); return h.value
+
+    def free_bases(self, handle): self._ck(lib.b200msm_free_bases(self._ctx, handle))
+
+    def multiexp_resident(self, handle, scalars, scalar_size, n, curve, out=None, want_stats=False):
+        ps, ks = _ptr(scalars)
+        st = Stats() if want_stats else None
+        if out is None:
+            o = ctypes.create_string_buffer(3 * N8[curve]); po = o
+        else:
+            po, ko = _ptr(out)
+        self._ck(lib.b200msm_g1_multiexp_resident(self._ctx, handle, ps, scalar_size, n, po, ctypes.byref(st) if st is not None else None))
+        res = o.raw if out is None else out
+        return (res, st.as_dict()) if want_stats else res
+
+    def normalize(self, curve, jac, count=1):
+        """g1m_normalize + fromMontgomery: canonical x||y bytes (plain LE ints; infinity = zeros)"""
+        pj, kj = _ptr(jac); o = ctypes.create_string_buffer(2 * N8[curve] * count)
+        self._ck(lib.b200msm_g1_normalize(self._ctx, curve, pj, count, o)); return o.raw
+
+    def sum_points(self, curve, jac_points, count):
+        pj, kj = _ptr(jac_points); o = ctypes.create_string_buffer(3 * N8[curve])
+        self._ck(lib.b200msm_g1_sum(self._ctx, curve, pj, count, o)); return o.raw
+
+    def generate_bases(self, curve, seed, first, n, device_out):
+        po, ko = _ptr(device_out)
+        self._ck(lib.b200msm_g1_generate_bases(self._ctx, curve, seed, first, n, po))
+
+    def fq_op(self, curve, op, a, b=None):
+        n = len(a) // N8[curve]
+        pa, ka = _ptr(a); pb_, kb = _ptr(b)
+        o = ctypes.create_string_buffer(max(1, len(a)))
+        self._ck(lib.b200msm_fq_op(self._ctx, curve, op, pa, pb_, o, n)); return o.raw[:len(a)]
+
+    def probe_imad(self):
+        v = ctypes.c_double(); self._ck(lib.b200msm_probe_imad(self._ctx, ctypes.byref(v))); return v.value
+
+    def probe_fqmul(self, curve):
+        v = ctypes.c_double(); self._ck(lib.b200msm_probe_fqmul(self._ctx, curve, ctypes.byref(v))); return v.value

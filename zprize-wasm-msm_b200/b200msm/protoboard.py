@@ -1,0 +1,102 @@
+"""Host-side mirror of the reference's test rig for the MSM path.
+
+The reference drives its WASM module through `wasmbuilder.buildProtoboard` (usage:
+wasmcurves/test/batchAffine.js:13-17, benchmarks/multiexp.js:9-31): one linear memory, `pb.alloc`,
+`pb.set`, `pb.get`, and every export as a method taking i32 "pointers".  This class offers the same
+names and argument meaning for the exports on the MSM path, with the work done by the GPU engine
+through the C ABI, so a parity test reads like the reference's own test:
+
+    pb = Protoboard("bls12381")
+    pBases = pb.alloc(n * 96); pScalars = pb.alloc(n * 32); pRes = pb.alloc(144)
+    ... pb.set(...) / pb.f1m_toMontgomery(p, p) ...
+    pb.g1m_multiexpAffine(pBases, pScalars, 32, n, pRes)
+    pb.g1m_normalize(pRes, pRes); pb.f1m_fromMontgomery(pRes, pRes); pb.f1m_fromMontgomery(pRes + 48, pRes + 48)
+    x, y = pb.get(pRes, 2, 48)
+
+"Pointers" are byte offsets into a host bytearray (the linear memory); errors are raised as
+B200MsmError where the reference would trap.
+"""
+import ctypes
+from ._lib import BLS12_381_G1, BN254_G1, N8, B200MsmError
+from .engine import Engine
+
+_OPS = {"mul": 0, "add": 1, "sub": 2, "square": 3, "inverse": 4, "toMontgomery": 5, "fromMontgomery": 6, "neg": 7}
+
+
+class Protoboard:
+    def __init__(self, curve="bls12381", mem_bytes=1 << 26, engine=None):
+        self.curve = BLS12_381_G1 if curve in ("bls12381", 0) else BN254_G1
+        self.n8 = N8[self.curve]
+        self.mem = bytearray(mem_bytes)
+        self._cbuf = (ctypes.c_char * mem_bytes).from_buffer(self.mem)
+        self._base = ctypes.addressof(self._cbuf)
+        self._top = 8
+        self.engine = engine or Engine()
+
+    # ---- memory (pb.alloc / pb.set / pb.get; bump pointer like the data segment at address 0)
+    def alloc(self, nbytes):
+        p = (self._top + 7) & ~7
+        if p + nbytes > len(self.mem): raise MemoryError("protoboard memory exhausted")
+        self._top = p + nbytes
+        return p
+
+    def set(self, ptr, value, nbytes=4):
+        self.mem[ptr:ptr + nbytes] = int(value).to_bytes(nbytes, "little")
+
+    def get(self, ptr, count=1, nbytes=4):
+        v = [int.from_bytes(self.mem[ptr + i * nbytes: ptr + (i + 1) * nbytes], "little") for i in range(count)]
+        return v[0] if count == 1 else v
+
+    def write(self, ptr, data): self.mem[ptr:ptr + len(data)] = data
+    def read(self, ptr, n): return bytes(self.mem[ptr:ptr + n])
+    def _p(self, ptr): return self._base + ptr
+
+    # ---- MSM exports (wasmcurves/src/build_multiexp.js:251-371, :96-249; build_multiexp_opt.js:1987-2110)
+    def g1m_multiexpAffine(self, pBases, pScalars, scalarSize, n, pr):
+        self.engine.multiexp_affine(self.curve, self._p(pBases), self._p(pScalars), scalarSize, n, out=self._p(pr))
+
+    g1m_multiexpAffine_wasmcurve = g1m_multiexpAffine      # the fork's name for the same export (build_curve_jacobian_a0.js:1429-1430)
+
+    def g1m_multiexpAffine_chunk(self, pBases, pScalars, scalarSize, n, startBit, chunkSize, pr):
+        out = self.engine.multiexp_affine_chunk(self.curve, self._p(pBases), self._p(pScalars), scalarSize, n, startBit, chunkSize)
+        self.write(pr, out)
+
+    g1m_multiexpAffine_wasmcurve_chunk = g1m_multiexpAffine_chunk
+
+    def g1m_multiexp_multiExp(self, pPoints, pScalars, numPoints, pResult):
+        """Manta entry point: affine points, 32-byte scalars (build_multiexp_opt.js:1987-1996, :2024)."""
+        self.g1m_multiexpAffine(pPoints, pScalars, 32, numPoints, pResult)
+
+    g1m_multiexpAffine_multiExp = g1m_multiexp_multiExp
+
+    # ---- the helpers every reference test uses around the MSM call
+    def _fq(self, op, pa, pb_, pr):
+        a = self.read(pa, self.n8); b = self.read(pb_, self.n8) if pb_ is not None else None
+        self.write(pr, self.engine.fq_op(self.curve, _OPS[op], a, b))
+
+    def f1m_toMontgomery(self, pa, pr): self._fq("toMontgomery", pa, None, pr)
+    def f1m_fromMontgomery(self, pa, pr): self._fq("fromMontgomery", pa, None, pr)
+    def f1m_mul(self, pa, pb_, pr): self._fq("mul", pa, pb_, pr)
+    def f1m_add(self, pa, pb_, pr): self._fq("add", pa, pb_, pr)
+    def f1m_sub(self, pa, pb_, pr): self._fq("sub", pa, pb_, pr)
+    def f1m_square(self, pa, pr): self._fq("square", pa, None, pr)
+    def f1m_inverse(self, pa, pr): self._fq("inverse", pa, None, pr)
+    def f1m_neg(self, pa, pr): self._fq("neg", pa, None, pr)
+
+    def g1m_isZero(self, p):
+        return int(self.read(p + 2 * self.n8, self.n8) == bytes(self.n8))
+
+    def g1m_normalize(self, p, pr):
+        """Jacobian -> Jacobian with z = 1 (Montgomery), infinity -> g1m_zero (build_curve_jacobian_a0.js:940-973)."""
+        n8 = self.n8
+        if self.g1m_isZero(p):
+            one = self.engine.fq_op(self.curve, _OPS["toMontgomery"], (1).to_bytes(n8, "little"))
+            self.write(pr, bytes(n8) + one + bytes(n8)); return
+        xy = self.engine.normalize(self.curve, self.read(p, 3 * n8))          # canonical, non-Montgomery
+        xm = self.engine.fq_op(self.curve, _OPS["toMontgomery"], xy[:n8]); ym = self.engine.fq_op(self.curve, _OPS["toMontgomery"], xy[n8:])
+        one = self.engine.fq_op(self.curve, _OPS["toMontgomery"], (1).to_bytes(n8, "little"))
+        self.write(pr, xm + ym + one)
+
+    def g1m_add(self, p1, p2, pr):
+        n8 = self.n8
+        self.write(pr, self.engine.sum_points(self.curve, self.read(p1, 3 * n8) + self.read(p2, 3 * n8), 2))

@@ -1,0 +1,228 @@
+// accumulate.cuh -- bucket accumulation by batch-affine additions with Montgomery batch inversion.
+//
+// GPU redesign of the reference's opt-path bucket phase:
+//   _constructAdditionChains / _evaluateAdditionChains / _addAffinePointsOneRound / _reduceBuckets
+//   wasmcurves/src/build_multiexp_opt.js:651-858, :1016-1245, :1336-1585 and f1m_batchInverse,
+//   wasmcurves/src/build_batchinverse.js:4-140.
+// The reference groups each bucket's points by the binary expansion of its count and walks the
+// levels serially.  Here every bucket is summed by a balanced pairwise tree: in round r every bucket
+// segment of n_r points becomes ceil(n_r/2) points (adjacent points are added, an odd last point is
+// carried over), for ALL buckets of ALL windows in one launch.  All additions of a round share ONE
+// field inversion: a grid-wide product tree (K-ary, K = BA_K) of the denominators is built level by
+// level, the single root is inverted by one thread, and the inverses are propagated back down.
+//
+//   per addition: forward 1M (running product) ; backward 2M (denominator inverse) + 2M + 1S (slope, x3, y3)
+//   = 6 field multiplications = 6*(2N^2+N) limb products, the reference's own count
+//   (build_multiexp_opt.js:1207-1233 + build_batchinverse.js:61-66,108-119).
+//
+// Segment bookkeeping: off[r][b] (exclusive scans of n_r[b] = ceil(n_0[b] / 2^r)) for every round are
+// computed up front from the sort histogram; bid[r][j] gives the bucket of output slot j of round r-1
+// and is propagated from round to round by the threads that own even local slots.
+#pragma once
+#include "msm_kernels.cuh"
+
+namespace b200 {
+
+constexpr int BA_K = 4;            // additions per thread per inversion chain (level 0) and product-tree arity
+constexpr int BA_THREADS = 128;
+constexpr int BA_TILE = BA_K * BA_THREADS;
+constexpr uint32_t BA_ROOT_MAX = 256;   // the product tree is reduced until at most this many values remain
+
+// n_{r+1}[b] = ceil(n_r[b] / 2)
+__global__ void k_halve_counts(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (in[i] + 1) >> 1;
+}
+// bid1[j] = bucket owning output slot j of round 0 (binary search in off1); one thread per slot
+__global__ void k_fill_bid(const uint32_t* __restrict__ off1, uint32_t nb, uint32_t* __restrict__ bid1) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t m = off1[nb];
+  if (j >= m) return;
+  uint32_t lo = 0, hi = nb;            // largest b with off1[b] <= j  (and non-empty: off1[b+1] > j)
+  while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (off1[mid] <= j) lo = mid; else hi = mid; }
+  bid1[j] = lo;
+}
+
+// ---- one tree round, level 0 --------------------------------------------------------------------------
+template <class C, bool FIRST>
+B200_DI void tree_load_point(Affine<C>& p, const void* __restrict__ bases, const uint32_t* __restrict__ sorted, const void* __restrict__ pin, uint32_t pos) {
+  if (FIRST) {
+    uint32_t e = __ldg(sorted + pos);
+    affine_load<C>(p, bases, e & 0x7fffffffu);
+    if (e >> 31) fe_neg<C>(p.y, p.y);
+  } else {
+    affine_load_cg<C>(p, pin, pos);
+  }
+}
+
+struct TreeRound {
+  const uint32_t* off_in;     // off[r]    (nb + 1)
+  const uint32_t* off_out;    // off[r+1]  (nb + 1)
+  const uint32_t* off_next;   // off[r+2]  or nullptr
+  const uint32_t* bid;        // bid[r+1]  (one per output slot)
+  uint32_t* bid_next;         // bid[r+2]  or nullptr
+  uint32_t nb;
+};
+
+// slot -> (input position of the first operand, has second operand)
+B200_DI bool tree_slot(const TreeRound& tr, uint32_t j, uint32_t& in0, bool& has2, bool write_next) {
+  uint32_t m = tr.off_out[tr.nb];
+  if (j >= m) return false;
+  uint32_t b = tr.bid[j];
+  uint32_t local = j - tr.off_out[b];
+  in0 = tr.off_in[b] + 2 * local;
+  has2 = in0 + 1 < tr.off_in[b + 1];
+  if (write_next && tr.bid_next && !(local & 1)) tr.bid_next[tr.off_next[b] + (local >> 1)] = b;
+  return true;
+}
+
+// forward: denominators, per-slot prefix products, per-thread products
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(BA_THREADS) k_tree_fwd(TreeRound tr, const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                         const void* __restrict__ pin, void* __restrict__ prefix, void* __restrict__ prod) {
+  uint32_t tile = blockIdx.x * BA_TILE;
+  Fe<C::N> p; fe_set_one<C>(p);
+#pragma unroll 1
+  for (int i = 0; i < BA_K; i++) {
+    uint32_t j = tile + i * BA_THREADS + threadIdx.x, in0; bool has2;
+    if (!tree_slot(tr, j, in0, has2, true)) continue;
+    if (!has2) continue;
+    Affine<C> p1, p2; Fe<C::N> d;
+    tree_load_point<C, FIRST>(p1, bases, sorted, pin, in0);
+    tree_load_point<C, FIRST>(p2, bases, sorted, pin, in0 + 1);
+    int kind = affine_add_denominator<C>(d, p1, p2);
+    if (kind <= 1) {
+      fe_store<C>(reinterpret_cast<char*>(prefix) + (uint64_t)j * 4 * C::N, p);
+      fe_mul<C>(p, p, d);
+    }
+  }
+  fe_store<C>(reinterpret_cast<char*>(prod) + (uint64_t)(blockIdx.x * BA_THREADS + threadIdx.x) * 4 * C::N, p);
+}
+
+// backward: consume the inverse of the thread's product, finish every addition, write the round's output points
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(BA_THREADS) k_tree_bwd(TreeRound tr, const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                         const void* __restrict__ pin, const void* __restrict__ prefix, const void* __restrict__ inv,
+                                                         void* __restrict__ pout) {
+  uint32_t tile = blockIdx.x * BA_TILE;
+  Fe<C::N> q;
+  fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)(blockIdx.x * BA_THREADS + threadIdx.x) * 4 * C::N);
+#pragma unroll 1
+  for (int i = BA_K - 1; i >= 0; i--) {
+    uint32_t j = tile + i * BA_THREADS + threadIdx.x, in0; bool has2;
+    if (!tree_slot(tr, j, in0, has2, false)) continue;
+    Affine<C> p1, p2, r;
+    tree_load_point<C, FIRST>(p1, bases, sorted, pin, in0);
+    if (!has2) { affine_store<C>(pout, j, p1); continue; }
+    tree_load_point<C, FIRST>(p2, bases, sorted, pin, in0 + 1);
+    Fe<C::N> d, dinv;
+    int kind = affine_add_denominator<C>(d, p1, p2);
+    if (kind <= 1) {
+      Fe<C::N> pre; fe_load_cg<C>(pre, reinterpret_cast<const char*>(prefix) + (uint64_t)j * 4 * C::N);
+      fe_mul<C>(dinv, q, pre);
+      fe_mul<C>(q, q, d);
+    }
+    affine_add_finish<C>(r, p1, p2, dinv, kind);
+    affine_store<C>(pout, j, r);
+  }
+}
+
+// ---- product tree, levels >= 1: plain arrays of field elements -----------------------------------------
+template <class C>
+__global__ void __launch_bounds__(BA_THREADS) k_prod_fwd(const void* __restrict__ vals, uint32_t n, void* __restrict__ prefix, void* __restrict__ prod) {
+  uint32_t tile = blockIdx.x * BA_TILE;
+  Fe<C::N> p; fe_set_one<C>(p);
+#pragma unroll 1
+  for (int i = 0; i < BA_K; i++) {
+    uint32_t e = tile + i * BA_THREADS + threadIdx.x;
+    if (e >= n) continue;
+    Fe<C::N> v; fe_load_cg<C>(v, reinterpret_cast<const char*>(vals) + (uint64_t)e * 4 * C::N);
+    fe_store<C>(reinterpret_cast<char*>(prefix) + (uint64_t)e * 4 * C::N, p);
+    fe_mul<C>(p, p, v);
+  }
+  fe_store<C>(reinterpret_cast<char*>(prod) + (uint64_t)(blockIdx.x * BA_THREADS + threadIdx.x) * 4 * C::N, p);
+}
+// in place: vals[e] <- 1 / vals[e], given the inverse of each thread's product in inv[]
+template <class C>
+__global__ void __launch_bounds__(BA_THREADS) k_prod_bwd(void* __restrict__ vals, uint32_t n, const void* __restrict__ prefix, const void* __restrict__ inv) {
+  uint32_t tile = blockIdx.x * BA_TILE;
+  Fe<C::N> q;
+  fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)(blockIdx.x * BA_THREADS + threadIdx.x) * 4 * C::N);
+#pragma unroll 1
+  for (int i = BA_K - 1; i >= 0; i--) {
+    uint32_t e = tile + i * BA_THREADS + threadIdx.x;
+    if (e >= n) continue;
+    Fe<C::N> v, pre, r;
+    fe_load_cg<C>(v, reinterpret_cast<const char*>(vals) + (uint64_t)e * 4 * C::N);
+    fe_load_cg<C>(pre, reinterpret_cast<const char*>(prefix) + (uint64_t)e * 4 * C::N);
+    fe_mul<C>(r, q, pre);
+    fe_mul<C>(q, q, v);
+    fe_store<C>(reinterpret_cast<char*>(vals) + (uint64_t)e * 4 * C::N, r);
+  }
+}
+// root: n <= BA_ROOT_MAX values inverted in place by ONE block: binary product tree in shared memory (log depth),
+// a single field inversion by thread 0 (f1m_inverse at build_batchinverse.js:90), then the tree is walked back down.
+template <class C>
+__global__ void __launch_bounds__(BA_ROOT_MAX) k_inv_root(void* __restrict__ vals, uint32_t n) {
+  constexpr int N = C::N;
+  __shared__ uint32_t tree[2 * BA_ROOT_MAX * N];       // node k (1-based heap order): leaves at [BA_ROOT_MAX, 2*BA_ROOT_MAX)
+  const uint32_t t = threadIdx.x;
+  Fe<N> v;
+  if (t < n) fe_load_cg<C>(v, reinterpret_cast<const char*>(vals) + (uint64_t)t * 4 * N); else fe_set_one<C>(v);
+#pragma unroll
+  for (int k = 0; k < N; k++) tree[(BA_ROOT_MAX + t) * N + k] = v.l[k];
+  __syncthreads();
+  for (uint32_t width = BA_ROOT_MAX / 2; width >= 1; width >>= 1) {     // up-sweep: node = left * right
+    if (t < width) {
+      Fe<N> a, b, c; uint32_t node = width + t;
+#pragma unroll
+      for (int k = 0; k < N; k++) { a.l[k] = tree[(2 * node) * N + k]; b.l[k] = tree[(2 * node + 1) * N + k]; }
+      fe_mul<C>(c, a, b);
+#pragma unroll
+      for (int k = 0; k < N; k++) tree[node * N + k] = c.l[k];
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    Fe<N> r, ri;
+#pragma unroll
+    for (int k = 0; k < N; k++) r.l[k] = tree[1 * N + k];
+    fe_inv_fast<C>(ri, r);
+#pragma unroll
+    for (int k = 0; k < N; k++) tree[1 * N + k] = ri.l[k];
+  }
+  __syncthreads();
+  for (uint32_t width = 1; width < BA_ROOT_MAX; width <<= 1) {          // down-sweep: inv(left) = inv(node) * right, inv(right) = inv(node) * left
+    if (t < width) {
+      Fe<N> a, b, ip, ia, ib; uint32_t node = width + t;
+#pragma unroll
+      for (int k = 0; k < N; k++) { ip.l[k] = tree[node * N + k]; a.l[k] = tree[(2 * node) * N + k]; b.l[k] = tree[(2 * node + 1) * N + k]; }
+      fe_mul<C>(ia, ip, b); fe_mul<C>(ib, ip, a);
+#pragma unroll
+      for (int k = 0; k < N; k++) { tree[(2 * node) * N + k] = ia.l[k]; tree[(2 * node + 1) * N + k] = ib.l[k]; }
+    }
+    __syncthreads();
+  }
+  if (t < n) {
+#pragma unroll
+    for (int k = 0; k < N; k++) v.l[k] = tree[(BA_ROOT_MAX + t) * N + k];
+    fe_store<C>(reinterpret_cast<char*>(vals) + (uint64_t)t * 4 * N, v);
+  }
+}
+
+// ---- finish: one thread per bucket sums what is left of its segment and writes the bucket as XYZZ -------
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(128) k_accum_finish(const void* __restrict__ bases, const uint32_t* __restrict__ sorted, const void* __restrict__ pin,
+                                                      const uint32_t* __restrict__ off, uint32_t nb, void* __restrict__ buckets) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  uint32_t lo = off[b], hi = off[b + 1];
+  XYZZ<C> acc; xyzz_set_inf<C>(acc);
+  for (uint32_t k = lo; k < hi; k++) {
+    Affine<C> p; tree_load_point<C, FIRST>(p, bases, sorted, pin, k);
+    xyzz_madd<C>(acc, p);
+  }
+  xyzz_store<C>(buckets, b, acc);
+}
+
+}  // namespace b200

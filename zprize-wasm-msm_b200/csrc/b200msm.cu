@@ -1,0 +1,552 @@
+// b200msm.cu -- context, pipeline orchestration and the C ABI declared in include/b200msm.h.
+//
+// Host-side counterpart of the orchestration functions of the reference:
+//   g1m_multiexpAffine       wasmcurves/src/build_multiexp.js:251-371
+//   g1m_multiexpAffine_chunk wasmcurves/src/build_multiexp.js:96-249
+//   g1m_multiexp_multiExp    wasmcurves/src/build_multiexp_opt.js:1987-2110 (scratch allocation :2037-2070)
+// The reference bump-allocates its scratch in WASM linear memory per call; here the context owns
+// grow-only device buffers that are reused across calls (no cudaMalloc in steady state).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <map>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/b200msm.h"
+#include "msm_kernels.cuh"
+#include "accumulate.cuh"
+
+using namespace b200;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + (bytes >> 3) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { p = nullptr; return e; }
+    cap = want; return cudaSuccess;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Resident { int curve; uint64_t n; void* d; };
+
+}  // namespace
+
+struct b200msm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr; bool own_stream = false;
+  std::string err;
+  int opt_window_bits = 0, opt_accumulate = 0, opt_tree_rounds = -1;
+  DevBuf bases, scalars, canon, counts, offsets, cursors, tiles, sorted, buckets, wsum, out, misc, acc_a, acc_b, acc_c, acc_d, acc_e;
+  DevBuf t_offs, t_cnt, t_bid, t_pa, t_pb, t_prefix, t_prod, t_lvlprefix;     // batch-affine tree scratch
+  uint32_t* h_pinned = nullptr;                                               // small pinned read-back area (1024 words)
+  std::map<uint64_t, Resident> residents; uint64_t next_handle = 1;
+  cudaEvent_t ev[8] = {};
+};
+
+namespace {
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); \
+  return e_ == cudaErrorMemoryAllocation ? B200MSM_E_NOMEM : B200MSM_E_CUDA; } } while (0)
+#define CKL() CK(cudaGetLastError())
+
+bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int n8_of(int curve) { return curve == B200MSM_BLS12_381_G1 ? 48 : 32; }
+bool curve_ok(int curve) { return curve == B200MSM_BLS12_381_G1 || curve == B200MSM_BN254_G1; }
+
+uint32_t auto_window_bits(uint64_t n, uint32_t nbits) {
+  uint32_t lg = 0; while ((2ull << lg) <= n) lg++;          // floor(log2 n)
+  int c = (int)lg - 4;
+  if (c > 16 && n < (1ull << 22)) c = 16;
+  if (c > 20) c = 20;
+  if (c < 2) c = 2;
+  if ((uint32_t)c > nbits + 1) c = (int)nbits + 1;
+  return (uint32_t)c;
+}
+
+int exclusive_scan(b200msm_ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* cursors) {
+  uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  CK(ctx->tiles.ensure((size_t)(ntiles + 1) * 4));
+  k_scan_tiles<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, ctx->tiles.as<uint32_t>()); CKL();
+  k_scan_sums<<<1, 1024, 0, ctx->stream>>>(ctx->tiles.as<uint32_t>(), ntiles); CKL();
+  k_scan_apply<<<(n + 255) / 256, 256, 0, ctx->stream>>>(out, n, ctx->tiles.as<uint32_t>(), ntiles, cursors); CKL();
+  return B200MSM_OK;
+}
+
+// ---- batch-affine tree over the bucket range [b0, b0 + nbg) (a group of whole windows) ------------------
+// off0 = sort offsets (absolute positions in sorted[]), cnt0 = bucket counts of the range (consumed: halved in place),
+// m0 = pairs in the range, maxcnt = largest bucket population in the range.  Writes buckets[b0 .. b0+nbg) as XYZZ.
+template <class C>
+int accumulate_batch_affine(b200msm_ctx* ctx, const void* d_bases, const uint32_t* off0, uint32_t* cnt0, uint32_t nbg, uint64_t m0, uint32_t maxcnt,
+                            void* buckets_g, uint32_t* rounds_out, uint64_t* adds_out) {
+  cudaStream_t s = ctx->stream;
+  const uint32_t* sorted = ctx->sorted.as<uint32_t>();
+  // number of tree rounds: until the largest segment is <= 3 points (the finish kernel sums the rest serially)
+  uint32_t R = 0;
+  if (ctx->opt_tree_rounds >= 0) R = (uint32_t)ctx->opt_tree_rounds;
+  else { uint32_t mc = maxcnt; while (mc > 3) { mc = (mc + 1) >> 1; R++; } }
+  if (m0 < 2) R = 0;
+  *rounds_out = std::max(*rounds_out, R);
+  if (R == 0) {
+    k_accum_finish<C, true><<<(nbg + 127) / 128, 128, 0, s>>>(d_bases, sorted, nullptr, off0, nbg, buckets_g); CKL();
+    return B200MSM_OK;
+  }
+  // upper bounds of the slot counts per round: sum ceil(n/2) <= (sum n + #non-empty) / 2
+  std::vector<uint64_t> U(R + 2); U[0] = m0;
+  for (uint32_t r = 0; r <= R; r++) U[r + 1] = std::min<uint64_t>(U[r], (U[r] + std::min<uint64_t>(nbg, U[r]) + 1) / 2);
+  // offsets for rounds 1..R (round 0 uses off0 directly)
+  const size_t offstride = (size_t)nbg + 1;
+  CK(ctx->t_offs.ensure(offstride * R * 4));
+  std::vector<const uint32_t*> off(R + 1); off[0] = off0;
+  for (uint32_t r = 1; r <= R; r++) {
+    uint32_t* o = ctx->t_offs.as<uint32_t>() + offstride * (r - 1);
+    k_halve_counts<<<(nbg + 255) / 256, 256, 0, s>>>(cnt0, cnt0, nbg); CKL();
+    int rc = exclusive_scan(ctx, cnt0, o, nbg, nullptr); if (rc) return rc;
+    off[r] = o;
+  }
+  // bid arrays for rounds 1..R
+  std::vector<uint32_t*> bid(R + 2, nullptr);
+  { size_t tot = 0; for (uint32_t r = 1; r <= R; r++) tot += U[r];
+    CK(ctx->t_bid.ensure(tot * 4 + 16));
+    size_t at = 0; for (uint32_t r = 1; r <= R; r++) { bid[r] = ctx->t_bid.as<uint32_t>() + at; at += U[r]; } }
+  k_fill_bid<<<(uint32_t)((U[1] + 255) / 256), 256, 0, s>>>(off[1], nbg, bid[1]); CKL();
+  const size_t fe = 4 * C::N, pt = 8 * C::N;
+  CK(ctx->t_pa.ensure(U[1] * pt + 16)); if (R > 1) CK(ctx->t_pb.ensure(U[2] * pt + 16));
+  CK(ctx->t_prefix.ensure(U[1] * fe + 16));
+  // product-tree level sizes for the largest round
+  { size_t tot = 0, totp = 0; uint64_t n = ((U[1] + BA_TILE - 1) / BA_TILE) * BA_THREADS;
+    for (;;) { tot += n; if (n <= BA_ROOT_MAX) break; totp += n; n = ((n + BA_TILE - 1) / BA_TILE) * BA_THREADS; }
+    CK(ctx->t_prod.ensure(tot * fe + 16)); CK(ctx->t_lvlprefix.ensure(totp * fe + 16)); }
+  void* pin = nullptr;
+  for (uint32_t r = 0; r < R; r++) {
+    void* pout = (r & 1) ? ctx->t_pb.p : ctx->t_pa.p;
+    TreeRound tr{off[r], off[r + 1], (r + 2 <= R) ? off[r + 2] : nullptr, bid[r + 1], (r + 2 <= R) ? bid[r + 2] : nullptr, nbg};
+    uint32_t grid = (uint32_t)((U[r + 1] + BA_TILE - 1) / BA_TILE);
+    if (grid == 0) grid = 1;
+    char* prod = ctx->t_prod.as<char>(); char* lpre = ctx->t_lvlprefix.as<char>();
+    if (r == 0) k_tree_fwd<C, true><<<grid, BA_THREADS, 0, s>>>(tr, d_bases, sorted, nullptr, ctx->t_prefix.p, prod);
+    else k_tree_fwd<C, false><<<grid, BA_THREADS, 0, s>>>(tr, nullptr, nullptr, pin, ctx->t_prefix.p, prod);
+    CKL();
+    // up the product tree
+    std::vector<uint64_t> ln; std::vector<char*> lv, lp;
+    uint64_t n = (uint64_t)grid * BA_THREADS; char* cur = prod; char* curp = lpre;
+    while (n > BA_ROOT_MAX) {
+      uint32_t g2 = (uint32_t)((n + BA_TILE - 1) / BA_TILE);
+      char* nxt = cur + n * fe;
+      k_prod_fwd<C><<<g2, BA_THREADS, 0, s>>>(cur, (uint32_t)n, curp, nxt); CKL();
+      ln.push_back(n); lv.push_back(cur); lp.push_back(curp);
+      curp += n * fe; cur = nxt; n = (uint64_t)g2 * BA_THREADS;
+    }
+    k_inv_root<C><<<1, BA_ROOT_MAX, 0, s>>>(cur, (uint32_t)n); CKL();
+    // back down
+    for (int l = (int)ln.size() - 1; l >= 0; l--) {
+      uint32_t g2 = (uint32_t)((ln[l] + BA_TILE - 1) / BA_TILE);
+      k_prod_bwd<C><<<g2, BA_THREADS, 0, s>>>(lv[l], (uint32_t)ln[l], lp[l], lv[l] + ln[l] * fe); CKL();
+    }
+    if (r == 0) k_tree_bwd<C, true><<<grid, BA_THREADS, 0, s>>>(tr, d_bases, sorted, nullptr, ctx->t_prefix.p, prod, pout);
+    else k_tree_bwd<C, false><<<grid, BA_THREADS, 0, s>>>(tr, nullptr, nullptr, pin, ctx->t_prefix.p, prod, pout);
+    CKL();
+    pin = pout;
+    *adds_out += U[r] - U[r + 1];
+  }
+  k_accum_finish<C, false><<<(nbg + 127) / 128, 128, 0, s>>>(nullptr, nullptr, pin, off[R], nbg, buckets_g); CKL();
+  return B200MSM_OK;
+}
+
+// Core pipeline: d_bases (affine Montgomery, device), d_scal (canonical 8-word scalars, device), result -> d_out (device, 3*n8 bytes)
+template <class C>
+int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, uint64_t n64, uint32_t nbits, void* d_out, b200msm_stats* st) {
+  cudaStream_t s = ctx->stream;
+  const uint32_t n = (uint32_t)n64;
+  MsmPlan pl;
+  pl.n = n; pl.nbits = nbits;
+  pl.c = ctx->opt_window_bits > 0 ? std::min<uint32_t>((uint32_t)ctx->opt_window_bits, std::min<uint32_t>(nbits + 1, 24)) : auto_window_bits(n, nbits);
+  pl.W = (nbits + 1 + pl.c - 1) / pl.c; pl.B = 1u << (pl.c - 1); pl.logB = pl.c - 1;
+  const uint32_t nb = pl.W * pl.B;
+  if ((uint64_t)pl.W * pl.B > (1ull << 31) || (uint64_t)n * pl.W >= (1ull << 32)) { ctx->err = "problem too large for 32-bit pair indices"; return B200MSM_E_UNSUPPORTED; }
+
+  if (st) CK(cudaEventRecord(ctx->ev[1], s));
+  CK(ctx->counts.ensure((size_t)nb * 4)); CK(ctx->offsets.ensure((size_t)(nb + 1) * 4)); CK(ctx->cursors.ensure((size_t)nb * 4));
+  CK(ctx->sorted.ensure((size_t)n * pl.W * 4 + 16));
+  CK(cudaMemsetAsync(ctx->counts.p, 0, (size_t)nb * 4, s));
+  const uint32_t tb = 256, gb = (n + tb - 1) / tb;
+  k_digits<false><<<gb, tb, 0, s>>>(d_scal, pl, ctx->counts.as<uint32_t>(), nullptr); CKL();
+  int rc = exclusive_scan(ctx, ctx->counts.as<uint32_t>(), ctx->offsets.as<uint32_t>(), nb, ctx->cursors.as<uint32_t>());
+  if (rc) return rc;
+  k_digits<true><<<gb, tb, 0, s>>>(d_scal, pl, ctx->cursors.as<uint32_t>(), ctx->sorted.as<uint32_t>()); CKL();
+  if (st) CK(cudaEventRecord(ctx->ev[2], s));
+
+  // ---- read back the per-window pair counts and largest bucket populations (one small D2H, one sync)
+  CK(ctx->misc.ensure(512 * 4));
+  CK(cudaMemsetAsync(ctx->misc.p, 0, 512 * 4, s));
+  { dim3 g((pl.B + 255) / 256, pl.W); k_window_max<<<g, 256, 0, s>>>(ctx->counts.as<uint32_t>(), pl.B, ctx->misc.as<uint32_t>()); CKL(); }
+  if (pl.W > 400) { ctx->err = "too many windows"; return B200MSM_E_UNSUPPORTED; }
+  CK(cudaMemcpyAsync(ctx->h_pinned, ctx->misc.p, pl.W * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpy2DAsync(ctx->h_pinned + 512, 4, ctx->offsets.as<uint32_t>(), (size_t)pl.B * 4, 4, pl.W + 1, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  // ---- accumulate: bucket sums in XYZZ
+  CK(ctx->buckets.ensure((size_t)nb * 16 * C::N));
+  int mode = ctx->opt_accumulate;
+  if (mode == 0) mode = 2;
+  uint32_t rounds = 0; uint64_t adds = 0;
+  if (mode == 2) {
+    // groups of whole windows, sized so that the tree scratch stays within a fraction of device memory
+    size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+    const uint64_t mtot = ctx->h_pinned[512 + pl.W];
+    const double per_pair = 8.0 * C::N * 0.75 + 4.0 * C::N * 0.75 + 6;      // points (pa+pb) + prefix/products + bid, per input pair
+    uint64_t budget_pairs = (uint64_t)std::max(1.0, 0.45 * (double)total_b / per_pair);
+    uint32_t wpg = pl.W;
+    if (mtot > budget_pairs) { uint64_t per_w = (mtot + pl.W - 1) / pl.W; wpg = (uint32_t)std::max<uint64_t>(1, budget_pairs / std::max<uint64_t>(1, per_w)); }
+    for (uint32_t w0 = 0; w0 < pl.W; w0 += wpg) {
+      uint32_t w1 = std::min(pl.W, w0 + wpg);
+      uint32_t mc = 0; for (uint32_t w = w0; w < w1; w++) mc = std::max(mc, ctx->h_pinned[w]);
+      uint64_t m0 = ctx->h_pinned[512 + w1] - ctx->h_pinned[512 + w0];
+      uint32_t b0 = w0 * pl.B, nbg = (w1 - w0) * pl.B;
+      rc = accumulate_batch_affine<C>(ctx, d_bases, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc,
+                                      ctx->buckets.as<char>() + (size_t)b0 * 16 * C::N, &rounds, &adds);
+      if (rc) return rc;
+    }
+  } else {
+    k_accum_serial<C><<<(nb + 127) / 128, 128, 0, s>>>(d_bases, ctx->sorted.as<uint32_t>(), ctx->offsets.as<uint32_t>(), nb, ctx->buckets.p); CKL();
+  }
+  if (st) CK(cudaEventRecord(ctx->ev[3], s));
+
+  // ---- bucket reduction: in-place folding, then per-window totals
+  for (uint32_t sz = pl.B; sz >= 2; sz >>= 1) {
+    uint32_t nblk = pl.B / sz, live = 1; for (uint32_t k = 1; k < nblk; k <<= 1) live++;
+    uint64_t threads = (uint64_t)live * (sz / 2) * pl.W;
+    k_fold<C><<<(uint32_t)((threads + 127) / 128), 128, 0, s>>>(ctx->buckets.p, pl.W, pl.B, sz); CKL();
+  }
+  CK(ctx->wsum.ensure((size_t)pl.W * 16 * C::N));
+  k_window_sums<C><<<(pl.W + 31) / 32, 32, 0, s>>>(ctx->buckets.p, pl.W, pl.B, pl.logB, ctx->wsum.p); CKL();
+  if (st) CK(cudaEventRecord(ctx->ev[4], s));
+  k_horner<C><<<1, 32, 0, s>>>(ctx->wsum.p, pl.W, pl.c, d_out); CKL();
+  if (st) {
+    CK(cudaEventRecord(ctx->ev[5], s));
+    st->n = n; st->window_bits = pl.c; st->windows = pl.W; st->buckets_per_window = pl.B; st->tree_rounds = rounds; st->affine_adds = adds;
+  }
+  return B200MSM_OK;
+}
+
+template <class C> int write_zero(b200msm_ctx* ctx, void* d_out) {
+  uint32_t z[3 * C::N]; memset(z, 0, sizeof z);
+  for (int i = 0; i < C::N; i++) z[C::N + i] = C::one(i);
+  CK(cudaMemcpyAsync(d_out, z, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return B200MSM_OK;
+}
+
+int deliver(b200msm_ctx* ctx, const void* d_src, void* user_out, size_t bytes) {
+  if (is_device_ptr(user_out)) { CK(cudaMemcpyAsync(user_out, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream)); }
+  else { CK(cudaMemcpyAsync(user_out, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
+  return B200MSM_OK;
+}
+
+// stage an input: returns a device pointer (the user's if already on device and aligned, else a copy in `buf`)
+int stage(b200msm_ctx* ctx, const void* src, size_t bytes, DevBuf& buf, const void** d) {
+  if (bytes == 0) { CK(buf.ensure(16)); *d = buf.p; return B200MSM_OK; }
+  if (is_device_ptr(src) && (reinterpret_cast<uintptr_t>(src) & 15) == 0) { *d = src; return B200MSM_OK; }
+  CK(buf.ensure(bytes + 16));
+  CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyDefault, ctx->stream));
+  *d = buf.p; return B200MSM_OK;
+}
+
+int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_resident, const void* scalars, uint32_t scalar_size, uint64_t n,
+              uint32_t bit0, uint32_t nbits, void* out, b200msm_stats* st) {
+  if (!ctx) return B200MSM_E_ARG;
+  if (!curve_ok(curve) || !out || (n && (!bases || !scalars)) || scalar_size == 0) { ctx->err = "bad argument"; return B200MSM_E_ARG; }
+  if (n >= (1ull << 31)) { ctx->err = "n must be < 2^31"; return B200MSM_E_UNSUPPORTED; }
+  CK(cudaSetDevice(ctx->device));
+  const int n8 = n8_of(curve);
+  CK(ctx->out.ensure(3 * 48));
+  if (st) { memset(st, 0, sizeof *st); CK(cudaEventRecord(ctx->ev[0], ctx->stream)); }
+  // clip the processed bit range at the scalar end (getChunk's bitsToEnd mask, build_multiexp.js:38-72)
+  if (bit0 >= 8 * scalar_size) nbits = 0; else if (bit0 + nbits > 8 * scalar_size) nbits = 8 * scalar_size - bit0;
+  if (nbits > 256) { ctx->err = "more than 256 scalar bits per call are not supported"; return B200MSM_E_UNSUPPORTED; }
+  int rc;
+  if (n == 0 || nbits == 0) {
+    rc = curve == 0 ? write_zero<BLS12_381>(ctx, ctx->out.p) : write_zero<BN254>(ctx, ctx->out.p);
+    if (rc) return rc;
+    return deliver(ctx, ctx->out.p, out, 3 * n8);
+  }
+  const void* d_bases = bases;
+  if (!bases_resident) { rc = stage(ctx, bases, (size_t)n * 2 * n8, ctx->bases, &d_bases); if (rc) return rc; }
+  const void* d_sraw; rc = stage(ctx, scalars, (size_t)n * scalar_size, ctx->scalars, &d_sraw); if (rc) return rc;
+  const uint32_t* d_scal;
+  if (scalar_size == 32 && bit0 == 0 && nbits == 256) d_scal = reinterpret_cast<const uint32_t*>(d_sraw);
+  else {
+    CK(ctx->canon.ensure((size_t)n * 32));
+    k_canon_scalars<<<(uint32_t)((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint8_t*>(d_sraw), scalar_size, (uint32_t)n, bit0, nbits, ctx->canon.as<uint32_t>()); CKL();
+    d_scal = ctx->canon.as<uint32_t>();
+  }
+  rc = curve == 0 ? run_pipeline<BLS12_381>(ctx, d_bases, d_scal, n, nbits, ctx->out.p, st)
+                  : run_pipeline<BN254>(ctx, d_bases, d_scal, n, nbits, ctx->out.p, st);
+  if (rc) return rc;
+  if (st) CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+  rc = deliver(ctx, ctx->out.p, out, 3 * n8); if (rc) return rc;
+  if (st) {
+    CK(cudaEventRecord(ctx->ev[7], ctx->stream)); CK(cudaEventSynchronize(ctx->ev[7]));
+    cudaEventElapsedTime(&st->ms_h2d, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&st->ms_digits_sort, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&st->ms_accumulate, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&st->ms_bucket_reduce, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&st->ms_window_combine, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&st->ms_d2h, ctx->ev[6], ctx->ev[7]);
+    cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[7]);
+    uint32_t total = 0;
+    uint32_t nb = st->windows * st->buckets_per_window;
+    CK(cudaMemcpy(&total, ctx->offsets.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost));
+    st->pairs = total;
+  }
+  return B200MSM_OK;
+}
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+const char* b200msm_version(void) { return "b200msm 0.1 (sm_100a)"; }
+
+const char* b200msm_strerror(int s) {
+  switch (s) {
+    case B200MSM_OK: return "ok";
+    case B200MSM_E_ARG: return "invalid argument";
+    case B200MSM_E_CUDA: return "CUDA error (no usable GPU, or a kernel/driver failure)";
+    case B200MSM_E_NOMEM: return "out of device memory";
+    case B200MSM_E_UNSUPPORTED: return "unsupported size or parameter";
+    default: return "unknown status";
+  }
+}
+const char* b200msm_last_error(const b200msm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int b200msm_create(b200msm_ctx** out, int device_id) {
+  if (!out) return B200MSM_E_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return B200MSM_E_CUDA; }
+  int dev = device_id;
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) return B200MSM_E_CUDA; }
+  if (dev >= ndev) return B200MSM_E_ARG;
+  if (cudaSetDevice(dev) != cudaSuccess) return B200MSM_E_CUDA;
+  b200msm_ctx* ctx = new b200msm_ctx();
+  ctx->device = dev;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200MSM_E_CUDA; }
+  ctx->own_stream = true;
+  for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return B200MSM_E_CUDA; }
+  if (cudaMallocHost(&ctx->h_pinned, 1024 * sizeof(uint32_t)) != cudaSuccess) { delete ctx; return B200MSM_E_CUDA; }
+  *out = ctx;
+  return B200MSM_OK;
+}
+
+void b200msm_destroy(b200msm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (DevBuf* b : {&ctx->bases, &ctx->scalars, &ctx->canon, &ctx->counts, &ctx->offsets, &ctx->cursors, &ctx->tiles, &ctx->sorted, &ctx->buckets,
+                    &ctx->wsum, &ctx->out, &ctx->misc, &ctx->acc_a, &ctx->acc_b, &ctx->acc_c, &ctx->acc_d, &ctx->acc_e,
+                    &ctx->t_offs, &ctx->t_cnt, &ctx->t_bid, &ctx->t_pa, &ctx->t_pb, &ctx->t_prefix, &ctx->t_prod, &ctx->t_lvlprefix}) b->release();
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (auto& kv : ctx->residents) cudaFree(kv.second.d);
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int b200msm_set_stream(b200msm_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return B200MSM_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream); ctx->own_stream = false;
+  return B200MSM_OK;
+}
+int b200msm_synchronize(b200msm_ctx* ctx) {
+  if (!ctx) return B200MSM_E_ARG;
+  CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return B200MSM_OK;
+}
+
+int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
+  if (!ctx || !key) return B200MSM_E_ARG;
+  if (!strcmp(key, "window_bits")) { if (v < 0 || v > 24) return B200MSM_E_ARG; ctx->opt_window_bits = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "accumulate")) { if (v < 0 || v > 2) return B200MSM_E_ARG; ctx->opt_accumulate = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "tree_rounds")) { ctx->opt_tree_rounds = (int)v; return B200MSM_OK; }
+  return B200MSM_E_ARG;
+}
+
+int b200msm_g1_multiexp_affine(b200msm_ctx* ctx, int curve, const void* bases, const void* scalars, uint32_t scalar_size, uint64_t n, void* out) {
+  return msm_entry(ctx, curve, bases, false, scalars, scalar_size, n, 0, scalar_size > 32 ? 257 : 8 * scalar_size, out, nullptr);
+}
+
+int b200msm_g1_multiexp_affine_chunk(b200msm_ctx* ctx, int curve, const void* bases, const void* scalars, uint32_t scalar_size, uint64_t n,
+                                     uint32_t start_bit, uint32_t chunk_bits, void* out) {
+  if (ctx && (chunk_bits == 0 || chunk_bits > 32)) { ctx->err = "chunk_bits must be in [1, 32]"; return B200MSM_E_ARG; }
+  return msm_entry(ctx, curve, bases, false, scalars, scalar_size, n, start_bit, chunk_bits, out, nullptr);
+}
+
+int b200msm_upload_bases(b200msm_ctx* ctx, int curve, const void* bases, uint64_t n, uint64_t* handle) {
+  if (!ctx || !handle || !curve_ok(curve) || (n && !bases)) return B200MSM_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  size_t bytes = (size_t)n * 2 * n8_of(curve);
+  void* d = nullptr;
+  CK(cudaMalloc(&d, bytes + 16));
+  cudaError_t e = cudaMemcpyAsync(d, bases, bytes, cudaMemcpyDefault, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { cudaFree(d); ctx->err = cudaGetErrorString(e); return B200MSM_E_CUDA; }
+  uint64_t h = ctx->next_handle++;
+  ctx->residents[h] = Resident{curve, n, d};
+  *handle = h;
+  return B200MSM_OK;
+}
+int b200msm_free_bases(b200msm_ctx* ctx, uint64_t handle) {
+  if (!ctx) return B200MSM_E_ARG;
+  auto it = ctx->residents.find(handle);
+  if (it == ctx->residents.end()) return B200MSM_E_ARG;
+  cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+  cudaFree(it->second.d); ctx->residents.erase(it);
+  return B200MSM_OK;
+}
+int b200msm_g1_multiexp_resident(b200msm_ctx* ctx, uint64_t handle, const void* scalars, uint32_t scalar_size, uint64_t n, void* out, b200msm_stats* stats) {
+  if (!ctx) return B200MSM_E_ARG;
+  auto it = ctx->residents.find(handle);
+  if (it == ctx->residents.end() || n > it->second.n) { ctx->err = "unknown handle or n larger than the uploaded base count"; return B200MSM_E_ARG; }
+  return msm_entry(ctx, it->second.curve, it->second.d, true, scalars, scalar_size, n, 0, scalar_size > 32 ? 257 : 8 * scalar_size, out, stats);
+}
+
+int b200msm_g1_normalize(b200msm_ctx* ctx, int curve, const void* jac, uint64_t count, void* xy) {
+  if (!ctx || !curve_ok(curve) || !jac || !xy) return B200MSM_E_ARG;
+  if (count == 0) return B200MSM_OK;
+  CK(cudaSetDevice(ctx->device));
+  const int n8 = n8_of(curve);
+  const void* d_in; int rc = stage(ctx, jac, (size_t)count * 3 * n8, ctx->misc, &d_in); if (rc) return rc;
+  CK(ctx->acc_e.ensure((size_t)count * 2 * n8));
+  uint32_t g = (uint32_t)((count + 63) / 64);
+  if (curve == 0) k_normalize<BLS12_381><<<g, 64, 0, ctx->stream>>>(d_in, ctx->acc_e.p, (uint32_t)count);
+  else k_normalize<BN254><<<g, 64, 0, ctx->stream>>>(d_in, ctx->acc_e.p, (uint32_t)count);
+  CKL();
+  return deliver(ctx, ctx->acc_e.p, xy, (size_t)count * 2 * n8);
+}
+
+int b200msm_g1_sum(b200msm_ctx* ctx, int curve, const void* pts, uint64_t count, void* out) {
+  if (!ctx || !curve_ok(curve) || !out || (count && !pts)) return B200MSM_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const int n8 = n8_of(curve);
+  const void* d_in; int rc = stage(ctx, pts, (size_t)count * 3 * n8, ctx->misc, &d_in); if (rc) return rc;
+  CK(ctx->out.ensure(3 * 48));
+  if (curve == 0) k_sum_jacobian<BLS12_381><<<1, 32, 0, ctx->stream>>>(d_in, (uint32_t)count, ctx->out.p);
+  else k_sum_jacobian<BN254><<<1, 32, 0, ctx->stream>>>(d_in, (uint32_t)count, ctx->out.p);
+  CKL();
+  return deliver(ctx, ctx->out.p, out, 3 * n8);
+}
+
+int b200msm_g1_generate_bases(b200msm_ctx* ctx, int curve, uint64_t seed, uint64_t first, uint64_t n, void* device_out) {
+  if (!ctx || !curve_ok(curve) || (n && !is_device_ptr(device_out)) || n >= (1ull << 31)) return B200MSM_E_ARG;
+  if (n == 0) return B200MSM_OK;
+  CK(cudaSetDevice(ctx->device));
+  const int n8 = n8_of(curve);
+  // generator in affine Montgomery form (build_bls12381.js:99-111, build_bn128.js:58-70)
+  static const uint32_t G_BLS[24] = {0xfd530c16u, 0x5cb38790u, 0x9976fff5u, 0x7817fc67u, 0x143ba1c1u, 0x154f95c7u, 0xf3d0e747u, 0xf0ae6acdu, 0x21dbf440u, 0xedce6eccu, 0x9e0bfb75u, 0x12017741u,
+                                     0x0ce72271u, 0xbaac93d5u, 0x7918fd8eu, 0x8c22631au, 0x570725ceu, 0xdd595f13u, 0x50405194u, 0x51ac5829u, 0xad0059c0u, 0x0e1c8c3fu, 0x5008a26au, 0x0bbc3efcu};
+  static const uint32_t G_BN[16] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u,
+                                    0x8b1e1b3au, 0xa6ba871bu, 0xeb8e167bu, 0x14f1d651u, 0xf0f28c58u, 0xccdd46deu, 0x340fbe5eu, 0x1c14ef83u};
+  CK(ctx->misc.ensure(256));
+  CK(cudaMemcpyAsync(ctx->misc.p, curve == 0 ? (const void*)G_BLS : (const void*)G_BN, 2 * n8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx->acc_a.ensure((size_t)n * 4 * n8));
+  uint32_t g = (uint32_t)((n + 127) / 128);
+  constexpr int GROUP = 16;
+  uint32_t g2 = (uint32_t)(((n + GROUP - 1) / GROUP + 127) / 128);
+  if (curve == 0) {
+    k_generate_xyzz<BLS12_381><<<g, 128, 0, ctx->stream>>>(ctx->misc.p, seed, first, (uint32_t)n, ctx->acc_a.p); CKL();
+    k_xyzz_to_affine<BLS12_381, GROUP><<<g2, 128, 0, ctx->stream>>>(ctx->acc_a.p, (uint32_t)n, device_out); CKL();
+  } else {
+    k_generate_xyzz<BN254><<<g, 128, 0, ctx->stream>>>(ctx->misc.p, seed, first, (uint32_t)n, ctx->acc_a.p); CKL();
+    k_xyzz_to_affine<BN254, GROUP><<<g2, 128, 0, ctx->stream>>>(ctx->acc_a.p, (uint32_t)n, device_out); CKL();
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return B200MSM_OK;
+}
+
+int b200msm_fq_op(b200msm_ctx* ctx, int curve, int op, const void* a, const void* b, void* r, uint64_t count) {
+  if (!ctx || !curve_ok(curve) || op < 0 || op > 8 || !a || !r) return B200MSM_E_ARG;
+  if (count == 0) return B200MSM_OK;
+  CK(cudaSetDevice(ctx->device));
+  const int n8 = n8_of(curve); size_t bytes = (size_t)count * n8;
+  const void *da, *db = nullptr; int rc;
+  rc = stage(ctx, a, bytes, ctx->acc_a, &da); if (rc) return rc;
+  if (b) { rc = stage(ctx, b, bytes, ctx->acc_b, &db); if (rc) return rc; }
+  CK(ctx->acc_c.ensure(bytes));
+  uint32_t g = (uint32_t)((count + 127) / 128);
+  if (curve == 0) k_fp_op<BLS12_381><<<g, 128, 0, ctx->stream>>>(op, da, db, ctx->acc_c.p, (uint32_t)count);
+  else k_fp_op<BN254><<<g, 128, 0, ctx->stream>>>(op, da, db, ctx->acc_c.p, (uint32_t)count);
+  CKL();
+  return deliver(ctx, ctx->acc_c.p, r, bytes);
+}
+
+int b200msm_probe_imad(b200msm_ctx* ctx, double* imad_per_s) {
+  if (!ctx || !imad_per_s) return B200MSM_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
+  CK(ctx->misc.ensure(256));
+  const uint32_t blocks = prop.multiProcessorCount * 8, iters = 2048;
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    k_imad_probe<<<blocks, 256, 0, ctx->stream>>>(iters, 12345u + rep, ctx->misc.as<unsigned long long>()); CKL();
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream)); CK(cudaEventSynchronize(ctx->ev[1]));
+    float ms; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    double rate = (double)blocks * 256.0 * iters * 64.0 / (ms * 1e-3);
+    if (rep && rate > best) best = rate;
+  }
+  *imad_per_s = best; return B200MSM_OK;
+}
+
+int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s) {
+  if (!ctx || !fqmul_per_s || !curve_ok(curve)) return B200MSM_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
+  const uint32_t blocks = prop.multiProcessorCount * 4, threads = 256, iters = 512;
+  const int n8 = n8_of(curve);
+  CK(ctx->acc_a.ensure(1024 * 48)); CK(ctx->acc_b.ensure((size_t)blocks * threads * n8));
+  CK(cudaMemsetAsync(ctx->acc_a.p, 0x17, 1024 * 48, ctx->stream));
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (curve == 0) k_fpmul_probe<BLS12_381><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
+    else k_fpmul_probe<BN254><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
+    CKL();
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream)); CK(cudaEventSynchronize(ctx->ev[1]));
+    float ms; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    double rate = (double)blocks * threads * iters / (ms * 1e-3);
+    if (rep && rate > best) best = rate;
+  }
+  *fqmul_per_s = best; return B200MSM_OK;
+}
+
+int b200msm_constants(int curve, uint32_t* n8, uint8_t* q, uint8_t* r_mod_q, uint8_t* r2_mod_q, uint32_t* np32) {
+  if (!curve_ok(curve)) return B200MSM_E_ARG;
+  auto put = [](uint8_t* d, int i, uint32_t v) { if (d) memcpy(d + 4 * i, &v, 4); };
+  if (curve == 0) {
+    if (n8) *n8 = 48; if (np32) *np32 = BLS12_381::NP;
+    for (int i = 0; i < BLS12_381::N; i++) { put(q, i, BLS12_381::q(i)); put(r_mod_q, i, BLS12_381::one(i)); put(r2_mod_q, i, BLS12_381::r2(i)); }
+  } else {
+    if (n8) *n8 = 32; if (np32) *np32 = BN254::NP;
+    for (int i = 0; i < BN254::N; i++) { put(q, i, BN254::q(i)); put(r_mod_q, i, BN254::one(i)); put(r2_mod_q, i, BN254::r2(i)); }
+  }
+  return B200MSM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,341 @@
+// fp.cuh -- Montgomery prime-field arithmetic on 32-bit limbs for sm_100a.
+//
+// Replaces (on the GPU) the reference's generated WASM field layer:
+//   wasmcurves/src/build_f1m.js:71-105 (add/sub), :466-777 (CIOS mul), :779-1076 (square),
+//   wasmcurves/src/build_int.js:148-279 (gte/add/sub on limbs).
+// Same value semantics: elements are n32 little-endian u32 limbs in Montgomery form a*R mod q,
+// R = 2^(32*n32), always fully reduced (< q) at every function boundary in this file.
+//
+// The multiplier is written for the Blackwell integer pipe: every 32x32->64 limb product is a
+// mad.lo.cc/madc.hi.cc pair that ptxas fuses into ONE IMAD.WIDE.U32 with carry in/out, and the
+// partial products are kept in two interleaved accumulators (even / odd limb alignment) so that a
+// whole row a*b_i is two independent carry chains of 64-bit adds -- no per-product carry fix-up.
+// Count per multiplication: 2*N*N + N limb products (300 for BLS12-381, 136 for BN254), the same
+// algorithmic figure the reference's CIOS has (build_f1m.js:575-660).
+#pragma once
+#include <stdint.h>
+
+namespace b200 {
+
+// ------------------------------------------------------------------ curve / field parameters
+struct BLS12_381 {
+  static constexpr int ID = 0;
+  static constexpr int N = 12;           // u32 limbs per Fq element (n8 = 48)
+  static constexpr uint32_t NP = 0xfffcfffdu;   // -q^-1 mod 2^32   (build_f1m.js:504)
+  static constexpr int QBITS = 381;
+  __host__ __device__ static constexpr uint32_t q(int i) {      // build_bls12381.js:22
+    constexpr uint32_t t[N] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                               0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+    return t[i];
+  }
+  __host__ __device__ static constexpr uint32_t one(int i) {    // R mod q
+    constexpr uint32_t t[N] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
+                               0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
+    return t[i];
+  }
+  __host__ __device__ static constexpr uint32_t r2(int i) {     // R^2 mod q
+    constexpr uint32_t t[N] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu,
+                               0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
+    return t[i];
+  }
+  __host__ __device__ static constexpr uint32_t r3(int i) {     // R^3 mod q
+    constexpr uint32_t t[N] = {0xd94ca1e0u, 0xed48ac6bu, 0x03a7adf8u, 0x315f831eu, 0x615e29ddu, 0x9a53352au,
+                               0x921e1761u, 0x34c04e5eu, 0x65724728u, 0x2512d435u, 0x91755d4du, 0x0aa63460u};
+    return t[i];
+  }
+};
+
+struct BN254 {
+  static constexpr int ID = 1;
+  static constexpr int N = 8;            // n8 = 32
+  static constexpr uint32_t NP = 0xe4866389u;
+  static constexpr int QBITS = 254;
+  __host__ __device__ static constexpr uint32_t q(int i) {      // build_bn128.js:20
+    constexpr uint32_t t[N] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return t[i];
+  }
+  __host__ __device__ static constexpr uint32_t one(int i) {
+    constexpr uint32_t t[N] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+    return t[i];
+  }
+  __host__ __device__ static constexpr uint32_t r2(int i) {
+    constexpr uint32_t t[N] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+    return t[i];
+  }
+  __host__ __device__ static constexpr uint32_t r3(int i) {
+    constexpr uint32_t t[N] = {0xda1530dfu, 0xb1cd6dafu, 0xa7283db6u, 0x62f210e6u, 0x0ada0afbu, 0xef7f0b0cu, 0x2d592544u, 0x20fd6e90u};
+    return t[i];
+  }
+};
+
+template <int N> struct alignas(16) Fe { uint32_t l[N]; };
+
+// ------------------------------------------------------------------ PTX carry-chain primitives
+// asm volatile keeps the statements in program order; the condition-code register is only written
+// by these instructions, so a chain spread over several statements is safe.
+#define B200_DI __device__ __forceinline__
+B200_DI uint32_t ptx_mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_DI uint32_t ptx_mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_DI void mad_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
+B200_DI void madc_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
+B200_DI void madc_hi_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
+B200_DI void madc_hi(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
+B200_DI void add_cc(uint32_t& d, uint32_t a, uint32_t b) { asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+B200_DI void addc_cc(uint32_t& d, uint32_t a, uint32_t b) { asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+B200_DI void addc(uint32_t& d, uint32_t a, uint32_t b) { asm volatile("addc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+B200_DI void sub_cc(uint32_t& d, uint32_t a, uint32_t b) { asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+B200_DI void subc_cc(uint32_t& d, uint32_t a, uint32_t b) { asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+B200_DI void subc(uint32_t& d, uint32_t a, uint32_t b) { asm volatile("subc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+
+// ------------------------------------------------------------------ basic predicates / moves
+template <class C> B200_DI bool fe_is_zero(const Fe<C::N>& a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < C::N; i++) o |= a.l[i];
+  return o == 0;
+}
+template <class C> B200_DI bool fe_eq(const Fe<C::N>& a, const Fe<C::N>& b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < C::N; i++) o |= a.l[i] ^ b.l[i];
+  return o == 0;
+}
+template <class C> B200_DI void fe_set_zero(Fe<C::N>& a) {
+#pragma unroll
+  for (int i = 0; i < C::N; i++) a.l[i] = 0;
+}
+template <class C> B200_DI void fe_set_one(Fe<C::N>& a) {
+#pragma unroll
+  for (int i = 0; i < C::N; i++) a.l[i] = C::one(i);
+}
+
+// r = a - q if a >= q else a   (input < 2q)
+template <class C> B200_DI void fe_reduce_once(Fe<C::N>& a) {
+  constexpr int N = C::N;
+  uint32_t t[N], borrow;
+  sub_cc(t[0], a.l[0], C::q(0));
+#pragma unroll
+  for (int i = 1; i < N; i++) subc_cc(t[i], a.l[i], C::q(i));
+  subc(borrow, 0, 0);                 // 0 if a >= q, 0xffffffff otherwise
+#pragma unroll
+  for (int i = 0; i < N; i++) a.l[i] = borrow ? a.l[i] : t[i];
+}
+
+// f1m_add (build_f1m.js:71-89)
+template <class C> B200_DI void fe_add(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
+  constexpr int N = C::N;
+  add_cc(r.l[0], a.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) addc_cc(r.l[i], a.l[i], b.l[i]);
+  addc(r.l[N - 1], a.l[N - 1], b.l[N - 1]);      // q < 2^(32N-1): a + b < 2q never carries out
+  fe_reduce_once<C>(r);
+}
+
+// f1m_sub (build_f1m.js:91-105)
+template <class C> B200_DI void fe_sub(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
+  constexpr int N = C::N;
+  uint32_t borrow;
+  sub_cc(r.l[0], a.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) subc_cc(r.l[i], a.l[i], b.l[i]);
+  subc(borrow, 0, 0);
+  // add q back under mask
+  add_cc(r.l[0], r.l[0], C::q(0) & borrow);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) addc_cc(r.l[i], r.l[i], C::q(i) & borrow);
+  addc(r.l[N - 1], r.l[N - 1], C::q(N - 1) & borrow);
+}
+
+template <class C> B200_DI void fe_neg(Fe<C::N>& r, const Fe<C::N>& a) {
+  constexpr int N = C::N;
+  uint32_t nz = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) nz |= a.l[i];
+  uint32_t t[N];
+  sub_cc(t[0], C::q(0), a.l[0]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) subc_cc(t[i], C::q(i), a.l[i]);
+  subc(t[N - 1], C::q(N - 1), a.l[N - 1]);
+#pragma unroll
+  for (int i = 0; i < N; i++) r.l[i] = nz ? t[i] : 0u;
+}
+
+template <class C> B200_DI void fe_dbl(Fe<C::N>& r, const Fe<C::N>& a) { fe_add<C>(r, a, a); }
+
+// ------------------------------------------------------------------ Montgomery multiplication
+// One CIOS step on the two interleaved accumulators.  Frame: value = sum E[k] 2^(32k) + sum O[k] 2^(32(k+1)).
+// On entry (not first) O still holds the previous step's even accumulator (low limb zero), which is
+// consumed with a two-limb right shift while the odd-limb products of this row are added.
+template <class C, bool FIRST>
+B200_DI void mont_row(uint32_t (&E)[C::N], uint32_t (&O)[C::N], const uint32_t (&a)[C::N], uint32_t bi) {
+  constexpr int N = C::N;
+  if (FIRST) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) { E[j] = ptx_mul_lo(a[j], bi); E[j + 1] = ptx_mul_hi(a[j], bi); }
+#pragma unroll
+    for (int j = 1; j < N; j += 2) { O[j - 1] = ptx_mul_lo(a[j], bi); O[j] = ptx_mul_hi(a[j], bi); }
+  } else {
+    add_cc(E[0], E[0], O[1]);
+#pragma unroll
+    for (int j = 1; j < N - 1; j += 2) { madc_lo_cc(O[j - 1], a[j], bi, O[j + 1]); madc_hi_cc(O[j], a[j], bi, O[j + 2]); }
+    madc_lo_cc(O[N - 2], a[N - 1], bi, 0);
+    madc_hi(O[N - 1], a[N - 1], bi, 0);
+    mad_lo_cc(E[0], a[0], bi, E[0]);
+    madc_hi_cc(E[1], a[0], bi, E[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) { madc_lo_cc(E[j], a[j], bi, E[j]); madc_hi_cc(E[j + 1], a[j], bi, E[j + 1]); }
+    addc(O[N - 1], O[N - 1], 0);
+  }
+  uint32_t m = E[0] * C::NP;
+  mad_lo_cc(O[0], C::q(1), m, O[0]);
+  madc_hi_cc(O[1], C::q(1), m, O[1]);
+#pragma unroll
+  for (int j = 3; j < N; j += 2) { madc_lo_cc(O[j - 1], C::q(j), m, O[j - 1]); madc_hi_cc(O[j], C::q(j), m, O[j]); }
+  mad_lo_cc(E[0], C::q(0), m, E[0]);
+  madc_hi_cc(E[1], C::q(0), m, E[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) { madc_lo_cc(E[j], C::q(j), m, E[j]); madc_hi_cc(E[j + 1], C::q(j), m, E[j + 1]); }
+  addc(O[N - 1], O[N - 1], 0);
+}
+
+// f1m_mul (build_f1m.js:466-777): r = a*b/R mod q, fully reduced.  r may alias a or b.
+template <class C> B200_DI void fe_mul(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
+  constexpr int N = C::N;
+  static_assert(N % 2 == 0, "even limb count");
+  uint32_t E[N], O[N];
+  mont_row<C, true>(E, O, a.l, b.l[0]);
+  mont_row<C, false>(O, E, a.l, b.l[1]);
+#pragma unroll
+  for (int i = 2; i < N; i += 2) {
+    mont_row<C, false>(E, O, a.l, b.l[i]);
+    mont_row<C, false>(O, E, a.l, b.l[i + 1]);
+  }
+  // after an even number of rows: E = live even accumulator, O = stale even (low limb zero), pending 1-limb shift
+  Fe<N> t;
+  add_cc(t.l[0], E[0], O[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) addc_cc(t.l[k], E[k], O[k + 1]);
+  addc(t.l[N - 1], E[N - 1], 0);
+  fe_reduce_once<C>(t);
+  r = t;
+}
+
+// f1m_square (build_f1m.js:779-1076) -- same value as mul(a, a)
+template <class C> B200_DI void fe_sqr(Fe<C::N>& r, const Fe<C::N>& a) { fe_mul<C>(r, a, a); }
+
+// to / from Montgomery (build_f1m.js:1089,1098)
+template <class C> B200_DI void fe_to_mont(Fe<C::N>& r, const Fe<C::N>& a) {
+  Fe<C::N> k;
+#pragma unroll
+  for (int i = 0; i < C::N; i++) k.l[i] = C::r2(i);
+  fe_mul<C>(r, a, k);
+}
+template <class C> B200_DI void fe_from_mont(Fe<C::N>& r, const Fe<C::N>& a) {
+  Fe<C::N> k;
+#pragma unroll
+  for (int i = 0; i < C::N; i++) k.l[i] = (i == 0);
+  fe_mul<C>(r, a, k);
+}
+
+// f1m_inverse (build_f1m.js:1112-1122) by Fermat: a^(q-2).  Montgomery in, Montgomery out; inv(0) = 0.
+// Left-to-right square-and-multiply over the constant exponent; the loop is NOT unrolled (code size).
+template <class C> __device__ __noinline__ void fe_inv(Fe<C::N>& r, const Fe<C::N>& a) {
+  constexpr int N = C::N;
+  uint32_t e[N];
+  // e = q - 2 (q is odd and its low limb is >= 2 for both fields)
+#pragma unroll
+  for (int i = 0; i < N; i++) e[i] = C::q(i);
+  e[0] -= 2;
+  Fe<N> acc; fe_set_one<C>(acc);
+  for (int i = C::QBITS - 1; i >= 0; i--) {
+    fe_sqr<C>(acc, acc);
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < N; k++) w = (k == (i >> 5)) ? e[k] : w;
+    if ((w >> (i & 31)) & 1) fe_mul<C>(acc, acc, a);
+  }
+  r = acc;
+}
+
+// f1m_inverse by the binary extended Euclidean algorithm (right-shift form): ~2*log2(q) shift/subtract
+// steps on N-limb integers instead of ~1.5*log2(q) field multiplications -- an order of magnitude fewer
+// instructions than Fermat, which matters because the batch inversion's root is a single serial chain.
+// The reference also uses an extended Euclid here (build_int.js:922-1064).  Variable time; inv(0) = 0.
+template <class C> B200_DI void limbs_shr1(uint32_t (&a)[C::N], uint32_t top) {
+#pragma unroll
+  for (int i = 0; i < C::N - 1; i++) a[i] = __funnelshift_r(a[i], a[i + 1], 1);
+  a[C::N - 1] = (a[C::N - 1] >> 1) | (top << 31);
+}
+template <class C> B200_DI void limbs_halve_mod(uint32_t (&x)[C::N]) {     // x <- x / 2 mod q
+  constexpr int N = C::N;
+  uint32_t carry = 0;
+  if (x[0] & 1) {
+    add_cc(x[0], x[0], C::q(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) addc_cc(x[i], x[i], C::q(i));
+    addc(carry, 0, 0);
+  }
+  limbs_shr1<C>(x, carry);
+}
+template <class C> B200_DI bool limbs_is_one(const uint32_t (&a)[C::N]) {
+  uint32_t o = a[0] ^ 1u;
+#pragma unroll
+  for (int i = 1; i < C::N; i++) o |= a[i];
+  return o == 0;
+}
+template <class C> __device__ __noinline__ void fe_inv_fast(Fe<C::N>& r, const Fe<C::N>& a) {
+  constexpr int N = C::N;
+  if (fe_is_zero<C>(a)) { fe_set_zero<C>(r); return; }
+  uint32_t u[N], v[N];
+  Fe<N> x1, x2;
+#pragma unroll
+  for (int i = 0; i < N; i++) { u[i] = a.l[i]; v[i] = C::q(i); x1.l[i] = (i == 0); x2.l[i] = 0; }
+  for (;;) {
+    while (!(u[0] & 1)) { limbs_shr1<C>(u, 0); limbs_halve_mod<C>(x1.l); }
+    if (limbs_is_one<C>(u)) { x2 = x1; break; }
+    while (!(v[0] & 1)) { limbs_shr1<C>(v, 0); limbs_halve_mod<C>(x2.l); }
+    if (limbs_is_one<C>(v)) break;
+    // u, v odd and different: subtract the smaller from the larger
+    uint32_t t[N], borrow;
+    sub_cc(t[0], u[0], v[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) subc_cc(t[i], u[i], v[i]);
+    subc(borrow, 0, 0);
+    if (!borrow) {
+#pragma unroll
+      for (int i = 0; i < N; i++) u[i] = t[i];
+      fe_sub<C>(x1, x1, x2);
+    } else {
+      sub_cc(v[0], v[0], u[0]);
+#pragma unroll
+      for (int i = 1; i < N - 1; i++) subc_cc(v[i], v[i], u[i]);
+      subc(v[N - 1], v[N - 1], u[N - 1]);
+      fe_sub<C>(x2, x2, x1);
+    }
+  }
+  // x2 = (aR)^-1 as a plain residue; a^-1 R = x2 * R^2 = montmul(x2, R^3)
+  Fe<N> k;
+#pragma unroll
+  for (int i = 0; i < N; i++) k.l[i] = C::r3(i);
+  fe_mul<C>(r, x2, k);
+}
+
+// ------------------------------------------------------------------ global-memory access helpers
+// Elements are 16-byte aligned in every buffer the engine owns; 128-bit vector loads/stores.
+template <class C> B200_DI void fe_load(Fe<C::N>& r, const void* p) {
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < C::N / 4; i++) { uint4 v = __ldg(s + i); r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w; }
+}
+template <class C> B200_DI void fe_load_cg(Fe<C::N>& r, const void* p) {      // coherent (written earlier in the same launch sequence)
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < C::N / 4; i++) { uint4 v = s[i]; r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w; }
+}
+template <class C> B200_DI void fe_store(void* p, const Fe<C::N>& a) {
+  uint4* d = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < C::N / 4; i++) d[i] = make_uint4(a.l[4 * i], a.l[4 * i + 1], a.l[4 * i + 2], a.l[4 * i + 3]);
+}
+
+}  // namespace b200

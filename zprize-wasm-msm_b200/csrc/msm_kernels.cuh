@@ -1,0 +1,368 @@
+// msm_kernels.cuh -- the Pippenger pipeline as sm_100a kernels.
+//
+// Path replaced: wasmcurves/src/build_multiexp.js:25-461 (getChunk, _chunk,
+// _reduceTable, multiexp) and the schedule / bucket phases of the Manta opt path,
+// wasmcurves/src/build_multiexp_opt.js:175-347 (computeSchedule), :364-633 (organizeBuckets),
+// :1336-1585 (reduceBuckets), :1597-1706 (reduceBucketsToSinglePoint), :1710-1746 (accumulateAcrossChunks).
+//
+// Pipeline for one MSM over the scalar bit range [bit0, bit0 + nbits):
+//   1. k_digits<COUNT>     signed-digit recoding of every scalar (window width c, digits in [-2^(c-1), 2^(c-1)]),
+//                          histogram of (window, |digit|) with global atomics                       [HBM / atomics]
+//   2. k_scan_*            exclusive scan of the W*B bucket counters -> segment offsets            [HBM]
+//   3. k_digits<SCATTER>   same recoding, each (point, sign) written into its bucket segment        [HBM / atomics]
+//   4. accumulate          per-bucket sums (see accumulate kernels)                                  [IMAD]
+//   5. k_fold              log-depth in-place folding of every window's bucket array:
+//                          after p = log2(B) levels  sum_b b*T[b-1] = T[0] + sum_j 2^j T[2^j]       [IMAD]
+//   6. k_window_sums, k_horner  per-window totals, then result = sum_w 2^(c*w) R_w                   [latency]
+#pragma once
+#include "ec.cuh"
+
+namespace b200 {
+
+struct MsmPlan {
+  uint32_t n;          // points
+  uint32_t c;          // window width in bits
+  uint32_t W;          // number of signed windows = ceil((nbits + 1) / c)
+  uint32_t B;          // buckets per window = 2^(c-1)   (bucket index = |digit| - 1)
+  uint32_t nbits;      // scalar bits processed
+  uint32_t logB;       // c - 1
+};
+
+// ------------------------------------------------------------------ scalars
+// Canonical scalar layout inside the engine: 8 u32 words (256 bit) little-endian per scalar, already
+// shifted so that bit 0 is the first processed bit and masked to nbits.  For the common case
+// (scalar_size == 32, bit0 == 0, nbits == 256) the caller's buffer is used in place.
+__global__ void k_canon_scalars(const uint8_t* __restrict__ in, uint32_t scalar_size, uint32_t n,
+                                uint32_t bit0, uint32_t nbits, uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* s = in + (uint64_t)i * scalar_size;
+  uint32_t w[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) w[k] = 0;
+  // gather the bytes covering [bit0, bit0 + nbits)
+  uint32_t byte0 = bit0 >> 3, sh = bit0 & 7;
+  for (uint32_t k = 0; k < 33; k++) {
+    uint32_t src = byte0 + k;
+    uint32_t v = (src < scalar_size) ? s[src] : 0u;
+    // place byte k at bit position 8k - sh (may straddle words)
+    int bitpos = (int)(8 * k) - (int)sh;
+    if (bitpos >= 0) {
+      if (bitpos < 256) { w[bitpos >> 5] |= v << (bitpos & 31); if ((bitpos & 31) > 24) w[(bitpos >> 5) + 1] |= v >> (32 - (bitpos & 31)); }
+    } else {
+      w[0] |= v >> sh;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    uint32_t lo = 32 * k;
+    uint32_t m = (nbits >= lo + 32) ? 0xffffffffu : (nbits <= lo ? 0u : ((1u << (nbits - lo)) - 1u));
+    out[(uint64_t)i * 8 + k] = w[k] & m;
+  }
+}
+
+// One signed digit stream: calls f(window, bucket_index(0-based), negative) for every non-zero digit.
+template <class F>
+B200_DI void for_each_digit(const uint32_t* __restrict__ s, const MsmPlan& pl, F f) {
+  uint32_t carry = 0;
+  const uint32_t mask = (1u << pl.c) - 1u, half = 1u << (pl.c - 1);
+  for (uint32_t w = 0; w < pl.W; w++) {
+    uint32_t bit = w * pl.c, k = bit >> 5, r = bit & 31;
+    uint32_t lo = (k < 8) ? __ldg(s + k) : 0u, hi = (k + 1 < 8) ? __ldg(s + k + 1) : 0u;
+    uint32_t raw = __funnelshift_r(lo, hi, r) & mask;
+    uint32_t d = raw + carry;
+    carry = d > half;
+    uint32_t mag = carry ? ((1u << pl.c) - d) : d;
+    if (mag) f(w, mag - 1, carry);
+  }
+}
+
+template <bool SCATTER>
+__global__ void k_digits(const uint32_t* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ counters,
+                         uint32_t* __restrict__ sorted) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pl.n) return;
+  const uint32_t* s = scalars + (uint64_t)i * 8;
+  for_each_digit(s, pl, [&](uint32_t w, uint32_t b, uint32_t neg) {
+    uint32_t slot = atomicAdd(&counters[w * pl.B + b], 1u);
+    if (SCATTER) sorted[slot] = i | (neg << 31);
+  });
+}
+
+// ------------------------------------------------------------------ exclusive scan (u32), three phases
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 16, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t warp_sums[32];
+  uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t s = (lane < blockDim.x / 32) ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+    warp_sums[lane] = s;
+  }
+  __syncthreads();
+  uint32_t base = wid ? warp_sums[wid - 1] : 0;
+  if (total) *total = warp_sums[blockDim.x / 32 - 1];
+  __syncthreads();
+  return base + x - v;
+}
+
+__global__ void k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, uint32_t* __restrict__ tile_sums) {
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? in[base + k] : 0; sum += v[k]; }
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(sum, &total);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+// single block: scan tile sums in place (exclusive), total appended at tile_sums[ntiles]
+__global__ void k_scan_sums(uint32_t* __restrict__ tile_sums, uint32_t ntiles) {
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < ntiles; base += blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = (i < ntiles) ? tile_sums[i] : 0, total;
+    uint32_t ex = block_exclusive_scan(v, &total);
+    uint32_t c = carry_s;
+    if (i < ntiles) tile_sums[i] = ex + c;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = c + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tile_sums[ntiles] = carry_s;
+}
+// add tile offsets; writes offsets[n] = grand total; optionally copies the offsets into a cursor array
+__global__ void k_scan_apply(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tile_sums, uint32_t ntiles,
+                             uint32_t* __restrict__ cursors) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { uint32_t v = out[i] + tile_sums[i / SCAN_TILE]; out[i] = v; if (cursors) cursors[i] = v; }
+  if (i == 0) out[n] = tile_sums[ntiles];
+}
+
+// per-window maximum bucket population (decides the number of tree rounds); out[w] must be zeroed
+__global__ void k_window_max(const uint32_t* __restrict__ counts, uint32_t B, uint32_t* __restrict__ out) {
+  uint32_t w = blockIdx.y;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t v = (i < B) ? counts[(uint64_t)w * B + i] : 0;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v) atomicMax(out + w, v);
+}
+
+// ------------------------------------------------------------------ accumulate, serial form (one thread per bucket)
+// Correct for any input; used for tiny problems and as the fallback when the batch-affine tree is disabled.
+template <class C>
+__global__ void __launch_bounds__(128) k_accum_serial(const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                      const uint32_t* __restrict__ offsets, uint32_t nbuckets, void* __restrict__ buckets) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbuckets) return;
+  uint32_t lo = offsets[b], hi = offsets[b + 1];
+  XYZZ<C> acc; xyzz_set_inf<C>(acc);
+  for (uint32_t k = lo; k < hi; k++) {
+    uint32_t e = sorted[k];
+    Affine<C> p; affine_load<C>(p, bases, e & 0x7fffffffu);
+    if (e >> 31) fe_neg<C>(p.y, p.y);
+    xyzz_madd<C>(acc, p);
+  }
+  xyzz_store<C>(buckets, b, acc);
+}
+
+// ------------------------------------------------------------------ bucket reduction by in-place folding
+// Level with block size s: for every aligned block [k*s, (k+1)*s) of every window: lower half += upper half.
+// After all logB levels:  sum_{b=1..B} b*T[b-1] = T[0] + sum_{j<logB} 2^j * T[2^j]   (see DESIGN.md).
+// Only blocks {0, 1, 2, 4, ...} are live at each level; the others are never read again and are skipped.
+template <class C>
+__global__ void __launch_bounds__(128) k_fold(void* __restrict__ buckets, uint32_t W, uint32_t B, uint32_t s) {
+  uint32_t half = s >> 1;
+  uint32_t nblk = B / s;                       // blocks per window at this level
+  uint32_t live = 1 + (nblk > 1 ? 32 - __clz(nblk - 1) : 0);   // {0} U {2^k < nblk}
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t per_win = (uint64_t)live * half;
+  if (t >= per_win * W) return;
+  uint32_t w = (uint32_t)(t / per_win);
+  uint32_t r = (uint32_t)(t % per_win);
+  uint32_t lb = r / half, i = r % half;
+  uint32_t blk = lb == 0 ? 0 : (1u << (lb - 1));
+  uint64_t lo = (uint64_t)w * B + (uint64_t)blk * s + i;
+  XYZZ<C> a, b;
+  xyzz_load<C>(a, buckets, lo); xyzz_load<C>(b, buckets, lo + half);
+  xyzz_add<C>(a, b);
+  xyzz_store<C>(buckets, lo, a);
+}
+
+// One thread per window: R_w = T[0] + sum_j 2^j T[2^j] by Horner over j (logB doublings).
+template <class C>
+__global__ void __launch_bounds__(32) k_window_sums(const void* __restrict__ buckets, uint32_t W, uint32_t B, uint32_t logB, void* __restrict__ wsum) {
+  uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  XYZZ<C> acc; xyzz_set_inf<C>(acc);
+  for (int j = (int)logB - 1; j >= 0; j--) {
+    XYZZ<C> t; xyzz_load<C>(t, buckets, (uint64_t)w * B + (1u << j));
+    xyzz_add<C>(acc, t);
+    if (j) { XYZZ<C> d; xyzz_dbl<C>(d, acc); acc = d; }
+  }
+  XYZZ<C> t0; xyzz_load<C>(t0, buckets, (uint64_t)w * B);
+  xyzz_add<C>(acc, t0);
+  xyzz_store<C>(wsum, w, acc);
+}
+
+// result = sum_w 2^(c*w) R_w, top window first (accumulateAcrossChunks, build_multiexp_opt.js:1710-1746;
+// multiexp Horner loop, build_multiexp.js:319-369).  Output: Jacobian Montgomery x||y||z, canonical zero for infinity.
+template <class C>
+__global__ void __launch_bounds__(32) k_horner(const void* __restrict__ wsum, uint32_t W, uint32_t c, void* __restrict__ out_jac) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  XYZZ<C> acc; xyzz_set_inf<C>(acc);
+  for (int w = (int)W - 1; w >= 0; w--) {
+    if (!xyzz_is_inf<C>(acc)) for (uint32_t k = 0; k < c; k++) { XYZZ<C> d; xyzz_dbl<C>(d, acc); acc = d; }
+    XYZZ<C> t; xyzz_load<C>(t, wsum, w);
+    xyzz_add<C>(acc, t);
+  }
+  Fe<C::N> X, Y, Z;
+  xyzz_to_jacobian<C>(X, Y, Z, acc);
+  char* o = reinterpret_cast<char*>(out_jac);
+  fe_store<C>(o, X); fe_store<C>(o + 4 * C::N, Y); fe_store<C>(o + 8 * C::N, Z);
+}
+
+// ------------------------------------------------------------------ small utility kernels behind the C ABI
+// g1m_normalize + f1m_fromMontgomery x2 (build_curve_jacobian_a0.js:940-973; test/batchAffine.js:1249-1254):
+// Jacobian Montgomery -> canonical affine x||y as plain integers; infinity -> zeros.
+template <class C>
+__global__ void k_normalize(const void* __restrict__ jac, void* __restrict__ xy, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const char* s = reinterpret_cast<const char*>(jac) + (uint64_t)i * 12 * C::N;
+  char* d = reinterpret_cast<char*>(xy) + (uint64_t)i * 8 * C::N;
+  Fe<C::N> X, Y, Z, zi, zi2, zi3;
+  fe_load<C>(X, s); fe_load<C>(Y, s + 4 * C::N); fe_load<C>(Z, s + 8 * C::N);
+  if (fe_is_zero<C>(Z)) { fe_set_zero<C>(X); fe_store<C>(d, X); fe_store<C>(d + 4 * C::N, X); return; }
+  fe_inv_fast<C>(zi, Z); fe_sqr<C>(zi2, zi); fe_mul<C>(zi3, zi2, zi);
+  fe_mul<C>(X, X, zi2); fe_mul<C>(Y, Y, zi3);
+  fe_from_mont<C>(X, X); fe_from_mont<C>(Y, Y);
+  fe_store<C>(d, X); fe_store<C>(d + 4 * C::N, Y);
+}
+
+// out = sum of n Jacobian points (g1m_add chain) -- combines per-GPU partial results.
+template <class C>
+__global__ void k_sum_jacobian(const void* __restrict__ pts, uint32_t n, void* __restrict__ out_jac) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  XYZZ<C> acc; xyzz_set_inf<C>(acc);
+  for (uint32_t i = 0; i < n; i++) {
+    const char* s = reinterpret_cast<const char*>(pts) + (uint64_t)i * 12 * C::N;
+    Fe<C::N> X, Y, Z; fe_load_cg<C>(X, s); fe_load_cg<C>(Y, s + 4 * C::N); fe_load_cg<C>(Z, s + 8 * C::N);
+    XYZZ<C> p;
+    if (fe_is_zero<C>(Z)) xyzz_set_inf<C>(p);
+    else { p.x = X; p.y = Y; fe_sqr<C>(p.zz, Z); fe_mul<C>(p.zzz, p.zz, Z); }
+    xyzz_add<C>(acc, p);
+  }
+  Fe<C::N> X, Y, Z; xyzz_to_jacobian<C>(X, Y, Z, acc);
+  char* o = reinterpret_cast<char*>(out_jac);
+  fe_store<C>(o, X); fe_store<C>(o + 4 * C::N, Y); fe_store<C>(o + 8 * C::N, Z);
+}
+
+// Synthetic bases: P_i = k_i * G with k_i = splitmix64(seed + first + i) -- the same stream as
+// oracle_point_scalar() in oracle/msm_oracle.c so that CPU and GPU generate identical inputs.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31);
+}
+template <class C>
+__global__ void __launch_bounds__(128) k_generate_xyzz(const void* __restrict__ gen_xy, uint64_t seed, uint64_t first, uint32_t n, void* __restrict__ out_xyzz) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t k = splitmix64(seed + first + i); if (!k) k = 1;
+  Affine<C> g; affine_load<C>(g, gen_xy, 0);
+  XYZZ<C> acc; xyzz_set_inf<C>(acc);
+  for (int b = 63; b >= 0; b--) {
+    XYZZ<C> d; xyzz_dbl<C>(d, acc); acc = d;
+    if ((k >> b) & 1) xyzz_madd<C>(acc, g);
+  }
+  xyzz_store<C>(out_xyzz, i, acc);
+}
+// XYZZ -> affine, one inversion per thread amortised over GROUP points (Montgomery trick, build_batchinverse.js:4-140)
+template <class C, int GROUP>
+__global__ void __launch_bounds__(128) k_xyzz_to_affine(const void* __restrict__ in_xyzz, uint32_t n, void* __restrict__ out_xy) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t base = (uint64_t)t * GROUP;
+  if (base >= n) return;
+  Fe<C::N> pre[GROUP], acc; fe_set_one<C>(acc);
+  uint32_t cnt = (n - base < GROUP) ? (uint32_t)(n - base) : GROUP;
+  for (uint32_t k = 0; k < cnt; k++) {
+    XYZZ<C> p; xyzz_load<C>(p, in_xyzz, base + k);
+    pre[k] = acc;
+    if (!xyzz_is_inf<C>(p)) fe_mul<C>(acc, acc, p.zzz);
+  }
+  Fe<C::N> inv; fe_inv<C>(inv, acc);
+  for (int k = (int)cnt - 1; k >= 0; k--) {
+    XYZZ<C> p; xyzz_load<C>(p, in_xyzz, base + k);
+    Affine<C> a;
+    if (xyzz_is_inf<C>(p)) { affine_set_inf<C>(a); }
+    else {
+      Fe<C::N> zi3, zi2; fe_mul<C>(zi3, inv, pre[k]); fe_mul<C>(inv, inv, p.zzz);
+      // 1/zz = zzz^-1 * ... : zz^3 = zzz^2  =>  1/zz = (zz / zzz)^2 ... use 1/zz = zi3^2 * zz^2 (since zi3 = 1/zzz, zz^3 = zzz^2)
+      fe_mul<C>(zi2, zi3, p.zz); fe_sqr<C>(zi2, zi2);
+      fe_mul<C>(a.x, p.x, zi2); fe_mul<C>(a.y, p.y, zi3);
+    }
+    affine_store<C>(out_xy, base + k, a);
+  }
+}
+
+// elementwise field ops for kernel-level parity tests (op: 0 mul, 1 add, 2 sub, 3 sqr, 4 inv, 5 toMont, 6 fromMont, 7 neg, 8 inv by Fermat)
+template <class C>
+__global__ void k_fp_op(int op, const void* __restrict__ a, const void* __restrict__ b, void* __restrict__ r, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<C::N> x, y, z;
+  fe_load<C>(x, reinterpret_cast<const char*>(a) + (uint64_t)i * 4 * C::N);
+  if (b) fe_load<C>(y, reinterpret_cast<const char*>(b) + (uint64_t)i * 4 * C::N); else fe_set_zero<C>(y);
+  switch (op) {
+    case 0: fe_mul<C>(z, x, y); break;
+    case 1: fe_add<C>(z, x, y); break;
+    case 2: fe_sub<C>(z, x, y); break;
+    case 3: fe_sqr<C>(z, x); break;
+    case 4: fe_inv_fast<C>(z, x); break;
+    case 5: fe_to_mont<C>(z, x); break;
+    case 6: fe_from_mont<C>(z, x); break;
+    case 7: fe_neg<C>(z, x); break;
+    default: fe_inv<C>(z, x); break;      // 8: Fermat inversion (cross-check of the binary-Euclid one)
+  }
+  fe_store<C>(reinterpret_cast<char*>(r) + (uint64_t)i * 4 * C::N, z);
+}
+
+// Register-resident IMAD.WIDE throughput probe: the roofline denominator for the accumulate phase
+// ("Peak = measured on the box by a register-resident mad.wide microbenchmark").
+// Each thread runs ITER dependent-chain groups of 8 independent 32x32+64 multiply-adds.
+__global__ void __launch_bounds__(256) k_imad_probe(uint32_t iters, uint32_t seed, unsigned long long* __restrict__ sink) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+  unsigned long long acc0 = a, acc1 = b, acc2 = a ^ b, acc3 = a + b, acc4 = 5, acc5 = 6, acc6 = 7, acc7 = 8;
+  for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\tmad.wide.u32 %2, %8, %9, %2;\n\tmad.wide.u32 %3, %8, %9, %3;\n\t"
+                   "mad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\tmad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
+                   : "+l"(acc0), "+l"(acc1), "+l"(acc2), "+l"(acc3), "+l"(acc4), "+l"(acc5), "+l"(acc6), "+l"(acc7) : "r"(a), "r"(b));
+    }
+  }
+  unsigned long long s = acc0 ^ acc1 ^ acc2 ^ acc3 ^ acc4 ^ acc5 ^ acc6 ^ acc7;
+  if (s == 0x1234567ull) sink[0] = s;
+}
+// Field-multiply throughput probe: ITER dependent Montgomery multiplications per thread (2N^2+N limb products each).
+template <class C>
+__global__ void __launch_bounds__(256) k_fpmul_probe(uint32_t iters, const void* __restrict__ in, void* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  Fe<C::N> x, y;
+  fe_load<C>(x, reinterpret_cast<const char*>(in) + (uint64_t)(i & 1023) * 4 * C::N);
+  y = x;
+  for (uint32_t k = 0; k < iters; k++) { fe_mul<C>(y, y, x); }
+  fe_store<C>(reinterpret_cast<char*>(out) + (uint64_t)i * 4 * C::N, y);
+}
+
+}  // namespace b200
