@@ -1,0 +1,325 @@
+#!/usr/bin/env python3
+"""bench.py -- headline measurement of the G1 MSM hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log2n 20] [--curve bls12381]
+
+A "step" is one complete MSM (g1m_multiexpAffine semantics) over one batch of synthetic input:
+  N = 1 : 2^log2n BLS12-381 G1 points (default 2^20 -- the size BASELINE.json's target is quoted on).
+  N > 1 : one MSM of N * 2^log2n points, sharded by point range (weak scaling): rank g owns slice g, computes a partial
+          G1 point, the N partials are exchanged with one NCCL all_gather (N * 144 B) and summed on every rank.
+`value`  = points of the whole job / second with bases and scalars already resident in HBM (device pointers through the
+           C ABI, result left on the device);  `e2e` = the same through b200msm_g1_multiexp_affine with pinned HOST
+           buffers for bases, scalars and result (H2D and D2H inside the timed region).
+`--impl reference` times the reference's own WASM MSM (compiled natively, oracle/_ref) on the host cores.
+Prints ONE JSON line (rank 0).
+"""
+import argparse, json, os, subprocess, sys, threading, time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "zprize-wasm-msm_b200")):
+    if p not in sys.path: sys.path.insert(0, p)
+
+METRIC = "bls12381_g1_msm_points_per_s"
+SEED = 0xB2000000
+LIMB_PRODUCTS_PER_FQMUL = {"bls12381": 300, "bn128": 136}     # 2*n32^2 + n32 (build_f1m.js:575-660)
+FQMUL_PER_AFFINE_ADD = 6                                       # build_multiexp_opt.js:1207-1233 + build_batchinverse.js
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--log2n", type=int, default=20, help="points per GPU = 2^log2n")
+    ap.add_argument("--curve", default="bls12381", choices=["bls12381", "bn128"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-log2n", type=int, default=16, help="points per reference step (bounded sample)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []; self.proc = None; self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc: return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try: self.proc.wait(timeout=2)
+        except Exception: self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p)); return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def _ref_worker(args):
+    cname, bases, scalars, n = args
+    import refwasm
+    pb = refwasm.RefModule(cname)
+    return pb.msm_affine_raw(bases, scalars, 32, n)
+
+
+def reference_msm_parallel(pool, cname, bases, scalars, n, nproc, n8):
+    """One MSM of n points on nproc host processes: point-range slices, each through the reference's own
+    g1m_multiexpAffine (one WASM instance per worker, as ffjavascript's worker pool does), partials summed with g1m_add."""
+    import refwasm
+    per = (n + nproc - 1) // nproc
+    jobs = []
+    for k in range(nproc):
+        lo, hi = k * per, min(n, (k + 1) * per)
+        if lo >= hi: break
+        jobs.append((cname, bases[lo * 2 * n8: hi * 2 * n8], scalars[lo * 32: hi * 32], hi - lo))
+    parts = pool.map(_ref_worker, jobs)
+    pb = reference_msm_parallel._pb.get(cname)
+    if pb is None:
+        pb = reference_msm_parallel._pb[cname] = refwasm.RefModule(cname)
+    mark = pb.heap_mark()
+    pacc = pb.alloc(3 * n8); pt = pb.alloc(3 * n8)
+    pb.write(pacc, parts[0])
+    for part in parts[1:]:
+        pb.write(pt, part); pb.g1m_add(pacc, pt, pacc)
+    out = pb.normalize_read(pacc)
+    pb.heap_release(mark)
+    return out
+
+
+reference_msm_parallel._pb = {}
+
+
+def time_reference(cname, log2n, steps, warmup):
+    """returns (points_per_s, ms_per_step, cores, kind, sample description)"""
+    import multiprocessing as mp
+    import pyref, coracle, refwasm
+    cv = pyref.CURVES[cname]
+    n = 1 << log2n
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    bases = coracle.generate_bases(cv.cid, pyref.affine_to_bytes(cv, cv.G), SEED + log2n, 0, n)
+    import random
+    rnd = random.Random(log2n)
+    scalars = rnd.getrandbits(256 * n).to_bytes(32 * n, "little")
+    if refwasm.available(cname):
+        kind = "reference"
+        ctx = mp.get_context("fork")
+        with ctx.Pool(cores) as pool:
+            for _ in range(warmup): reference_msm_parallel(pool, cname, bases, scalars, n, cores, cv.n8)
+            t0 = time.perf_counter()
+            for _ in range(steps): res = reference_msm_parallel(pool, cname, bases, scalars, n, cores, cv.n8)
+            dt = (time.perf_counter() - t0) / steps
+        check = coracle.normalize(cv.cid, coracle.multiexp_affine(cv.cid, bases, scalars, 32, n))
+        assert pyref.canonical_bytes(cv, res) == check, "reference arm result differs from the C oracle"
+        what = "reference WASM (upstream wasmcurves g1m_multiexpAffine) AOT-compiled via C"
+    else:
+        kind = "port"; cores = 1
+        for _ in range(warmup): coracle.multiexp_affine(cv.cid, bases, scalars, 32, n)
+        t0 = time.perf_counter()
+        for _ in range(steps): coracle.multiexp_affine(cv.cid, bases, scalars, 32, n)
+        dt = (time.perf_counter() - t0) / steps
+        what = "C port of the upstream algorithm (oracle/msm_oracle.c)"
+    sample = "%s; one MSM of 2^%d points per step, point-range slices over %d host processes, partials summed with g1m_add" % (what, log2n, cores)
+    return n / dt, dt * 1e3, cores, kind, sample
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0: return
+    cname = a.curve
+    steps = max(1, min(a.steps, 5)); warm = max(1, min(a.warmup, 1))
+    pps, ms, cores, kind, sample = time_reference(cname, a.ref_log2n, steps, warm)
+    line = {"impl": "reference", "metric": METRIC if cname == "bls12381" else "bn254_g1_msm_points_per_s", "value": pps, "unit": "points/s",
+            "n_gpus": a.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 limbs (Montgomery Fq)", "data": "synthetic",
+            "config": {"workload": "%s G1 MSM, bounded sample 2^%d points per step (of the 2^%d-point workload), uniform 256-bit scalars" % (cname, a.ref_log2n, a.log2n),
+                       "curve": cname, "log2n_per_step": a.ref_log2n},
+            "cpu_baseline": {"value": pps, "unit": "points/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": pps, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import b200msm
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cname = a.curve; cid = 0 if cname == "bls12381" else 1; n8 = b200msm.N8[cid]
+    n = 1 << a.log2n
+    eng = b200msm.Engine(local)
+    stream = torch.cuda.current_stream(dev)
+    eng.set_stream(stream.cuda_stream)
+
+    # ---- synthetic inputs, generated on the device: bases P_i = k_i * G (global index range of this rank), uniform 256-bit scalars
+    bases = torch.empty(n * 2 * n8, dtype=torch.uint8, device=dev)
+    eng.generate_bases(cid, SEED + a.log2n, rank * n, n, bases)
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    NSETS = 2
+    scal = [torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device=dev, generator=g) for _ in range(NSETS)]
+    handle = eng.upload_bases(cid, bases, n)        # device -> device copy: the engine's own resident copy
+    out_dev = torch.zeros(3 * n8, dtype=torch.uint8, device=dev)
+    gathered = torch.zeros(world * 3 * n8, dtype=torch.uint8, device=dev) if world > 1 else None
+    total_dev = torch.zeros(3 * n8, dtype=torch.uint8, device=dev)
+
+    def step_device(i):
+        eng.multiexp_resident(handle, scal[i % NSETS], 32, n, cid, out=out_dev)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out_dev)
+            rc = b200msm.lib.b200msm_g1_sum(eng._ctx, cid, gathered.data_ptr(), world, total_dev.data_ptr())
+            assert rc == 0, rc
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- correctness guard on a small prefix (device path vs the oracle) -- not timed
+    if rank == 0:
+        import pyref, coracle
+        cv = pyref.CURVES[cname]; m = 1 << 10
+        hb = bytes(bases[: m * 2 * n8].cpu().numpy()); hs = bytes(scal[0][: m * 32].cpu().numpy())
+        got = eng.normalize(cid, eng.multiexp_affine(cid, hb, hs, 32, m))
+        assert got == coracle.normalize(cid, coracle.multiexp_affine(cid, hb, hs, 32, m)), "GPU result differs from the oracle"
+
+    for i in range(max(3, a.warmup)): step_device(i)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0: sampler.start()
+    launches0 = eng.counter("launches")
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record(stream)
+    for i in range(a.steps): step_device(i)
+    e1.record(stream)
+    sync_all()
+    ms = e0.elapsed_time(e1) / a.steps
+    launches = (eng.counter("launches") - launches0) // max(1, a.steps)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    # ---- e2e: host buffers through the reference-facing entry point (H2D of bases + scalars, D2H of the result, every step)
+    hb = torch.empty(n * 2 * n8, dtype=torch.uint8).pin_memory(); hb.copy_(bases)
+    hs = [torch.empty(n * 32, dtype=torch.uint8).pin_memory() for _ in range(NSETS)]
+    for k in range(NSETS): hs[k].copy_(scal[k])
+    hout = torch.zeros(3 * n8, dtype=torch.uint8).pin_memory()
+    gout = [torch.zeros(3 * n8, dtype=torch.uint8) for _ in range(world)] if world > 1 else None
+
+    def step_host(i):
+        eng.multiexp_affine(cid, hb, hs[i % NSETS], 32, n, out=hout)          # synchronous: result is in host memory on return
+        if world > 1:
+            out_dev.copy_(hout, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, out_dev)
+            rc = b200msm.lib.b200msm_g1_sum(eng._ctx, cid, gathered.data_ptr(), world, hout.data_ptr())
+            assert rc == 0, rc
+
+    for i in range(2): step_host(i)
+    sync_all()
+    e2e_steps = max(3, min(a.steps, 10))
+    t0 = time.perf_counter(); e0.record(stream)
+    for i in range(e2e_steps): step_host(i)
+    e1.record(stream)
+    sync_all()
+    e2e_ms = max((time.perf_counter() - t0) * 1e3, e0.elapsed_time(e1)) / e2e_steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- kernel-level timings (per-phase CUDA events inside the engine) for the roofline, same inputs, rank 0 only
+    line = None
+    if rank == 0:
+        agg = {}; reps = max(3, min(a.steps, 10))
+        for i in range(reps):
+            _, st = eng.multiexp_resident(handle, scal[i % NSETS], 32, n, cid, out=out_dev, want_stats=True)
+            for k, v in st.items(): agg[k] = agg.get(k, 0) + v
+        st = {k: v / reps for k, v in agg.items()}
+        imad = eng.probe_imad(); fq = eng.probe_fqmul(cid)
+        hbm_peak, hbm_src = measured_peaks()
+        lp = LIMB_PRODUCTS_PER_FQMUL[cname]
+        adds = st["affine_adds"]
+        # dominant kernel group: k_tree_bwd (5 of the 6 field multiplications of every batch-affine addition)
+        bwd_ms = st["ms_k_tree_bwd"]; rounds = max(1, int(round(st["tree_rounds"])))
+        alg_lp_bwd = adds * 5 * lp
+        achieved = alg_lp_bwd / (bwd_ms * 1e-3) if bwd_ms > 0 else 0.0
+        # algorithmic HBM bytes of the same kernel group per addition: 2 input points + prefix + inverse share + output point
+        bytes_per_add = 2 * 2 * n8 + n8 + n8 / 4 + 2 * n8
+        roof = {"bound": "imad", "kernel": "k_tree_bwd (batch-affine backward pass, all rounds)", "achieved": achieved / 1e12, "peak": imad / 1e12,
+                "unit": "T limb-products/s (32x32->64 IMAD.WIDE)", "frac": (achieved / imad) if imad else None, "traffic": None,
+                "launches_per_step": rounds, "avg_launch_ms": bwd_ms / rounds, "algorithmic_units_per_step": alg_lp_bwd,
+                "peak_source": "measured in this run by b200msm_probe_imad (register-resident mad.wide.u32 loop on all SMs)",
+                "hbm": {"achieved": adds * bytes_per_add / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": (adds * bytes_per_add / (bwd_ms * 1e-3) / 1e9 / hbm_peak) if bwd_ms > 0 else None, "peak_source": hbm_src},
+                "whole_accumulate": {"limb_products": adds * FQMUL_PER_AFFINE_ADD * lp, "ms": st["ms_accumulate"],
+                                     "frac_of_imad_peak": (adds * FQMUL_PER_AFFINE_ADD * lp / (st["ms_accumulate"] * 1e-3) / imad) if imad and st["ms_accumulate"] > 0 else None},
+                "fqmul_per_s_measured": fq, "fqmul_frac_of_imad_peak": fq * lp / imad if imad else None}
+        total_points = n * world
+        line = {"metric": METRIC if cname == "bls12381" else "bn254_g1_msm_points_per_s", "value": total_points / (ms * 1e-3), "unit": "points/s",
+                "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u32 limbs (Montgomery Fq, 32x32->64 IMAD)", "data": "synthetic",
+                "config": {"workload": "%s G1 MSM, 2^%d points per GPU (%d points per step), uniform 256-bit scalars, bases P_i = k_i*G resident in HBM"
+                                       % ("BLS12-381" if cid == 0 else "BN254", a.log2n, total_points),
+                           "curve": cname, "log2n_per_gpu": a.log2n, "parallelism": "point-range shards x%d + all_gather of partials" % world if world > 1 else "single GPU",
+                           "window_bits": int(st["window_bits"]), "windows": int(st["windows"]), "tree_rounds": int(round(st["tree_rounds"])),
+                           "cache": "no L2 flush: per-step working set (bases %d MiB + scalars %d MiB + sort/tree scratch > 1 GiB) exceeds the 126 MB L2; %d scalar sets alternate"
+                                    % (n * 2 * n8 >> 20, n * 32 >> 20, NSETS)},
+                "clocks": clocks,
+                "e2e": {"value": total_points / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": n * (2 * n8 + 32), "d2h_bytes_per_step": 3 * n8, "api": "b200msm_g1_multiexp_affine with pinned host buffers"},
+                "gpu_launches": int(launches),
+                "roofline": roof,
+                "phases_ms": {k: round(v, 4) for k, v in st.items() if k.startswith("ms_")},
+                "pairs": st["pairs"], "affine_adds": adds}
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own code on the host cores, bounded sample
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            pps, rms, cores, kind, sample = time_reference(cname, a.ref_log2n, 2, 1)
+            line["cpu_baseline"] = {"value": pps, "unit": "points/s", "cores": cores, "kind": kind, "sample": sample, "ms_per_sample": rms}
+        except Exception as ex:  # the baseline must never take the GPU number down with it
+            line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+    elif rank == 0:
+        line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": 0, "kind": "skipped", "sample": "measured at N=1 only"}
+    if rank == 0: print(json.dumps(line), flush=True)
+    eng.free_bases(handle)
+    if world > 1: dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference": run_reference(args)
+    else: run_ours(args)

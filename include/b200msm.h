@@ -40,6 +40,10 @@ typedef struct b200msm_stats {
   uint64_t pairs;            /* non-zero (point, window) digits = bucket insertions                     */
   uint64_t affine_adds;      /* batch-affine additions executed                                          */
   float ms_total, ms_h2d, ms_digits_sort, ms_accumulate, ms_bucket_reduce, ms_window_combine, ms_d2h;
+  /* kernel-group times inside the phases above (sums over all rounds / launches of that kernel group) */
+  float ms_k_sort, ms_k_plan, ms_k_tree_fwd, ms_k_inv_tree, ms_k_tree_bwd, ms_k_finish, ms_k_fold, ms_k_wsum, ms_k_horner;
+  float ms_host_combine;     /* host part of the window combination (inside ms_window_combine) */
+  uint64_t launches;         /* kernels + memset/memcpy nodes launched by this call */
 } b200msm_stats;
 
 /* ---- life cycle.  device_id < 0 selects the current CUDA device. */
@@ -96,10 +100,15 @@ int b200msm_fq_op(b200msm_ctx* ctx, int curve, int op, const void* a, const void
  * imad_per_s: 32x32+64 multiply-adds per second (register-resident mad.wide.u32 loop, all SMs);
  * fqmul_per_s: dependent Montgomery multiplications per second for the given curve. */
 int b200msm_probe_imad(b200msm_ctx* ctx, double* imad_per_s);
+int b200msm_probe_imad_carry(b200msm_ctx* ctx, double* imad_per_s);   /* same with carry in/out on every multiply-add (IMAD.WIDE.U32.X) */
 int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s);
 
-/* ---- tuning knobs (never change results).  key: "window_bits" (0 = auto), "accumulate" (0 = auto, 1 = serial, 2 = batch-affine). */
+/* ---- tuning knobs (never change results).  key: "window_bits" (0 = auto), "accumulate" (0 = auto, 1 = serial, 2 = batch-affine),
+ * "tree_rounds" (-1 = auto), "combine" (0 = serial tail on the host (default), 1 = device chain k_window_sums + k_horner). */
 int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t value);
+
+/* ---- counters since context creation.  key: "launches" (kernel launches issued by this context). */
+int b200msm_get_counter(b200msm_ctx* ctx, const char* key, uint64_t* value);
 
 /* ---- host-only: field constants as the engine uses them (q, R mod q, R^2 mod q as n8-byte LE; np32). No GPU needed. */
 int b200msm_constants(int curve, uint32_t* n8, uint8_t* q, uint8_t* r_mod_q, uint8_t* r2_mod_q, uint32_t* np32);

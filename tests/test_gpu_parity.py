@@ -80,6 +80,22 @@ def test_msm_window_widths(eng, cname, wb):
 
 
 @pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+@pytest.mark.parametrize("wb", [1, 7, 16])
+def test_device_window_combination_matches_host_tail(eng, cname, wb):
+    """combine=1 runs k_window_sums + k_horner on the device instead of the host-side serial tail: same point."""
+    cv = curve(cname); n = 900
+    bases = make_bases(cv, n, 41); sc = make_scalars(n, 42, "u256")
+    exp = oracle_msm(cv, bases, sc, 32, n)
+    eng.set_option("window_bits", wb)
+    try:
+        for mode in (1, 0):
+            eng.set_option("combine", mode)
+            assert msm(eng, cv, bases, sc, 32, n) == exp, mode
+    finally:
+        eng.set_option("combine", 0); eng.set_option("window_bits", 0)
+
+
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
 def test_msm_edge_cases(eng, cname):
     cv = curve(cname); n8 = cv.n8
     zero = bytes(2 * n8)

@@ -1,0 +1,42 @@
+#!/usr/bin/env python3
+"""Phase-time sweep over problem sizes (development tool): python tools/sweep.py [--curve bls12381] [--sizes 14,16,18,20] [--opt key=val ...]"""
+import argparse, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "zprize-wasm-msm_b200")): sys.path.insert(0, p)
+import torch, b200msm
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--curve", default="bls12381"); ap.add_argument("--sizes", default="14,16,18,20"); ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--opt", action="append", default=[]); ap.add_argument("--probe", action="store_true")
+a = ap.parse_args()
+cid = 0 if a.curve == "bls12381" else 1; n8 = b200msm.N8[cid]
+eng = b200msm.Engine(0); dev = torch.device("cuda", 0)
+eng.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+for kv in a.opt:
+    k, v = kv.split("="); eng.set_option(k, int(v))
+if a.probe:
+    imad = eng.probe_imad(); fq = eng.probe_fqmul(cid); imx = eng.probe_imad_carry()
+    print(json.dumps({"imad_per_s": imad, "imad_carry_per_s": imx, "fqmul_per_s": fq, "fqmul_limb_frac": fq * (300 if cid == 0 else 136) / imad}))
+for lg in [int(x) for x in a.sizes.split(",")]:
+    n = 1 << lg
+    bases = torch.empty(n * 2 * n8, dtype=torch.uint8, device=dev)
+    eng.generate_bases(cid, 0xB2000000 + lg, 0, n, bases)
+    g = torch.Generator(device=dev); g.manual_seed(lg)
+    sc = torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device=dev, generator=g)
+    h = eng.upload_bases(cid, bases, n); out = torch.zeros(3 * n8, dtype=torch.uint8, device=dev)
+    for _ in range(2): eng.multiexp_resident(h, sc, 32, n, cid, out=out)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.reps): eng.multiexp_resident(h, sc, 32, n, cid, out=out)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.reps
+    agg = {}
+    for _ in range(a.reps):
+        _, st = eng.multiexp_resident(h, sc, 32, n, cid, out=out, want_stats=True)
+        for k, v in st.items(): agg[k] = agg.get(k, 0) + v / a.reps
+    row = {"log2n": lg, "ms": round(ms, 3), "c": int(agg["window_bits"]), "W": int(agg["windows"]), "rounds": int(agg["tree_rounds"]),
+           "pairs": int(agg["pairs"]), "adds": int(agg["affine_adds"]), "launches": int(agg["launches"])}
+    row.update({k[3:]: round(v, 3) for k, v in agg.items() if k.startswith("ms_")})
+    print(json.dumps(row), flush=True)
+    eng.free_bases(h); del bases, sc

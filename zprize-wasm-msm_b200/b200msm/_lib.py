@@ -16,8 +16,8 @@ EXPORTS = [  # every symbol include/b200msm.h declares (checked by tests/test_ab
     "b200msm_create", "b200msm_destroy", "b200msm_strerror", "b200msm_last_error", "b200msm_version",
     "b200msm_set_stream", "b200msm_synchronize", "b200msm_g1_multiexp_affine", "b200msm_g1_multiexp_affine_chunk",
     "b200msm_upload_bases", "b200msm_free_bases", "b200msm_g1_multiexp_resident", "b200msm_g1_normalize",
-    "b200msm_g1_sum", "b200msm_g1_generate_bases", "b200msm_fq_op", "b200msm_probe_imad", "b200msm_probe_fqmul",
-    "b200msm_set_option", "b200msm_constants",
+    "b200msm_g1_sum", "b200msm_g1_generate_bases", "b200msm_fq_op", "b200msm_probe_imad", "b200msm_probe_imad_carry", "b200msm_probe_fqmul",
+    "b200msm_set_option", "b200msm_constants", "b200msm_get_counter",
 ]
 
 
@@ -27,10 +27,13 @@ class Stats(ctypes.Structure):
                 ("pairs", ctypes.c_uint64), ("affine_adds", ctypes.c_uint64),
                 ("ms_total", ctypes.c_float), ("ms_h2d", ctypes.c_float), ("ms_digits_sort", ctypes.c_float),
                 ("ms_accumulate", ctypes.c_float), ("ms_bucket_reduce", ctypes.c_float), ("ms_window_combine", ctypes.c_float),
-                ("ms_d2h", ctypes.c_float)]
+                ("ms_d2h", ctypes.c_float),
+                ("ms_k_sort", ctypes.c_float), ("ms_k_plan", ctypes.c_float), ("ms_k_tree_fwd", ctypes.c_float), ("ms_k_inv_tree", ctypes.c_float),
+                ("ms_k_tree_bwd", ctypes.c_float), ("ms_k_finish", ctypes.c_float), ("ms_k_fold", ctypes.c_float), ("ms_k_wsum", ctypes.c_float),
+                ("ms_k_horner", ctypes.c_float), ("ms_host_combine", ctypes.c_float), ("launches", ctypes.c_uint64)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
 
 
 class B200MsmError(RuntimeError):
@@ -62,8 +65,10 @@ lib.b200msm_g1_sum.argtypes = [_vp, _i, _vp, _u64, _vp]
 lib.b200msm_g1_generate_bases.argtypes = [_vp, _i, _u64, _u64, _u64, _vp]
 lib.b200msm_fq_op.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _u64]
 lib.b200msm_probe_imad.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
+lib.b200msm_probe_imad_carry.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
 lib.b200msm_probe_fqmul.argtypes = [_vp, _i, ctypes.POINTER(ctypes.c_double)]
 lib.b200msm_set_option.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int64]
+lib.b200msm_get_counter.argtypes = [_vp, ctypes.c_char_p, ctypes.POINTER(_u64)]
 lib.b200msm_constants.argtypes = [_i, ctypes.POINTER(_u32), _vp, _vp, _vp, ctypes.POINTER(_u32)]
 
 

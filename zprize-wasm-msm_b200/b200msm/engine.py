@@ -95,8 +95,14 @@ class Engine:
         o = ctypes.create_string_buffer(max(1, len(a)))
         self._ck(lib.b200msm_fq_op(self._ctx, curve, op, pa, pb_, o, n)); return o.raw[:len(a)]
 
+    def counter(self, key):
+        v = ctypes.c_uint64(); self._ck(lib.b200msm_get_counter(self._ctx, key.encode(), ctypes.byref(v))); return v.value
+
     def probe_imad(self):
         v = ctypes.c_double(); self._ck(lib.b200msm_probe_imad(self._ctx, ctypes.byref(v))); return v.value
+
+    def probe_imad_carry(self):
+        v = ctypes.c_double(); self._ck(lib.b200msm_probe_imad_carry(self._ctx, ctypes.byref(v))); return v.value
 
     def probe_fqmul(self, curve):
         v = ctypes.c_double(); self._ck(lib.b200msm_probe_fqmul(self._ctx, curve, ctypes.byref(v))); return v.value

@@ -18,6 +18,8 @@
 #include "../../include/b200msm.h"
 #include "msm_kernels.cuh"
 #include "accumulate.cuh"
+#include "host_ec.h"
+#include <chrono>
 
 using namespace b200;
 
@@ -48,16 +50,32 @@ struct b200msm_ctx {
   int opt_window_bits = 0, opt_accumulate = 0, opt_tree_rounds = -1;
   DevBuf bases, scalars, canon, counts, offsets, cursors, tiles, sorted, buckets, wsum, out, misc, acc_a, acc_b, acc_c, acc_d, acc_e;
   DevBuf t_offs, t_cnt, t_bid, t_pa, t_pb, t_prefix, t_prod, t_lvlprefix;     // batch-affine tree scratch
-  uint32_t* h_pinned = nullptr;                                               // small pinned read-back area (1024 words)
+  uint32_t* h_pinned = nullptr;
+  void* h_folded = nullptr; size_t h_folded_cap = 0;                         // pinned staging of the folded bucket entries
+  int opt_combine = 0;                                                        // 0 = host serial tail (default), 1 = device k_window_sums + k_horner
+  float host_combine_ms = 0;                                               // small pinned read-back area (1024 words)
   std::map<uint64_t, Resident> residents; uint64_t next_handle = 1;
   cudaEvent_t ev[8] = {};
+  // fine-grained phase profiler (active only while a stats struct is being filled)
+  std::vector<cudaEvent_t> pev; std::vector<int> ptag; size_t pused = 0; bool prof = false;
+  uint64_t launches = 0;
 };
 
 namespace {
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); \
   return e_ == cudaErrorMemoryAllocation ? B200MSM_E_NOMEM : B200MSM_E_CUDA; } } while (0)
-#define CKL() CK(cudaGetLastError())
+#define CKL() do { ctx->launches++; CK(cudaGetLastError()); } while (0)
+enum { T_SORT = 0, T_PLAN, T_TREE_FWD, T_INV_TREE, T_TREE_BWD, T_FINISH, T_FOLD, T_WSUM, T_HORNER, T_NTAGS };
+#define MARK(tag) do { if (ctx->prof) { int rc_ = prof_mark(ctx, tag); if (rc_) return rc_; } } while (0)
+
+int prof_mark(b200msm_ctx* ctx, int tag) {
+  if (ctx->pused == ctx->pev.size()) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->pev.push_back(e); ctx->ptag.push_back(0); }
+  ctx->ptag[ctx->pused] = tag;
+  CK(cudaEventRecord(ctx->pev[ctx->pused], ctx->stream));
+  ctx->pused++;
+  return B200MSM_OK;
+}
 
 bool is_device_ptr(const void* p) {
   if (!p) return false;
@@ -104,6 +122,7 @@ int accumulate_batch_affine(b200msm_ctx* ctx, const void* d_bases, const uint32_
   *rounds_out = std::max(*rounds_out, R);
   if (R == 0) {
     k_accum_finish<C, true><<<(nbg + 127) / 128, 128, 0, s>>>(d_bases, sorted, nullptr, off0, nbg, buckets_g); CKL();
+    MARK(T_FINISH);
     return B200MSM_OK;
   }
   // upper bounds of the slot counts per round: sum ceil(n/2) <= (sum n + #non-empty) / 2
@@ -125,6 +144,7 @@ int accumulate_batch_affine(b200msm_ctx* ctx, const void* d_bases, const uint32_
     CK(ctx->t_bid.ensure(tot * 4 + 16));
     size_t at = 0; for (uint32_t r = 1; r <= R; r++) { bid[r] = ctx->t_bid.as<uint32_t>() + at; at += U[r]; } }
   k_fill_bid<<<(uint32_t)((U[1] + 255) / 256), 256, 0, s>>>(off[1], nbg, bid[1]); CKL();
+  MARK(T_PLAN);
   const size_t fe = 4 * C::N, pt = 8 * C::N;
   CK(ctx->t_pa.ensure(U[1] * pt + 16)); if (R > 1) CK(ctx->t_pb.ensure(U[2] * pt + 16));
   CK(ctx->t_prefix.ensure(U[1] * fe + 16));
@@ -141,7 +161,7 @@ int accumulate_batch_affine(b200msm_ctx* ctx, const void* d_bases, const uint32_
     char* prod = ctx->t_prod.as<char>(); char* lpre = ctx->t_lvlprefix.as<char>();
     if (r == 0) k_tree_fwd<C, true><<<grid, BA_THREADS, 0, s>>>(tr, d_bases, sorted, nullptr, ctx->t_prefix.p, prod);
     else k_tree_fwd<C, false><<<grid, BA_THREADS, 0, s>>>(tr, nullptr, nullptr, pin, ctx->t_prefix.p, prod);
-    CKL();
+    CKL(); MARK(T_TREE_FWD);
     // up the product tree
     std::vector<uint64_t> ln; std::vector<char*> lv, lp;
     uint64_t n = (uint64_t)grid * BA_THREADS; char* cur = prod; char* curp = lpre;
@@ -158,13 +178,15 @@ int accumulate_batch_affine(b200msm_ctx* ctx, const void* d_bases, const uint32_
       uint32_t g2 = (uint32_t)((ln[l] + BA_TILE - 1) / BA_TILE);
       k_prod_bwd<C><<<g2, BA_THREADS, 0, s>>>(lv[l], (uint32_t)ln[l], lp[l], lv[l] + ln[l] * fe); CKL();
     }
+    MARK(T_INV_TREE);
     if (r == 0) k_tree_bwd<C, true><<<grid, BA_THREADS, 0, s>>>(tr, d_bases, sorted, nullptr, ctx->t_prefix.p, prod, pout);
     else k_tree_bwd<C, false><<<grid, BA_THREADS, 0, s>>>(tr, nullptr, nullptr, pin, ctx->t_prefix.p, prod, pout);
-    CKL();
+    CKL(); MARK(T_TREE_BWD);
     pin = pout;
     *adds_out += U[r] - U[r + 1];
   }
   k_accum_finish<C, false><<<(nbg + 127) / 128, 128, 0, s>>>(nullptr, nullptr, pin, off[R], nbg, buckets_g); CKL();
+  MARK(T_FINISH);
   return B200MSM_OK;
 }
 
@@ -176,7 +198,8 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   MsmPlan pl;
   pl.n = n; pl.nbits = nbits;
   pl.c = ctx->opt_window_bits > 0 ? std::min<uint32_t>((uint32_t)ctx->opt_window_bits, std::min<uint32_t>(nbits + 1, 24)) : auto_window_bits(n, nbits);
-  pl.W = (nbits + 1 + pl.c - 1) / pl.c; pl.B = 1u << (pl.c - 1); pl.logB = pl.c - 1;
+  pl.Wd = (nbits + pl.c - 1) / pl.c; pl.B = 1u << (pl.c - 1); pl.logB = pl.c - 1;
+  pl.W = pl.Wd + ((nbits - (pl.Wd - 1) * pl.c == pl.c) ? 1 : 0);
   const uint32_t nb = pl.W * pl.B;
   if ((uint64_t)pl.W * pl.B > (1ull << 31) || (uint64_t)n * pl.W >= (1ull << 32)) { ctx->err = "problem too large for 32-bit pair indices"; return B200MSM_E_UNSUPPORTED; }
 
@@ -199,6 +222,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   CK(cudaMemcpyAsync(ctx->h_pinned, ctx->misc.p, pl.W * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpy2DAsync(ctx->h_pinned + 512, 4, ctx->offsets.as<uint32_t>(), (size_t)pl.B * 4, 4, pl.W + 1, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  MARK(T_SORT);
   // ---- accumulate: bucket sums in XYZZ
   CK(ctx->buckets.ensure((size_t)nb * 16 * C::N));
   int mode = ctx->opt_accumulate;
@@ -232,13 +256,40 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
     uint64_t threads = (uint64_t)live * (sz / 2) * pl.W;
     k_fold<C><<<(uint32_t)((threads + 127) / 128), 128, 0, s>>>(ctx->buckets.p, pl.W, pl.B, sz); CKL();
   }
-  CK(ctx->wsum.ensure((size_t)pl.W * 16 * C::N));
-  k_window_sums<C><<<(pl.W + 31) / 32, 32, 0, s>>>(ctx->buckets.p, pl.W, pl.B, pl.logB, ctx->wsum.p); CKL();
-  if (st) CK(cudaEventRecord(ctx->ev[4], s));
-  k_horner<C><<<1, 32, 0, s>>>(ctx->wsum.p, pl.W, pl.c, d_out); CKL();
+  MARK(T_FOLD);
+  if (ctx->opt_combine == 1) {
+    CK(ctx->wsum.ensure((size_t)pl.W * 16 * C::N));
+    k_window_sums<C><<<(pl.W + 31) / 32, 32, 0, s>>>(ctx->buckets.p, pl.W, pl.Wd, pl.B, pl.logB, ctx->wsum.p); CKL();
+    MARK(T_WSUM);
+    if (st) CK(cudaEventRecord(ctx->ev[4], s));
+    k_horner<C><<<1, 32, 0, s>>>(ctx->wsum.p, pl.W, pl.Wd, pl.c, d_out); CKL();
+    MARK(T_HORNER);
+  } else {
+    // serial tail on the host: fetch the (logB + 1) live entries of every folded slot, combine, push the point back
+    const uint32_t per = pl.logB + 1, npts = pl.W * per;
+    const size_t bytes = (size_t)npts * 16 * C::N;
+    CK(ctx->wsum.ensure(bytes));
+    if (ctx->h_folded_cap < bytes) { if (ctx->h_folded) cudaFreeHost(ctx->h_folded); ctx->h_folded = nullptr; ctx->h_folded_cap = 0;
+      CK(cudaMallocHost(&ctx->h_folded, bytes + 4096)); ctx->h_folded_cap = bytes + 4096; }
+    k_gather_folded<C><<<(npts + 127) / 128, 128, 0, s>>>(ctx->buckets.p, pl.W, pl.B, pl.logB, ctx->wsum.p); CKL();
+    CK(cudaMemcpyAsync(ctx->h_folded, ctx->wsum.p, bytes, cudaMemcpyDeviceToHost, s));
+    MARK(T_WSUM);
+    if (st) CK(cudaEventRecord(ctx->ev[4], s));
+    CK(cudaStreamSynchronize(s));
+    auto t0 = std::chrono::steady_clock::now();
+    constexpr int L = C::N / 2;
+    b200host::Field<L> f;
+    for (int i = 0; i < L; i++) { f.q[i] = (uint64_t)C::q(2 * i) | ((uint64_t)C::q(2 * i + 1) << 32); f.one[i] = (uint64_t)C::one(2 * i) | ((uint64_t)C::one(2 * i + 1) << 32); }
+    { uint64_t x = 1; for (int k = 0; k < 6; k++) x *= 2 - f.q[0] * x; f.np = 0 - x; }      // -q^-1 mod 2^64 (Newton)
+    uint64_t* res = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ctx->h_folded) + bytes);   // 3*n8 bytes in the pinned tail
+    b200host::combine_windows<L>(f, reinterpret_cast<const b200host::XYZZ<L>*>(ctx->h_folded), pl.W, pl.Wd, pl.c, pl.logB, res);
+    ctx->host_combine_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    CK(cudaMemcpyAsync(d_out, res, 12 * C::N, cudaMemcpyHostToDevice, s));
+    MARK(T_HORNER);
+  }
   if (st) {
     CK(cudaEventRecord(ctx->ev[5], s));
-    st->n = n; st->window_bits = pl.c; st->windows = pl.W; st->buckets_per_window = pl.B; st->tree_rounds = rounds; st->affine_adds = adds;
+    st->n = n; st->window_bits = pl.c; st->windows = pl.Wd; st->reserved = pl.W; st->buckets_per_window = pl.B; st->tree_rounds = rounds; st->affine_adds = adds;
   }
   return B200MSM_OK;
 }
@@ -274,7 +325,9 @@ int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_residen
   CK(cudaSetDevice(ctx->device));
   const int n8 = n8_of(curve);
   CK(ctx->out.ensure(3 * 48));
-  if (st) { memset(st, 0, sizeof *st); CK(cudaEventRecord(ctx->ev[0], ctx->stream)); }
+  ctx->prof = false;
+  if (st) { memset(st, 0, sizeof *st); CK(cudaEventRecord(ctx->ev[0], ctx->stream)); ctx->prof = true; ctx->pused = 0; }
+  const uint64_t launches0 = ctx->launches;
   // clip the processed bit range at the scalar end (getChunk's bitsToEnd mask, build_multiexp.js:38-72)
   if (bit0 >= 8 * scalar_size) nbits = 0; else if (bit0 + nbits > 8 * scalar_size) nbits = 8 * scalar_size - bit0;
   if (nbits > 256) { ctx->err = "more than 256 scalar bits per call are not supported"; return B200MSM_E_UNSUPPORTED; }
@@ -294,9 +347,10 @@ int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_residen
     k_canon_scalars<<<(uint32_t)((n + 255) / 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint8_t*>(d_sraw), scalar_size, (uint32_t)n, bit0, nbits, ctx->canon.as<uint32_t>()); CKL();
     d_scal = ctx->canon.as<uint32_t>();
   }
+  MARK(T_NTAGS);
   rc = curve == 0 ? run_pipeline<BLS12_381>(ctx, d_bases, d_scal, n, nbits, ctx->out.p, st)
                   : run_pipeline<BN254>(ctx, d_bases, d_scal, n, nbits, ctx->out.p, st);
-  if (rc) return rc;
+  if (rc) { ctx->prof = false; return rc; }
   if (st) CK(cudaEventRecord(ctx->ev[6], ctx->stream));
   rc = deliver(ctx, ctx->out.p, out, 3 * n8); if (rc) return rc;
   if (st) {
@@ -306,12 +360,19 @@ int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_residen
     cudaEventElapsedTime(&st->ms_accumulate, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&st->ms_bucket_reduce, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&st->ms_window_combine, ctx->ev[4], ctx->ev[5]);
+    st->ms_host_combine = ctx->opt_combine == 1 ? 0.f : ctx->host_combine_ms;
     cudaEventElapsedTime(&st->ms_d2h, ctx->ev[6], ctx->ev[7]);
     cudaEventElapsedTime(&st->ms_total, ctx->ev[0], ctx->ev[7]);
     uint32_t total = 0;
-    uint32_t nb = st->windows * st->buckets_per_window;
+    uint32_t nb = st->reserved * st->buckets_per_window;
     CK(cudaMemcpy(&total, ctx->offsets.as<uint32_t>() + nb, 4, cudaMemcpyDeviceToHost));
     st->pairs = total;
+    float acc[T_NTAGS + 1] = {0};
+    for (size_t i = 1; i < ctx->pused; i++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->pev[i - 1], ctx->pev[i]); acc[ctx->ptag[i]] += ms; }
+    st->ms_k_sort = acc[T_SORT]; st->ms_k_plan = acc[T_PLAN]; st->ms_k_tree_fwd = acc[T_TREE_FWD]; st->ms_k_inv_tree = acc[T_INV_TREE];
+    st->ms_k_tree_bwd = acc[T_TREE_BWD]; st->ms_k_finish = acc[T_FINISH]; st->ms_k_fold = acc[T_FOLD]; st->ms_k_wsum = acc[T_WSUM]; st->ms_k_horner = acc[T_HORNER];
+    st->launches = ctx->launches - launches0;
+    ctx->prof = false;
   }
   return B200MSM_OK;
 }
@@ -362,8 +423,10 @@ void b200msm_destroy(b200msm_ctx* ctx) {
                     &ctx->wsum, &ctx->out, &ctx->misc, &ctx->acc_a, &ctx->acc_b, &ctx->acc_c, &ctx->acc_d, &ctx->acc_e,
                     &ctx->t_offs, &ctx->t_cnt, &ctx->t_bid, &ctx->t_pa, &ctx->t_pb, &ctx->t_prefix, &ctx->t_prod, &ctx->t_lvlprefix}) b->release();
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_folded) cudaFreeHost(ctx->h_folded);
   for (auto& kv : ctx->residents) cudaFree(kv.second.d);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->pev) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -385,6 +448,7 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "window_bits")) { if (v < 0 || v > 24) return B200MSM_E_ARG; ctx->opt_window_bits = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "accumulate")) { if (v < 0 || v > 2) return B200MSM_E_ARG; ctx->opt_accumulate = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "tree_rounds")) { ctx->opt_tree_rounds = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "combine")) { if (v < 0 || v > 1) return B200MSM_E_ARG; ctx->opt_combine = (int)v; return B200MSM_OK; }
   return B200MSM_E_ARG;
 }
 
@@ -514,6 +578,24 @@ int b200msm_probe_imad(b200msm_ctx* ctx, double* imad_per_s) {
   *imad_per_s = best; return B200MSM_OK;
 }
 
+int b200msm_probe_imad_carry(b200msm_ctx* ctx, double* imad_per_s) {
+  if (!ctx || !imad_per_s) return B200MSM_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
+  CK(ctx->misc.ensure(256));
+  const uint32_t blocks = prop.multiProcessorCount * 8, iters = 4096;
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    k_imadx_probe<<<blocks, 256, 0, ctx->stream>>>(iters, 12345u + rep, ctx->misc.as<uint32_t>()); CKL();
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream)); CK(cudaEventSynchronize(ctx->ev[1]));
+    float ms; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    double rate = (double)blocks * 256.0 * iters * 16.0 / (ms * 1e-3);
+    if (rep && rate > best) best = rate;
+  }
+  *imad_per_s = best; return B200MSM_OK;
+}
+
 int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s) {
   if (!ctx || !fqmul_per_s || !curve_ok(curve)) return B200MSM_E_ARG;
   CK(cudaSetDevice(ctx->device));
@@ -534,6 +616,12 @@ int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s) {
     if (rep && rate > best) best = rate;
   }
   *fqmul_per_s = best; return B200MSM_OK;
+}
+
+int b200msm_get_counter(b200msm_ctx* ctx, const char* key, uint64_t* value) {
+  if (!ctx || !key || !value) return B200MSM_E_ARG;
+  if (!strcmp(key, "launches")) { *value = ctx->launches; return B200MSM_OK; }
+  return B200MSM_E_ARG;
 }
 
 int b200msm_constants(int curve, uint32_t* n8, uint8_t* q, uint8_t* r_mod_q, uint8_t* r2_mod_q, uint32_t* np32) {

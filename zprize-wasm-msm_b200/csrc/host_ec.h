@@ -1,0 +1,131 @@
+// host_ec.h -- the serial tail of the MSM on one host core.
+//
+// After the GPU has folded every window's bucket array, what remains is
+//     result = sum_w 2^(c*w) * ( T_w[0] + sum_j 2^j * T_w[2^j] )
+// (accumulateAcrossChunks, wasmcurves/src/build_multiexp_opt.js:1710-1746; multiexp Horner loop,
+// wasmcurves/src/build_multiexp.js:319-369): ONE dependent chain of ~nbits point doublings over fewer than 300 points.
+// A dependent chain is the worst case for a GPU (measured: 10.7 us per XYZZ doubling on one B200 thread, 2.9 ms for
+// 272 of them) and the best case for a CPU core (~0.3 us per doubling), so this step -- and only this step -- runs
+// on the host, on the ~50 KB of folded points the device hands back.  It is part of the engine (not a fallback:
+// there is no other implementation of this step on the default path) and it is exact integer arithmetic, so the
+// result is the same group element the device chain (k_horner, kept for cross-checking) produces.
+//
+// Field: Montgomery form, R = 2^(64*L), 64-bit limbs via unsigned __int128 (same values as fp.cuh's 32-bit limbs).
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+namespace b200host {
+
+typedef unsigned __int128 u128;
+
+template <int L> struct Field {
+  uint64_t q[L], one[L], np;
+};
+
+template <int L> struct Fe { uint64_t l[L]; };
+
+template <int L> static inline bool is_zero(const Fe<L>& a) { uint64_t o = 0; for (int i = 0; i < L; i++) o |= a.l[i]; return o == 0; }
+template <int L> static inline bool ge_q(const Field<L>& f, const uint64_t* a) {
+  for (int i = L - 1; i >= 0; i--) { if (a[i] > f.q[i]) return true; if (a[i] < f.q[i]) return false; }
+  return true;
+}
+template <int L> static inline void add(const Field<L>& f, Fe<L>& r, const Fe<L>& a, const Fe<L>& b) {
+  uint64_t c = 0;
+  for (int i = 0; i < L; i++) { u128 s = (u128)a.l[i] + b.l[i] + c; r.l[i] = (uint64_t)s; c = (uint64_t)(s >> 64); }
+  if (c || ge_q<L>(f, r.l)) { uint64_t br = 0; for (int i = 0; i < L; i++) { u128 d = (u128)r.l[i] - f.q[i] - br; r.l[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; } }
+}
+template <int L> static inline void sub(const Field<L>& f, Fe<L>& r, const Fe<L>& a, const Fe<L>& b) {
+  uint64_t br = 0;
+  for (int i = 0; i < L; i++) { u128 d = (u128)a.l[i] - b.l[i] - br; r.l[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; }
+  if (br) { uint64_t c = 0; for (int i = 0; i < L; i++) { u128 s = (u128)r.l[i] + f.q[i] + c; r.l[i] = (uint64_t)s; c = (uint64_t)(s >> 64); } }
+}
+template <int L> static inline void mul(const Field<L>& f, Fe<L>& r, const Fe<L>& a, const Fe<L>& b) {
+  uint64_t t[L + 2];
+  for (int i = 0; i < L + 2; i++) t[i] = 0;
+  for (int i = 0; i < L; i++) {
+    u128 c = 0;
+    for (int j = 0; j < L; j++) { c += (u128)a.l[j] * b.l[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+    c += t[L]; t[L] = (uint64_t)c; t[L + 1] = (uint64_t)(c >> 64);
+    uint64_t m = t[0] * f.np;
+    c = ((u128)m * f.q[0] + t[0]) >> 64;
+    for (int j = 1; j < L; j++) { c += (u128)m * f.q[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+    c += t[L]; t[L - 1] = (uint64_t)c; t[L] = t[L + 1] + (uint64_t)(c >> 64);
+  }
+  if (t[L] || ge_q<L>(f, t)) { uint64_t br = 0; for (int i = 0; i < L; i++) { u128 d = (u128)t[i] - f.q[i] - br; t[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; } }
+  for (int i = 0; i < L; i++) r.l[i] = t[i];
+}
+template <int L> static inline void sqr(const Field<L>& f, Fe<L>& r, const Fe<L>& a) { mul<L>(f, r, a, a); }
+template <int L> static inline void dbl(const Field<L>& f, Fe<L>& r, const Fe<L>& a) { add<L>(f, r, a, a); }
+
+template <int L> struct XYZZ { Fe<L> x, y, zz, zzz; };       // same layout as the device's XYZZ<C> (4 field elements)
+
+template <int L> static inline bool is_inf(const XYZZ<L>& p) { return is_zero<L>(p.zz); }
+template <int L> static inline void set_inf(const Field<L>& f, XYZZ<L>& p) {
+  memset(&p, 0, sizeof p); for (int i = 0; i < L; i++) p.y.l[i] = f.one[i];
+}
+// dbl-2008-s-1 (a = 0)
+template <int L> static inline void pdbl(const Field<L>& f, XYZZ<L>& r, const XYZZ<L>& p) {
+  if (is_inf<L>(p)) { r = p; return; }
+  Fe<L> U, V, W, S, M, t, X3, Y3;
+  dbl<L>(f, U, p.y); sqr<L>(f, V, U); mul<L>(f, W, U, V); mul<L>(f, S, p.x, V);
+  sqr<L>(f, t, p.x); dbl<L>(f, M, t); add<L>(f, M, M, t);
+  sqr<L>(f, X3, M); sub<L>(f, X3, X3, S); sub<L>(f, X3, X3, S);
+  sub<L>(f, t, S, X3); mul<L>(f, t, M, t); mul<L>(f, U, W, p.y); sub<L>(f, Y3, t, U);
+  Fe<L> zz, zzz; mul<L>(f, zz, V, p.zz); mul<L>(f, zzz, W, p.zzz);
+  r.x = X3; r.y = Y3; r.zz = zz; r.zzz = zzz;
+}
+// add-2008-s, complete
+template <int L> static inline void padd(const Field<L>& f, XYZZ<L>& acc, const XYZZ<L>& q) {
+  if (is_inf<L>(q)) return;
+  if (is_inf<L>(acc)) { acc = q; return; }
+  Fe<L> U1, U2, S1, S2, P, R, PP, PPP, Q, t;
+  mul<L>(f, U1, acc.x, q.zz); mul<L>(f, U2, q.x, acc.zz);
+  mul<L>(f, S1, acc.y, q.zzz); mul<L>(f, S2, q.y, acc.zzz);
+  sub<L>(f, P, U2, U1); sub<L>(f, R, S2, S1);
+  if (is_zero<L>(P)) {
+    if (is_zero<L>(R)) { XYZZ<L> d; pdbl<L>(f, d, q); acc = d; } else set_inf<L>(f, acc);
+    return;
+  }
+  sqr<L>(f, PP, P); mul<L>(f, PPP, P, PP); mul<L>(f, Q, U1, PP);
+  sqr<L>(f, t, R); sub<L>(f, t, t, PPP); sub<L>(f, t, t, Q); sub<L>(f, acc.x, t, Q);
+  sub<L>(f, t, Q, acc.x); mul<L>(f, t, R, t); mul<L>(f, Q, S1, PPP); sub<L>(f, acc.y, t, Q);
+  mul<L>(f, t, acc.zz, q.zz); mul<L>(f, acc.zz, t, PP);
+  mul<L>(f, t, acc.zzz, q.zzz); mul<L>(f, acc.zzz, t, PPP);
+}
+
+// folded: W slots of (logB + 1) XYZZ points as written by k_gather_folded.  out_jac: 3*L words, Jacobian Montgomery.
+template <int L>
+static void combine_windows(const Field<L>& f, const XYZZ<L>* folded, uint32_t W, uint32_t Wd, uint32_t c, uint32_t logB, uint64_t* out_jac) {
+  const uint32_t per = logB + 1;
+  XYZZ<L> acc; set_inf<L>(f, acc);
+  for (int w = (int)Wd - 1; w >= 0; w--) {
+    // window value R_w = T[0] + sum_j 2^j T[2^j]   (+ the extra slot's  (2^logB + 1) T'[0] + sum_j 2^j T'[2^j]  for the last window)
+    XYZZ<L> rw; set_inf<L>(f, rw);
+    const bool extra = (w + 1 == (int)Wd) && (W > Wd);
+    const XYZZ<L>* T = folded + (size_t)w * per;
+    const XYZZ<L>* E = folded + (size_t)Wd * per;
+    if (extra) rw = E[0];
+    for (int j = (int)logB - 1; j >= 0; j--) {
+      XYZZ<L> d; pdbl<L>(f, d, rw); rw = d;
+      padd<L>(f, rw, T[1 + j]);
+      if (extra) padd<L>(f, rw, E[1 + j]);
+    }
+    padd<L>(f, rw, T[0]);
+    if (extra) padd<L>(f, rw, E[0]);
+    // Horner across windows: acc = 2^c * acc + R_w
+    if (!is_inf<L>(acc)) for (uint32_t k = 0; k < c; k++) { XYZZ<L> d; pdbl<L>(f, d, acc); acc = d; }
+    padd<L>(f, acc, rw);
+  }
+  // XYZZ -> Jacobian without inversion: Z = ZZ*ZZZ, X = x*ZZ*ZZZ^2, Y = y*ZZ^3*ZZZ^2; infinity -> (0, R mod q, 0)
+  Fe<L> X, Y, Z;
+  if (is_inf<L>(acc)) { memset(&X, 0, sizeof X); memset(&Z, 0, sizeof Z); for (int i = 0; i < L; i++) Y.l[i] = f.one[i]; }
+  else {
+    Fe<L> t, u;
+    mul<L>(f, Z, acc.zz, acc.zzz); mul<L>(f, t, Z, acc.zzz); mul<L>(f, X, acc.x, t);
+    sqr<L>(f, u, acc.zz); mul<L>(f, t, t, u); mul<L>(f, Y, acc.y, t);
+  }
+  memcpy(out_jac, X.l, 8 * L); memcpy(out_jac + L, Y.l, 8 * L); memcpy(out_jac + 2 * L, Z.l, 8 * L);
+}
+
+}  // namespace b200host

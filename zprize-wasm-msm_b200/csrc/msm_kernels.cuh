@@ -22,8 +22,10 @@ namespace b200 {
 struct MsmPlan {
   uint32_t n;          // points
   uint32_t c;          // window width in bits
-  uint32_t W;          // number of signed windows = ceil((nbits + 1) / c)
-  uint32_t B;          // buckets per window = 2^(c-1)   (bucket index = |digit| - 1)
+  uint32_t Wd;         // digit windows = ceil(nbits / c): windows 0..Wd-2 are signed ([-2^(c-1), 2^(c-1)]), the last one
+                       // is unsigned and absorbs the final carry: digit in [0, 2^rb], rb = nbits - (Wd-1)*c
+  uint32_t W;          // bucket-array slots of B buckets each: Wd, or Wd + 1 when the last window needs 2B buckets (rb == c)
+  uint32_t B;          // buckets per slot = 2^(c-1)   (bucket index = |digit| - 1)
   uint32_t nbits;      // scalar bits processed
   uint32_t logB;       // c - 1
 };
@@ -61,19 +63,22 @@ __global__ void k_canon_scalars(const uint8_t* __restrict__ in, uint32_t scalar_
   }
 }
 
-// One signed digit stream: calls f(window, bucket_index(0-based), negative) for every non-zero digit.
+// One digit stream: calls f(global_bucket_index, negative) for every non-zero digit.  Windows below the last one use
+// signed digits with a carry into the next window; the last window keeps its digit unsigned (it may reach 2^rb and
+// then indexes into the extra slot), so no carry ever leaves the scalar and no "carry-only" window exists.
 template <class F>
 B200_DI void for_each_digit(const uint32_t* __restrict__ s, const MsmPlan& pl, F f) {
   uint32_t carry = 0;
   const uint32_t mask = (1u << pl.c) - 1u, half = 1u << (pl.c - 1);
-  for (uint32_t w = 0; w < pl.W; w++) {
+  for (uint32_t w = 0; w < pl.Wd; w++) {
     uint32_t bit = w * pl.c, k = bit >> 5, r = bit & 31;
     uint32_t lo = (k < 8) ? __ldg(s + k) : 0u, hi = (k + 1 < 8) ? __ldg(s + k + 1) : 0u;
     uint32_t raw = __funnelshift_r(lo, hi, r) & mask;
     uint32_t d = raw + carry;
+    if (w + 1 == pl.Wd) { if (d) f(w * pl.B + d - 1, 0u); break; }
     carry = d > half;
     uint32_t mag = carry ? ((1u << pl.c) - d) : d;
-    if (mag) f(w, mag - 1, carry);
+    if (mag) f(w * pl.B + mag - 1, carry);
   }
 }
 
@@ -83,8 +88,8 @@ __global__ void k_digits(const uint32_t* __restrict__ scalars, MsmPlan pl, uint3
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pl.n) return;
   const uint32_t* s = scalars + (uint64_t)i * 8;
-  for_each_digit(s, pl, [&](uint32_t w, uint32_t b, uint32_t neg) {
-    uint32_t slot = atomicAdd(&counters[w * pl.B + b], 1u);
+  for_each_digit(s, pl, [&](uint32_t gb, uint32_t neg) {
+    uint32_t slot = atomicAdd(&counters[gb], 1u);
     if (SCATTER) sorted[slot] = i | (neg << 31);
   });
 }
@@ -200,16 +205,18 @@ __global__ void __launch_bounds__(128) k_fold(void* __restrict__ buckets, uint32
   xyzz_store<C>(buckets, lo, a);
 }
 
-// One thread per window: R_w = T[0] + sum_j 2^j T[2^j] by Horner over j (logB doublings).
+// One thread per slot: R_w = T[0] + sum_j 2^j T[2^j] by Horner over j (logB doublings).  The extra slot (index Wd,
+// present when W == Wd + 1) holds buckets B+1 .. 2B of the last window: its value is the same expression + B * T[0].
 template <class C>
-__global__ void __launch_bounds__(32) k_window_sums(const void* __restrict__ buckets, uint32_t W, uint32_t B, uint32_t logB, void* __restrict__ wsum) {
+__global__ void __launch_bounds__(32) k_window_sums(const void* __restrict__ buckets, uint32_t W, uint32_t Wd, uint32_t B, uint32_t logB, void* __restrict__ wsum) {
   uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= W) return;
   XYZZ<C> acc; xyzz_set_inf<C>(acc);
+  if (w >= Wd) xyzz_load<C>(acc, buckets, (uint64_t)w * B);          // + B*T[0] = 2^logB * T[0]: seed the Horner chain one step higher
   for (int j = (int)logB - 1; j >= 0; j--) {
+    if (w >= Wd || j + 1 < (int)logB) { XYZZ<C> d; xyzz_dbl<C>(d, acc); acc = d; }
     XYZZ<C> t; xyzz_load<C>(t, buckets, (uint64_t)w * B + (1u << j));
     xyzz_add<C>(acc, t);
-    if (j) { XYZZ<C> d; xyzz_dbl<C>(d, acc); acc = d; }
   }
   XYZZ<C> t0; xyzz_load<C>(t0, buckets, (uint64_t)w * B);
   xyzz_add<C>(acc, t0);
@@ -218,19 +225,35 @@ __global__ void __launch_bounds__(32) k_window_sums(const void* __restrict__ buc
 
 // result = sum_w 2^(c*w) R_w, top window first (accumulateAcrossChunks, build_multiexp_opt.js:1710-1746;
 // multiexp Horner loop, build_multiexp.js:319-369).  Output: Jacobian Montgomery x||y||z, canonical zero for infinity.
+// GPU form of the window combination; a single dependent chain of Wd*c doublings (see DESIGN.md for why the engine's
+// default performs this last serial step on the host from the folded bucket arrays instead).
 template <class C>
-__global__ void __launch_bounds__(32) k_horner(const void* __restrict__ wsum, uint32_t W, uint32_t c, void* __restrict__ out_jac) {
+__global__ void __launch_bounds__(32) k_horner(const void* __restrict__ wsum, uint32_t W, uint32_t Wd, uint32_t c, void* __restrict__ out_jac) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   XYZZ<C> acc; xyzz_set_inf<C>(acc);
-  for (int w = (int)W - 1; w >= 0; w--) {
+  for (int w = (int)Wd - 1; w >= 0; w--) {
     if (!xyzz_is_inf<C>(acc)) for (uint32_t k = 0; k < c; k++) { XYZZ<C> d; xyzz_dbl<C>(d, acc); acc = d; }
     XYZZ<C> t; xyzz_load<C>(t, wsum, w);
     xyzz_add<C>(acc, t);
+    if (w + 1 == (int)Wd && W > Wd) { xyzz_load<C>(t, wsum, Wd); xyzz_add<C>(acc, t); }
   }
   Fe<C::N> X, Y, Z;
   xyzz_to_jacobian<C>(X, Y, Z, acc);
   char* o = reinterpret_cast<char*>(out_jac);
   fe_store<C>(o, X); fe_store<C>(o + 4 * C::N, Y); fe_store<C>(o + 8 * C::N, Z);
+}
+
+// Collect the logB + 1 live entries of every folded slot (T[0], T[1], T[2], T[4], ...) into a compact array for the
+// host-side window combination: out[w * (logB + 1) + 0] = T_w[0], out[w * (logB + 1) + 1 + j] = T_w[2^j].
+template <class C>
+__global__ void k_gather_folded(const void* __restrict__ buckets, uint32_t W, uint32_t B, uint32_t logB, void* __restrict__ out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t per = logB + 1;
+  if (t >= W * per) return;
+  uint32_t w = t / per, k = t % per;
+  uint64_t src = (uint64_t)w * B + (k == 0 ? 0u : (1u << (k - 1)));
+  XYZZ<C> p; xyzz_load<C>(p, buckets, src);
+  xyzz_store<C>(out, t, p);
 }
 
 // ------------------------------------------------------------------ small utility kernels behind the C ABI
@@ -353,6 +376,28 @@ __global__ void __launch_bounds__(256) k_imad_probe(uint32_t iters, uint32_t see
   }
   unsigned long long s = acc0 ^ acc1 ^ acc2 ^ acc3 ^ acc4 ^ acc5 ^ acc6 ^ acc7;
   if (s == 0x1234567ull) sink[0] = s;
+}
+// Same, but every multiply-add consumes and produces a carry (IMAD.WIDE.U32.X with predicate carry in/out),
+// which is the form the Montgomery multiplier is made of: 4 independent carry chains of 4 wide mads each.
+__global__ void __launch_bounds__(256) k_imadx_probe(uint32_t iters, uint32_t seed, uint32_t* __restrict__ sink) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+  uint32_t r[32];
+#pragma unroll
+  for (int k = 0; k < 32; k++) r[k] = a + k;
+  for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      uint32_t* x = r + 8 * c;
+      mad_lo_cc(x[0], a, b, x[0]); madc_hi_cc(x[1], a, b, x[1]);
+      madc_lo_cc(x[2], a, b, x[2]); madc_hi_cc(x[3], a, b, x[3]);
+      madc_lo_cc(x[4], a, b, x[4]); madc_hi_cc(x[5], a, b, x[5]);
+      madc_lo_cc(x[6], a, b, x[6]); madc_hi(x[7], a, b, x[7]);
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 32; k++) s ^= r[k];
+  if (s == 0x1234567u) sink[0] = s;
 }
 // Field-multiply throughput probe: ITER dependent Montgomery multiplications per thread (2N^2+N limb products each).
 template <class C>
