@@ -25,6 +25,7 @@ for lg in [int(x) for x in a.sizes.split(",")]:
     sc = torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device=dev, generator=g)
     h = eng.upload_bases(cid, bases, n); out = torch.zeros(3 * n8, dtype=torch.uint8, device=dev)
     for _ in range(2): eng.multiexp_resident(h, sc, 32, n, cid, out=out)
+    eng.multiexp_resident(h, sc, 32, n, cid, out=out, want_stats=True)
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()

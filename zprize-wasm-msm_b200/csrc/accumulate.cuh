@@ -8,7 +8,7 @@
 // levels serially.  Here every bucket is summed by a balanced pairwise tree: in round r every bucket
 // segment of n_r points becomes ceil(n_r/2) points (adjacent points are added, an odd last point is
 // carried over), for ALL buckets of ALL windows in one launch.  All additions of a round share ONE
-// field inversion: a grid-wide product tree (K-ary, K = BA_K) of the denominators is built level by
+// field inversion: a grid-wide product tree (K-ary, run-time K) of the denominators is built level by
 // level, the single root is inverted by one thread, and the inverses are propagated back down.
 //
 //   per addition: forward 1M (running product) ; backward 2M (denominator inverse) + 2M + 1S (slope, x3, y3)
@@ -23,9 +23,8 @@
 
 namespace b200 {
 
-constexpr int BA_K = 4;            // additions per thread per inversion chain (level 0) and product-tree arity
-constexpr int BA_THREADS = 128;
-constexpr int BA_TILE = BA_K * BA_THREADS;
+constexpr int BA_THREADS = 128;     // threads per block in the tree kernels; a block owns a tile of K * BA_THREADS consecutive slots,
+                                    // K = additions per thread per inversion chain (level 0) or product-tree arity (levels >= 1): run-time parameters
 constexpr uint32_t BA_ROOT_MAX = 256;   // the product tree is reduced until at most this many values remain
 
 // n_{r+1}[b] = ceil(n_r[b] / 2)
@@ -33,6 +32,51 @@ __global__ void k_halve_counts(const uint32_t* __restrict__ in, uint32_t* __rest
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (in[i] + 1) >> 1;
 }
+// All rounds' segment offsets in one three-phase scan: off[r][b] = exclusive scan over b of ceil(n_0[b] / 2^r), r = 1..R.
+// offs: R arrays of (n + 1) words; tile_sums: R arrays of (ntiles + 1) words.
+__global__ void __launch_bounds__(SCAN_THREADS) k_mscan_tiles(const uint32_t* __restrict__ cnt0, uint32_t n, uint32_t R,
+                                                              uint32_t* __restrict__ offs, uint32_t* __restrict__ tile_sums, uint32_t ntiles) {
+  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t v0[SCAN_ITEMS];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) v0[k] = (base + k < n) ? cnt0[base + k] : 0;
+  for (uint32_t r = 1; r <= R; r++) {
+    uint32_t sum = 0, add = (1u << r) - 1u;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) sum += (v0[k] + add) >> r;
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(sum, &total);
+    uint32_t* out = offs + (size_t)(r - 1) * (n + 1);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += (v0[k] + add) >> r; }
+    if (threadIdx.x == 0) tile_sums[(size_t)(r - 1) * (ntiles + 1) + blockIdx.x] = total;
+  }
+}
+__global__ void k_mscan_sums(uint32_t* __restrict__ tile_sums, uint32_t ntiles) {      // one block per round
+  uint32_t* ts = tile_sums + (size_t)blockIdx.x * (ntiles + 1);
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < ntiles; base += blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = (i < ntiles) ? ts[i] : 0, total;
+    uint32_t ex = block_exclusive_scan(v, &total);
+    uint32_t c = carry_s;
+    if (i < ntiles) ts[i] = ex + c;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = c + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ts[ntiles] = carry_s;
+}
+__global__ void k_mscan_apply(uint32_t* __restrict__ offs, uint32_t n, const uint32_t* __restrict__ tile_sums, uint32_t ntiles) {   // grid.y = round
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t* out = offs + (size_t)blockIdx.y * (n + 1);
+  const uint32_t* ts = tile_sums + (size_t)blockIdx.y * (ntiles + 1);
+  if (i < n) out[i] += ts[i / SCAN_TILE];
+  if (i == 0) out[n] = ts[ntiles];
+}
+
 // bid1[j] = bucket owning output slot j of round 0 (binary search in off1); one thread per slot
 __global__ void k_fill_bid(const uint32_t* __restrict__ off1, uint32_t nb, uint32_t* __restrict__ bid1) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -79,11 +123,11 @@ B200_DI bool tree_slot(const TreeRound& tr, uint32_t j, uint32_t& in0, bool& has
 // forward: denominators, per-slot prefix products, per-thread products
 template <class C, bool FIRST>
 __global__ void __launch_bounds__(BA_THREADS) k_tree_fwd(TreeRound tr, const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                         const void* __restrict__ pin, void* __restrict__ prefix, void* __restrict__ prod) {
-  uint32_t tile = blockIdx.x * BA_TILE;
+                                                         const void* __restrict__ pin, void* __restrict__ prefix, void* __restrict__ prod, int K) {
+  uint32_t tile = blockIdx.x * (K * BA_THREADS);
   Fe<C::N> p; fe_set_one<C>(p);
 #pragma unroll 1
-  for (int i = 0; i < BA_K; i++) {
+  for (int i = 0; i < K; i++) {
     uint32_t j = tile + i * BA_THREADS + threadIdx.x, in0; bool has2;
     if (!tree_slot(tr, j, in0, has2, true)) continue;
     if (!has2) continue;
@@ -103,12 +147,12 @@ __global__ void __launch_bounds__(BA_THREADS) k_tree_fwd(TreeRound tr, const voi
 template <class C, bool FIRST>
 __global__ void __launch_bounds__(BA_THREADS) k_tree_bwd(TreeRound tr, const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                          const void* __restrict__ pin, const void* __restrict__ prefix, const void* __restrict__ inv,
-                                                         void* __restrict__ pout) {
-  uint32_t tile = blockIdx.x * BA_TILE;
+                                                         void* __restrict__ pout, int K) {
+  uint32_t tile = blockIdx.x * (K * BA_THREADS);
   Fe<C::N> q;
   fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)(blockIdx.x * BA_THREADS + threadIdx.x) * 4 * C::N);
 #pragma unroll 1
-  for (int i = BA_K - 1; i >= 0; i--) {
+  for (int i = K - 1; i >= 0; i--) {
     uint32_t j = tile + i * BA_THREADS + threadIdx.x, in0; bool has2;
     if (!tree_slot(tr, j, in0, has2, false)) continue;
     Affine<C> p1, p2, r;
@@ -129,11 +173,11 @@ __global__ void __launch_bounds__(BA_THREADS) k_tree_bwd(TreeRound tr, const voi
 
 // ---- product tree, levels >= 1: plain arrays of field elements -----------------------------------------
 template <class C>
-__global__ void __launch_bounds__(BA_THREADS) k_prod_fwd(const void* __restrict__ vals, uint32_t n, void* __restrict__ prefix, void* __restrict__ prod) {
-  uint32_t tile = blockIdx.x * BA_TILE;
+__global__ void __launch_bounds__(BA_THREADS) k_prod_fwd(const void* __restrict__ vals, uint32_t n, void* __restrict__ prefix, void* __restrict__ prod, int K) {
+  uint32_t tile = blockIdx.x * (K * BA_THREADS);
   Fe<C::N> p; fe_set_one<C>(p);
 #pragma unroll 1
-  for (int i = 0; i < BA_K; i++) {
+  for (int i = 0; i < K; i++) {
     uint32_t e = tile + i * BA_THREADS + threadIdx.x;
     if (e >= n) continue;
     Fe<C::N> v; fe_load_cg<C>(v, reinterpret_cast<const char*>(vals) + (uint64_t)e * 4 * C::N);
@@ -144,12 +188,12 @@ __global__ void __launch_bounds__(BA_THREADS) k_prod_fwd(const void* __restrict_
 }
 // in place: vals[e] <- 1 / vals[e], given the inverse of each thread's product in inv[]
 template <class C>
-__global__ void __launch_bounds__(BA_THREADS) k_prod_bwd(void* __restrict__ vals, uint32_t n, const void* __restrict__ prefix, const void* __restrict__ inv) {
-  uint32_t tile = blockIdx.x * BA_TILE;
+__global__ void __launch_bounds__(BA_THREADS) k_prod_bwd(void* __restrict__ vals, uint32_t n, const void* __restrict__ prefix, const void* __restrict__ inv, int K) {
+  uint32_t tile = blockIdx.x * (K * BA_THREADS);
   Fe<C::N> q;
   fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)(blockIdx.x * BA_THREADS + threadIdx.x) * 4 * C::N);
 #pragma unroll 1
-  for (int i = BA_K - 1; i >= 0; i--) {
+  for (int i = K - 1; i >= 0; i--) {
     uint32_t e = tile + i * BA_THREADS + threadIdx.x;
     if (e >= n) continue;
     Fe<C::N> v, pre, r;

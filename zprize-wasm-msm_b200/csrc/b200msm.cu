@@ -41,6 +41,13 @@ struct DevBuf {
 
 struct Resident { int curve; uint64_t n; void* d; };
 
+// one accumulate lane: a stream with its own tree scratch (see accumulate_batch_affine)
+struct TreeLane {
+  cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
+  DevBuf offs, tiles, bid, pa, pb, prefix, prod, lvlprefix;
+};
+constexpr int MAX_LANES = 4;
+
 }  // namespace
 
 struct b200msm_ctx {
@@ -49,7 +56,9 @@ struct b200msm_ctx {
   std::string err;
   int opt_window_bits = 0, opt_accumulate = 0, opt_tree_rounds = -1;
   DevBuf bases, scalars, canon, counts, offsets, cursors, tiles, sorted, buckets, wsum, out, misc, acc_a, acc_b, acc_c, acc_d, acc_e;
-  DevBuf t_offs, t_cnt, t_bid, t_pa, t_pb, t_prefix, t_prod, t_lvlprefix;     // batch-affine tree scratch
+  TreeLane lane[MAX_LANES];                                                   // batch-affine tree lanes
+  int opt_lanes = 2, opt_ba_k = 8, opt_pt_k = 4;
+  cudaEvent_t ev_plan = nullptr, ev_sorted = nullptr;
   uint32_t* h_pinned = nullptr;
   void* h_folded = nullptr; size_t h_folded_cap = 0;                         // pinned staging of the folded bucket entries
   int opt_combine = 0;                                                        // 0 = host serial tail (default), 1 = device k_window_sums + k_horner
@@ -59,6 +68,7 @@ struct b200msm_ctx {
   // fine-grained phase profiler (active only while a stats struct is being filled)
   std::vector<cudaEvent_t> pev; std::vector<int> ptag; size_t pused = 0; bool prof = false;
   uint64_t launches = 0;
+  size_t total_mem = 0;
 };
 
 namespace {
@@ -68,6 +78,17 @@ namespace {
 #define CKL() do { ctx->launches++; CK(cudaGetLastError()); } while (0)
 enum { T_SORT = 0, T_PLAN, T_TREE_FWD, T_INV_TREE, T_TREE_BWD, T_FINISH, T_FOLD, T_WSUM, T_HORNER, T_NTAGS };
 #define MARK(tag) do { if (ctx->prof) { int rc_ = prof_mark(ctx, tag); if (rc_) return rc_; } } while (0)
+
+int lane_init(b200msm_ctx* ctx, TreeLane& ln) {
+  if (!ln.stream) {
+    int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);          // hi = numerically smallest = highest priority
+    int idx = (int)(&ln - &ctx->lane[0]);
+    int prio = std::min(lo, hi + idx);                                        // lane 0 highest: its kernels drain first, so the lanes' serial tails do not coincide
+    CK(cudaStreamCreateWithPriority(&ln.stream, cudaStreamNonBlocking, prio));
+  }
+  if (!ln.done) CK(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+  return B200MSM_OK;
+}
 
 int prof_mark(b200msm_ctx* ctx, int tag) {
   if (ctx->pused == ctx->pev.size()) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->pev.push_back(e); ctx->ptag.push_back(0); }
@@ -93,7 +114,8 @@ uint32_t auto_window_bits(uint64_t n, uint32_t nbits) {
   if (c > 16 && n < (1ull << 22)) c = 16;
   if (c > 20) c = 20;
   if (c < 2) c = 2;
-  if ((uint32_t)c > nbits + 1) c = (int)nbits + 1;
+  if (nbits < 2) c = 1;
+  if ((uint32_t)c > nbits) c = (int)nbits;
   return (uint32_t)c;
 }
 
@@ -106,19 +128,22 @@ int exclusive_scan(b200msm_ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t
   return B200MSM_OK;
 }
 
-// ---- batch-affine tree over the bucket range [b0, b0 + nbg) (a group of whole windows) ------------------
-// off0 = sort offsets (absolute positions in sorted[]), cnt0 = bucket counts of the range (consumed: halved in place),
-// m0 = pairs in the range, maxcnt = largest bucket population in the range.  Writes buckets[b0 .. b0+nbg) as XYZZ.
+// ---- batch-affine tree over a bucket range (a group of whole window slots), issued on one lane ----------------
+// A lane = one CUDA stream + its own scratch.  Consecutive groups alternate between lanes so that the latency-bound
+// tail of one group's round (product tree, root inversion) overlaps the throughput-bound kernels of the other group.
+// off0 = sort offsets (absolute positions in sorted[]), cnt0 = bucket counts of the range,
+// m0 = pairs in the range, maxcnt = largest bucket population in the range.  Writes buckets_g[0 .. nbg) as XYZZ.
 template <class C>
-int accumulate_batch_affine(b200msm_ctx* ctx, const void* d_bases, const uint32_t* off0, uint32_t* cnt0, uint32_t nbg, uint64_t m0, uint32_t maxcnt,
-                            void* buckets_g, uint32_t* rounds_out, uint64_t* adds_out) {
-  cudaStream_t s = ctx->stream;
+int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases, const uint32_t* off0, const uint32_t* cnt0, uint32_t nbg, uint64_t m0,
+                            uint32_t maxcnt, void* buckets_g, uint32_t* rounds_out, uint64_t* adds_out) {
+  cudaStream_t s = ln_.stream;
   const uint32_t* sorted = ctx->sorted.as<uint32_t>();
   // number of tree rounds: until the largest segment is <= 3 points (the finish kernel sums the rest serially)
   uint32_t R = 0;
   if (ctx->opt_tree_rounds >= 0) R = (uint32_t)ctx->opt_tree_rounds;
   else { uint32_t mc = maxcnt; while (mc > 3) { mc = (mc + 1) >> 1; R++; } }
   if (m0 < 2) R = 0;
+  if (R > 30) R = 30;
   *rounds_out = std::max(*rounds_out, R);
   if (R == 0) {
     k_accum_finish<C, true><<<(nbg + 127) / 128, 128, 0, s>>>(d_bases, sorted, nullptr, off0, nbg, buckets_g); CKL();
@@ -128,65 +153,77 @@ int accumulate_batch_affine(b200msm_ctx* ctx, const void* d_bases, const uint32_
   // upper bounds of the slot counts per round: sum ceil(n/2) <= (sum n + #non-empty) / 2
   std::vector<uint64_t> U(R + 2); U[0] = m0;
   for (uint32_t r = 0; r <= R; r++) U[r + 1] = std::min<uint64_t>(U[r], (U[r] + std::min<uint64_t>(nbg, U[r]) + 1) / 2);
-  // offsets for rounds 1..R (round 0 uses off0 directly)
+  // offsets for rounds 1..R in one fused scan (round 0 uses off0 directly)
   const size_t offstride = (size_t)nbg + 1;
-  CK(ctx->t_offs.ensure(offstride * R * 4));
+  const uint32_t ntiles = (nbg + SCAN_TILE - 1) / SCAN_TILE;
+  CK(ln_.offs.ensure(offstride * R * 4)); CK(ln_.tiles.ensure((size_t)(ntiles + 1) * R * 4));
+  k_mscan_tiles<<<ntiles, SCAN_THREADS, 0, s>>>(cnt0, nbg, R, ln_.offs.as<uint32_t>(), ln_.tiles.as<uint32_t>(), ntiles); CKL();
+  k_mscan_sums<<<R, 1024, 0, s>>>(ln_.tiles.as<uint32_t>(), ntiles); CKL();
+  { dim3 g((nbg + 255) / 256, R); k_mscan_apply<<<g, 256, 0, s>>>(ln_.offs.as<uint32_t>(), nbg, ln_.tiles.as<uint32_t>(), ntiles); CKL(); }
   std::vector<const uint32_t*> off(R + 1); off[0] = off0;
-  for (uint32_t r = 1; r <= R; r++) {
-    uint32_t* o = ctx->t_offs.as<uint32_t>() + offstride * (r - 1);
-    k_halve_counts<<<(nbg + 255) / 256, 256, 0, s>>>(cnt0, cnt0, nbg); CKL();
-    int rc = exclusive_scan(ctx, cnt0, o, nbg, nullptr); if (rc) return rc;
-    off[r] = o;
-  }
+  for (uint32_t r = 1; r <= R; r++) off[r] = ln_.offs.as<uint32_t>() + offstride * (r - 1);
   // bid arrays for rounds 1..R
   std::vector<uint32_t*> bid(R + 2, nullptr);
   { size_t tot = 0; for (uint32_t r = 1; r <= R; r++) tot += U[r];
-    CK(ctx->t_bid.ensure(tot * 4 + 16));
-    size_t at = 0; for (uint32_t r = 1; r <= R; r++) { bid[r] = ctx->t_bid.as<uint32_t>() + at; at += U[r]; } }
+    CK(ln_.bid.ensure(tot * 4 + 16));
+    size_t at = 0; for (uint32_t r = 1; r <= R; r++) { bid[r] = ln_.bid.as<uint32_t>() + at; at += U[r]; } }
   k_fill_bid<<<(uint32_t)((U[1] + 255) / 256), 256, 0, s>>>(off[1], nbg, bid[1]); CKL();
   MARK(T_PLAN);
   const size_t fe = 4 * C::N, pt = 8 * C::N;
-  CK(ctx->t_pa.ensure(U[1] * pt + 16)); if (R > 1) CK(ctx->t_pb.ensure(U[2] * pt + 16));
-  CK(ctx->t_prefix.ensure(U[1] * fe + 16));
+  const int BK = ctx->opt_ba_k, PK = ctx->opt_pt_k;
+  const uint64_t BA_TILE = (uint64_t)BK * BA_THREADS, PT_TILE = (uint64_t)PK * BA_THREADS;
+  CK(ln_.pa.ensure(U[1] * pt + 16)); if (R > 1) CK(ln_.pb.ensure(U[2] * pt + 16));
+  CK(ln_.prefix.ensure(U[1] * fe + 16));
   // product-tree level sizes for the largest round
   { size_t tot = 0, totp = 0; uint64_t n = ((U[1] + BA_TILE - 1) / BA_TILE) * BA_THREADS;
-    for (;;) { tot += n; if (n <= BA_ROOT_MAX) break; totp += n; n = ((n + BA_TILE - 1) / BA_TILE) * BA_THREADS; }
-    CK(ctx->t_prod.ensure(tot * fe + 16)); CK(ctx->t_lvlprefix.ensure(totp * fe + 16)); }
+    for (;;) { tot += n; if (n <= BA_ROOT_MAX) break; totp += n; n = ((n + PT_TILE - 1) / PT_TILE) * BA_THREADS; }
+    CK(ln_.prod.ensure(tot * fe + 16)); CK(ln_.lvlprefix.ensure(totp * fe + 16)); }
   void* pin = nullptr;
   for (uint32_t r = 0; r < R; r++) {
-    void* pout = (r & 1) ? ctx->t_pb.p : ctx->t_pa.p;
+    void* pout = (r & 1) ? ln_.pb.p : ln_.pa.p;
     TreeRound tr{off[r], off[r + 1], (r + 2 <= R) ? off[r + 2] : nullptr, bid[r + 1], (r + 2 <= R) ? bid[r + 2] : nullptr, nbg};
     uint32_t grid = (uint32_t)((U[r + 1] + BA_TILE - 1) / BA_TILE);
     if (grid == 0) grid = 1;
-    char* prod = ctx->t_prod.as<char>(); char* lpre = ctx->t_lvlprefix.as<char>();
-    if (r == 0) k_tree_fwd<C, true><<<grid, BA_THREADS, 0, s>>>(tr, d_bases, sorted, nullptr, ctx->t_prefix.p, prod);
-    else k_tree_fwd<C, false><<<grid, BA_THREADS, 0, s>>>(tr, nullptr, nullptr, pin, ctx->t_prefix.p, prod);
+    char* prod = ln_.prod.as<char>(); char* lpre = ln_.lvlprefix.as<char>();
+    if (r == 0) k_tree_fwd<C, true><<<grid, BA_THREADS, 0, s>>>(tr, d_bases, sorted, nullptr, ln_.prefix.p, prod, BK);
+    else k_tree_fwd<C, false><<<grid, BA_THREADS, 0, s>>>(tr, nullptr, nullptr, pin, ln_.prefix.p, prod, BK);
     CKL(); MARK(T_TREE_FWD);
     // up the product tree
     std::vector<uint64_t> ln; std::vector<char*> lv, lp;
     uint64_t n = (uint64_t)grid * BA_THREADS; char* cur = prod; char* curp = lpre;
     while (n > BA_ROOT_MAX) {
-      uint32_t g2 = (uint32_t)((n + BA_TILE - 1) / BA_TILE);
+      uint32_t g2 = (uint32_t)((n + PT_TILE - 1) / PT_TILE);
       char* nxt = cur + n * fe;
-      k_prod_fwd<C><<<g2, BA_THREADS, 0, s>>>(cur, (uint32_t)n, curp, nxt); CKL();
+      k_prod_fwd<C><<<g2, BA_THREADS, 0, s>>>(cur, (uint32_t)n, curp, nxt, PK); CKL();
       ln.push_back(n); lv.push_back(cur); lp.push_back(curp);
       curp += n * fe; cur = nxt; n = (uint64_t)g2 * BA_THREADS;
     }
     k_inv_root<C><<<1, BA_ROOT_MAX, 0, s>>>(cur, (uint32_t)n); CKL();
     // back down
     for (int l = (int)ln.size() - 1; l >= 0; l--) {
-      uint32_t g2 = (uint32_t)((ln[l] + BA_TILE - 1) / BA_TILE);
-      k_prod_bwd<C><<<g2, BA_THREADS, 0, s>>>(lv[l], (uint32_t)ln[l], lp[l], lv[l] + ln[l] * fe); CKL();
+      uint32_t g2 = (uint32_t)((ln[l] + PT_TILE - 1) / PT_TILE);
+      k_prod_bwd<C><<<g2, BA_THREADS, 0, s>>>(lv[l], (uint32_t)ln[l], lp[l], lv[l] + ln[l] * fe, PK); CKL();
     }
     MARK(T_INV_TREE);
-    if (r == 0) k_tree_bwd<C, true><<<grid, BA_THREADS, 0, s>>>(tr, d_bases, sorted, nullptr, ctx->t_prefix.p, prod, pout);
-    else k_tree_bwd<C, false><<<grid, BA_THREADS, 0, s>>>(tr, nullptr, nullptr, pin, ctx->t_prefix.p, prod, pout);
+    if (r == 0) k_tree_bwd<C, true><<<grid, BA_THREADS, 0, s>>>(tr, d_bases, sorted, nullptr, ln_.prefix.p, prod, pout, BK);
+    else k_tree_bwd<C, false><<<grid, BA_THREADS, 0, s>>>(tr, nullptr, nullptr, pin, ln_.prefix.p, prod, pout, BK);
     CKL(); MARK(T_TREE_BWD);
     pin = pout;
     *adds_out += U[r] - U[r + 1];
   }
   k_accum_finish<C, false><<<(nbg + 127) / 128, 128, 0, s>>>(nullptr, nullptr, pin, off[R], nbg, buckets_g); CKL();
   MARK(T_FINISH);
+  return B200MSM_OK;
+}
+
+// in-place folding of `slots` consecutive bucket arrays of B buckets each (see k_fold)
+template <class C>
+int fold_slots(b200msm_ctx* ctx, cudaStream_t s, void* buckets_g, uint32_t slots, uint32_t B) {
+  for (uint32_t sz = B; sz >= 2; sz >>= 1) {
+    uint32_t nblk = B / sz, live = 1; for (uint32_t k = 1; k < nblk; k <<= 1) live++;
+    uint64_t threads = (uint64_t)live * (sz / 2) * slots;
+    k_fold<C><<<(uint32_t)((threads + 127) / 128), 128, 0, s>>>(buckets_g, slots, B, sz); CKL();
+  }
   return B200MSM_OK;
 }
 
@@ -197,11 +234,14 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   const uint32_t n = (uint32_t)n64;
   MsmPlan pl;
   pl.n = n; pl.nbits = nbits;
-  pl.c = ctx->opt_window_bits > 0 ? std::min<uint32_t>((uint32_t)ctx->opt_window_bits, std::min<uint32_t>(nbits + 1, 24)) : auto_window_bits(n, nbits);
-  pl.Wd = (nbits + pl.c - 1) / pl.c; pl.B = 1u << (pl.c - 1); pl.logB = pl.c - 1;
-  pl.W = pl.Wd + ((nbits - (pl.Wd - 1) * pl.c == pl.c) ? 1 : 0);
+  { // window plan: target width ct, then equalise: Wd windows whose widths differ by at most one bit
+    uint32_t ct = ctx->opt_window_bits > 0 ? std::min<uint32_t>((uint32_t)ctx->opt_window_bits, std::min<uint32_t>(nbits, 24)) : auto_window_bits(n, nbits);
+    pl.Wd = (nbits + ct - 1) / ct; pl.c0 = nbits / pl.Wd; pl.rem = nbits - pl.c0 * pl.Wd;
+    pl.c = pl.c0 + (pl.rem ? 1 : 0); pl.B = 1u << (pl.c - 1); pl.logB = pl.c - 1;
+    pl.W = pl.Wd + (pl.rem == 0 ? 1 : 0); }
   const uint32_t nb = pl.W * pl.B;
   if ((uint64_t)pl.W * pl.B > (1ull << 31) || (uint64_t)n * pl.W >= (1ull << 32)) { ctx->err = "problem too large for 32-bit pair indices"; return B200MSM_E_UNSUPPORTED; }
+  if (pl.W > 400) { ctx->err = "too many windows"; return B200MSM_E_UNSUPPORTED; }
 
   if (st) CK(cudaEventRecord(ctx->ev[1], s));
   CK(ctx->counts.ensure((size_t)nb * 4)); CK(ctx->offsets.ensure((size_t)(nb + 1) * 4)); CK(ctx->cursors.ensure((size_t)nb * 4));
@@ -211,50 +251,58 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   k_digits<false><<<gb, tb, 0, s>>>(d_scal, pl, ctx->counts.as<uint32_t>(), nullptr); CKL();
   int rc = exclusive_scan(ctx, ctx->counts.as<uint32_t>(), ctx->offsets.as<uint32_t>(), nb, ctx->cursors.as<uint32_t>());
   if (rc) return rc;
-  k_digits<true><<<gb, tb, 0, s>>>(d_scal, pl, ctx->cursors.as<uint32_t>(), ctx->sorted.as<uint32_t>()); CKL();
-  if (st) CK(cudaEventRecord(ctx->ev[2], s));
-
-  // ---- read back the per-window pair counts and largest bucket populations (one small D2H, one sync)
+  // ---- per-slot pair counts and largest bucket populations go back to the host while the scatter runs
   CK(ctx->misc.ensure(512 * 4));
   CK(cudaMemsetAsync(ctx->misc.p, 0, 512 * 4, s));
   { dim3 g((pl.B + 255) / 256, pl.W); k_window_max<<<g, 256, 0, s>>>(ctx->counts.as<uint32_t>(), pl.B, ctx->misc.as<uint32_t>()); CKL(); }
-  if (pl.W > 400) { ctx->err = "too many windows"; return B200MSM_E_UNSUPPORTED; }
   CK(cudaMemcpyAsync(ctx->h_pinned, ctx->misc.p, pl.W * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpy2DAsync(ctx->h_pinned + 512, 4, ctx->offsets.as<uint32_t>(), (size_t)pl.B * 4, 4, pl.W + 1, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  CK(cudaEventRecord(ctx->ev_plan, s));
+  k_digits<true><<<gb, tb, 0, s>>>(d_scal, pl, ctx->cursors.as<uint32_t>(), ctx->sorted.as<uint32_t>()); CKL();
+  if (st) CK(cudaEventRecord(ctx->ev[2], s));
+  CK(cudaEventRecord(ctx->ev_sorted, s));
+  CK(cudaEventSynchronize(ctx->ev_plan));
   MARK(T_SORT);
-  // ---- accumulate: bucket sums in XYZZ
+  // ---- accumulate: bucket sums in XYZZ, then fold every slot in place
   CK(ctx->buckets.ensure((size_t)nb * 16 * C::N));
   int mode = ctx->opt_accumulate;
   if (mode == 0) mode = 2;
   uint32_t rounds = 0; uint64_t adds = 0;
   if (mode == 2) {
-    // groups of whole windows, sized so that the tree scratch stays within a fraction of device memory
-    size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+    // groups of whole slots: at least `lanes` of them (overlap), more if the tree scratch would not fit in device memory
     const uint64_t mtot = ctx->h_pinned[512 + pl.W];
+    uint32_t lanes = ctx->prof ? 1u : (uint32_t)std::max(1, std::min(ctx->opt_lanes, (int)MAX_LANES));
+    if (mtot < (1u << 16)) lanes = 1;
     const double per_pair = 8.0 * C::N * 0.75 + 4.0 * C::N * 0.75 + 6;      // points (pa+pb) + prefix/products + bid, per input pair
-    uint64_t budget_pairs = (uint64_t)std::max(1.0, 0.45 * (double)total_b / per_pair);
-    uint32_t wpg = pl.W;
-    if (mtot > budget_pairs) { uint64_t per_w = (mtot + pl.W - 1) / pl.W; wpg = (uint32_t)std::max<uint64_t>(1, budget_pairs / std::max<uint64_t>(1, per_w)); }
-    for (uint32_t w0 = 0; w0 < pl.W; w0 += wpg) {
-      uint32_t w1 = std::min(pl.W, w0 + wpg);
+    const uint64_t budget_pairs = (uint64_t)std::max(1.0, 0.45 * (double)ctx->total_mem / per_pair / lanes);
+    uint32_t ngroups = std::max<uint32_t>(lanes, (uint32_t)((mtot + budget_pairs - 1) / budget_pairs));
+    ngroups = std::min(ngroups, pl.W);
+    // slot boundaries with (nearly) equal pair counts
+    std::vector<uint32_t> cut(ngroups + 1, 0); cut[ngroups] = pl.W;
+    { uint32_t w = 0; for (uint32_t g = 1; g < ngroups; g++) { uint64_t target = mtot * g / ngroups;
+        while (w < pl.W && ctx->h_pinned[512 + w] < target) w++;
+        cut[g] = std::min(std::max(w, cut[g - 1] + 1), pl.W - (ngroups - g)); } }
+    for (uint32_t l = 0; l < lanes; l++) { rc = lane_init(ctx, ctx->lane[l]); if (rc) return rc; if (lanes > 1) CK(cudaStreamWaitEvent(ctx->lane[l].stream, ctx->ev_sorted, 0)); }
+    for (uint32_t g = 0; g < ngroups; g++) {
+      TreeLane& ln = ctx->lane[g % lanes];
+      uint32_t w0 = cut[g], w1 = cut[g + 1];
       uint32_t mc = 0; for (uint32_t w = w0; w < w1; w++) mc = std::max(mc, ctx->h_pinned[w]);
       uint64_t m0 = ctx->h_pinned[512 + w1] - ctx->h_pinned[512 + w0];
       uint32_t b0 = w0 * pl.B, nbg = (w1 - w0) * pl.B;
-      rc = accumulate_batch_affine<C>(ctx, d_bases, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc,
-                                      ctx->buckets.as<char>() + (size_t)b0 * 16 * C::N, &rounds, &adds);
+      cudaStream_t keep = ln.stream; if (lanes == 1) ln.stream = s;
+      char* bg = ctx->buckets.as<char>() + (size_t)b0 * 16 * C::N;
+      rc = accumulate_batch_affine<C>(ctx, ln, d_bases, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc, bg, &rounds, &adds);
+      if (!rc && lanes > 1) rc = fold_slots<C>(ctx, ln.stream, bg, w1 - w0, pl.B);
+      ln.stream = keep;
       if (rc) return rc;
     }
+    if (lanes > 1) for (uint32_t l = 0; l < lanes; l++) { CK(cudaEventRecord(ctx->lane[l].done, ctx->lane[l].stream)); CK(cudaStreamWaitEvent(s, ctx->lane[l].done, 0)); }
+    if (st) CK(cudaEventRecord(ctx->ev[3], s));
+    if (lanes == 1) { rc = fold_slots<C>(ctx, s, ctx->buckets.p, pl.W, pl.B); if (rc) return rc; }
   } else {
     k_accum_serial<C><<<(nb + 127) / 128, 128, 0, s>>>(d_bases, ctx->sorted.as<uint32_t>(), ctx->offsets.as<uint32_t>(), nb, ctx->buckets.p); CKL();
-  }
-  if (st) CK(cudaEventRecord(ctx->ev[3], s));
-
-  // ---- bucket reduction: in-place folding, then per-window totals
-  for (uint32_t sz = pl.B; sz >= 2; sz >>= 1) {
-    uint32_t nblk = pl.B / sz, live = 1; for (uint32_t k = 1; k < nblk; k <<= 1) live++;
-    uint64_t threads = (uint64_t)live * (sz / 2) * pl.W;
-    k_fold<C><<<(uint32_t)((threads + 127) / 128), 128, 0, s>>>(ctx->buckets.p, pl.W, pl.B, sz); CKL();
+    if (st) CK(cudaEventRecord(ctx->ev[3], s));
+    rc = fold_slots<C>(ctx, s, ctx->buckets.p, pl.W, pl.B); if (rc) return rc;
   }
   MARK(T_FOLD);
   if (ctx->opt_combine == 1) {
@@ -262,7 +310,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
     k_window_sums<C><<<(pl.W + 31) / 32, 32, 0, s>>>(ctx->buckets.p, pl.W, pl.Wd, pl.B, pl.logB, ctx->wsum.p); CKL();
     MARK(T_WSUM);
     if (st) CK(cudaEventRecord(ctx->ev[4], s));
-    k_horner<C><<<1, 32, 0, s>>>(ctx->wsum.p, pl.W, pl.Wd, pl.c, d_out); CKL();
+    k_horner<C><<<1, 32, 0, s>>>(ctx->wsum.p, pl.W, pl.Wd, pl.c0, pl.rem, d_out); CKL();
     MARK(T_HORNER);
   } else {
     // serial tail on the host: fetch the (logB + 1) live entries of every folded slot, combine, push the point back
@@ -282,7 +330,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
     for (int i = 0; i < L; i++) { f.q[i] = (uint64_t)C::q(2 * i) | ((uint64_t)C::q(2 * i + 1) << 32); f.one[i] = (uint64_t)C::one(2 * i) | ((uint64_t)C::one(2 * i + 1) << 32); }
     { uint64_t x = 1; for (int k = 0; k < 6; k++) x *= 2 - f.q[0] * x; f.np = 0 - x; }      // -q^-1 mod 2^64 (Newton)
     uint64_t* res = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ctx->h_folded) + bytes);   // 3*n8 bytes in the pinned tail
-    b200host::combine_windows<L>(f, reinterpret_cast<const b200host::XYZZ<L>*>(ctx->h_folded), pl.W, pl.Wd, pl.c, pl.logB, res);
+    b200host::combine_windows<L>(f, reinterpret_cast<const b200host::XYZZ<L>*>(ctx->h_folded), pl.W, pl.Wd, pl.c0, pl.rem, pl.logB, res);
     ctx->host_combine_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     CK(cudaMemcpyAsync(d_out, res, 12 * C::N, cudaMemcpyHostToDevice, s));
     MARK(T_HORNER);
@@ -407,10 +455,12 @@ int b200msm_create(b200msm_ctx** out, int device_id) {
   if (cudaSetDevice(dev) != cudaSuccess) return B200MSM_E_CUDA;
   b200msm_ctx* ctx = new b200msm_ctx();
   ctx->device = dev;
+  { size_t fr = 0, tot = 0; if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) ctx->total_mem = tot; else ctx->total_mem = (size_t)64 << 30; }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200MSM_E_CUDA; }
   ctx->own_stream = true;
   for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return B200MSM_E_CUDA; }
   if (cudaMallocHost(&ctx->h_pinned, 1024 * sizeof(uint32_t)) != cudaSuccess) { delete ctx; return B200MSM_E_CUDA; }
+  if (cudaEventCreateWithFlags(&ctx->ev_plan, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_sorted, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return B200MSM_E_CUDA; }
   *out = ctx;
   return B200MSM_OK;
 }
@@ -420,8 +470,14 @@ void b200msm_destroy(b200msm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->bases, &ctx->scalars, &ctx->canon, &ctx->counts, &ctx->offsets, &ctx->cursors, &ctx->tiles, &ctx->sorted, &ctx->buckets,
-                    &ctx->wsum, &ctx->out, &ctx->misc, &ctx->acc_a, &ctx->acc_b, &ctx->acc_c, &ctx->acc_d, &ctx->acc_e,
-                    &ctx->t_offs, &ctx->t_cnt, &ctx->t_bid, &ctx->t_pa, &ctx->t_pb, &ctx->t_prefix, &ctx->t_prod, &ctx->t_lvlprefix}) b->release();
+                    &ctx->wsum, &ctx->out, &ctx->misc, &ctx->acc_a, &ctx->acc_b, &ctx->acc_c, &ctx->acc_d, &ctx->acc_e}) b->release();
+  for (auto& ln : ctx->lane) {
+    for (DevBuf* b : {&ln.offs, &ln.tiles, &ln.bid, &ln.pa, &ln.pb, &ln.prefix, &ln.prod, &ln.lvlprefix}) b->release();
+    if (ln.done) cudaEventDestroy(ln.done);
+    if (ln.stream) cudaStreamDestroy(ln.stream);
+  }
+  if (ctx->ev_plan) cudaEventDestroy(ctx->ev_plan);
+  if (ctx->ev_sorted) cudaEventDestroy(ctx->ev_sorted);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->h_folded) cudaFreeHost(ctx->h_folded);
   for (auto& kv : ctx->residents) cudaFree(kv.second.d);
@@ -448,6 +504,9 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "window_bits")) { if (v < 0 || v > 24) return B200MSM_E_ARG; ctx->opt_window_bits = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "accumulate")) { if (v < 0 || v > 2) return B200MSM_E_ARG; ctx->opt_accumulate = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "tree_rounds")) { ctx->opt_tree_rounds = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "ba_k")) { if (v < 1 || v > 64) return B200MSM_E_ARG; ctx->opt_ba_k = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "pt_k")) { if (v < 2 || v > 64) return B200MSM_E_ARG; ctx->opt_pt_k = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "lanes")) { if (v < 1 || v > MAX_LANES) return B200MSM_E_ARG; ctx->opt_lanes = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "combine")) { if (v < 0 || v > 1) return B200MSM_E_ARG; ctx->opt_combine = (int)v; return B200MSM_OK; }
   return B200MSM_E_ARG;
 }

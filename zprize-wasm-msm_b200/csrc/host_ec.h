@@ -96,7 +96,7 @@ template <int L> static inline void padd(const Field<L>& f, XYZZ<L>& acc, const 
 
 // folded: W slots of (logB + 1) XYZZ points as written by k_gather_folded.  out_jac: 3*L words, Jacobian Montgomery.
 template <int L>
-static void combine_windows(const Field<L>& f, const XYZZ<L>* folded, uint32_t W, uint32_t Wd, uint32_t c, uint32_t logB, uint64_t* out_jac) {
+static void combine_windows(const Field<L>& f, const XYZZ<L>* folded, uint32_t W, uint32_t Wd, uint32_t c0, uint32_t rem, uint32_t logB, uint64_t* out_jac) {
   const uint32_t per = logB + 1;
   XYZZ<L> acc; set_inf<L>(f, acc);
   for (int w = (int)Wd - 1; w >= 0; w--) {
@@ -113,8 +113,9 @@ static void combine_windows(const Field<L>& f, const XYZZ<L>* folded, uint32_t W
     }
     padd<L>(f, rw, T[0]);
     if (extra) padd<L>(f, rw, E[0]);
-    // Horner across windows: acc = 2^c * acc + R_w
-    if (!is_inf<L>(acc)) for (uint32_t k = 0; k < c; k++) { XYZZ<L> d; pdbl<L>(f, d, acc); acc = d; }
+    // Horner across windows: acc = 2^(width of window w) * acc + R_w
+    const uint32_t cw = c0 + ((uint32_t)w < rem ? 1u : 0u);
+    if (!is_inf<L>(acc)) for (uint32_t k = 0; k < cw; k++) { XYZZ<L> d; pdbl<L>(f, d, acc); acc = d; }
     padd<L>(f, acc, rw);
   }
   // XYZZ -> Jacobian without inversion: Z = ZZ*ZZZ, X = x*ZZ*ZZZ^2, Y = y*ZZ^3*ZZZ^2; infinity -> (0, R mod q, 0)

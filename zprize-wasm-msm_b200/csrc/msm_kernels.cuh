@@ -21,10 +21,12 @@ namespace b200 {
 
 struct MsmPlan {
   uint32_t n;          // points
-  uint32_t c;          // window width in bits
-  uint32_t Wd;         // digit windows = ceil(nbits / c): windows 0..Wd-2 are signed ([-2^(c-1), 2^(c-1)]), the last one
-                       // is unsigned and absorbs the final carry: digit in [0, 2^rb], rb = nbits - (Wd-1)*c
-  uint32_t W;          // bucket-array slots of B buckets each: Wd, or Wd + 1 when the last window needs 2B buckets (rb == c)
+  uint32_t c;          // widest window in bits (= c0 + 1 if rem > 0 else c0)
+  uint32_t c0, rem;    // the nbits are split into Wd windows whose widths differ by at most one bit: windows 0..rem-1 are
+                       // c0 + 1 bits wide, windows rem..Wd-1 are c0 bits wide (bit offset of window w: w*c0 + min(w, rem))
+  uint32_t Wd;         // digit windows: 0..Wd-2 are signed (digit in [-2^(cw-1), 2^(cw-1)]), the last one is unsigned and
+                       // absorbs the final carry (digit in [0, 2^c0])
+  uint32_t W;          // bucket-array slots of B buckets each: Wd, or Wd + 1 when the last window needs 2B buckets (rem == 0)
   uint32_t B;          // buckets per slot = 2^(c-1)   (bucket index = |digit| - 1)
   uint32_t nbits;      // scalar bits processed
   uint32_t logB;       // c - 1
@@ -69,15 +71,15 @@ __global__ void k_canon_scalars(const uint8_t* __restrict__ in, uint32_t scalar_
 template <class F>
 B200_DI void for_each_digit(const uint32_t* __restrict__ s, const MsmPlan& pl, F f) {
   uint32_t carry = 0;
-  const uint32_t mask = (1u << pl.c) - 1u, half = 1u << (pl.c - 1);
   for (uint32_t w = 0; w < pl.Wd; w++) {
-    uint32_t bit = w * pl.c, k = bit >> 5, r = bit & 31;
+    const uint32_t cw = pl.c0 + (w < pl.rem ? 1u : 0u);
+    const uint32_t bit = w * pl.c0 + min(w, pl.rem), k = bit >> 5, r = bit & 31;
     uint32_t lo = (k < 8) ? __ldg(s + k) : 0u, hi = (k + 1 < 8) ? __ldg(s + k + 1) : 0u;
-    uint32_t raw = __funnelshift_r(lo, hi, r) & mask;
+    uint32_t raw = __funnelshift_r(lo, hi, r) & ((1u << cw) - 1u);
     uint32_t d = raw + carry;
     if (w + 1 == pl.Wd) { if (d) f(w * pl.B + d - 1, 0u); break; }
-    carry = d > half;
-    uint32_t mag = carry ? ((1u << pl.c) - d) : d;
+    carry = d > (1u << (cw - 1));
+    uint32_t mag = carry ? ((1u << cw) - d) : d;
     if (mag) f(w * pl.B + mag - 1, carry);
   }
 }
@@ -228,11 +230,12 @@ __global__ void __launch_bounds__(32) k_window_sums(const void* __restrict__ buc
 // GPU form of the window combination; a single dependent chain of Wd*c doublings (see DESIGN.md for why the engine's
 // default performs this last serial step on the host from the folded bucket arrays instead).
 template <class C>
-__global__ void __launch_bounds__(32) k_horner(const void* __restrict__ wsum, uint32_t W, uint32_t Wd, uint32_t c, void* __restrict__ out_jac) {
+__global__ void __launch_bounds__(32) k_horner(const void* __restrict__ wsum, uint32_t W, uint32_t Wd, uint32_t c0, uint32_t rem, void* __restrict__ out_jac) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   XYZZ<C> acc; xyzz_set_inf<C>(acc);
   for (int w = (int)Wd - 1; w >= 0; w--) {
-    if (!xyzz_is_inf<C>(acc)) for (uint32_t k = 0; k < c; k++) { XYZZ<C> d; xyzz_dbl<C>(d, acc); acc = d; }
+    const uint32_t cw = c0 + ((uint32_t)w < rem ? 1u : 0u);       // acc holds windows > w: shift it by the width of window w
+    if (!xyzz_is_inf<C>(acc)) for (uint32_t k = 0; k < cw; k++) { XYZZ<C> d; xyzz_dbl<C>(d, acc); acc = d; }
     XYZZ<C> t; xyzz_load<C>(t, wsum, w);
     xyzz_add<C>(acc, t);
     if (w + 1 == (int)Wd && W > Wd) { xyzz_load<C>(t, wsum, Wd); xyzz_add<C>(acc, t); }
