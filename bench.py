@@ -282,7 +282,7 @@ def run_ours(a):
         roof = {"bound": "imad", "kernel": "k_tree_bwd (batch-affine backward pass, all rounds)", "achieved": achieved / 1e12, "peak": imad / 1e12,
                 "unit": "T limb-products/s (32x32->64 IMAD.WIDE)", "frac": (achieved / imad) if imad else None, "traffic": None,
                 "launches_per_step": rounds, "avg_launch_ms": bwd_ms / rounds, "algorithmic_units_per_step": alg_lp_bwd,
-                "peak_source": "measured in this run by b200msm_probe_imad (register-resident mad.wide.u32 loop on all SMs)",
+                "peak_source": "measured in this run by b200msm_probe_imad: register-resident IMAD.WIDE.U32 carry chains on all SMs (the instruction the field multiplier is made of); plain 32-bit IMAD runs at twice this rate",
                 "hbm": {"achieved": adds * bytes_per_add / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
                         "frac": (adds * bytes_per_add / (bwd_ms * 1e-3) / 1e9 / hbm_peak) if bwd_ms > 0 else None, "peak_source": hbm_src},
                 "whole_accumulate": {"limb_products": adds * FQMUL_PER_AFFINE_ADD * lp, "ms": st["ms_accumulate"],

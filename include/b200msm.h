@@ -96,11 +96,13 @@ int b200msm_g1_generate_bases(b200msm_ctx* ctx, int curve, uint64_t seed, uint64
  * (src/build_f1m.js:71-105, 466-777, 779-1076, 1089-1122) */
 int b200msm_fq_op(b200msm_ctx* ctx, int curve, int op, const void* a, const void* b, void* r, uint64_t count);
 
-/* ---- measurement hooks: integer-multiply roofline denominator and field-multiply rate, measured on this GPU.
- * imad_per_s: 32x32+64 multiply-adds per second (register-resident mad.wide.u32 loop, all SMs);
- * fqmul_per_s: dependent Montgomery multiplications per second for the given curve. */
-int b200msm_probe_imad(b200msm_ctx* ctx, double* imad_per_s);
-int b200msm_probe_imad_carry(b200msm_ctx* ctx, double* imad_per_s);   /* same with carry in/out on every multiply-add (IMAD.WIDE.U32.X) */
+/* ---- measurement hooks: integer-multiply roofline denominators and the field-multiply rate, measured on this GPU.
+ * imad_wide_per_s: 32x32+64 -> 64 multiply-adds per second in the form the field multiplier uses (IMAD.WIDE.U32 carry
+ *                  chains, register-resident, all SMs) -- the roofline peak for the accumulate phase;
+ * imad32_per_s   : plain 32-bit IMAD per second, for context (twice the wide rate on B200);
+ * fqmul_per_s    : dependent Montgomery multiplications per second for the given curve. */
+int b200msm_probe_imad(b200msm_ctx* ctx, double* imad_wide_per_s);
+int b200msm_probe_imad32(b200msm_ctx* ctx, double* imad32_per_s);
 int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s);
 
 /* ---- tuning knobs (never change results).  key: "window_bits" (0 = auto), "accumulate" (0 = auto, 1 = serial, 2 = batch-affine),

@@ -41,6 +41,20 @@ def test_fq_ops_bit_exact(eng, cname):
     assert eng.fq_op(cv.cid, 8, small) == inv          # Fermat
 
 
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+def test_radix29_multiplier_bit_exact(eng, cname):
+    """fp29.cuh: carry-free radix-2^29 Montgomery product (R' = 2^(29L)) and its change of radix to/from the reference's R."""
+    cv = curve(cname); rnd = random.Random(29)
+    L = (cv.q.bit_length() + 28) // 29; Rp = 1 << (29 * L)
+    edge = [0, 1, 2, cv.q - 1, cv.q - 2, (cv.q - 1) // 2, cv.R % cv.q, Rp % cv.q]
+    xs = edge + [rnd.randrange(cv.q) for _ in range(3000)]
+    ys = list(reversed(edge)) + [rnd.randrange(cv.q) for _ in range(3000)]
+    a = b"".join(pyref.fe_bytes(cv, x) for x in xs); b = b"".join(pyref.fe_bytes(cv, y) for y in ys)
+    Rpi = pow(Rp, -1, cv.q)
+    assert eng.fq_op(cv.cid, 9, a, b) == b"".join(pyref.fe_bytes(cv, x * y * Rpi % cv.q) for x, y in zip(xs, ys))
+    assert eng.fq_op(cv.cid, 10, a, b) == coracle.fe_mul(cv.cid, a, b)      # enter -> mul -> leave == f1m_mul
+
+
 # ---------------------------------------------------------------- synthetic bases generator
 @pytest.mark.parametrize("cname", ["bls12381", "bn128"])
 def test_generate_bases_matches_oracle(eng, cname):

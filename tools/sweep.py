@@ -15,8 +15,10 @@ eng.set_stream(torch.cuda.current_stream(dev).cuda_stream)
 for kv in a.opt:
     k, v = kv.split("="); eng.set_option(k, int(v))
 if a.probe:
-    imad = eng.probe_imad(); fq = eng.probe_fqmul(cid); imx = eng.probe_imad_carry()
-    print(json.dumps({"imad_per_s": imad, "imad_carry_per_s": imx, "fqmul_per_s": fq, "fqmul_limb_frac": fq * (300 if cid == 0 else 136) / imad}))
+    imad = eng.probe_imad(); fq = eng.probe_fqmul(cid); im32 = eng.probe_imad32()
+    eng.set_option("probe29", 1); fq29 = eng.probe_fqmul(cid); eng.set_option("probe29", 0)
+    print(json.dumps({"imad_wide_per_s": imad, "imad32_per_s": im32, "fqmul_per_s": fq, "fqmul29_per_s": fq29,
+                      "fqmul_frac_of_imad_wide_peak": fq * (300 if cid == 0 else 136) / imad}))
 for lg in [int(x) for x in a.sizes.split(",")]:
     n = 1 << lg
     bases = torch.empty(n * 2 * n8, dtype=torch.uint8, device=dev)

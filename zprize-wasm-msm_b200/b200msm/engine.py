@@ -101,8 +101,8 @@ class Engine:
     def probe_imad(self):
         v = ctypes.c_double(); self._ck(lib.b200msm_probe_imad(self._ctx, ctypes.byref(v))); return v.value
 
-    def probe_imad_carry(self):
-        v = ctypes.c_double(); self._ck(lib.b200msm_probe_imad_carry(self._ctx, ctypes.byref(v))); return v.value
+    def probe_imad32(self):
+        v = ctypes.c_double(); self._ck(lib.b200msm_probe_imad32(self._ctx, ctypes.byref(v))); return v.value
 
     def probe_fqmul(self, curve):
         v = ctypes.c_double(); self._ck(lib.b200msm_probe_fqmul(self._ctx, curve, ctypes.byref(v))); return v.value

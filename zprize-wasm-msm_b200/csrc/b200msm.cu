@@ -18,6 +18,7 @@
 #include "../../include/b200msm.h"
 #include "msm_kernels.cuh"
 #include "accumulate.cuh"
+#include "fp29.cuh"
 #include "host_ec.h"
 #include <chrono>
 
@@ -58,6 +59,7 @@ struct b200msm_ctx {
   DevBuf bases, scalars, canon, counts, offsets, cursors, tiles, sorted, buckets, wsum, out, misc, acc_a, acc_b, acc_c, acc_d, acc_e;
   TreeLane lane[MAX_LANES];                                                   // batch-affine tree lanes
   int opt_lanes = 2, opt_ba_k = 8, opt_pt_k = 4;
+  bool probe29 = false;
   cudaEvent_t ev_plan = nullptr, ev_sorted = nullptr;
   uint32_t* h_pinned = nullptr;
   void* h_folded = nullptr; size_t h_folded_cap = 0;                         // pinned staging of the folded bucket entries
@@ -506,6 +508,7 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "tree_rounds")) { ctx->opt_tree_rounds = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "ba_k")) { if (v < 1 || v > 64) return B200MSM_E_ARG; ctx->opt_ba_k = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "pt_k")) { if (v < 2 || v > 64) return B200MSM_E_ARG; ctx->opt_pt_k = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "probe29")) { ctx->probe29 = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "lanes")) { if (v < 1 || v > MAX_LANES) return B200MSM_E_ARG; ctx->opt_lanes = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "combine")) { if (v < 0 || v > 1) return B200MSM_E_ARG; ctx->opt_combine = (int)v; return B200MSM_OK; }
   return B200MSM_E_ARG;
@@ -604,7 +607,7 @@ int b200msm_g1_generate_bases(b200msm_ctx* ctx, int curve, uint64_t seed, uint64
 }
 
 int b200msm_fq_op(b200msm_ctx* ctx, int curve, int op, const void* a, const void* b, void* r, uint64_t count) {
-  if (!ctx || !curve_ok(curve) || op < 0 || op > 8 || !a || !r) return B200MSM_E_ARG;
+  if (!ctx || !curve_ok(curve) || op < 0 || op > 10 || !a || !r) return B200MSM_E_ARG;
   if (count == 0) return B200MSM_OK;
   CK(cudaSetDevice(ctx->device));
   const int n8 = n8_of(curve); size_t bytes = (size_t)count * n8;
@@ -613,32 +616,19 @@ int b200msm_fq_op(b200msm_ctx* ctx, int curve, int op, const void* a, const void
   if (b) { rc = stage(ctx, b, bytes, ctx->acc_b, &db); if (rc) return rc; }
   CK(ctx->acc_c.ensure(bytes));
   uint32_t g = (uint32_t)((count + 127) / 128);
-  if (curve == 0) k_fp_op<BLS12_381><<<g, 128, 0, ctx->stream>>>(op, da, db, ctx->acc_c.p, (uint32_t)count);
+  if (op >= 9) {
+    if (!db) { ctx->err = "op 9/10 need two operands"; return B200MSM_E_ARG; }
+    if (curve == 0) k_fp29_mul<BLS12_381><<<g, 128, 0, ctx->stream>>>(da, db, ctx->acc_c.p, (uint32_t)count, op - 9);
+    else k_fp29_mul<BN254><<<g, 128, 0, ctx->stream>>>(da, db, ctx->acc_c.p, (uint32_t)count, op - 9);
+  } else if (curve == 0) k_fp_op<BLS12_381><<<g, 128, 0, ctx->stream>>>(op, da, db, ctx->acc_c.p, (uint32_t)count);
   else k_fp_op<BN254><<<g, 128, 0, ctx->stream>>>(op, da, db, ctx->acc_c.p, (uint32_t)count);
   CKL();
   return deliver(ctx, ctx->acc_c.p, r, bytes);
 }
 
-int b200msm_probe_imad(b200msm_ctx* ctx, double* imad_per_s) {
-  if (!ctx || !imad_per_s) return B200MSM_E_ARG;
-  CK(cudaSetDevice(ctx->device));
-  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
-  CK(ctx->misc.ensure(256));
-  const uint32_t blocks = prop.multiProcessorCount * 8, iters = 2048;
-  double best = 0;
-  for (int rep = 0; rep < 5; rep++) {
-    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    k_imad_probe<<<blocks, 256, 0, ctx->stream>>>(iters, 12345u + rep, ctx->misc.as<unsigned long long>()); CKL();
-    CK(cudaEventRecord(ctx->ev[1], ctx->stream)); CK(cudaEventSynchronize(ctx->ev[1]));
-    float ms; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    double rate = (double)blocks * 256.0 * iters * 64.0 / (ms * 1e-3);
-    if (rep && rate > best) best = rate;
-  }
-  *imad_per_s = best; return B200MSM_OK;
-}
-
-int b200msm_probe_imad_carry(b200msm_ctx* ctx, double* imad_per_s) {
-  if (!ctx || !imad_per_s) return B200MSM_E_ARG;
+// kind 0: IMAD.WIDE.U32 (32x32+64 with carry, the multiplier's instruction); kind 1: 32-bit IMAD
+static int probe_int_pipe(b200msm_ctx* ctx, int kind, double* per_s) {
+  if (!ctx || !per_s) return B200MSM_E_ARG;
   CK(cudaSetDevice(ctx->device));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
   CK(ctx->misc.ensure(256));
@@ -646,14 +636,18 @@ int b200msm_probe_imad_carry(b200msm_ctx* ctx, double* imad_per_s) {
   double best = 0;
   for (int rep = 0; rep < 5; rep++) {
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    k_imadx_probe<<<blocks, 256, 0, ctx->stream>>>(iters, 12345u + rep, ctx->misc.as<uint32_t>()); CKL();
+    if (kind == 0) k_imadx_probe<<<blocks, 256, 0, ctx->stream>>>(iters, 12345u + rep, ctx->misc.as<uint32_t>());
+    else k_imad_probe<1><<<blocks, 256, 0, ctx->stream>>>(iters, 12345u + rep, ctx->misc.as<unsigned long long>());
+    CKL();
     CK(cudaEventRecord(ctx->ev[1], ctx->stream)); CK(cudaEventSynchronize(ctx->ev[1]));
     float ms; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    double rate = (double)blocks * 256.0 * iters * 16.0 / (ms * 1e-3);
+    double rate = (double)blocks * 256.0 * iters * (kind == 0 ? 16.0 : 64.0) / (ms * 1e-3);
     if (rep && rate > best) best = rate;
   }
-  *imad_per_s = best; return B200MSM_OK;
+  *per_s = best; return B200MSM_OK;
 }
+int b200msm_probe_imad(b200msm_ctx* ctx, double* imad_wide_per_s) { return probe_int_pipe(ctx, 0, imad_wide_per_s); }
+int b200msm_probe_imad32(b200msm_ctx* ctx, double* imad32_per_s) { return probe_int_pipe(ctx, 1, imad32_per_s); }
 
 int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s) {
   if (!ctx || !fqmul_per_s || !curve_ok(curve)) return B200MSM_E_ARG;
@@ -666,7 +660,10 @@ int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s) {
   double best = 0;
   for (int rep = 0; rep < 4; rep++) {
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    if (curve == 0) k_fpmul_probe<BLS12_381><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
+    if (ctx->probe29) {
+      if (curve == 0) k_fpmul29_probe<BLS12_381><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
+      else k_fpmul29_probe<BN254><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
+    } else if (curve == 0) k_fpmul_probe<BLS12_381><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
     else k_fpmul_probe<BN254><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
     CKL();
     CK(cudaEventRecord(ctx->ev[1], ctx->stream)); CK(cudaEventSynchronize(ctx->ev[1]));

@@ -363,25 +363,36 @@ __global__ void k_fp_op(int op, const void* __restrict__ a, const void* __restri
   fe_store<C>(reinterpret_cast<char*>(r) + (uint64_t)i * 4 * C::N, z);
 }
 
-// Register-resident IMAD.WIDE throughput probe: the roofline denominator for the accumulate phase
+// Register-resident integer-multiply throughput probes: the roofline denominators for the accumulate phase
 // ("Peak = measured on the box by a register-resident mad.wide microbenchmark").
-// Each thread runs ITER dependent-chain groups of 8 independent 32x32+64 multiply-adds.
+// What was learnt writing them (all verified in SASS with cuobjdump):
+//  * a loop-invariant product is hoisted and the "multiply-adds" become IADD3s -- every multiply below takes one
+//    operand from its own accumulator;
+//  * mad.wide.u32 without a carry is NOT kept as one instruction: ptxas splits it into IMAD.WIDE.U32 (RZ addend) +
+//    IADD3/IADD3.X, and a mul.wide whose high half is unused becomes a 32-bit IMAD;
+//  * the only form that stays a single 32x32+64 instruction is the carry-chain one (mad.lo.cc/madc.hi.cc ->
+//    IMAD.WIDE.U32[.X] with predicate carry), which is exactly what the Montgomery multiplier in fp.cuh is made of.
+// Measured on B200: 32-bit IMAD 18.5e12 /s (64 lanes/clk/SM); IMAD.WIDE.U32 carry chains 9.18e12 /s (32 lanes/clk/SM).
+// The second number is the peak of the instruction the field arithmetic uses: the roofline denominator.
+template <int MODE>   // 1: IMAD (32-bit, acc = acc * b + a), 8 independent chains
 __global__ void __launch_bounds__(256) k_imad_probe(uint32_t iters, uint32_t seed, unsigned long long* __restrict__ sink) {
-  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
-  unsigned long long acc0 = a, acc1 = b, acc2 = a ^ b, acc3 = a + b, acc4 = 5, acc5 = 6, acc6 = 7, acc7 = 8;
+  uint32_t a = seed + threadIdx.x, b = (seed * 3 + blockIdx.x) | 1u;
+  uint32_t acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc[k] = a * (2 * k + 3) + b;
   for (uint32_t i = 0; i < iters; i++) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\tmad.wide.u32 %2, %8, %9, %2;\n\tmad.wide.u32 %3, %8, %9, %3;\n\t"
-                   "mad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\tmad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
-                   : "+l"(acc0), "+l"(acc1), "+l"(acc2), "+l"(acc3), "+l"(acc4), "+l"(acc5), "+l"(acc6), "+l"(acc7) : "r"(a), "r"(b));
+    for (int u = 0; u < 8; u++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(acc[k]) : "r"(b), "r"(a));
     }
   }
-  unsigned long long s = acc0 ^ acc1 ^ acc2 ^ acc3 ^ acc4 ^ acc5 ^ acc6 ^ acc7;
-  if (s == 0x1234567ull) sink[0] = s;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s ^= acc[k];
+  if (s == 0x1234567u) sink[0] = s;
 }
-// Same, but every multiply-add consumes and produces a carry (IMAD.WIDE.U32.X with predicate carry in/out),
-// which is the form the Montgomery multiplier is made of: 4 independent carry chains of 4 wide mads each.
+// IMAD.WIDE.U32 with carry in/out: 4 independent carry chains of 4 wide multiply-adds each (16 per inner iteration).
 __global__ void __launch_bounds__(256) k_imadx_probe(uint32_t iters, uint32_t seed, uint32_t* __restrict__ sink) {
   uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
   uint32_t r[32];
