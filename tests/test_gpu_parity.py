@@ -228,3 +228,57 @@ def test_sum_and_resident_api(eng, cname):
         assert eng.normalize(cv.cid, eng.sum_points(cv.cid, a + b, 2)) == eng.normalize(cv.cid, full)
     finally:
         eng.free_bases(h)
+
+
+# ---------------------------------------------------------------- BASELINE.json full sizes: exact known answers
+def _splitmix64_np(x):
+    import numpy as np
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+@pytest.mark.parametrize("cname,lg", [("bls12381", 16), ("bls12381", 18), ("bls12381", 20), ("bn128", 20)])
+def test_full_size_known_answer(eng, cname, lg):
+    """BASELINE configs at full size.  The synthetic bases are P_i = k_i*G with known k_i (splitmix64 stream), so the
+    exact answer of sum_i s_i*P_i is (sum_i s_i*k_i mod r)*G -- computed with host big integers and ONE oracle scalar
+    multiplication, independent of any MSM code.  Bit-exact on canonical affine output, plus linearity and sharding."""
+    import numpy as np, torch
+    cv = curve(cname); n = 1 << lg; n8 = cv.n8
+    seed = 0xB2000000 + lg
+    d = torch.empty(n * 2 * n8, dtype=torch.uint8, device="cuda")
+    eng.generate_bases(cv.cid, seed, 0, n, d)
+    with np.errstate(over="ignore"):
+        k = _splitmix64_np(np.uint64(seed) + np.arange(n, dtype=np.uint64))
+    k[k == 0] = 1
+    rng = np.random.default_rng(lg)
+    sc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x7F                                  # < 2^255 so that s1 + s2 below stays a 256-bit integer
+    sb = sc.tobytes()
+    sd = torch.from_numpy(sc.reshape(-1).copy()).cuda()
+    got = eng.normalize(cv.cid, eng.multiexp_affine(cv.cid, d, sd, 32, n))
+    # exact expectation
+    words = sc.view("<u8").astype(object)              # n x 4 little-endian 64-bit words
+    svals = words[:, 0] + (words[:, 1] << 64) + (words[:, 2] << 128) + (words[:, 3] << 192)
+    total = int((svals * k.astype(object)).sum() % cv.r)
+    exp = coracle.normalize(cv.cid, coracle.times_scalar_affine(cv.cid, gen_bytes(cv), total.to_bytes(32, "little")))
+    assert got == exp
+    # sharding property at full size: two halves summed == whole
+    h = n // 2
+    a = eng.multiexp_affine(cv.cid, d[: h * 2 * n8], sd[: h * 32], 32, h)
+    b = eng.multiexp_affine(cv.cid, d[h * 2 * n8:], sd[h * 32:], 32, n - h)
+    assert eng.normalize(cv.cid, eng.sum_points(cv.cid, a + b, 2)) == exp
+    # linearity: MSM(s) + MSM(s') == MSM(s + s') for a second scalar vector (s' = byte-reversed s, also < 2^255)
+    sc2 = np.ascontiguousarray(sc[::-1]); sd2 = torch.from_numpy(sc2.reshape(-1).copy()).cuda()
+    w2 = sc2.view("<u8").astype(object); s2 = w2[:, 0] + (w2[:, 1] << 64) + (w2[:, 2] << 128) + (w2[:, 3] << 192)
+    ssum = svals + s2
+    sums = np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in ssum), dtype=np.uint8) if lg <= 16 else None
+    r2 = eng.multiexp_affine(cv.cid, d, sd2, 32, n)
+    r1 = eng.multiexp_affine(cv.cid, d, sd, 32, n)
+    lhs = eng.normalize(cv.cid, eng.sum_points(cv.cid, r1 + r2, 2))
+    total2 = int((ssum * k.astype(object)).sum() % cv.r)
+    assert lhs == coracle.normalize(cv.cid, coracle.times_scalar_affine(cv.cid, gen_bytes(cv), total2.to_bytes(32, "little")))
+    if sums is not None:
+        r3 = eng.multiexp_affine(cv.cid, d, torch.from_numpy(sums.copy()).cuda(), 32, n)
+        assert eng.normalize(cv.cid, r3) == lhs

@@ -120,32 +120,62 @@ B200_DI bool tree_slot(const TreeRound& tr, uint32_t j, uint32_t& in0, bool& has
   return true;
 }
 
-// forward: denominators, per-slot prefix products, per-thread products
+// forward: denominators, per-slot prefix products, per-thread products.
+// The kernel is gather-bound (two scattered 96-byte points per slot in round 0), so the loads of slot i+1 are issued
+// before the multiplication of slot i (two slots in flight per thread).
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS) k_tree_fwd(TreeRound tr, const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                         const void* __restrict__ pin, void* __restrict__ prefix, void* __restrict__ prod, int K) {
+struct FwdSlot { Fe<C::N> x1, x2; uint32_t j, in0; bool valid, has2; };
+
+// x coordinate only (the y coordinates are needed only in the rare equal-x / zero-x cases and are fetched then)
+template <class C, bool FIRST>
+B200_DI void tree_load_x(Fe<C::N>& x, const void* __restrict__ bases, const uint32_t* __restrict__ sorted, const void* __restrict__ pin, uint32_t pos) {
+  if (FIRST) fe_load<C>(x, reinterpret_cast<const char*>(bases) + (uint64_t)(__ldg(sorted + pos) & 0x7fffffffu) * (8 * C::N));
+  else fe_load_cg<C>(x, reinterpret_cast<const char*>(pin) + (uint64_t)pos * (8 * C::N));
+}
+
+template <class C, bool FIRST>
+B200_DI void fwd_fetch(FwdSlot<C, FIRST>& sl, const TreeRound& tr, const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                       const void* __restrict__ pin, uint32_t j) {
+  sl.j = j; sl.has2 = false;
+  sl.valid = tree_slot(tr, j, sl.in0, sl.has2, true);
+  if (sl.valid && sl.has2) {
+    tree_load_x<C, FIRST>(sl.x1, bases, sorted, pin, sl.in0);
+    tree_load_x<C, FIRST>(sl.x2, bases, sorted, pin, sl.in0 + 1);
+  }
+}
+
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(BA_THREADS, 6) k_tree_fwd(TreeRound tr, const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                            const void* __restrict__ pin, void* __restrict__ prefix, void* __restrict__ prod, int K) {
   uint32_t tile = blockIdx.x * (K * BA_THREADS);
   Fe<C::N> p; fe_set_one<C>(p);
+  FwdSlot<C, FIRST> cur, nxt;
+  fwd_fetch<C, FIRST>(cur, tr, bases, sorted, pin, tile + threadIdx.x);
 #pragma unroll 1
   for (int i = 0; i < K; i++) {
-    uint32_t j = tile + i * BA_THREADS + threadIdx.x, in0; bool has2;
-    if (!tree_slot(tr, j, in0, has2, true)) continue;
-    if (!has2) continue;
-    Affine<C> p1, p2; Fe<C::N> d;
-    tree_load_point<C, FIRST>(p1, bases, sorted, pin, in0);
-    tree_load_point<C, FIRST>(p2, bases, sorted, pin, in0 + 1);
-    int kind = affine_add_denominator<C>(d, p1, p2);
-    if (kind <= 1) {
-      fe_store<C>(reinterpret_cast<char*>(prefix) + (uint64_t)j * 4 * C::N, p);
-      fe_mul<C>(p, p, d);
+    if (i + 1 < K) fwd_fetch<C, FIRST>(nxt, tr, bases, sorted, pin, tile + (i + 1) * BA_THREADS + threadIdx.x);
+    if (cur.valid && cur.has2) {
+      Fe<C::N> d; int kind = 0;
+      fe_sub<C>(d, cur.x2, cur.x1);
+      if (fe_is_zero<C>(d) || fe_is_zero<C>(cur.x1) || fe_is_zero<C>(cur.x2)) {        // rare: decide with the full points
+        Affine<C> p1, p2;
+        tree_load_point<C, FIRST>(p1, bases, sorted, pin, cur.in0);
+        tree_load_point<C, FIRST>(p2, bases, sorted, pin, cur.in0 + 1);
+        kind = affine_add_denominator<C>(d, p1, p2);
+      }
+      if (kind <= 1) {
+        fe_store<C>(reinterpret_cast<char*>(prefix) + (uint64_t)cur.j * 4 * C::N, p);
+        fe_mul<C>(p, p, d);
+      }
     }
+    cur = nxt;
   }
   fe_store<C>(reinterpret_cast<char*>(prod) + (uint64_t)(blockIdx.x * BA_THREADS + threadIdx.x) * 4 * C::N, p);
 }
 
 // backward: consume the inverse of the thread's product, finish every addition, write the round's output points
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS) k_tree_bwd(TreeRound tr, const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
+__global__ void __launch_bounds__(BA_THREADS, 4) k_tree_bwd(TreeRound tr, const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                          const void* __restrict__ pin, const void* __restrict__ prefix, const void* __restrict__ inv,
                                                          void* __restrict__ pout, int K) {
   uint32_t tile = blockIdx.x * (K * BA_THREADS);
