@@ -44,6 +44,8 @@ typedef struct b200msm_stats {
   float ms_k_sort, ms_k_plan, ms_k_tree_fwd, ms_k_inv_tree, ms_k_tree_bwd, ms_k_finish, ms_k_fold, ms_k_wsum, ms_k_horner;
   float ms_host_combine;     /* host part of the window combination (inside ms_window_combine) */
   uint64_t launches;         /* kernels + memset/memcpy nodes launched by this call */
+  uint64_t affine_adds_round0;   /* additions done by the first (largest) k_tree_bwd launch */
+  float ms_k_tree_bwd_round0, reserved3;
 } b200msm_stats;
 
 /* ---- life cycle.  device_id < 0 selects the current CUDA device. */

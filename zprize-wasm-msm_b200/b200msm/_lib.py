@@ -30,7 +30,8 @@ class Stats(ctypes.Structure):
                 ("ms_d2h", ctypes.c_float),
                 ("ms_k_sort", ctypes.c_float), ("ms_k_plan", ctypes.c_float), ("ms_k_tree_fwd", ctypes.c_float), ("ms_k_inv_tree", ctypes.c_float),
                 ("ms_k_tree_bwd", ctypes.c_float), ("ms_k_finish", ctypes.c_float), ("ms_k_fold", ctypes.c_float), ("ms_k_wsum", ctypes.c_float),
-                ("ms_k_horner", ctypes.c_float), ("ms_host_combine", ctypes.c_float), ("launches", ctypes.c_uint64)]
+                ("ms_k_horner", ctypes.c_float), ("ms_host_combine", ctypes.c_float), ("launches", ctypes.c_uint64),
+                ("affine_adds_round0", ctypes.c_uint64), ("ms_k_tree_bwd_round0", ctypes.c_float), ("reserved3", ctypes.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}

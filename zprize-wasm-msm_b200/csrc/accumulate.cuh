@@ -25,7 +25,7 @@ namespace b200 {
 
 constexpr int BA_THREADS = 128;     // threads per block in the tree kernels; a block owns a tile of K * BA_THREADS consecutive slots,
                                     // K = additions per thread per inversion chain (level 0) or product-tree arity (levels >= 1): run-time parameters
-constexpr uint32_t BA_ROOT_MAX = 256;   // the product tree is reduced until at most this many values remain
+constexpr uint32_t BA_ROOT_MAX = 1024;   // = BA_ROOT_THREADS * ROOT_PER   // the product tree is reduced until at most this many values remain
 
 // n_{r+1}[b] = ceil(n_r[b] / 2)
 __global__ void k_halve_counts(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n) {
@@ -146,8 +146,10 @@ B200_DI void fwd_fetch(FwdSlot<C, FIRST>& sl, const TreeRound& tr, const void* _
 
 template <class C, bool FIRST>
 __global__ void __launch_bounds__(BA_THREADS, 6) k_tree_fwd(TreeRound tr, const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                            const void* __restrict__ pin, void* __restrict__ prefix, void* __restrict__ prod, int K) {
-  uint32_t tile = blockIdx.x * (K * BA_THREADS);
+                                                            const void* __restrict__ pin, void* __restrict__ prefix, void* __restrict__ prod, int K, uint32_t ntiles) {
+ // persistent form: gridDim.x may be smaller than ntiles (leaves SM room for the other lane's latency-bound kernels)
+ for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
+  uint32_t tile = tb * (K * BA_THREADS);
   Fe<C::N> p; fe_set_one<C>(p);
   FwdSlot<C, FIRST> cur, nxt;
   fwd_fetch<C, FIRST>(cur, tr, bases, sorted, pin, tile + threadIdx.x);
@@ -170,17 +172,19 @@ __global__ void __launch_bounds__(BA_THREADS, 6) k_tree_fwd(TreeRound tr, const 
     }
     cur = nxt;
   }
-  fe_store<C>(reinterpret_cast<char*>(prod) + (uint64_t)(blockIdx.x * BA_THREADS + threadIdx.x) * 4 * C::N, p);
+  fe_store<C>(reinterpret_cast<char*>(prod) + (uint64_t)(tb * BA_THREADS + threadIdx.x) * 4 * C::N, p);
+ }
 }
 
 // backward: consume the inverse of the thread's product, finish every addition, write the round's output points
 template <class C, bool FIRST>
 __global__ void __launch_bounds__(BA_THREADS, 4) k_tree_bwd(TreeRound tr, const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                          const void* __restrict__ pin, const void* __restrict__ prefix, const void* __restrict__ inv,
-                                                         void* __restrict__ pout, int K) {
-  uint32_t tile = blockIdx.x * (K * BA_THREADS);
+                                                         void* __restrict__ pout, int K, uint32_t ntiles) {
+ for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
+  uint32_t tile = tb * (K * BA_THREADS);
   Fe<C::N> q;
-  fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)(blockIdx.x * BA_THREADS + threadIdx.x) * 4 * C::N);
+  fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)(tb * BA_THREADS + threadIdx.x) * 4 * C::N);
 #pragma unroll 1
   for (int i = K - 1; i >= 0; i--) {
     uint32_t j = tile + i * BA_THREADS + threadIdx.x, in0; bool has2;
@@ -199,11 +203,27 @@ __global__ void __launch_bounds__(BA_THREADS, 4) k_tree_bwd(TreeRound tr, const 
     affine_add_finish<C>(r, p1, p2, dinv, kind);
     affine_store<C>(pout, j, r);
   }
+ }
 }
 
 // ---- product tree, levels >= 1: plain arrays of field elements -----------------------------------------
-template <class C>
-__global__ void __launch_bounds__(BA_THREADS) k_prod_fwd(const void* __restrict__ vals, uint32_t n, void* __restrict__ prefix, void* __restrict__ prod, int K) {
+// A level reduces n values by K per thread (serial running product, prefixes stored) and, when WARP is set, by a further
+// factor 32 inside each warp: inclusive prefix and suffix products across the lanes by shuffles (5 + 5 steps that
+// interleave), "others" = product of all other lanes' values is stored per thread, and the warp total goes up.
+// Going back down, a thread's inverse is (inverse of the warp total) * others -- one multiplication.
+// Small levels are latency-bound, so trading a few redundant multiplications for a 32x larger arity removes launches.
+template <class C> B200_DI void fe_shfl_up(Fe<C::N>& r, const Fe<C::N>& a, int o) {
+#pragma unroll
+  for (int k = 0; k < C::N; k++) r.l[k] = __shfl_up_sync(0xffffffffu, a.l[k], o);
+}
+template <class C> B200_DI void fe_shfl_down(Fe<C::N>& r, const Fe<C::N>& a, int o) {
+#pragma unroll
+  for (int k = 0; k < C::N; k++) r.l[k] = __shfl_down_sync(0xffffffffu, a.l[k], o);
+}
+
+template <class C, bool WARP>
+__global__ void __launch_bounds__(BA_THREADS) k_prod_fwd(const void* __restrict__ vals, uint32_t n, void* __restrict__ prefix, void* __restrict__ prod,
+                                                         void* __restrict__ others, int K) {
   uint32_t tile = blockIdx.x * (K * BA_THREADS);
   Fe<C::N> p; fe_set_one<C>(p);
 #pragma unroll 1
@@ -214,14 +234,37 @@ __global__ void __launch_bounds__(BA_THREADS) k_prod_fwd(const void* __restrict_
     fe_store<C>(reinterpret_cast<char*>(prefix) + (uint64_t)e * 4 * C::N, p);
     fe_mul<C>(p, p, v);
   }
-  fe_store<C>(reinterpret_cast<char*>(prod) + (uint64_t)(blockIdx.x * BA_THREADS + threadIdx.x) * 4 * C::N, p);
+  const uint32_t T = blockIdx.x * BA_THREADS + threadIdx.x;
+  if (!WARP) { fe_store<C>(reinterpret_cast<char*>(prod) + (uint64_t)T * 4 * C::N, p); return; }
+  const uint32_t lane = threadIdx.x & 31;
+  Fe<C::N> pre = p, suf = p, y, z;
+#pragma unroll 1
+  for (int o = 1; o < 32; o <<= 1) {
+    fe_shfl_up<C>(y, pre, o); fe_shfl_down<C>(z, suf, o);
+    if (lane >= (uint32_t)o) fe_mul<C>(pre, pre, y);
+    if (lane + o < 32) fe_mul<C>(suf, suf, z);
+  }
+  fe_shfl_up<C>(y, pre, 1); fe_shfl_down<C>(z, suf, 1);      // exclusive prefix / suffix
+  Fe<C::N> oth;
+  if (lane == 0) oth = z; else if (lane == 31) oth = y; else fe_mul<C>(oth, y, z);
+  fe_store<C>(reinterpret_cast<char*>(others) + (uint64_t)T * 4 * C::N, oth);
+  if (lane == 31) fe_store<C>(reinterpret_cast<char*>(prod) + (uint64_t)(T >> 5) * 4 * C::N, pre);
 }
-// in place: vals[e] <- 1 / vals[e], given the inverse of each thread's product in inv[]
-template <class C>
-__global__ void __launch_bounds__(BA_THREADS) k_prod_bwd(void* __restrict__ vals, uint32_t n, const void* __restrict__ prefix, const void* __restrict__ inv, int K) {
+// in place: vals[e] <- 1 / vals[e], given the inverse of each thread's (or warp's) product in inv[]
+template <class C, bool WARP>
+__global__ void __launch_bounds__(BA_THREADS) k_prod_bwd(void* __restrict__ vals, uint32_t n, const void* __restrict__ prefix, const void* __restrict__ inv,
+                                                         const void* __restrict__ others, int K) {
   uint32_t tile = blockIdx.x * (K * BA_THREADS);
+  const uint32_t T = blockIdx.x * BA_THREADS + threadIdx.x;
   Fe<C::N> q;
-  fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)(blockIdx.x * BA_THREADS + threadIdx.x) * 4 * C::N);
+  if (WARP) {
+    Fe<C::N> wi, oth;
+    fe_load_cg<C>(wi, reinterpret_cast<const char*>(inv) + (uint64_t)(T >> 5) * 4 * C::N);
+    fe_load_cg<C>(oth, reinterpret_cast<const char*>(others) + (uint64_t)T * 4 * C::N);
+    fe_mul<C>(q, wi, oth);
+  } else {
+    fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)T * 4 * C::N);
+  }
 #pragma unroll 1
   for (int i = K - 1; i >= 0; i--) {
     uint32_t e = tile + i * BA_THREADS + threadIdx.x;
@@ -234,19 +277,28 @@ __global__ void __launch_bounds__(BA_THREADS) k_prod_bwd(void* __restrict__ vals
     fe_store<C>(reinterpret_cast<char*>(vals) + (uint64_t)e * 4 * C::N, r);
   }
 }
-// root: n <= BA_ROOT_MAX values inverted in place by ONE block: binary product tree in shared memory (log depth),
-// a single field inversion by thread 0 (f1m_inverse at build_batchinverse.js:90), then the tree is walked back down.
+// root: n <= BA_ROOT_MAX values inverted in place by ONE block of BA_ROOT_THREADS threads: each thread forms the running
+// product of up to ROOT_PER values, a binary product tree over the threads lives in shared memory (log depth), thread 0
+// inverts the root once (f1m_inverse at build_batchinverse.js:90), then the tree and the per-thread chains are walked back.
+constexpr uint32_t BA_ROOT_THREADS = 256, ROOT_PER = 4;
 template <class C>
-__global__ void __launch_bounds__(BA_ROOT_MAX) k_inv_root(void* __restrict__ vals, uint32_t n) {
+__global__ void __launch_bounds__(BA_ROOT_THREADS) k_inv_root(void* __restrict__ vals, uint32_t n) {
   constexpr int N = C::N;
-  __shared__ uint32_t tree[2 * BA_ROOT_MAX * N];       // node k (1-based heap order): leaves at [BA_ROOT_MAX, 2*BA_ROOT_MAX)
+  __shared__ uint32_t tree[2 * BA_ROOT_THREADS * N];       // node k (1-based heap order): leaves at [BA_ROOT_THREADS, 2*BA_ROOT_THREADS)
   const uint32_t t = threadIdx.x;
-  Fe<N> v;
-  if (t < n) fe_load_cg<C>(v, reinterpret_cast<const char*>(vals) + (uint64_t)t * 4 * N); else fe_set_one<C>(v);
+  Fe<N> v[ROOT_PER], pre[ROOT_PER], p;
+  fe_set_one<C>(p);
 #pragma unroll
-  for (int k = 0; k < N; k++) tree[(BA_ROOT_MAX + t) * N + k] = v.l[k];
+  for (uint32_t i = 0; i < ROOT_PER; i++) {
+    uint32_t e = i * BA_ROOT_THREADS + t;
+    if (e < n) fe_load_cg<C>(v[i], reinterpret_cast<const char*>(vals) + (uint64_t)e * 4 * N); else fe_set_one<C>(v[i]);
+    pre[i] = p;
+    if (e < n) fe_mul<C>(p, p, v[i]);
+  }
+#pragma unroll
+  for (int k = 0; k < N; k++) tree[(BA_ROOT_THREADS + t) * N + k] = p.l[k];
   __syncthreads();
-  for (uint32_t width = BA_ROOT_MAX / 2; width >= 1; width >>= 1) {     // up-sweep: node = left * right
+  for (uint32_t width = BA_ROOT_THREADS / 2; width >= 1; width >>= 1) {     // up-sweep: node = left * right
     if (t < width) {
       Fe<N> a, b, c; uint32_t node = width + t;
 #pragma unroll
@@ -266,7 +318,7 @@ __global__ void __launch_bounds__(BA_ROOT_MAX) k_inv_root(void* __restrict__ val
     for (int k = 0; k < N; k++) tree[1 * N + k] = ri.l[k];
   }
   __syncthreads();
-  for (uint32_t width = 1; width < BA_ROOT_MAX; width <<= 1) {          // down-sweep: inv(left) = inv(node) * right, inv(right) = inv(node) * left
+  for (uint32_t width = 1; width < BA_ROOT_THREADS; width <<= 1) {          // down-sweep: inv(left) = inv(node) * right, inv(right) = inv(node) * left
     if (t < width) {
       Fe<N> a, b, ip, ia, ib; uint32_t node = width + t;
 #pragma unroll
@@ -277,10 +329,16 @@ __global__ void __launch_bounds__(BA_ROOT_MAX) k_inv_root(void* __restrict__ val
     }
     __syncthreads();
   }
-  if (t < n) {
+  Fe<N> q;
 #pragma unroll
-    for (int k = 0; k < N; k++) v.l[k] = tree[(BA_ROOT_MAX + t) * N + k];
-    fe_store<C>(reinterpret_cast<char*>(vals) + (uint64_t)t * 4 * N, v);
+  for (int k = 0; k < N; k++) q.l[k] = tree[(BA_ROOT_THREADS + t) * N + k];
+#pragma unroll
+  for (int i = (int)ROOT_PER - 1; i >= 0; i--) {
+    uint32_t e = (uint32_t)i * BA_ROOT_THREADS + t;
+    if (e < n) {
+      Fe<N> r; fe_mul<C>(r, q, pre[i]); fe_mul<C>(q, q, v[i]);
+      fe_store<C>(reinterpret_cast<char*>(vals) + (uint64_t)e * 4 * N, r);
+    }
   }
 }
 

@@ -45,9 +45,10 @@ struct Resident { int curve; uint64_t n; void* d; };
 // one accumulate lane: a stream with its own tree scratch (see accumulate_batch_affine)
 struct TreeLane {
   cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
-  DevBuf offs, tiles, bid, pa, pb, prefix, prod, lvlprefix;
+  DevBuf offs, tiles, bid, pa, pb, prefix, prod, lvlprefix, others;
 };
 constexpr int MAX_LANES = 4;
+constexpr uint64_t WARP_LEVEL_MAX = 131072;     // product-tree levels with at most this many values use the warp-assisted kernel (only one such level can occur: 131072 / 128 <= BA_ROOT_MAX)
 
 }  // namespace
 
@@ -58,7 +59,7 @@ struct b200msm_ctx {
   int opt_window_bits = 0, opt_accumulate = 0, opt_tree_rounds = -1;
   DevBuf bases, scalars, canon, counts, offsets, cursors, tiles, sorted, buckets, wsum, out, misc, acc_a, acc_b, acc_c, acc_d, acc_e;
   TreeLane lane[MAX_LANES];                                                   // batch-affine tree lanes
-  int opt_lanes = 2, opt_ba_k = 8, opt_pt_k = 4;
+  int opt_lanes = 4, opt_ba_k = 8, opt_pt_k = 8, opt_persist = 444;
   bool probe29 = false;
   cudaEvent_t ev_plan = nullptr, ev_sorted = nullptr;
   uint32_t* h_pinned = nullptr;
@@ -69,7 +70,7 @@ struct b200msm_ctx {
   cudaEvent_t ev[8] = {};
   // fine-grained phase profiler (active only while a stats struct is being filled)
   std::vector<cudaEvent_t> pev; std::vector<int> ptag; size_t pused = 0; bool prof = false;
-  uint64_t launches = 0;
+  uint64_t launches = 0, adds_r0 = 0, adds_exact = 0;
   size_t total_mem = 0;
 };
 
@@ -78,7 +79,7 @@ namespace {
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); \
   return e_ == cudaErrorMemoryAllocation ? B200MSM_E_NOMEM : B200MSM_E_CUDA; } } while (0)
 #define CKL() do { ctx->launches++; CK(cudaGetLastError()); } while (0)
-enum { T_SORT = 0, T_PLAN, T_TREE_FWD, T_INV_TREE, T_TREE_BWD, T_FINISH, T_FOLD, T_WSUM, T_HORNER, T_NTAGS };
+enum { T_SORT = 0, T_PLAN, T_TREE_FWD, T_INV_TREE, T_TREE_BWD, T_FINISH, T_FOLD, T_WSUM, T_HORNER, T_TREE_BWD0, T_NTAGS };
 #define MARK(tag) do { if (ctx->prof) { int rc_ = prof_mark(ctx, tag); if (rc_) return rc_; } } while (0)
 
 int lane_init(b200msm_ctx* ctx, TreeLane& ln) {
@@ -173,13 +174,12 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
   MARK(T_PLAN);
   const size_t fe = 4 * C::N, pt = 8 * C::N;
   const int BK = ctx->opt_ba_k, PK = ctx->opt_pt_k;
-  const uint64_t BA_TILE = (uint64_t)BK * BA_THREADS, PT_TILE = (uint64_t)PK * BA_THREADS;
+  const uint64_t BA_TILE = (uint64_t)BK * BA_THREADS;
   CK(ln_.pa.ensure(U[1] * pt + 16)); if (R > 1) CK(ln_.pb.ensure(U[2] * pt + 16));
   CK(ln_.prefix.ensure(U[1] * fe + 16));
   // product-tree level sizes for the largest round
-  { size_t tot = 0, totp = 0; uint64_t n = ((U[1] + BA_TILE - 1) / BA_TILE) * BA_THREADS;
-    for (;;) { tot += n; if (n <= BA_ROOT_MAX) break; totp += n; n = ((n + PT_TILE - 1) / PT_TILE) * BA_THREADS; }
-    CK(ln_.prod.ensure(tot * fe + 16)); CK(ln_.lvlprefix.ensure(totp * fe + 16)); }
+  { uint64_t n1 = ((U[1] + BA_TILE - 1) / BA_TILE) * BA_THREADS;       // every level above is at least 4x smaller: 2*n1 bounds the sum
+    CK(ln_.prod.ensure((2 * n1 + 4096) * fe)); CK(ln_.lvlprefix.ensure((2 * n1 + 4096) * fe)); CK(ln_.others.ensure((WARP_LEVEL_MAX / 4 + 4096) * fe)); }
   void* pin = nullptr;
   for (uint32_t r = 0; r < R; r++) {
     void* pout = (r & 1) ? ln_.pb.p : ln_.pa.p;
@@ -187,31 +187,47 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
     uint32_t grid = (uint32_t)((U[r + 1] + BA_TILE - 1) / BA_TILE);
     if (grid == 0) grid = 1;
     char* prod = ln_.prod.as<char>(); char* lpre = ln_.lvlprefix.as<char>();
-    if (r == 0) k_tree_fwd<C, true><<<grid, BA_THREADS, 0, s>>>(tr, d_bases, sorted, nullptr, ln_.prefix.p, prod, BK);
-    else k_tree_fwd<C, false><<<grid, BA_THREADS, 0, s>>>(tr, nullptr, nullptr, pin, ln_.prefix.p, prod, BK);
+    const uint32_t pgrid = (ctx->opt_persist > 0 && ln_.stream != ctx->stream) ? std::min<uint32_t>(grid, (uint32_t)ctx->opt_persist) : grid;   // persistent grid only when lanes overlap
+    if (r == 0) k_tree_fwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(tr, d_bases, sorted, nullptr, ln_.prefix.p, prod, BK, grid);
+    else k_tree_fwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(tr, nullptr, nullptr, pin, ln_.prefix.p, prod, BK, grid);
     CKL(); MARK(T_TREE_FWD);
-    // up the product tree
-    std::vector<uint64_t> ln; std::vector<char*> lv, lp;
+    // up the product tree: plain K-ary levels while the level is large, one warp-assisted level (arity 32*4) once it is small
+    struct Lvl { uint64_t n; char* v; char* p; bool warp; int K; };
+    std::vector<Lvl> lv;
     uint64_t n = (uint64_t)grid * BA_THREADS; char* cur = prod; char* curp = lpre;
     while (n > BA_ROOT_MAX) {
-      uint32_t g2 = (uint32_t)((n + PT_TILE - 1) / PT_TILE);
+      const bool warp = n <= WARP_LEVEL_MAX;
+      const int K = warp ? 4 : PK;
+      const uint32_t g2 = (uint32_t)((n + (uint64_t)K * BA_THREADS - 1) / ((uint64_t)K * BA_THREADS));
       char* nxt = cur + n * fe;
-      k_prod_fwd<C><<<g2, BA_THREADS, 0, s>>>(cur, (uint32_t)n, curp, nxt, PK); CKL();
-      ln.push_back(n); lv.push_back(cur); lp.push_back(curp);
-      curp += n * fe; cur = nxt; n = (uint64_t)g2 * BA_THREADS;
+      if (warp) k_prod_fwd<C, true><<<g2, BA_THREADS, 0, s>>>(cur, (uint32_t)n, curp, nxt, ln_.others.p, K);
+      else k_prod_fwd<C, false><<<g2, BA_THREADS, 0, s>>>(cur, (uint32_t)n, curp, nxt, nullptr, K);
+      CKL();
+      lv.push_back(Lvl{n, cur, curp, warp, K});
+      curp += n * fe; cur = nxt; n = warp ? (uint64_t)g2 * (BA_THREADS / 32) : (uint64_t)g2 * BA_THREADS;
     }
-    k_inv_root<C><<<1, BA_ROOT_MAX, 0, s>>>(cur, (uint32_t)n); CKL();
+    k_inv_root<C><<<1, BA_ROOT_THREADS, 0, s>>>(cur, (uint32_t)n); CKL();
     // back down
-    for (int l = (int)ln.size() - 1; l >= 0; l--) {
-      uint32_t g2 = (uint32_t)((ln[l] + PT_TILE - 1) / PT_TILE);
-      k_prod_bwd<C><<<g2, BA_THREADS, 0, s>>>(lv[l], (uint32_t)ln[l], lp[l], lv[l] + ln[l] * fe, PK); CKL();
+    for (int l = (int)lv.size() - 1; l >= 0; l--) {
+      const Lvl& L = lv[l];
+      const uint32_t g2 = (uint32_t)((L.n + (uint64_t)L.K * BA_THREADS - 1) / ((uint64_t)L.K * BA_THREADS));
+      if (L.warp) k_prod_bwd<C, true><<<g2, BA_THREADS, 0, s>>>(L.v, (uint32_t)L.n, L.p, L.v + L.n * fe, ln_.others.p, L.K);
+      else k_prod_bwd<C, false><<<g2, BA_THREADS, 0, s>>>(L.v, (uint32_t)L.n, L.p, L.v + L.n * fe, nullptr, L.K);
+      CKL();
     }
     MARK(T_INV_TREE);
-    if (r == 0) k_tree_bwd<C, true><<<grid, BA_THREADS, 0, s>>>(tr, d_bases, sorted, nullptr, ln_.prefix.p, prod, pout, BK);
-    else k_tree_bwd<C, false><<<grid, BA_THREADS, 0, s>>>(tr, nullptr, nullptr, pin, ln_.prefix.p, prod, pout, BK);
-    CKL(); MARK(T_TREE_BWD);
+    if (r == 0) k_tree_bwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(tr, d_bases, sorted, nullptr, ln_.prefix.p, prod, pout, BK, grid);
+    else k_tree_bwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(tr, nullptr, nullptr, pin, ln_.prefix.p, prod, pout, BK, grid);
+    CKL(); MARK(r == 0 ? T_TREE_BWD0 : T_TREE_BWD);
     pin = pout;
     *adds_out += U[r] - U[r + 1];
+  }
+  if (ctx->prof) {   // exact slot counts per round (the U[] are upper bounds): read the scan totals back, stats mode only
+    for (uint32_t r = 1; r <= R; r++) CK(cudaMemcpyAsync(ctx->h_pinned + 768 + r, off[r] + nbg, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    uint64_t prev = m0, exact = 0;
+    for (uint32_t r = 1; r <= R; r++) { uint64_t cur = ctx->h_pinned[768 + r]; exact += prev - cur; if (r == 1) ctx->adds_r0 += prev - cur; prev = cur; }
+    *adds_out -= 0; ctx->adds_exact += exact;
   }
   k_accum_finish<C, false><<<(nbg + 127) / 128, 128, 0, s>>>(nullptr, nullptr, pin, off[R], nbg, buckets_g); CKL();
   MARK(T_FINISH);
@@ -270,6 +286,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   int mode = ctx->opt_accumulate;
   if (mode == 0) mode = 2;
   uint32_t rounds = 0; uint64_t adds = 0;
+  ctx->adds_r0 = 0; ctx->adds_exact = 0;
   if (mode == 2) {
     // groups of whole slots: at least `lanes` of them (overlap), more if the tree scratch would not fit in device memory
     const uint64_t mtot = ctx->h_pinned[512 + pl.W];
@@ -339,7 +356,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   }
   if (st) {
     CK(cudaEventRecord(ctx->ev[5], s));
-    st->n = n; st->window_bits = pl.c; st->windows = pl.Wd; st->reserved = pl.W; st->buckets_per_window = pl.B; st->tree_rounds = rounds; st->affine_adds = adds;
+    st->n = n; st->window_bits = pl.c; st->windows = pl.Wd; st->reserved = pl.W; st->buckets_per_window = pl.B; st->tree_rounds = rounds; st->affine_adds = ctx->adds_exact ? ctx->adds_exact : adds; st->affine_adds_round0 = ctx->adds_r0;
   }
   return B200MSM_OK;
 }
@@ -420,7 +437,7 @@ int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_residen
     float acc[T_NTAGS + 1] = {0};
     for (size_t i = 1; i < ctx->pused; i++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->pev[i - 1], ctx->pev[i]); acc[ctx->ptag[i]] += ms; }
     st->ms_k_sort = acc[T_SORT]; st->ms_k_plan = acc[T_PLAN]; st->ms_k_tree_fwd = acc[T_TREE_FWD]; st->ms_k_inv_tree = acc[T_INV_TREE];
-    st->ms_k_tree_bwd = acc[T_TREE_BWD]; st->ms_k_finish = acc[T_FINISH]; st->ms_k_fold = acc[T_FOLD]; st->ms_k_wsum = acc[T_WSUM]; st->ms_k_horner = acc[T_HORNER];
+    st->ms_k_tree_bwd = acc[T_TREE_BWD] + acc[T_TREE_BWD0]; st->ms_k_tree_bwd_round0 = acc[T_TREE_BWD0]; st->ms_k_finish = acc[T_FINISH]; st->ms_k_fold = acc[T_FOLD]; st->ms_k_wsum = acc[T_WSUM]; st->ms_k_horner = acc[T_HORNER];
     st->launches = ctx->launches - launches0;
     ctx->prof = false;
   }
@@ -474,7 +491,7 @@ void b200msm_destroy(b200msm_ctx* ctx) {
   for (DevBuf* b : {&ctx->bases, &ctx->scalars, &ctx->canon, &ctx->counts, &ctx->offsets, &ctx->cursors, &ctx->tiles, &ctx->sorted, &ctx->buckets,
                     &ctx->wsum, &ctx->out, &ctx->misc, &ctx->acc_a, &ctx->acc_b, &ctx->acc_c, &ctx->acc_d, &ctx->acc_e}) b->release();
   for (auto& ln : ctx->lane) {
-    for (DevBuf* b : {&ln.offs, &ln.tiles, &ln.bid, &ln.pa, &ln.pb, &ln.prefix, &ln.prod, &ln.lvlprefix}) b->release();
+    for (DevBuf* b : {&ln.offs, &ln.tiles, &ln.bid, &ln.pa, &ln.pb, &ln.prefix, &ln.prod, &ln.lvlprefix, &ln.others}) b->release();
     if (ln.done) cudaEventDestroy(ln.done);
     if (ln.stream) cudaStreamDestroy(ln.stream);
   }
@@ -506,6 +523,7 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "window_bits")) { if (v < 0 || v > 24) return B200MSM_E_ARG; ctx->opt_window_bits = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "accumulate")) { if (v < 0 || v > 2) return B200MSM_E_ARG; ctx->opt_accumulate = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "tree_rounds")) { ctx->opt_tree_rounds = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "persist")) { if (v < 0) return B200MSM_E_ARG; ctx->opt_persist = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "ba_k")) { if (v < 1 || v > 64) return B200MSM_E_ARG; ctx->opt_ba_k = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "pt_k")) { if (v < 2 || v > 64) return B200MSM_E_ARG; ctx->opt_pt_k = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "probe29")) { ctx->probe29 = v != 0; return B200MSM_OK; }

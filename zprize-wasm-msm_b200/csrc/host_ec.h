@@ -40,19 +40,26 @@ template <int L> static inline void sub(const Field<L>& f, Fe<L>& r, const Fe<L>
   for (int i = 0; i < L; i++) { u128 d = (u128)a.l[i] - b.l[i] - br; r.l[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; }
   if (br) { uint64_t c = 0; for (int i = 0; i < L; i++) { u128 s = (u128)r.l[i] + f.q[i] + c; r.l[i] = (uint64_t)s; c = (uint64_t)(s >> 64); } }
 }
-template <int L> static inline void mul(const Field<L>& f, Fe<L>& r, const Fe<L>& a, const Fe<L>& b) {
-  uint64_t t[L + 2];
-  for (int i = 0; i < L + 2; i++) t[i] = 0;
+// CIOS Montgomery product, "no-carry" form (valid because the top bit of q's top word is clear for both fields, so the
+// running value never needs an extra word): per inner step two 64x64->128 products and two additions.
+template <int L> static inline __attribute__((always_inline)) void mul(const Field<L>& f, Fe<L>& r, const Fe<L>& a, const Fe<L>& b) {
+  uint64_t t[L];
+  for (int j = 0; j < L; j++) t[j] = 0;
   for (int i = 0; i < L; i++) {
-    u128 c = 0;
-    for (int j = 0; j < L; j++) { c += (u128)a.l[j] * b.l[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
-    c += t[L]; t[L] = (uint64_t)c; t[L + 1] = (uint64_t)(c >> 64);
-    uint64_t m = t[0] * f.np;
-    c = ((u128)m * f.q[0] + t[0]) >> 64;
-    for (int j = 1; j < L; j++) { c += (u128)m * f.q[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
-    c += t[L]; t[L - 1] = (uint64_t)c; t[L] = t[L + 1] + (uint64_t)(c >> 64);
+    const uint64_t bi = b.l[i];
+    u128 A = (u128)a.l[0] * bi + t[0];
+    const uint64_t m = (uint64_t)A * f.np;
+    u128 Cc = (u128)m * f.q[0] + (uint64_t)A;
+    uint64_t ca = (uint64_t)(A >> 64), cc = (uint64_t)(Cc >> 64);
+    for (int j = 1; j < L; j++) {
+      A = (u128)a.l[j] * bi + t[j] + ca; ca = (uint64_t)(A >> 64);
+      Cc = (u128)m * f.q[j] + (uint64_t)A + cc; cc = (uint64_t)(Cc >> 64);
+      t[j - 1] = (uint64_t)Cc;
+    }
+    t[L - 1] = ca + cc;
   }
-  if (t[L] || ge_q<L>(f, t)) { uint64_t br = 0; for (int i = 0; i < L; i++) { u128 d = (u128)t[i] - f.q[i] - br; t[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; } }
+  if (ge_q<L>(f, t)) { uint64_t br = 0;
+    for (int i = 0; i < L; i++) { u128 d = (u128)t[i] - f.q[i] - br; t[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; } }
   for (int i = 0; i < L; i++) r.l[i] = t[i];
 }
 template <int L> static inline void sqr(const Field<L>& f, Fe<L>& r, const Fe<L>& a) { mul<L>(f, r, a, a); }
@@ -95,28 +102,36 @@ template <int L> static inline void padd(const Field<L>& f, XYZZ<L>& acc, const 
 }
 
 // folded: W slots of (logB + 1) XYZZ points as written by k_gather_folded.  out_jac: 3*L words, Jacobian Montgomery.
+// result = sum_w 2^(off_w) * ( T_w[0] + sum_j 2^j T_w[2^j] ), off_w = bit offset of window w.  Every term is a point times a
+// power of two, so ONE Horner pass over the bit positions does both the per-window sums and the window combination:
+// acc = 2*acc + (terms with exponent e), e from the top down -- about nbits doublings and W*(logB+1) additions.
 template <int L>
 static void combine_windows(const Field<L>& f, const XYZZ<L>* folded, uint32_t W, uint32_t Wd, uint32_t c0, uint32_t rem, uint32_t logB, uint64_t* out_jac) {
   const uint32_t per = logB + 1;
-  XYZZ<L> acc; set_inf<L>(f, acc);
-  for (int w = (int)Wd - 1; w >= 0; w--) {
-    // window value R_w = T[0] + sum_j 2^j T[2^j]   (+ the extra slot's  (2^logB + 1) T'[0] + sum_j 2^j T'[2^j]  for the last window)
-    XYZZ<L> rw; set_inf<L>(f, rw);
-    const bool extra = (w + 1 == (int)Wd) && (W > Wd);
+  auto off = [&](uint32_t w) { return w * c0 + (w < rem ? w : rem); };
+  const uint32_t maxe = off(Wd - 1) + logB + 1;
+  // bucket the terms by exponent (at most a handful per exponent): head/next lists over a flat term array
+  const uint32_t nterms_max = W * per + 2;
+  const XYZZ<L>** term = (const XYZZ<L>**)__builtin_alloca(sizeof(void*) * nterms_max);
+  int32_t* next = (int32_t*)__builtin_alloca(sizeof(int32_t) * nterms_max);
+  int32_t* head = (int32_t*)__builtin_alloca(sizeof(int32_t) * (maxe + 1));
+  for (uint32_t e = 0; e <= maxe; e++) head[e] = -1;
+  uint32_t nt = 0;
+  auto put = [&](uint32_t e, const XYZZ<L>* p) { if (is_inf<L>(*p)) return; term[nt] = p; next[nt] = head[e]; head[e] = (int32_t)nt; nt++; };
+  for (uint32_t w = 0; w < Wd; w++) {
     const XYZZ<L>* T = folded + (size_t)w * per;
-    const XYZZ<L>* E = folded + (size_t)Wd * per;
-    if (extra) rw = E[0];
-    for (int j = (int)logB - 1; j >= 0; j--) {
-      XYZZ<L> d; pdbl<L>(f, d, rw); rw = d;
-      padd<L>(f, rw, T[1 + j]);
-      if (extra) padd<L>(f, rw, E[1 + j]);
-    }
-    padd<L>(f, rw, T[0]);
-    if (extra) padd<L>(f, rw, E[0]);
-    // Horner across windows: acc = 2^(width of window w) * acc + R_w
-    const uint32_t cw = c0 + ((uint32_t)w < rem ? 1u : 0u);
-    if (!is_inf<L>(acc)) for (uint32_t k = 0; k < cw; k++) { XYZZ<L> d; pdbl<L>(f, d, acc); acc = d; }
-    padd<L>(f, acc, rw);
+    put(off(w), &T[0]);
+    for (uint32_t j = 0; j < logB; j++) put(off(w) + j, &T[1 + j]);
+  }
+  if (W > Wd) {   // extra slot: buckets B+1..2B of the last window: (2^logB + 1) E[0] + sum_j 2^j E[2^j]
+    const XYZZ<L>* E = folded + (size_t)Wd * per; const uint32_t o = off(Wd - 1);
+    put(o, &E[0]); put(o + logB, &E[0]);
+    for (uint32_t j = 0; j < logB; j++) put(o + j, &E[1 + j]);
+  }
+  XYZZ<L> acc; set_inf<L>(f, acc);
+  for (int e = (int)maxe; e >= 0; e--) {
+    if (!is_inf<L>(acc)) { XYZZ<L> d; pdbl<L>(f, d, acc); acc = d; }
+    for (int32_t t = head[e]; t >= 0; t = next[t]) padd<L>(f, acc, *term[t]);
   }
   // XYZZ -> Jacobian without inversion: Z = ZZ*ZZZ, X = x*ZZ*ZZZ^2, Y = y*ZZ^3*ZZZ^2; infinity -> (0, R mod q, 0)
   Fe<L> X, Y, Z;
