@@ -61,7 +61,9 @@ struct b200msm_ctx {
   TreeLane lane[MAX_LANES];                                                   // batch-affine tree lanes
   int opt_lanes = 4, opt_ba_k = 8, opt_pt_k = 8, opt_persist = 444;
   bool probe29 = false;
-  cudaEvent_t ev_plan = nullptr, ev_sorted = nullptr;
+  cudaEvent_t ev_plan = nullptr, ev_sorted = nullptr, ev_bases = nullptr, ev_done = nullptr;
+  cudaStream_t copy_stream = nullptr; bool bases_pending = false;
+  std::vector<cudaEvent_t> gev;                                               // one event per window group (folded points on the host)
   uint32_t* h_pinned = nullptr;
   void* h_folded = nullptr; size_t h_folded_cap = 0;                         // pinned staging of the folded bucket entries
   int opt_combine = 0;                                                        // 0 = host serial tail (default), 1 = device k_window_sums + k_horner
@@ -282,6 +284,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   CK(cudaEventSynchronize(ctx->ev_plan));
   MARK(T_SORT);
   // ---- accumulate: bucket sums in XYZZ, then fold every slot in place
+  if (ctx->bases_pending) CK(cudaStreamWaitEvent(s, ctx->ev_bases, 0));
   CK(ctx->buckets.ensure((size_t)nb * 16 * C::N));
   int mode = ctx->opt_accumulate;
   if (mode == 0) mode = 2;
@@ -295,63 +298,93 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
     const double per_pair = 8.0 * C::N * 0.75 + 4.0 * C::N * 0.75 + 6;      // points (pa+pb) + prefix/products + bid, per input pair
     const uint64_t budget_pairs = (uint64_t)std::max(1.0, 0.45 * (double)ctx->total_mem / per_pair / lanes);
     uint32_t ngroups = std::max<uint32_t>(lanes, (uint32_t)((mtot + budget_pairs - 1) / budget_pairs));
-    ngroups = std::min(ngroups, pl.W);
+    const uint32_t wlim = pl.W > pl.Wd ? pl.Wd : pl.W;          // the extra slot stays in the group of the last window
+    ngroups = std::min(ngroups, wlim);
     // slot boundaries with (nearly) equal pair counts
     std::vector<uint32_t> cut(ngroups + 1, 0); cut[ngroups] = pl.W;
     { uint32_t w = 0; for (uint32_t g = 1; g < ngroups; g++) { uint64_t target = mtot * g / ngroups;
         while (w < pl.W && ctx->h_pinned[512 + w] < target) w++;
-        cut[g] = std::min(std::max(w, cut[g - 1] + 1), pl.W - (ngroups - g)); } }
-    for (uint32_t l = 0; l < lanes; l++) { rc = lane_init(ctx, ctx->lane[l]); if (rc) return rc; if (lanes > 1) CK(cudaStreamWaitEvent(ctx->lane[l].stream, ctx->ev_sorted, 0)); }
-    for (uint32_t g = 0; g < ngroups; g++) {
-      TreeLane& ln = ctx->lane[g % lanes];
+        cut[g] = std::min(std::max(w, cut[g - 1] + 1), wlim - (ngroups - g)); } }
+    for (uint32_t l = 0; l < lanes; l++) { rc = lane_init(ctx, ctx->lane[l]); if (rc) return rc; if (lanes > 1) { CK(cudaStreamWaitEvent(ctx->lane[l].stream, ctx->ev_sorted, 0)); if (ctx->bases_pending) CK(cudaStreamWaitEvent(ctx->lane[l].stream, ctx->ev_bases, 0)); } }
+    // host staging for the folded entries of every slot, and one event per group
+    const uint32_t per = pl.logB + 1, npts = pl.W * per;
+    const size_t fbytes = (size_t)npts * 16 * C::N;
+    const bool host_tail = ctx->opt_combine == 0;
+    if (host_tail) {
+      CK(ctx->wsum.ensure(fbytes));
+      if (ctx->h_folded_cap < fbytes + 4096) { if (ctx->h_folded) cudaFreeHost(ctx->h_folded); ctx->h_folded = nullptr; ctx->h_folded_cap = 0;
+        CK(cudaMallocHost(&ctx->h_folded, fbytes + 4096)); ctx->h_folded_cap = fbytes + 4096; }
+      while (ctx->gev.size() < ngroups) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->gev.push_back(e); }
+    }
+    // groups are issued from the TOP windows down: lane 0 (highest priority) owns the top group, so its folded points
+    // reach the host first and the serial window combination runs while the GPU is still busy with the lower windows
+    for (uint32_t gi = 0; gi < ngroups; gi++) {
+      const uint32_t g = ngroups - 1 - gi;
+      TreeLane& ln = ctx->lane[gi % lanes];
       uint32_t w0 = cut[g], w1 = cut[g + 1];
       uint32_t mc = 0; for (uint32_t w = w0; w < w1; w++) mc = std::max(mc, ctx->h_pinned[w]);
       uint64_t m0 = ctx->h_pinned[512 + w1] - ctx->h_pinned[512 + w0];
       uint32_t b0 = w0 * pl.B, nbg = (w1 - w0) * pl.B;
       cudaStream_t keep = ln.stream; if (lanes == 1) ln.stream = s;
+      cudaStream_t ls = ln.stream;
       char* bg = ctx->buckets.as<char>() + (size_t)b0 * 16 * C::N;
       rc = accumulate_batch_affine<C>(ctx, ln, d_bases, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc, bg, &rounds, &adds);
-      if (!rc && lanes > 1) rc = fold_slots<C>(ctx, ln.stream, bg, w1 - w0, pl.B);
+      if (!rc && (lanes > 1 || host_tail)) {
+        if (st && gi + 1 == ngroups) CK(cudaEventRecord(ctx->ev[3], s));          // stats mode is single-lane: accumulate ends here
+        rc = fold_slots<C>(ctx, ls, bg, w1 - w0, pl.B); }
+      if (!rc && host_tail) {
+        const uint32_t np = (w1 - w0) * per; const size_t o = (size_t)w0 * per * 16 * C::N;
+        k_gather_folded<C><<<(np + 127) / 128, 128, 0, ls>>>(bg, w1 - w0, pl.B, pl.logB, ctx->wsum.as<char>() + o); CKL();
+        CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->h_folded) + o, ctx->wsum.as<char>() + o, (size_t)np * 16 * C::N, cudaMemcpyDeviceToHost, ls));
+        CK(cudaEventRecord(ctx->gev[gi], ls));
+      }
       ln.stream = keep;
       if (rc) return rc;
     }
-    if (lanes > 1) for (uint32_t l = 0; l < lanes; l++) { CK(cudaEventRecord(ctx->lane[l].done, ctx->lane[l].stream)); CK(cudaStreamWaitEvent(s, ctx->lane[l].done, 0)); }
-    if (st) CK(cudaEventRecord(ctx->ev[3], s));
-    if (lanes == 1) { rc = fold_slots<C>(ctx, s, ctx->buckets.p, pl.W, pl.B); if (rc) return rc; }
+    if (st) { if (!host_tail) CK(cudaEventRecord(ctx->ev[3], s)); else { MARK(T_FOLD); } CK(cudaEventRecord(ctx->ev[4], s)); }
+    if (host_tail) {
+      constexpr int L = C::N / 2;
+      b200host::Field<L> f;
+      for (int i = 0; i < L; i++) { f.q[i] = (uint64_t)C::q(2 * i) | ((uint64_t)C::q(2 * i + 1) << 32); f.one[i] = (uint64_t)C::one(2 * i) | ((uint64_t)C::one(2 * i + 1) << 32); }
+      { uint64_t x = 1; for (int k = 0; k < 6; k++) x *= 2 - f.q[0] * x; f.np = 0 - x; }      // -q^-1 mod 2^64 (Newton)
+      b200host::Combiner<L> cb; cb.begin(f, pl.W, pl.Wd, pl.c0, pl.rem, pl.logB);
+      float host_ms = 0;
+      for (uint32_t gi = 0; gi < ngroups; gi++) {
+        const uint32_t g = ngroups - 1 - gi;
+        CK(cudaEventSynchronize(ctx->gev[gi]));
+        auto t0 = std::chrono::steady_clock::now();
+        cb.feed(reinterpret_cast<const b200host::XYZZ<L>*>(ctx->h_folded), cut[g], cut[g + 1]);
+        host_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      }
+      auto t0 = std::chrono::steady_clock::now();
+      uint64_t* res = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ctx->h_folded) + fbytes);   // 3*n8 bytes in the pinned tail
+      cb.finish(res);
+      ctx->host_combine_ms = host_ms + std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (lanes > 1) for (uint32_t l = 0; l < lanes; l++) { CK(cudaEventRecord(ctx->lane[l].done, ctx->lane[l].stream)); CK(cudaStreamWaitEvent(s, ctx->lane[l].done, 0)); }
+      CK(cudaMemcpyAsync(d_out, res, 12 * C::N, cudaMemcpyHostToDevice, s));
+      MARK(T_HORNER);
+    } else {
+      if (lanes > 1) for (uint32_t l = 0; l < lanes; l++) { CK(cudaEventRecord(ctx->lane[l].done, ctx->lane[l].stream)); CK(cudaStreamWaitEvent(s, ctx->lane[l].done, 0)); }
+      if (lanes == 1) { rc = fold_slots<C>(ctx, s, ctx->buckets.p, pl.W, pl.B); if (rc) return rc; }
+      MARK(T_FOLD);
+      if (st) CK(cudaEventRecord(ctx->ev[4], s));
+      CK(ctx->wsum.ensure((size_t)pl.W * 16 * C::N));
+      k_window_sums<C><<<(pl.W + 31) / 32, 32, 0, s>>>(ctx->buckets.p, pl.W, pl.Wd, pl.B, pl.logB, ctx->wsum.p); CKL();
+      MARK(T_WSUM);
+      k_horner<C><<<1, 32, 0, s>>>(ctx->wsum.p, pl.W, pl.Wd, pl.c0, pl.rem, d_out); CKL();
+      MARK(T_HORNER);
+    }
   } else {
+    // serial accumulate (one thread per bucket): small problems / cross-check; device-side combination
     k_accum_serial<C><<<(nb + 127) / 128, 128, 0, s>>>(d_bases, ctx->sorted.as<uint32_t>(), ctx->offsets.as<uint32_t>(), nb, ctx->buckets.p); CKL();
     if (st) CK(cudaEventRecord(ctx->ev[3], s));
     rc = fold_slots<C>(ctx, s, ctx->buckets.p, pl.W, pl.B); if (rc) return rc;
-  }
-  MARK(T_FOLD);
-  if (ctx->opt_combine == 1) {
+    MARK(T_FOLD);
+    if (st) CK(cudaEventRecord(ctx->ev[4], s));
     CK(ctx->wsum.ensure((size_t)pl.W * 16 * C::N));
     k_window_sums<C><<<(pl.W + 31) / 32, 32, 0, s>>>(ctx->buckets.p, pl.W, pl.Wd, pl.B, pl.logB, ctx->wsum.p); CKL();
     MARK(T_WSUM);
-    if (st) CK(cudaEventRecord(ctx->ev[4], s));
     k_horner<C><<<1, 32, 0, s>>>(ctx->wsum.p, pl.W, pl.Wd, pl.c0, pl.rem, d_out); CKL();
-    MARK(T_HORNER);
-  } else {
-    // serial tail on the host: fetch the (logB + 1) live entries of every folded slot, combine, push the point back
-    const uint32_t per = pl.logB + 1, npts = pl.W * per;
-    const size_t bytes = (size_t)npts * 16 * C::N;
-    CK(ctx->wsum.ensure(bytes));
-    if (ctx->h_folded_cap < bytes) { if (ctx->h_folded) cudaFreeHost(ctx->h_folded); ctx->h_folded = nullptr; ctx->h_folded_cap = 0;
-      CK(cudaMallocHost(&ctx->h_folded, bytes + 4096)); ctx->h_folded_cap = bytes + 4096; }
-    k_gather_folded<C><<<(npts + 127) / 128, 128, 0, s>>>(ctx->buckets.p, pl.W, pl.B, pl.logB, ctx->wsum.p); CKL();
-    CK(cudaMemcpyAsync(ctx->h_folded, ctx->wsum.p, bytes, cudaMemcpyDeviceToHost, s));
-    MARK(T_WSUM);
-    if (st) CK(cudaEventRecord(ctx->ev[4], s));
-    CK(cudaStreamSynchronize(s));
-    auto t0 = std::chrono::steady_clock::now();
-    constexpr int L = C::N / 2;
-    b200host::Field<L> f;
-    for (int i = 0; i < L; i++) { f.q[i] = (uint64_t)C::q(2 * i) | ((uint64_t)C::q(2 * i + 1) << 32); f.one[i] = (uint64_t)C::one(2 * i) | ((uint64_t)C::one(2 * i + 1) << 32); }
-    { uint64_t x = 1; for (int k = 0; k < 6; k++) x *= 2 - f.q[0] * x; f.np = 0 - x; }      // -q^-1 mod 2^64 (Newton)
-    uint64_t* res = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ctx->h_folded) + bytes);   // 3*n8 bytes in the pinned tail
-    b200host::combine_windows<L>(f, reinterpret_cast<const b200host::XYZZ<L>*>(ctx->h_folded), pl.W, pl.Wd, pl.c0, pl.rem, pl.logB, res);
-    ctx->host_combine_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    CK(cudaMemcpyAsync(d_out, res, 12 * C::N, cudaMemcpyHostToDevice, s));
     MARK(T_HORNER);
   }
   if (st) {
@@ -404,9 +437,24 @@ int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_residen
     if (rc) return rc;
     return deliver(ctx, ctx->out.p, out, 3 * n8);
   }
-  const void* d_bases = bases;
-  if (!bases_resident) { rc = stage(ctx, bases, (size_t)n * 2 * n8, ctx->bases, &d_bases); if (rc) return rc; }
+  // scalars first (the digit / sort phase needs only them); host-resident bases follow on a separate copy stream and are
+  // awaited only where the tree's first round starts gathering points, so their transfer overlaps the sort
   const void* d_sraw; rc = stage(ctx, scalars, (size_t)n * scalar_size, ctx->scalars, &d_sraw); if (rc) return rc;
+  const void* d_bases = bases;
+  ctx->bases_pending = false;
+  if (!bases_resident) {
+    const size_t bytes = (size_t)n * 2 * n8;
+    if (is_device_ptr(bases) && (reinterpret_cast<uintptr_t>(bases) & 15) == 0) d_bases = bases;
+    else {
+      CK(ctx->bases.ensure(bytes + 16));
+      if (!ctx->copy_stream) { CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ctx->ev_bases, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming)); }
+      CK(cudaEventRecord(ctx->ev_done, ctx->stream));                       // everything issued so far (previous calls may still read ctx->bases)
+      CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0));
+      CK(cudaMemcpyAsync(ctx->bases.p, bases, bytes, cudaMemcpyDefault, ctx->copy_stream));
+      CK(cudaEventRecord(ctx->ev_bases, ctx->copy_stream));
+      ctx->bases_pending = true; d_bases = ctx->bases.p;
+    }
+  }
   const uint32_t* d_scal;
   if (scalar_size == 32 && bit0 == 0 && nbits == 256) d_scal = reinterpret_cast<const uint32_t*>(d_sraw);
   else {
@@ -497,6 +545,10 @@ void b200msm_destroy(b200msm_ctx* ctx) {
   }
   if (ctx->ev_plan) cudaEventDestroy(ctx->ev_plan);
   if (ctx->ev_sorted) cudaEventDestroy(ctx->ev_sorted);
+  if (ctx->ev_bases) cudaEventDestroy(ctx->ev_bases);
+  if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (auto& e : ctx->gev) cudaEventDestroy(e);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->h_folded) cudaFreeHost(ctx->h_folded);
   for (auto& kv : ctx->residents) cudaFree(kv.second.d);

@@ -101,47 +101,66 @@ template <int L> static inline void padd(const Field<L>& f, XYZZ<L>& acc, const 
   mul<L>(f, t, acc.zzz, q.zzz); mul<L>(f, acc.zzz, t, PPP);
 }
 
-// folded: W slots of (logB + 1) XYZZ points as written by k_gather_folded.  out_jac: 3*L words, Jacobian Montgomery.
+// Incremental window combination.  folded: slots of (logB + 1) XYZZ points as written by k_gather_folded.
 // result = sum_w 2^(off_w) * ( T_w[0] + sum_j 2^j T_w[2^j] ), off_w = bit offset of window w.  Every term is a point times a
 // power of two, so ONE Horner pass over the bit positions does both the per-window sums and the window combination:
-// acc = 2*acc + (terms with exponent e), e from the top down -- about nbits doublings and W*(logB+1) additions.
+// acc = 2*acc + (terms with exponent e), e from the top down -- about nbits doublings and W*(logB+1) additions in total.
+// Groups of slots are fed from the TOP window down (their exponent ranges do not interleave: a window's terms span
+// off_w .. off_w + logB - 1 < off_(w+1)), so the host can consume a group while the GPU still works on the lower ones.
+template <int L> struct Combiner {
+  Field<L> f; uint32_t W, Wd, c0, rem, logB, per; int cur;      // cur = lowest exponent already folded into acc (acc is scaled by 2^cur)
+  XYZZ<L> acc;
+  uint32_t off(uint32_t w) const { return w * c0 + (w < rem ? w : rem); }
+  void begin(const Field<L>& f_, uint32_t W_, uint32_t Wd_, uint32_t c0_, uint32_t rem_, uint32_t logB_) {
+    f = f_; W = W_; Wd = Wd_; c0 = c0_; rem = rem_; logB = logB_; per = logB + 1;
+    cur = (int)(off(Wd - 1) + logB + 1); set_inf<L>(f, acc);
+  }
+  // slots [w0, w1) of the bucket array (w1 may be W, i.e. include the extra slot); `folded` points at slot 0
+  void feed(const XYZZ<L>* folded, uint32_t w0, uint32_t w1) {
+    const uint32_t lastw = (w1 > Wd ? Wd : w1);                 // digit windows in this group: [w0, lastw)
+    if (lastw <= w0) return;                                     // (a group holding only the extra slot cannot occur: it is cut with the last window)
+    const int lo = (int)off(w0), hi = cur - 1;
+    const uint32_t span = (uint32_t)(hi - lo + 1), nterms_max = (w1 - w0) * per + 2;
+    const XYZZ<L>** term = (const XYZZ<L>**)__builtin_alloca(sizeof(void*) * nterms_max);
+    int32_t* next = (int32_t*)__builtin_alloca(sizeof(int32_t) * nterms_max);
+    int32_t* head = (int32_t*)__builtin_alloca(sizeof(int32_t) * span);
+    for (uint32_t e = 0; e < span; e++) head[e] = -1;
+    uint32_t nt = 0;
+    auto put = [&](uint32_t e, const XYZZ<L>* p) { if (is_inf<L>(*p)) return; term[nt] = p; next[nt] = head[e - lo]; head[e - lo] = (int32_t)nt; nt++; };
+    for (uint32_t w = w0; w < lastw; w++) {
+      const XYZZ<L>* T = folded + (size_t)w * per;
+      put(off(w), &T[0]);
+      for (uint32_t j = 0; j < logB; j++) put(off(w) + j, &T[1 + j]);
+    }
+    if (w1 > Wd) {   // extra slot: buckets B+1..2B of the last window: (2^logB + 1) E[0] + sum_j 2^j E[2^j]
+      const XYZZ<L>* E = folded + (size_t)Wd * per; const uint32_t o = off(Wd - 1);
+      put(o, &E[0]); put(o + logB, &E[0]);
+      for (uint32_t j = 0; j < logB; j++) put(o + j, &E[1 + j]);
+    }
+    for (int e = hi; e >= lo; e--) {
+      if (!is_inf<L>(acc)) { XYZZ<L> d; pdbl<L>(f, d, acc); acc = d; }
+      for (int32_t t = head[e - lo]; t >= 0; t = next[t]) padd<L>(f, acc, *term[t]);
+    }
+    cur = lo;
+  }
+  // out_jac: 3*L words, Jacobian Montgomery
+  void finish(uint64_t* out_jac) {
+    for (; cur > 0; cur--) if (!is_inf<L>(acc)) { XYZZ<L> d; pdbl<L>(f, d, acc); acc = d; }
+    // XYZZ -> Jacobian without inversion: Z = ZZ*ZZZ, X = x*ZZ*ZZZ^2, Y = y*ZZ^3*ZZZ^2; infinity -> (0, R mod q, 0)
+    Fe<L> X, Y, Z;
+    if (is_inf<L>(acc)) { memset(&X, 0, sizeof X); memset(&Z, 0, sizeof Z); for (int i = 0; i < L; i++) Y.l[i] = f.one[i]; }
+    else {
+      Fe<L> t, u;
+      mul<L>(f, Z, acc.zz, acc.zzz); mul<L>(f, t, Z, acc.zzz); mul<L>(f, X, acc.x, t);
+      sqr<L>(f, u, acc.zz); mul<L>(f, t, t, u); mul<L>(f, Y, acc.y, t);
+    }
+    memcpy(out_jac, X.l, 8 * L); memcpy(out_jac + L, Y.l, 8 * L); memcpy(out_jac + 2 * L, Z.l, 8 * L);
+  }
+};
+
 template <int L>
 static void combine_windows(const Field<L>& f, const XYZZ<L>* folded, uint32_t W, uint32_t Wd, uint32_t c0, uint32_t rem, uint32_t logB, uint64_t* out_jac) {
-  const uint32_t per = logB + 1;
-  auto off = [&](uint32_t w) { return w * c0 + (w < rem ? w : rem); };
-  const uint32_t maxe = off(Wd - 1) + logB + 1;
-  // bucket the terms by exponent (at most a handful per exponent): head/next lists over a flat term array
-  const uint32_t nterms_max = W * per + 2;
-  const XYZZ<L>** term = (const XYZZ<L>**)__builtin_alloca(sizeof(void*) * nterms_max);
-  int32_t* next = (int32_t*)__builtin_alloca(sizeof(int32_t) * nterms_max);
-  int32_t* head = (int32_t*)__builtin_alloca(sizeof(int32_t) * (maxe + 1));
-  for (uint32_t e = 0; e <= maxe; e++) head[e] = -1;
-  uint32_t nt = 0;
-  auto put = [&](uint32_t e, const XYZZ<L>* p) { if (is_inf<L>(*p)) return; term[nt] = p; next[nt] = head[e]; head[e] = (int32_t)nt; nt++; };
-  for (uint32_t w = 0; w < Wd; w++) {
-    const XYZZ<L>* T = folded + (size_t)w * per;
-    put(off(w), &T[0]);
-    for (uint32_t j = 0; j < logB; j++) put(off(w) + j, &T[1 + j]);
-  }
-  if (W > Wd) {   // extra slot: buckets B+1..2B of the last window: (2^logB + 1) E[0] + sum_j 2^j E[2^j]
-    const XYZZ<L>* E = folded + (size_t)Wd * per; const uint32_t o = off(Wd - 1);
-    put(o, &E[0]); put(o + logB, &E[0]);
-    for (uint32_t j = 0; j < logB; j++) put(o + j, &E[1 + j]);
-  }
-  XYZZ<L> acc; set_inf<L>(f, acc);
-  for (int e = (int)maxe; e >= 0; e--) {
-    if (!is_inf<L>(acc)) { XYZZ<L> d; pdbl<L>(f, d, acc); acc = d; }
-    for (int32_t t = head[e]; t >= 0; t = next[t]) padd<L>(f, acc, *term[t]);
-  }
-  // XYZZ -> Jacobian without inversion: Z = ZZ*ZZZ, X = x*ZZ*ZZZ^2, Y = y*ZZ^3*ZZZ^2; infinity -> (0, R mod q, 0)
-  Fe<L> X, Y, Z;
-  if (is_inf<L>(acc)) { memset(&X, 0, sizeof X); memset(&Z, 0, sizeof Z); for (int i = 0; i < L; i++) Y.l[i] = f.one[i]; }
-  else {
-    Fe<L> t, u;
-    mul<L>(f, Z, acc.zz, acc.zzz); mul<L>(f, t, Z, acc.zzz); mul<L>(f, X, acc.x, t);
-    sqr<L>(f, u, acc.zz); mul<L>(f, t, t, u); mul<L>(f, Y, acc.y, t);
-  }
-  memcpy(out_jac, X.l, 8 * L); memcpy(out_jac + L, Y.l, 8 * L); memcpy(out_jac + 2 * L, Z.l, 8 * L);
+  Combiner<L> cb; cb.begin(f, W, Wd, c0, rem, logB); cb.feed(folded, 0, W); cb.finish(out_jac);
 }
 
 }  // namespace b200host
