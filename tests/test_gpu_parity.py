@@ -110,6 +110,23 @@ def test_device_window_combination_matches_host_tail(eng, cname, wb):
 
 
 @pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+@pytest.mark.parametrize("lanes,group_pairs", [(1, 0), (2, 0), (4, 0), (3, 9000), (1, 30000), (4, 2000)])
+def test_window_groups_and_lanes(eng, cname, lanes, group_pairs):
+    """Window slots are processed in groups (memory budget) that alternate between stream lanes; any grouping gives the same point."""
+    cv = curve(cname); n = 6000
+    bases = make_bases(cv, n, 51); sc = make_scalars(n, 52, "u256")
+    exp = oracle_msm(cv, bases, sc, 32, n)
+    eng.set_option("lanes", lanes); eng.set_option("group_pairs", group_pairs)
+    try:
+        assert msm(eng, cv, bases, sc, 32, n) == exp
+        # skewed input: only the two lowest windows are populated, the top groups are empty
+        sc2 = b"".join((int.from_bytes(sc[i * 32:i * 32 + 3], "little")).to_bytes(32, "little") for i in range(n))
+        assert msm(eng, cv, bases, sc2, 32, n) == oracle_msm(cv, bases, sc2, 32, n)
+    finally:
+        eng.set_option("lanes", 4); eng.set_option("group_pairs", 0)
+
+
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
 def test_msm_edge_cases(eng, cname):
     cv = curve(cname); n8 = cv.n8
     zero = bytes(2 * n8)

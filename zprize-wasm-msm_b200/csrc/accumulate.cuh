@@ -77,14 +77,20 @@ __global__ void k_mscan_apply(uint32_t* __restrict__ offs, uint32_t n, const uin
   if (i == 0) out[n] = ts[ntiles];
 }
 
-// bid1[j] = bucket owning output slot j of round 0 (binary search in off1); one thread per slot
-__global__ void k_fill_bid(const uint32_t* __restrict__ off1, uint32_t nb, uint32_t* __restrict__ bid1) {
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t m = off1[nb];
-  if (j >= m) return;
-  uint32_t lo = 0, hi = nb;            // largest b with off1[b] <= j  (and non-empty: off1[b+1] > j)
-  while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (off1[mid] <= j) lo = mid; else hi = mid; }
-  bid1[j] = lo;
+// bid1[j] = bucket owning output slot j of round 0.  One warp per 32 buckets: each lane fetches the slot range of its
+// bucket, then the warp writes the 32 ranges one after the other with coalesced stores (a range is ~16 slots for
+// uniform scalars; a heavy bucket's range is simply more iterations of the whole warp -- no per-slot binary search).
+__global__ void __launch_bounds__(256) k_fill_bid(const uint32_t* __restrict__ off1, uint32_t nb, uint32_t* __restrict__ bid1) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t b = warp * 32 + lane;
+  uint32_t lo = 0, hi = 0;
+  if (b < nb) { lo = off1[b]; hi = off1[b + 1]; }
+#pragma unroll 1
+  for (int k = 0; k < 32; k++) {
+    const uint32_t l = __shfl_sync(0xffffffffu, lo, k), h = __shfl_sync(0xffffffffu, hi, k);
+    for (uint32_t j = l + lane; j < h; j += 32) bid1[j] = warp * 32 + k;
+  }
 }
 
 // ---- one tree round, level 0 --------------------------------------------------------------------------

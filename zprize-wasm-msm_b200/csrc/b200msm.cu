@@ -60,7 +60,7 @@ struct b200msm_ctx {
   DevBuf bases, scalars, canon, counts, offsets, cursors, tiles, sorted, buckets, wsum, out, misc, acc_a, acc_b, acc_c, acc_d, acc_e;
   TreeLane lane[MAX_LANES];                                                   // batch-affine tree lanes
   int opt_lanes = 4, opt_ba_k = 8, opt_pt_k = 8, opt_persist = 444;
-  bool probe29 = false;
+  bool probe29 = false; int64_t opt_group_pairs = 0;
   cudaEvent_t ev_plan = nullptr, ev_sorted = nullptr, ev_bases = nullptr, ev_done = nullptr;
   cudaStream_t copy_stream = nullptr; bool bases_pending = false;
   std::vector<cudaEvent_t> gev;                                               // one event per window group (folded points on the host)
@@ -72,7 +72,7 @@ struct b200msm_ctx {
   cudaEvent_t ev[8] = {};
   // fine-grained phase profiler (active only while a stats struct is being filled)
   std::vector<cudaEvent_t> pev; std::vector<int> ptag; size_t pused = 0; bool prof = false;
-  uint64_t launches = 0, adds_r0 = 0, adds_exact = 0;
+  uint64_t launches = 0, adds_r0 = 0, adds_exact = 0, cur_n = 0;
   size_t total_mem = 0;
 };
 
@@ -146,7 +146,16 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
   // number of tree rounds: until the largest segment is <= 3 points (the finish kernel sums the rest serially)
   uint32_t R = 0;
   if (ctx->opt_tree_rounds >= 0) R = (uint32_t)ctx->opt_tree_rounds;
-  else { uint32_t mc = maxcnt; while (mc > 3) { mc = (mc + 1) >> 1; R++; } }
+  else {
+    // full tree: until the largest segment is <= 3 points.  Every round ends in a latency-bound tail (product tree + one
+    // inversion, ~0.2 ms), so small problems stop earlier and let k_accum_finish sum up to 16 leftover points per bucket
+    // serially (measured optimum: 2 rounds up to 2^16 pairs-per-window-scale inputs, 3 up to 2^18, 4 up to 2^19).
+    uint32_t full = 0, need16 = 0, mc = maxcnt;
+    while (mc > 3) { if (mc > 16) need16++; mc = (mc + 1) >> 1; full++; }
+    const uint64_t npts = ctx->cur_n;
+    const uint32_t pref = npts <= (1u << 16) ? 2u : npts <= (1u << 18) ? 3u : npts <= (1u << 19) ? 4u : 99u;
+    R = std::min(full, std::max(pref, need16));
+  }
   if (m0 < 2) R = 0;
   if (R > 30) R = 30;
   *rounds_out = std::max(*rounds_out, R);
@@ -172,7 +181,7 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
   { size_t tot = 0; for (uint32_t r = 1; r <= R; r++) tot += U[r];
     CK(ln_.bid.ensure(tot * 4 + 16));
     size_t at = 0; for (uint32_t r = 1; r <= R; r++) { bid[r] = ln_.bid.as<uint32_t>() + at; at += U[r]; } }
-  k_fill_bid<<<(uint32_t)((U[1] + 255) / 256), 256, 0, s>>>(off[1], nbg, bid[1]); CKL();
+  k_fill_bid<<<(nbg + 255) / 256, 256, 0, s>>>(off[1], nbg, bid[1]); CKL();
   MARK(T_PLAN);
   const size_t fe = 4 * C::N, pt = 8 * C::N;
   const int BK = ctx->opt_ba_k, PK = ctx->opt_pt_k;
@@ -289,14 +298,14 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   int mode = ctx->opt_accumulate;
   if (mode == 0) mode = 2;
   uint32_t rounds = 0; uint64_t adds = 0;
-  ctx->adds_r0 = 0; ctx->adds_exact = 0;
+  ctx->adds_r0 = 0; ctx->adds_exact = 0; ctx->cur_n = n;
   if (mode == 2) {
     // groups of whole slots: at least `lanes` of them (overlap), more if the tree scratch would not fit in device memory
     const uint64_t mtot = ctx->h_pinned[512 + pl.W];
     uint32_t lanes = ctx->prof ? 1u : (uint32_t)std::max(1, std::min(ctx->opt_lanes, (int)MAX_LANES));
     if (mtot < (1u << 16)) lanes = 1;
     const double per_pair = 8.0 * C::N * 0.75 + 4.0 * C::N * 0.75 + 6;      // points (pa+pb) + prefix/products + bid, per input pair
-    const uint64_t budget_pairs = (uint64_t)std::max(1.0, 0.45 * (double)ctx->total_mem / per_pair / lanes);
+    const uint64_t budget_pairs = ctx->opt_group_pairs > 0 ? (uint64_t)ctx->opt_group_pairs : (uint64_t)std::max(1.0, 0.45 * (double)ctx->total_mem / per_pair / lanes);
     uint32_t ngroups = std::max<uint32_t>(lanes, (uint32_t)((mtot + budget_pairs - 1) / budget_pairs));
     const uint32_t wlim = pl.W > pl.Wd ? pl.Wd : pl.W;          // the extra slot stays in the group of the last window
     ngroups = std::min(ngroups, wlim);
@@ -575,6 +584,7 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "window_bits")) { if (v < 0 || v > 24) return B200MSM_E_ARG; ctx->opt_window_bits = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "accumulate")) { if (v < 0 || v > 2) return B200MSM_E_ARG; ctx->opt_accumulate = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "tree_rounds")) { ctx->opt_tree_rounds = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "group_pairs")) { if (v < 0) return B200MSM_E_ARG; ctx->opt_group_pairs = v; return B200MSM_OK; }
   if (!strcmp(key, "persist")) { if (v < 0) return B200MSM_E_ARG; ctx->opt_persist = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "ba_k")) { if (v < 1 || v > 64) return B200MSM_E_ARG; ctx->opt_ba_k = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "pt_k")) { if (v < 2 || v > 64) return B200MSM_E_ARG; ctx->opt_pt_k = (int)v; return B200MSM_OK; }
