@@ -6,7 +6,7 @@ and if no GPU is usable every compute call returns B200MSM_E_CUDA which is raise
 import ctypes, os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200msm.so")
+LIB_PATH = os.environ.get("B200MSM_LIB") or os.path.join(_HERE, "libb200msm.so")     # B200MSM_LIB: alternative build of the same ABI (A/B experiments)
 
 OK, E_ARG, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4
 BLS12_381_G1, BN254_G1 = 0, 1

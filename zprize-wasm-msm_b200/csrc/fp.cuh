@@ -198,8 +198,8 @@ B200_DI void mont_row(uint32_t (&E)[C::N], uint32_t (&O)[C::N], const uint32_t (
   addc(O[N - 1], O[N - 1], 0);
 }
 
-// f1m_mul (build_f1m.js:466-777): r = a*b/R mod q, fully reduced.  r may alias a or b.
-template <class C> B200_DI void fe_mul(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
+// f1m_mul (build_f1m.js:466-777): r = a*b/R mod q, fully reduced.  r may alias a or b.  Interleaved (CIOS) form.
+template <class C> B200_DI void fe_mul_cios(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
   constexpr int N = C::N;
   static_assert(N % 2 == 0, "even limb count");
   uint32_t E[N], O[N];
@@ -220,8 +220,203 @@ template <class C> B200_DI void fe_mul(Fe<C::N>& r, const Fe<C::N>& a, const Fe<
   r = t;
 }
 
-// f1m_square (build_f1m.js:779-1076) -- same value as mul(a, a)
-template <class C> B200_DI void fe_sqr(Fe<C::N>& r, const Fe<C::N>& a) { fe_mul<C>(r, a, a); }
+// ---- separated product + Montgomery reduction (used by the dedicated squaring) ---------------------------------
+// One reduction row on the interleaved accumulators (see mont_row): m = low limb * np, add m*q, and take in the next
+// limb `tn` of the double-width product at the top.  `c` collects the (rare) overflow bit of the frame's top limb.
+template <class C, bool FIRST>
+B200_DI void red_row(uint32_t (&E)[C::N], uint32_t (&O)[C::N], uint32_t tn, uint32_t c2, uint32_t& c) {
+  constexpr int N = C::N;
+  uint32_t m;
+  if (FIRST) {
+    m = E[0] * C::NP;
+    mad_lo_cc(O[0], C::q(1), m, O[0]);
+    madc_hi_cc(O[1], C::q(1), m, O[1]);
+#pragma unroll
+    for (int j = 3; j < N; j += 2) { madc_lo_cc(O[j - 1], C::q(j), m, O[j - 1]); madc_hi_cc(O[j], C::q(j), m, O[j]); }
+    addc(c, 0, 0);
+  } else {
+    add_cc(E[0], E[0], O[1]);
+    m = E[0] * C::NP;
+#pragma unroll
+    for (int j = 1; j < N - 1; j += 2) { madc_lo_cc(O[j - 1], C::q(j), m, O[j + 1]); madc_hi_cc(O[j], C::q(j), m, O[j + 2]); }
+    madc_lo_cc(O[N - 2], C::q(N - 1), m, 0);
+    madc_hi_cc(O[N - 1], C::q(N - 1), m, tn);
+    addc(c, c2, 0);
+  }
+  mad_lo_cc(E[0], C::q(0), m, E[0]);
+  madc_hi_cc(E[1], C::q(0), m, E[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) { madc_lo_cc(E[j], C::q(j), m, E[j]); madc_hi_cc(E[j + 1], C::q(j), m, E[j + 1]); }
+  addc_cc(O[N - 1], O[N - 1], 0);
+  addc(c, c, 0);
+}
+// r = T / R mod q for a 2N-limb T < q * 2^(32N); result fully reduced.  N*N + N limb products.
+template <class C> B200_DI void mont_reduce(Fe<C::N>& r, const uint32_t (&T)[2 * C::N]) {
+  constexpr int N = C::N;
+  uint32_t E[N], O[N], c = 0;
+#pragma unroll
+  for (int k = 0; k < N; k++) { E[k] = T[k]; O[k] = 0; }
+  O[N - 1] = T[N];
+  red_row<C, true>(E, O, 0, 0, c);
+#pragma unroll
+  for (int i = 1; i < N; i++) {
+    uint32_t tn, c2;
+    add_cc(tn, T[N + i], c);
+    addc(c2, 0, 0);
+    if (i & 1) red_row<C, false>(O, E, tn, c2, c); else red_row<C, false>(E, O, tn, c2, c);
+  }
+  Fe<N> t;
+  add_cc(t.l[0], E[0], O[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) addc_cc(t.l[k], E[k], O[k + 1]);
+  addc(t.l[N - 1], E[N - 1], 0);
+  fe_reduce_once<C>(t);
+  r = t;
+}
+// T = a * a (2N limbs): off-diagonal products a_i*a_j (i < j) in two interleaved accumulators (even / odd position), each row
+// one carry chain per parity; then doubled, then the N squares a_i^2 are added in one chain.  N(N-1)/2 + N limb products.
+template <class C> B200_DI void sqr_product(uint32_t (&T)[2 * C::N], const uint32_t (&a)[C::N]) {
+  constexpr int N = C::N;
+  uint32_t Ev[2 * N], Od[2 * N];
+#pragma unroll
+  for (int k = 0; k < 2 * N; k++) { Ev[k] = 0; Od[k] = 0; }
+#pragma unroll
+  for (int i = 0; i < N - 1; i++) {
+    {   // odd positions: j = i+1, i+3, ...   product at position i+j held in Od[i+j-1], Od[i+j]
+      mad_lo_cc(Od[2 * i], a[i], a[i + 1], Od[2 * i]);
+      madc_hi_cc(Od[2 * i + 1], a[i], a[i + 1], Od[2 * i + 1]);
+      int last = i + 1;
+#pragma unroll
+      for (int j = i + 3; j < N; j += 2) { madc_lo_cc(Od[i + j - 1], a[i], a[j], Od[i + j - 1]); madc_hi_cc(Od[i + j], a[i], a[j], Od[i + j]); last = j; }
+      addc(Od[i + last + 1], Od[i + last + 1], 0);
+    }
+    if (i + 2 < N) {   // even positions: j = i+2, i+4, ...   product held in Ev[i+j], Ev[i+j+1]
+      mad_lo_cc(Ev[2 * i + 2], a[i], a[i + 2], Ev[2 * i + 2]);
+      madc_hi_cc(Ev[2 * i + 3], a[i], a[i + 2], Ev[2 * i + 3]);
+      int last = i + 2;
+#pragma unroll
+      for (int j = i + 4; j < N; j += 2) { madc_lo_cc(Ev[i + j], a[i], a[j], Ev[i + j]); madc_hi_cc(Ev[i + j + 1], a[i], a[j], Ev[i + j + 1]); last = j; }
+      addc(Ev[i + last + 2], Ev[i + last + 2], 0);
+    }
+  }
+  T[0] = Ev[0];
+  add_cc(T[1], Ev[1], Od[0]);
+#pragma unroll
+  for (int p = 2; p < 2 * N - 1; p++) addc_cc(T[p], Ev[p], Od[p - 1]);
+  addc(T[2 * N - 1], Ev[2 * N - 1], Od[2 * N - 2]);
+#pragma unroll
+  for (int p = 2 * N - 1; p > 0; p--) T[p] = __funnelshift_l(T[p - 1], T[p], 1);
+  T[0] <<= 1;
+  mad_lo_cc(T[0], a[0], a[0], T[0]);
+  madc_hi_cc(T[1], a[0], a[0], T[1]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) { madc_lo_cc(T[2 * i], a[i], a[i], T[2 * i]); madc_hi_cc(T[2 * i + 1], a[i], a[i], T[2 * i + 1]); }
+  madc_lo_cc(T[2 * N - 2], a[N - 1], a[N - 1], T[2 * N - 2]);
+  madc_hi(T[2 * N - 1], a[N - 1], a[N - 1], T[2 * N - 1]);
+}
+// H x H limb product (2H limbs) in the same two-accumulator carry-chain form: every row x*y_i is two chains of H/2 wide
+// multiply-adds (even j, odd j); the word after a chain's end has not been touched by earlier rows, so its carry just lands.
+template <int H> B200_DI void half_product(uint32_t (&T)[2 * H], const uint32_t* x, const uint32_t* y) {
+  uint32_t Ev[2 * H + 2], Od[2 * H + 2];
+#pragma unroll
+  for (int k = 0; k < 2 * H + 2; k++) { Ev[k] = 0; Od[k] = 0; }
+#pragma unroll
+  for (int i = 0; i < H; i++) {
+#pragma unroll
+    for (int par = 0; par < 2; par++) {
+      const int p0 = i + par;
+      if ((p0 & 1) == 0) { mad_lo_cc(Ev[p0], x[par], y[i], Ev[p0]); madc_hi_cc(Ev[p0 + 1], x[par], y[i], Ev[p0 + 1]); }
+      else { mad_lo_cc(Od[p0 - 1], x[par], y[i], Od[p0 - 1]); madc_hi_cc(Od[p0], x[par], y[i], Od[p0]); }
+      int last = par;
+#pragma unroll
+      for (int j = par + 2; j < H; j += 2) {
+        const int p = i + j;
+        if ((p & 1) == 0) { madc_lo_cc(Ev[p], x[j], y[i], Ev[p]); madc_hi_cc(Ev[p + 1], x[j], y[i], Ev[p + 1]); }
+        else { madc_lo_cc(Od[p - 1], x[j], y[i], Od[p - 1]); madc_hi_cc(Od[p], x[j], y[i], Od[p]); }
+        last = j;
+      }
+      const int pl = i + last;
+      if ((pl & 1) == 0) addc(Ev[pl + 2], Ev[pl + 2], 0); else addc(Od[pl + 1], Od[pl + 1], 0);
+    }
+  }
+  T[0] = Ev[0];
+  add_cc(T[1], Ev[1], Od[0]);
+#pragma unroll
+  for (int p = 2; p < 2 * H - 1; p++) addc_cc(T[p], Ev[p], Od[p - 1]);
+  addc(T[2 * H - 1], Ev[2 * H - 1], Od[2 * H - 2]);
+}
+// One level of Karatsuba on the a*b half of the Montgomery product: three (N/2)x(N/2) products instead of NxN, i.e.
+// 3N^2/4 + N^2 + N limb products (264 for BLS12-381, 120 for BN254) instead of 2N^2 + N, paid for with ~100 extra
+// additions on the ALU pipe, which has slack while IMAD.WIDE (32 lanes/clk/SM) is the bound.
+template <class C> B200_DI void fe_mul_karatsuba(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
+  constexpr int N = C::N, H = N / 2;
+  uint32_t T[2 * N], zm[2 * H + 1], sa[H], sb[H], ca, cb;
+  {
+    uint32_t z0[2 * H], z2[2 * H];
+    half_product<H>(z0, a.l, b.l);
+    half_product<H>(z2, a.l + H, b.l + H);
+    add_cc(sa[0], a.l[0], a.l[H]);
+#pragma unroll
+    for (int k = 1; k < H; k++) addc_cc(sa[k], a.l[k], a.l[H + k]);
+    addc(ca, 0, 0);
+    add_cc(sb[0], b.l[0], b.l[H]);
+#pragma unroll
+    for (int k = 1; k < H; k++) addc_cc(sb[k], b.l[k], b.l[H + k]);
+    addc(cb, 0, 0);
+    {
+      uint32_t zz[2 * H];
+      half_product<H>(zz, sa, sb);
+#pragma unroll
+      for (int k = 0; k < 2 * H; k++) zm[k] = zz[k];
+      zm[2 * H] = 0;
+    }
+    const uint32_t ma = 0u - ca, mb = 0u - cb;
+    add_cc(zm[H], zm[H], sb[0] & ma);
+#pragma unroll
+    for (int k = 1; k < H; k++) addc_cc(zm[H + k], zm[H + k], sb[k] & ma);
+    addc(zm[2 * H], zm[2 * H], 0);
+    add_cc(zm[H], zm[H], sa[0] & mb);
+#pragma unroll
+    for (int k = 1; k < H; k++) addc_cc(zm[H + k], zm[H + k], sa[k] & mb);
+    addc(zm[2 * H], zm[2 * H], ca & cb);
+    sub_cc(zm[0], zm[0], z0[0]);
+#pragma unroll
+    for (int k = 1; k < 2 * H; k++) subc_cc(zm[k], zm[k], z0[k]);
+    subc(zm[2 * H], zm[2 * H], 0);
+    sub_cc(zm[0], zm[0], z2[0]);
+#pragma unroll
+    for (int k = 1; k < 2 * H; k++) subc_cc(zm[k], zm[k], z2[k]);
+    subc(zm[2 * H], zm[2 * H], 0);
+#pragma unroll
+    for (int k = 0; k < 2 * H; k++) { T[k] = z0[k]; T[2 * H + k] = z2[k]; }
+  }
+  add_cc(T[H], T[H], zm[0]);
+#pragma unroll
+  for (int k = 1; k < 2 * H + 1; k++) addc_cc(T[H + k], T[H + k], zm[k]);
+#pragma unroll
+  for (int k = 3 * H + 1; k < 2 * N - 1; k++) addc_cc(T[k], T[k], 0);
+  addc(T[2 * N - 1], T[2 * N - 1], 0);
+  mont_reduce<C>(r, T);
+}
+template <class C> B200_DI void fe_mul(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
+#if defined(B200_KARATSUBA)
+  fe_mul_karatsuba<C>(r, a, b);
+#else
+  fe_mul_cios<C>(r, a, b);
+#endif
+}
+
+// f1m_square (build_f1m.js:779-1076): dedicated squaring, N(N-1)/2 + N + N*N + N limb products (234 for BLS12-381, 108 for BN254)
+// instead of the 2N*N + N of a general multiplication.
+template <class C> B200_DI void fe_sqr(Fe<C::N>& r, const Fe<C::N>& a) {
+#if defined(B200_SQR_AS_MUL)
+  fe_mul<C>(r, a, a);
+#else
+  uint32_t T[2 * C::N];
+  sqr_product<C>(T, a.l);
+  mont_reduce<C>(r, T);
+#endif
+}
 
 // to / from Montgomery (build_f1m.js:1089,1098)
 template <class C> B200_DI void fe_to_mont(Fe<C::N>& r, const Fe<C::N>& a) {

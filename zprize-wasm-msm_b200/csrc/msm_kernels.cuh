@@ -420,7 +420,8 @@ __global__ void __launch_bounds__(256) k_fpmul_probe(uint32_t iters, const void*
   Fe<C::N> x, y;
   fe_load<C>(x, reinterpret_cast<const char*>(in) + (uint64_t)(i & 1023) * 4 * C::N);
   y = x;
-  for (uint32_t k = 0; k < iters; k++) { fe_mul<C>(y, y, x); }
+  if (iters & 0x80000000u) { for (uint32_t k = 0; k < (iters & 0x7fffffffu); k++) { fe_sqr<C>(y, y); } }
+  else for (uint32_t k = 0; k < iters; k++) { fe_mul<C>(y, y, x); }
   fe_store<C>(reinterpret_cast<char*>(out) + (uint64_t)i * 4 * C::N, y);
 }
 
