@@ -88,6 +88,14 @@ int b200msm_g1_normalize(b200msm_ctx* ctx, int curve, const void* jac, uint64_t 
  * Used to merge the per-GPU partial results of a point-range-sharded MSM. */
 int b200msm_g1_sum(b200msm_ctx* ctx, int curve, const void* jac_points, uint64_t count, void* out);
 
+/* ---- point codecs and batch conversions on either side of the MSM (the formats an ffjavascript / snarkjs host holds its
+ * points in): op 0 == g1m_batchLEMtoU, 1 == g1m_batchLEMtoC, 2 == g1m_batchUtoLEM, 3 == g1m_batchCtoLEM
+ * (src/build_curve_jacobian_a0.js:1166-1328,1413-1416), 4 == g1m_batchToAffine (:1040-1125), 5 == g1m_batchToJacobian (:1418).
+ * Element sizes in -> out (bytes): 0: 2n8 -> 2n8, 1: 2n8 -> n8, 2: 2n8 -> 2n8, 3: n8 -> 2n8, 4: 3n8 -> 2n8, 5: 2n8 -> 3n8.
+ * "LEM" = little-endian Montgomery affine (the MSM's input format); "U"/"C" = big-endian plain uncompressed/compressed,
+ * first byte 0x40 = infinity, 0x80 (compressed only) = y is the greater of the two roots. */
+int b200msm_g1_batch_convert(b200msm_ctx* ctx, int curve, int op, const void* in, uint64_t n, void* out);
+
 /* ---- synthetic inputs (benchmarks/multiexp.js:16-23 builds bases on the module itself):
  * device_out[i] = k_i * G for i in [0, n), affine Montgomery, k_i = splitmix64(seed + first + i) (0 mapped to 1).
  * device_out must be a device pointer with room for n * 2*n8 bytes. */

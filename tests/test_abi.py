@@ -57,3 +57,13 @@ def test_product_path_does_not_import_oracle():
                         # comments may cite oracle/msm_oracle.c for the shared input generator stream
                         continue
                     assert bad not in src, (f, bad)
+
+
+def test_ffjs_surface_validates_before_touching_the_gpu():
+    """size checks of the ffjavascript-style surface raise the same messages without needing an engine"""
+    import b200msm
+    G = b200msm.G1(None, "bls12381")
+    with pytest.raises(ValueError, match="Scalar size does not match"): G.multiExpAffine(bytes(96 * 3), bytes(32 * 3 - 1))
+    with pytest.raises(ValueError, match="Base size does not match"): G.multiExpAffine(bytes(95), bytes(32))
+    with pytest.raises(ValueError, match="Invalid buffer size"): G.batchLEMtoU(bytes(97))
+    assert G.zero()[48:96] == pyref.fe_bytes(pyref.BLS12_381, pyref.BLS12_381.R % pyref.BLS12_381.q)

@@ -89,6 +89,15 @@ class Engine:
         po, ko = _ptr(device_out)
         self._ck(lib.b200msm_g1_generate_bases(self._ctx, curve, seed, first, n, po))
 
+    CONVERT = {"LEMtoU": 0, "LEMtoC": 1, "UtoLEM": 2, "CtoLEM": 3, "toAffine": 4, "toJacobian": 5}
+
+    def batch_convert(self, curve, op, data, n):
+        """g1m_batchLEMtoU / LEMtoC / UtoLEM / CtoLEM / batchToAffine / batchToJacobian on n points -> bytes"""
+        k = self.CONVERT[op] if isinstance(op, str) else op
+        n8 = N8[curve]; out_sz = [2 * n8, n8, 2 * n8, 2 * n8, 2 * n8, 3 * n8][k]
+        pi, ki = _ptr(data); o = ctypes.create_string_buffer(max(1, out_sz * n))
+        self._ck(lib.b200msm_g1_batch_convert(self._ctx, curve, k, pi, n, o)); return o.raw[:out_sz * n]
+
     def fq_op(self, curve, op, a, b=None):
         n = len(a) // N8[curve]
         pa, ka = _ptr(a); pb_, kb = _ptr(b)

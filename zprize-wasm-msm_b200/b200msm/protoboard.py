@@ -69,6 +69,17 @@ class Protoboard:
 
     g1m_multiexpAffine_multiExp = g1m_multiexp_multiExp
 
+    # ---- batch conversions / codecs (wasmcurves/src/build_curve_jacobian_a0.js:1040-1328,1413-1418): (pIn, n, pOut)
+    def _batch(self, op, pIn, n, pOut, in_sz, out_sz):
+        self.write(pOut, self.engine.batch_convert(self.curve, op, self.read(pIn, n * in_sz), n))
+
+    def g1m_batchLEMtoU(self, pIn, n, pOut): self._batch("LEMtoU", pIn, n, pOut, 2 * self.n8, 2 * self.n8)
+    def g1m_batchUtoLEM(self, pIn, n, pOut): self._batch("UtoLEM", pIn, n, pOut, 2 * self.n8, 2 * self.n8)
+    def g1m_batchLEMtoC(self, pIn, n, pOut): self._batch("LEMtoC", pIn, n, pOut, 2 * self.n8, self.n8)
+    def g1m_batchCtoLEM(self, pIn, n, pOut): self._batch("CtoLEM", pIn, n, pOut, self.n8, 2 * self.n8)
+    def g1m_batchToAffine(self, pIn, n, pOut): self._batch("toAffine", pIn, n, pOut, 3 * self.n8, 2 * self.n8)
+    def g1m_batchToJacobian(self, pIn, n, pOut): self._batch("toJacobian", pIn, n, pOut, 2 * self.n8, 3 * self.n8)
+
     # ---- the helpers every reference test uses around the MSM call
     def _fq(self, op, pa, pb_, pr):
         a = self.read(pa, self.n8); b = self.read(pb_, self.n8) if pb_ is not None else None

@@ -19,6 +19,7 @@
 #include "msm_kernels.cuh"
 #include "accumulate.cuh"
 #include "fp29.cuh"
+#include "codecs.cuh"
 #include "host_ec.h"
 #include <chrono>
 
@@ -248,10 +249,16 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
 // in-place folding of `slots` consecutive bucket arrays of B buckets each (see k_fold)
 template <class C>
 int fold_slots(b200msm_ctx* ctx, cudaStream_t s, void* buckets_g, uint32_t slots, uint32_t B) {
-  for (uint32_t sz = B; sz >= 2; sz >>= 1) {
+  const uint32_t tail = std::min<uint32_t>(B, FOLD_TAIL);
+  uint32_t sz = B;
+  for (; sz > tail; sz >>= 1) {          // wide levels: one launch each (throughput-bound)
     uint32_t nblk = B / sz, live = 1; for (uint32_t k = 1; k < nblk; k <<= 1) live++;
     uint64_t threads = (uint64_t)live * (sz / 2) * slots;
     k_fold<C><<<(uint32_t)((threads + 127) / 128), 128, 0, s>>>(buckets_g, slots, B, sz); CKL();
+  }
+  if (tail >= 2) {                        // remaining levels of every live block of `tail` buckets: one launch
+    uint32_t nblk = B / tail, live = 1; for (uint32_t k = 1; k < nblk; k <<= 1) live++;
+    k_fold_tail<C><<<slots * live, 256, 0, s>>>(buckets_g, B, tail, live); CKL();
   }
   return B200MSM_OK;
 }
@@ -685,6 +692,26 @@ int b200msm_g1_generate_bases(b200msm_ctx* ctx, int curve, uint64_t seed, uint64
   }
   CK(cudaStreamSynchronize(ctx->stream));
   return B200MSM_OK;
+}
+
+int b200msm_g1_batch_convert(b200msm_ctx* ctx, int curve, int op, const void* in, uint64_t n, void* out) {
+  if (!ctx || !curve_ok(curve) || op < 0 || op > 5 || (n && (!in || !out)) || n >= (1ull << 31)) return B200MSM_E_ARG;
+  if (n == 0) return B200MSM_OK;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n8 = n8_of(curve);
+  const size_t in_sz[6] = {2 * n8, 2 * n8, 2 * n8, n8, 3 * n8, 2 * n8}, out_sz[6] = {2 * n8, n8, 2 * n8, 2 * n8, 2 * n8, 3 * n8};
+  const void* d_in; int rc = stage(ctx, in, n * in_sz[op], ctx->acc_a, &d_in); if (rc) return rc;
+  CK(ctx->acc_c.ensure(n * out_sz[op] + 16));
+  const uint32_t g = (uint32_t)((n + 127) / 128);
+  if (op == CODEC_TO_AFFINE) {
+    constexpr int GROUP = 8;
+    const uint32_t g2 = (uint32_t)(((n + GROUP - 1) / GROUP + 127) / 128);
+    if (curve == 0) k_jacobian_to_affine<BLS12_381, GROUP><<<g2, 128, 0, ctx->stream>>>((const uint8_t*)d_in, (uint32_t)n, ctx->acc_c.as<uint8_t>());
+    else k_jacobian_to_affine<BN254, GROUP><<<g2, 128, 0, ctx->stream>>>((const uint8_t*)d_in, (uint32_t)n, ctx->acc_c.as<uint8_t>());
+  } else if (curve == 0) k_codec<BLS12_381><<<g, 128, 0, ctx->stream>>>(op, (const uint8_t*)d_in, (uint32_t)n, ctx->acc_c.as<uint8_t>(), 4u);
+  else k_codec<BN254><<<g, 128, 0, ctx->stream>>>(op, (const uint8_t*)d_in, (uint32_t)n, ctx->acc_c.as<uint8_t>(), 3u);
+  CKL();
+  return deliver(ctx, ctx->acc_c.p, out, n * out_sz[op]);
 }
 
 int b200msm_fq_op(b200msm_ctx* ctx, int curve, int op, const void* a, const void* b, void* r, uint64_t count) {

@@ -207,6 +207,32 @@ __global__ void __launch_bounds__(128) k_fold(void* __restrict__ buckets, uint32
   xyzz_store<C>(buckets, lo, a);
 }
 
+// The last levels of the folding in ONE launch.  After the levels with block size > TAIL have run, every live block of
+// TAIL buckets is an independent instance of the same problem (everything that happens to an aligned block stays inside it),
+// so one CTA takes one live block and runs its remaining log2(TAIL) levels with a CTA barrier between levels instead of a
+// kernel launch (these levels are latency-bound: one XYZZ addition deep each).
+constexpr uint32_t FOLD_TAIL = 1024;
+template <class C>
+__global__ void __launch_bounds__(256) k_fold_tail(void* __restrict__ buckets, uint32_t B, uint32_t tail, uint32_t live_blocks) {
+  const uint32_t w = blockIdx.x / live_blocks, lb0 = blockIdx.x % live_blocks;
+  const uint32_t blk0 = lb0 == 0 ? 0 : (1u << (lb0 - 1));
+  const uint64_t base = (uint64_t)w * B + (uint64_t)blk0 * tail;
+  uint32_t live = 1;
+  for (uint32_t sz = tail; sz >= 2; sz >>= 1, live++) {
+    const uint32_t half = sz >> 1, work = live * half;
+    for (uint32_t r = threadIdx.x; r < work; r += blockDim.x) {
+      const uint32_t lb = r / half, i = r % half;
+      const uint32_t blk = lb == 0 ? 0 : (1u << (lb - 1));
+      const uint64_t lo = base + (uint64_t)blk * sz + i;
+      XYZZ<C> a, b;
+      xyzz_load<C>(a, buckets, lo); xyzz_load<C>(b, buckets, lo + half);
+      xyzz_add<C>(a, b);
+      xyzz_store<C>(buckets, lo, a);
+    }
+    __syncthreads();
+  }
+}
+
 // One thread per slot: R_w = T[0] + sum_j 2^j T[2^j] by Horner over j (logB doublings).  The extra slot (index Wd,
 // present when W == Wd + 1) holds buckets B+1 .. 2B of the last window: its value is the same expression + B * T[0].
 template <class C>
