@@ -203,8 +203,12 @@ __global__ void __launch_bounds__(BA_THREADS, 4) k_tree_bwd(TreeRound tr, const 
     int kind = affine_add_denominator<C>(d, p1, p2);
     if (kind <= 1) {
       Fe<C::N> pre; fe_load_cg<C>(pre, reinterpret_cast<const char*>(prefix) + (uint64_t)j * 4 * C::N);
+#if defined(B200_MUL2)
+      Fe<C::N> qn; fe_mul2<C>(dinv, q, pre, qn, q, d); q = qn;
+#else
       fe_mul<C>(dinv, q, pre);
       fe_mul<C>(q, q, d);
+#endif
     }
     affine_add_finish<C>(r, p1, p2, dinv, kind);
     affine_store<C>(pout, j, r);

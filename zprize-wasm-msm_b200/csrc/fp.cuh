@@ -220,6 +220,36 @@ template <class C> B200_DI void fe_mul_cios(Fe<C::N>& r, const Fe<C::N>& a, cons
   r = t;
 }
 
+// Two independent multiplications with their rows interleaved in program order: r1 = a1*b1, r2 = a2*b2.  The carry chains of
+// one multiplication are serial (asm volatile keeps them in order), so a single multiplication exposes only the parallelism of
+// its two accumulators; interleaving a second, independent one doubles the work available between dependent instructions.
+template <class C> B200_DI void fe_mul2(Fe<C::N>& r1, const Fe<C::N>& a1, const Fe<C::N>& b1, Fe<C::N>& r2, const Fe<C::N>& a2, const Fe<C::N>& b2) {
+  constexpr int N = C::N;
+  uint32_t E1[N], O1[N], E2[N], O2[N];
+  mont_row<C, true>(E1, O1, a1.l, b1.l[0]);
+  mont_row<C, true>(E2, O2, a2.l, b2.l[0]);
+  mont_row<C, false>(O1, E1, a1.l, b1.l[1]);
+  mont_row<C, false>(O2, E2, a2.l, b2.l[1]);
+#pragma unroll
+  for (int i = 2; i < N; i += 2) {
+    mont_row<C, false>(E1, O1, a1.l, b1.l[i]);
+    mont_row<C, false>(E2, O2, a2.l, b2.l[i]);
+    mont_row<C, false>(O1, E1, a1.l, b1.l[i + 1]);
+    mont_row<C, false>(O2, E2, a2.l, b2.l[i + 1]);
+  }
+  Fe<N> t1, t2;
+  add_cc(t1.l[0], E1[0], O1[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) addc_cc(t1.l[k], E1[k], O1[k + 1]);
+  addc(t1.l[N - 1], E1[N - 1], 0);
+  add_cc(t2.l[0], E2[0], O2[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) addc_cc(t2.l[k], E2[k], O2[k + 1]);
+  addc(t2.l[N - 1], E2[N - 1], 0);
+  fe_reduce_once<C>(t1); fe_reduce_once<C>(t2);
+  r1 = t1; r2 = t2;
+}
+
 // ---- separated product + Montgomery reduction (used by the dedicated squaring) ---------------------------------
 // One reduction row on the interleaved accumulators (see mont_row): m = low limb * np, add m*q, and take in the next
 // limb `tn` of the double-width product at the top.  `c` collects the (rare) overflow bit of the frame's top limb.

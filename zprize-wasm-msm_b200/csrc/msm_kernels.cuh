@@ -65,35 +65,51 @@ __global__ void k_canon_scalars(const uint8_t* __restrict__ in, uint32_t scalar_
   }
 }
 
-// One digit stream: calls f(global_bucket_index, negative) for every non-zero digit.  Windows below the last one use
-// signed digits with a carry into the next window; the last window keeps its digit unsigned (it may reach 2^rb and
-// then indexes into the extra slot), so no carry ever leaves the scalar and no "carry-only" window exists.
-template <class F>
-B200_DI void for_each_digit(const uint32_t* __restrict__ s, const MsmPlan& pl, F f) {
-  uint32_t carry = 0;
-  for (uint32_t w = 0; w < pl.Wd; w++) {
-    const uint32_t cw = pl.c0 + (w < pl.rem ? 1u : 0u);
-    const uint32_t bit = w * pl.c0 + min(w, pl.rem), k = bit >> 5, r = bit & 31;
-    uint32_t lo = (k < 8) ? __ldg(s + k) : 0u, hi = (k + 1 < 8) ? __ldg(s + k + 1) : 0u;
-    uint32_t raw = __funnelshift_r(lo, hi, r) & ((1u << cw) - 1u);
-    uint32_t d = raw + carry;
-    if (w + 1 == pl.Wd) { if (d) f(w * pl.B + d - 1, 0u); break; }
-    carry = d > (1u << (cw - 1));
-    uint32_t mag = carry ? ((1u << cw) - d) : d;
-    if (mag) f(w * pl.B + mag - 1, carry);
-  }
-}
-
+// Digit recoding.  Windows below the last one use signed digits with a carry into the next window; the last window keeps
+// its digit unsigned (it may reach 2^c0 and then indexes into the extra slot), so no carry ever leaves the scalar and no
+// "carry-only" window exists.  A non-zero digit d of window w lands in global bucket w*B + |d| - 1 with its sign.
+// Digits of 8 consecutive windows at a time: the recoding is a serial carry chain, but the 8 atomics (and, when scattering,
+// the 8 dependent stores) that follow are independent, so they are issued back to back instead of one L2 round trip per window.
 template <bool SCATTER>
-__global__ void k_digits(const uint32_t* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ counters,
-                         uint32_t* __restrict__ sorted) {
+__global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ counters,
+                                                uint32_t* __restrict__ sorted) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pl.n) return;
   const uint32_t* s = scalars + (uint64_t)i * 8;
-  for_each_digit(s, pl, [&](uint32_t gb, uint32_t neg) {
-    uint32_t slot = atomicAdd(&counters[gb], 1u);
-    if (SCATTER) sorted[slot] = i | (neg << 31);
-  });
+  uint32_t sw[8];
+  { const uint4 a = __ldg(reinterpret_cast<const uint4*>(s)), b = __ldg(reinterpret_cast<const uint4*>(s) + 1);
+    sw[0] = a.x; sw[1] = a.y; sw[2] = a.z; sw[3] = a.w; sw[4] = b.x; sw[5] = b.y; sw[6] = b.z; sw[7] = b.w; }
+  uint32_t carry = 0;
+  for (uint32_t w0 = 0; w0 < pl.Wd; w0 += 8) {
+    uint32_t gb[8], val[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const uint32_t w = w0 + u;
+      gb[u] = 0xffffffffu; val[u] = i;
+      if (w < pl.Wd) {
+        const uint32_t cw = pl.c0 + (w < pl.rem ? 1u : 0u);
+        const uint32_t bit = w * pl.c0 + min(w, pl.rem), k = bit >> 5, r = bit & 31;
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { lo = (k == (uint32_t)q) ? sw[q] : lo; hi = (k + 1 == (uint32_t)q) ? sw[q] : hi; }
+        const uint32_t raw = __funnelshift_r(lo, hi, r) & ((1u << cw) - 1u);
+        const uint32_t d = raw + carry;
+        if (w + 1 == pl.Wd) { if (d) gb[u] = w * pl.B + d - 1; }
+        else {
+          carry = d > (1u << (cw - 1));
+          const uint32_t mag = carry ? ((1u << cw) - d) : d;
+          if (mag) { gb[u] = w * pl.B + mag - 1; val[u] = i | (carry << 31); }
+        }
+      }
+    }
+    uint32_t slot[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) if (gb[u] != 0xffffffffu) slot[u] = atomicAdd(&counters[gb[u]], 1u);
+    if (SCATTER) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) if (gb[u] != 0xffffffffu) sorted[slot[u]] = val[u];
+    }
+  }
 }
 
 // ------------------------------------------------------------------ exclusive scan (u32), three phases
