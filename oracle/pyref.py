@@ -243,3 +243,36 @@ def organize_buckets_one_round(sched_k, c):
 
 BLS_Z = 0xd201000000010000
 BLS_LAMBDA = BLS12_381.r - BLS_Z * BLS_Z        # lambda with phi(P) = lambda*P, SURVEY section 4
+
+
+# GLV constants and decomposition, restated from src/build_glv.js:13-22 and :53-146 (BLS12-381 only, like the reference)
+GLV_NEG_V1 = 228988810152649578064853576960394133503          # -v1   (build_glv.js:19)
+GLV_U0 = 228988810152649578064853576960394133504              # u0    (build_glv.js:17); u1 = v0 = 1
+GLV_BETA = 793479390729215512621379701633421447060886740281060493010456487427281649075476305620758731620350   # :21
+GLV_DIVISOR = BLS12_381.r                                      # v0*u1 - v1*u0 = r (build_glv.js:22)
+
+
+def glv_decompose(k):
+    """g1m_glv_decomposeScalar (build_glv.js:53-146): returns (|k1| mod 2^128, |k2| mod 2^128, sign) with
+    sign bit 0 = (k1 >= 0), bit 1 = (k2 >= 0); q1 = floor(k / r), q2 = floor(k * (-v1) / r),
+    k1 = k - q1*v0 - q2*u0, k2 = -q1*v1 - q2*u1.  The reference keeps only the low two 64-bit words of |k1|, |k2| (:133-136)."""
+    q1 = k // GLV_DIVISOR
+    q2 = (k * GLV_NEG_V1) // GLV_DIVISOR
+    k1 = k - q1 - q2 * GLV_U0
+    k2 = q1 * GLV_NEG_V1 - q2
+    sign = (1 if k1 >= 0 else 0) | (2 if k2 >= 0 else 0)
+    m = (1 << 128) - 1
+    return abs(k1) & m, abs(k2) & m, sign
+
+
+def glv_preprocess(points, scalars):
+    """g1m_glv_preprocessEndomorphism (build_glv.js:178-263): N points/scalars -> 2N points, 2N scalars (each < 2^128)."""
+    cv = BLS12_381
+    out_p, out_s = [], []
+    for P, k in zip(points, scalars):
+        k1, k2, sign = glv_decompose(k)
+        x, y = P
+        out_p.append((x, y if sign & 1 else (-y) % cv.q))
+        out_p.append((GLV_BETA * x % cv.q, y if sign & 2 else (-y) % cv.q))     # g1m_glv_endomorphism :150-174
+        out_s += [k1, k2]
+    return out_p, out_s

@@ -1,8 +1,7 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -1
-for cfg in "tree_rounds=-1" "tree_rounds=2" "tree_rounds=3" "tree_rounds=4"; do
+for cfg in "ba_k=8" "ba_k=12" "ba_k=16" "ba_k=16 pt_k=4" "ba_k=8 pt_k=16"; do
   args=""; for kv in $cfg; do args="$args --opt $kv"; done
-  echo "== $cfg"; python tools/sweep.py --sizes 14,16,18,20 $args 2>&1 | tail -4 | python -c "
+  echo "== $cfg"; python tools/sweep.py --sizes 18,20,22 --reps 8 $args 2>&1 | tail -3 | python -c "
 import sys, json
 for l in sys.stdin:
-    d = json.loads(l); print({k: d[k] for k in ('log2n','ms','k_finish')})"
+    d = json.loads(l); print({k: d[k] for k in ('log2n','ms')})"
 done

@@ -8,7 +8,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "zprize-wasm-ms
 import numpy as np, torch
 import b200msm, pyref, coracle
 
-ap = argparse.ArgumentParser(); ap.add_argument("--sizes", default="22,24"); ap.add_argument("--curve", default="bls12381")
+ap = argparse.ArgumentParser(); ap.add_argument("--sizes", default="22,24"); ap.add_argument("--curve", default="bls12381"); ap.add_argument("--pattern", default="uniform", choices=["uniform", "equal", "small", "sparse"])
 a = ap.parse_args()
 cv = pyref.CURVES[a.curve]; cid = cv.cid; n8 = cv.n8
 eng = b200msm.Engine(0); dev = torch.device("cuda", 0)
@@ -29,6 +29,9 @@ for lg in [int(x) for x in a.sizes.split(",")]:
     eng.generate_bases(cid, seed, 0, n, bases)
     g = torch.Generator(device=dev); g.manual_seed(lg)
     sc = torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device=dev, generator=g)
+    if a.pattern == "equal": sc = sc[:32].repeat(n)                                   # every scalar identical: one bucket per window holds all points
+    elif a.pattern == "small": sc = (sc.view(n, 32) * (torch.arange(32, device=dev) < 1)).reshape(-1).contiguous()   # scalars < 256
+    elif a.pattern == "sparse": sc = (sc.view(n, 32) * (torch.rand(n, 1, device=dev, generator=g) < 0.05)).to(torch.uint8).reshape(-1).contiguous()   # 95 % zero scalars
     tgen = time.time() - t0
     out = torch.zeros(3 * n8, dtype=torch.uint8, device=dev)
     h = eng.upload_bases(cid, bases, n)
@@ -49,6 +52,6 @@ for lg in [int(x) for x in a.sizes.split(",")]:
             s = w[:, 0] + (w[:, 1] << 64) + (w[:, 2] << 128) + (w[:, 3] << 192)
             total = (total + int((s * k.astype(object)).sum())) % cv.r
     exp = coracle.normalize(cid, coracle.times_scalar_affine(cid, pyref.affine_to_bytes(cv, cv.G), total.to_bytes(32, "little")))
-    print(json.dumps({"curve": a.curve, "log2n": lg, "ms": round(ms, 3), "Mpoints_per_s": round(n / ms / 1e3, 1), "exact_match": got == exp,
+    print(json.dumps({"curve": a.curve, "pattern": a.pattern, "log2n": lg, "ms": round(ms, 3), "Mpoints_per_s": round(n / ms / 1e3, 1), "exact_match": got == exp,
                       "gen_s": round(tgen, 2), "host_check_s": round(time.time() - t0, 1), "gpu_mem_GiB": round(torch.cuda.mem_get_info()[0] / 2**30, 1)}), flush=True)
     eng.free_bases(h); del bases, sc

@@ -68,7 +68,7 @@ struct b200msm_ctx {
   uint32_t* h_pinned = nullptr;
   void* h_folded = nullptr; size_t h_folded_cap = 0;                         // pinned staging of the folded bucket entries
   int opt_combine = 0;                                                        // 0 = host serial tail (default), 1 = device k_window_sums + k_horner
-  float host_combine_ms = 0;                                               // small pinned read-back area (1024 words)
+  float host_combine_ms = 0;                                               // small pinned read-back area (2048 words: [0,512) slot maxima, [512,1024) slot pair offsets, [1024,..) per-round totals)
   std::map<uint64_t, Resident> residents; uint64_t next_handle = 1;
   cudaEvent_t ev[8] = {};
   // fine-grained phase profiler (active only while a stats struct is being filled)
@@ -235,10 +235,10 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
     *adds_out += U[r] - U[r + 1];
   }
   if (ctx->prof) {   // exact slot counts per round (the U[] are upper bounds): read the scan totals back, stats mode only
-    for (uint32_t r = 1; r <= R; r++) CK(cudaMemcpyAsync(ctx->h_pinned + 768 + r, off[r] + nbg, 4, cudaMemcpyDeviceToHost, s));
+    for (uint32_t r = 1; r <= R; r++) CK(cudaMemcpyAsync(ctx->h_pinned + 1024 + r, off[r] + nbg, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     uint64_t prev = m0, exact = 0;
-    for (uint32_t r = 1; r <= R; r++) { uint64_t cur = ctx->h_pinned[768 + r]; exact += prev - cur; if (r == 1) ctx->adds_r0 += prev - cur; prev = cur; }
+    for (uint32_t r = 1; r <= R; r++) { uint64_t cur = ctx->h_pinned[1024 + r]; exact += prev - cur; if (r == 1) ctx->adds_r0 += prev - cur; prev = cur; }
     *adds_out -= 0; ctx->adds_exact += exact;
   }
   k_accum_finish<C, false><<<(nbg + 127) / 128, 128, 0, s>>>(nullptr, nullptr, pin, off[R], nbg, buckets_g); CKL();
@@ -314,12 +314,22 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
     const double per_pair = 8.0 * C::N * 0.75 + 4.0 * C::N * 0.75 + 6;      // points (pa+pb) + prefix/products + bid, per input pair
     const uint64_t budget_pairs = ctx->opt_group_pairs > 0 ? (uint64_t)ctx->opt_group_pairs : (uint64_t)std::max(1.0, 0.45 * (double)ctx->total_mem / per_pair / lanes);
     uint32_t ngroups = std::max<uint32_t>(lanes, (uint32_t)((mtot + budget_pairs - 1) / budget_pairs));
-    const uint32_t wlim = pl.W > pl.Wd ? pl.Wd : pl.W;          // the extra slot stays in the group of the last window
+    // slots above the highest non-empty one are skipped altogether (short scalars in wide containers, e.g. GLV halves)
+    uint32_t Wuse = pl.W; while (Wuse > 0 && ctx->h_pinned[512 + Wuse] == ctx->h_pinned[512 + Wuse - 1]) Wuse--;
+    if (Wuse == 0) {                                              // every digit is zero: the sum is the point at infinity
+      uint32_t z[3 * C::N]; memset(z, 0, sizeof z); for (int i = 0; i < C::N; i++) z[C::N + i] = C::one(i);
+      memcpy(ctx->h_pinned + 1100, z, sizeof z);
+      CK(cudaMemcpyAsync(d_out, ctx->h_pinned + 1100, sizeof z, cudaMemcpyHostToDevice, s));
+      if (st) { CK(cudaEventRecord(ctx->ev[3], s)); CK(cudaEventRecord(ctx->ev[4], s)); CK(cudaEventRecord(ctx->ev[5], s));
+                st->n = n; st->window_bits = pl.c; st->windows = pl.Wd; st->reserved = pl.W; st->buckets_per_window = pl.B; }
+      return B200MSM_OK;
+    }
+    const uint32_t wlim = Wuse > pl.Wd ? pl.Wd : Wuse;            // the extra slot stays in the group of the last window
     ngroups = std::min(ngroups, wlim);
     // slot boundaries with (nearly) equal pair counts
-    std::vector<uint32_t> cut(ngroups + 1, 0); cut[ngroups] = pl.W;
+    std::vector<uint32_t> cut(ngroups + 1, 0); cut[ngroups] = Wuse;
     { uint32_t w = 0; for (uint32_t g = 1; g < ngroups; g++) { uint64_t target = mtot * g / ngroups;
-        while (w < pl.W && ctx->h_pinned[512 + w] < target) w++;
+        while (w < Wuse && ctx->h_pinned[512 + w] < target) w++;
         cut[g] = std::min(std::max(w, cut[g - 1] + 1), wlim - (ngroups - g)); } }
     for (uint32_t l = 0; l < lanes; l++) { rc = lane_init(ctx, ctx->lane[l]); if (rc) return rc; if (lanes > 1) { CK(cudaStreamWaitEvent(ctx->lane[l].stream, ctx->ev_sorted, 0)); if (ctx->bases_pending) CK(cudaStreamWaitEvent(ctx->lane[l].stream, ctx->ev_bases, 0)); } }
     // host staging for the folded entries of every slot, and one event per group
@@ -381,6 +391,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
       MARK(T_HORNER);
     } else {
       if (lanes > 1) for (uint32_t l = 0; l < lanes; l++) { CK(cudaEventRecord(ctx->lane[l].done, ctx->lane[l].stream)); CK(cudaStreamWaitEvent(s, ctx->lane[l].done, 0)); }
+      if (Wuse < pl.W) CK(cudaMemsetAsync(ctx->buckets.as<char>() + (size_t)Wuse * pl.B * 16 * C::N, 0, (size_t)(pl.W - Wuse) * pl.B * 16 * C::N, s));   // skipped slots = infinity (zz = 0)
       if (lanes == 1) { rc = fold_slots<C>(ctx, s, ctx->buckets.p, pl.W, pl.B); if (rc) return rc; }
       MARK(T_FOLD);
       if (st) CK(cudaEventRecord(ctx->ev[4], s));
@@ -542,7 +553,7 @@ int b200msm_create(b200msm_ctx** out, int device_id) {
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B200MSM_E_CUDA; }
   ctx->own_stream = true;
   for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return B200MSM_E_CUDA; }
-  if (cudaMallocHost(&ctx->h_pinned, 1024 * sizeof(uint32_t)) != cudaSuccess) { delete ctx; return B200MSM_E_CUDA; }
+  if (cudaMallocHost(&ctx->h_pinned, 2048 * sizeof(uint32_t)) != cudaSuccess) { delete ctx; return B200MSM_E_CUDA; }
   if (cudaEventCreateWithFlags(&ctx->ev_plan, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_sorted, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return B200MSM_E_CUDA; }
   *out = ctx;
   return B200MSM_OK;
