@@ -96,6 +96,17 @@ int b200msm_g1_sum(b200msm_ctx* ctx, int curve, const void* jac_points, uint64_t
  * first byte 0x40 = infinity, 0x80 (compressed only) = y is the greater of the two roots. */
 int b200msm_g1_batch_convert(b200msm_ctx* ctx, int curve, int op, const void* in, uint64_t n, void* out);
 
+/* ---- GLV pre-pass, BLS12-381 only like the reference (src/build_glv.js:3; other curves: B200MSM_E_UNSUPPORTED).
+ * == g1m_glv_decomposeScalar(pScalar, pScalarRes) -> sign over a batch                     src/build_glv.js:53-146
+ * scalars: n x 32 bytes.  out_scalars: n x 64 bytes = |k1| (bytes 0..15) and |k2| (bytes 32..47), other bytes zero,
+ * exactly the reference's pScalarRes; out_signs (nullable): n x uint32, bit 0 = (k1 >= 0), bit 1 = (k2 >= 0). */
+int b200msm_glv_decompose_scalars(b200msm_ctx* ctx, int curve, const void* scalars, uint64_t n, void* out_scalars, void* out_signs);
+/* == g1m_glv_preprocessEndomorphism(pPoints, pScalars, numPoints, pPointsRes, pScalarsRes)  src/build_glv.js:178-263
+ * n affine points (96 B) / n scalars (32 B) -> 2n points [P_i or -P_i, phi(P_i) or -phi(P_i)] and 2n scalars of 32 bytes
+ * (each < 2^128); feeding them to b200msm_g1_multiexp_affine(scalar_size = 32, 2n) gives the same sum (test/glv.js:103-192). */
+int b200msm_g1_glv_preprocess(b200msm_ctx* ctx, int curve, const void* points, const void* scalars, uint64_t n,
+                              void* out_points, void* out_scalars);
+
 /* ---- synthetic inputs (benchmarks/multiexp.js:16-23 builds bases on the module itself):
  * device_out[i] = k_i * G for i in [0, n), affine Montgomery, k_i = splitmix64(seed + first + i) (0 mapped to 1).
  * device_out must be a device pointer with room for n * 2*n8 bytes. */

@@ -276,3 +276,6 @@ def glv_preprocess(points, scalars):
         out_p.append((GLV_BETA * x % cv.q, y if sign & 2 else (-y) % cv.q))     # g1m_glv_endomorphism :150-174
         out_s += [k1, k2]
     return out_p, out_s
+
+
+GLV_LAMBDA = BLS_LAMBDA      # phi(x, y) = (GLV_BETA * x, y) = GLV_LAMBDA * (x, y); signed halves satisfy k = k1 + k2 * GLV_LAMBDA (mod r)

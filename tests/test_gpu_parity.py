@@ -362,3 +362,61 @@ def test_ffjavascript_style_surface(eng, cname):
     with pytest.raises(ValueError, match="Scalar size does not match"): G.multiExpAffine(bases, sc[:-1])
     assert G.isZero(G.multiExpAffine(b"", b"")) and G.eq(G.add(r, G.zero()), r)
     assert G.batchUtoLEM(G.batchLEMtoU(bases)) == bases and G.batchCtoLEM(G.batchLEMtoC(bases)) == bases
+
+
+# ---------------------------------------------------------------- "next" row 2: GLV pre-pass (src/build_glv.js)
+GLV_KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "glv.json")))["tests"]
+
+
+def test_glv_decompose_kat_and_random(eng):
+    """g1m_glv_decomposeScalar: the reference's KAT (test/glv.js:50-65), then edge and random 256-bit scalars against
+    the restated algorithm (oracle/pyref.py::glv_decompose, pinned on the same KAT) -- exact halves and sign bits."""
+    cv = curve("bls12381")
+    v = GLV_KAT["decomposeScalar is correct."]["values"]
+    k = int(v["scalar"], 16)
+    out, signs = eng.glv_decompose_scalars(cv.cid, k.to_bytes(32, "little"), 1)
+    assert [int.from_bytes(out[0:32], "little"), int.from_bytes(out[32:64], "little")] == [int(x, 16) for x in v["expectedOutput"]]
+    assert signs == [1]
+    rnd = random.Random(5)
+    ks = [0, 1, 2, cv.r - 1, cv.r, cv.r + 1, 2 * cv.r - 1, 2 * cv.r, 2 * cv.r + 1, (1 << 256) - 1, 1 << 128, (1 << 128) - 1,
+          pyref.GLV_LAMBDA, pyref.GLV_U0, pyref.GLV_NEG_V1] + [rnd.getrandbits(256) for _ in range(4000)] + [rnd.getrandbits(rnd.randrange(1, 257)) for _ in range(1000)]
+    out, signs = eng.glv_decompose_scalars(cv.cid, b"".join(x.to_bytes(32, "little") for x in ks), len(ks))
+    for i, x in enumerate(ks):
+        k1, k2, sg = pyref.glv_decompose(x)
+        assert (int.from_bytes(out[64 * i:64 * i + 32], "little"), int.from_bytes(out[64 * i + 32:64 * i + 64], "little"), signs[i]) == (k1, k2, sg), hex(x)
+
+
+def test_glv_preprocess_kat(eng):
+    """g1m_glv_preprocessEndomorphism on the reference's own inputs (test/glv.js:103-192): scalar halves match its expected
+    output, the points match the restated algorithm, and the MSM over the 2N outputs equals the MSM over the N inputs."""
+    cv = curve("bls12381")
+    v = GLV_KAT["preprocessEndomorphism is correct."]["values"]
+    n = int(v["numPoints"], 16)
+    P = [(int(v["inputPoints"][2 * i], 16), int(v["inputPoints"][2 * i + 1], 16)) for i in range(n)]
+    S = [int(x, 16) for x in v["inputScalars"][:n]]
+    bases = b"".join(pyref.affine_to_bytes(cv, p) for p in P); sc = b"".join(s.to_bytes(32, "little") for s in S)
+    p2, s2 = eng.glv_preprocess(cv.cid, bases, sc, n)
+    assert [int.from_bytes(s2[32 * i:32 * i + 32], "little") for i in range(2 * n)] == [int(x, 16) for x in v["expectedScalarOutput"][:2 * n]]
+    P2, S2 = pyref.glv_preprocess(P, S)
+    assert p2 == b"".join(pyref.affine_to_bytes(cv, p) for p in P2)
+    assert msm(eng, cv, p2, s2, 32, 2 * n) == oracle_msm(cv, bases, sc, 32, n)
+
+
+@pytest.mark.parametrize("n", [1, 1000, 1 << 16])
+def test_glv_msm_equals_plain_msm(eng, n):
+    """test/glv.js:194-252 (the reference's commented-out benchmark check): MSM after the GLV pre-pass == plain MSM, incl. scalars >= r,
+    an infinity input and a point with y-negation on both halves.  Also: BN254 is refused like the reference (BLS12-381 only)."""
+    cv = curve("bls12381")
+    bases = bytearray(make_bases(cv, n, 91)); sc = bytearray(make_scalars(n, 92, "u256"))
+    if n >= 1000:
+        bases[96 * 7:96 * 8] = bytes(96)                                  # affine infinity
+        sc[32 * 9:32 * 10] = (cv.r + 5).to_bytes(32, "little"); sc[32 * 10:32 * 11] = bytes(32)
+    bases = bytes(bases); sc = bytes(sc)
+    p2, s2 = eng.glv_preprocess(cv.cid, bases, sc, n)
+    assert all(s2[32 * i + 16:32 * i + 32] == bytes(16) for i in range(0, 2 * n, max(1, n // 50)))
+    plain = msm(eng, cv, bases, sc, 32, n)
+    assert msm(eng, cv, p2, s2, 32, 2 * n) == plain
+    assert msm(eng, cv, p2, b"".join(s2[32 * i:32 * i + 16] for i in range(2 * n)), 16, 2 * n) == plain   # halves as 16-byte scalars
+    if n <= 1000: assert plain == oracle_msm(cv, bases, sc, 32, n)
+    import b200msm
+    with pytest.raises(b200msm.B200MsmError): eng.glv_preprocess(curve("bn128").cid, bytes(64), bytes(32), 1)

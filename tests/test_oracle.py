@@ -121,10 +121,35 @@ def test_reduce_buckets_kat():
 
 
 def test_glv_decompose_kat():
-    """test/glv.js:50-65: k = k1 - k2*lambda (mod r) with the reference's sign convention."""
+    """test/glv.js:50-65: exact |k1|, |k2| and sign of g1m_glv_decomposeScalar; k = k1 - k2*lambda (mod r)."""
     v = vals("decomposeScalar is correct.", GLV)
-    k = v["scalar"]; k1, k2 = v["expectedOutput"][0], v["expectedOutput"][1]
-    assert (k1 - k2 * pyref.BLS_LAMBDA) % BLS.r == k % BLS.r or (k1 + k2 * pyref.BLS_LAMBDA) % BLS.r == k % BLS.r
+    k = v["scalar"]
+    k1, k2, sign = pyref.glv_decompose(k)
+    assert [k1, k2] == v["expectedOutput"] and sign == 1
+    s1 = k1 if sign & 1 else -k1; s2 = k2 if sign & 2 else -k2
+    assert (s1 + s2 * pyref.GLV_LAMBDA) % BLS.r == k % BLS.r
+
+
+def test_glv_preprocess_kat():
+    """test/glv.js:103-192: scalar halves of g1m_glv_preprocessEndomorphism, and the MSM over the 2N outputs equals the
+    MSM over the N inputs."""
+    v = vals("preprocessEndomorphism is correct.", GLV)
+    n = v["numPoints"]; P = pts_of(v["inputPoints"])[:n]; S = v["inputScalars"][:n]
+    P2, S2 = pyref.glv_preprocess(P, S)
+    assert S2 == v["expectedScalarOutput"][:2 * n]
+    assert all(pyref.is_on_curve(BLS, p) for p in P2)
+    assert pyref.msm_naive(BLS, P2, S2) == pyref.msm_naive(BLS, P, S)
+
+
+def test_glv_decompose_edge_scalars():
+    """the decomposition holds (mod r) for every 256-bit scalar, including those >= r, and both halves fit in 128 bits"""
+    rnd = random.Random(77)
+    edge = [0, 1, 2, BLS.r - 1, BLS.r, BLS.r + 1, 2 * BLS.r - 1, 2 * BLS.r, 2 * BLS.r + 1, (1 << 256) - 1, 1 << 128, (1 << 128) - 1, pyref.GLV_LAMBDA]
+    for k in edge + [rnd.getrandbits(256) for _ in range(300)]:
+        k1, k2, sign = pyref.glv_decompose(k)
+        assert k1 < (1 << 128) and k2 < (1 << 128)
+        s1 = k1 if sign & 1 else -k1; s2 = k2 if sign & 2 else -k2
+        assert (s1 + s2 * pyref.GLV_LAMBDA) % BLS.r == k % BLS.r
 
 
 # ---- oracle <-> reference WASM differential (random inputs, both curves)

@@ -98,6 +98,20 @@ class Engine:
         pi, ki = _ptr(data); o = ctypes.create_string_buffer(max(1, out_sz * n))
         self._ck(lib.b200msm_g1_batch_convert(self._ctx, curve, k, pi, n, o)); return o.raw[:out_sz * n]
 
+    def glv_decompose_scalars(self, curve, scalars, n):
+        """g1m_glv_decomposeScalar over n 32-byte scalars -> (n x 64 bytes [|k1| .. |k2| ..], [sign, ...])"""
+        ps, ks = _ptr(scalars); o = ctypes.create_string_buffer(max(1, 64 * n)); sg = (ctypes.c_uint32 * max(1, n))()
+        self._ck(lib.b200msm_glv_decompose_scalars(self._ctx, curve, ps, n, o, sg)); return o.raw[:64 * n], list(sg)[:n]
+
+    def glv_preprocess(self, curve, points, scalars, n, out_points=None, out_scalars=None):
+        """g1m_glv_preprocessEndomorphism: -> (2n points, 2n 32-byte scalars); bytes unless output buffers are given"""
+        pp, kp = _ptr(points); ps, ks = _ptr(scalars)
+        if out_points is None:
+            op_ = ctypes.create_string_buffer(max(1, 192 * n)); os_ = ctypes.create_string_buffer(max(1, 64 * n))
+            self._ck(lib.b200msm_g1_glv_preprocess(self._ctx, curve, pp, ps, n, op_, os_)); return op_.raw[:192 * n], os_.raw[:64 * n]
+        po, ko = _ptr(out_points); pso, kso = _ptr(out_scalars)
+        self._ck(lib.b200msm_g1_glv_preprocess(self._ctx, curve, pp, ps, n, po, pso)); return out_points, out_scalars
+
     def fq_op(self, curve, op, a, b=None):
         n = len(a) // N8[curve]
         pa, ka = _ptr(a); pb_, kb = _ptr(b)

@@ -20,6 +20,7 @@
 #include "accumulate.cuh"
 #include "fp29.cuh"
 #include "codecs.cuh"
+#include "glv.cuh"
 #include "host_ec.h"
 #include <chrono>
 
@@ -723,6 +724,43 @@ int b200msm_g1_batch_convert(b200msm_ctx* ctx, int curve, int op, const void* in
   else k_codec<BN254><<<g, 128, 0, ctx->stream>>>(op, (const uint8_t*)d_in, (uint32_t)n, ctx->acc_c.as<uint8_t>(), 3u);
   CKL();
   return deliver(ctx, ctx->acc_c.p, out, n * out_sz[op]);
+}
+
+// g1m_glv_decomposeScalar over a batch (build_glv.js:53-146): out_scalars n x 64 bytes, out_signs n x u32 (nullable)
+int b200msm_glv_decompose_scalars(b200msm_ctx* ctx, int curve, const void* scalars, uint64_t n, void* out_scalars, void* out_signs) {
+  if (!ctx || (n && (!scalars || !out_scalars)) || n >= (1ull << 31)) return B200MSM_E_ARG;
+  if (curve != B200MSM_BLS12_381_G1) { ctx->err = "GLV constants exist for BLS12-381 only (build_glv.js:3)"; return B200MSM_E_UNSUPPORTED; }
+  if (n == 0) return B200MSM_OK;
+  CK(cudaSetDevice(ctx->device));
+  const void* d_s; int rc = stage(ctx, scalars, n * 32, ctx->acc_a, &d_s); if (rc) return rc;
+  CK(ctx->acc_c.ensure(n * 64 + 16)); CK(ctx->acc_d.ensure(n * 4 + 16));
+  k_glv_decompose<<<(uint32_t)((n + 127) / 128), 128, 0, ctx->stream>>>((const uint32_t*)d_s, (uint32_t)n, ctx->acc_c.as<uint32_t>(), ctx->acc_d.as<uint32_t>()); CKL();
+  rc = deliver(ctx, ctx->acc_c.p, out_scalars, n * 64); if (rc) return rc;
+  if (out_signs) return deliver(ctx, ctx->acc_d.p, out_signs, n * 4);
+  return B200MSM_OK;
+}
+
+// g1m_glv_preprocessEndomorphism (build_glv.js:178-263): n points / n scalars -> 2n points / 2n scalars of 32 bytes (< 2^128)
+int b200msm_g1_glv_preprocess(b200msm_ctx* ctx, int curve, const void* points, const void* scalars, uint64_t n, void* out_points, void* out_scalars) {
+  if (!ctx || (n && (!points || !scalars || !out_points || !out_scalars)) || n >= (1ull << 30)) return B200MSM_E_ARG;
+  if (curve != B200MSM_BLS12_381_G1) { ctx->err = "GLV constants exist for BLS12-381 only (build_glv.js:3)"; return B200MSM_E_UNSUPPORTED; }
+  if (n == 0) return B200MSM_OK;
+  CK(cudaSetDevice(ctx->device));
+  const void *d_s, *d_p; int rc = stage(ctx, scalars, n * 32, ctx->acc_a, &d_s); if (rc) return rc;
+  rc = stage(ctx, points, n * 96, ctx->acc_b, &d_p); if (rc) return rc;
+  const bool so_dev = is_device_ptr(out_scalars) && (reinterpret_cast<uintptr_t>(out_scalars) & 15) == 0;
+  const bool po_dev = is_device_ptr(out_points) && (reinterpret_cast<uintptr_t>(out_points) & 15) == 0;
+  if (!so_dev) CK(ctx->acc_c.ensure(n * 64 + 16));
+  if (!po_dev) CK(ctx->acc_e.ensure(n * 192 + 16));
+  CK(ctx->acc_d.ensure(n * 4 + 16));
+  uint32_t* d_so = so_dev ? (uint32_t*)out_scalars : ctx->acc_c.as<uint32_t>();
+  void* d_po = po_dev ? out_points : ctx->acc_e.p;
+  const uint32_t g = (uint32_t)((n + 127) / 128);
+  k_glv_decompose<<<g, 128, 0, ctx->stream>>>((const uint32_t*)d_s, (uint32_t)n, d_so, ctx->acc_d.as<uint32_t>()); CKL();
+  k_glv_points<<<g, 128, 0, ctx->stream>>>(d_p, ctx->acc_d.as<uint32_t>(), (uint32_t)n, d_po); CKL();
+  if (!so_dev) { rc = deliver(ctx, d_so, out_scalars, n * 64); if (rc) return rc; }
+  if (!po_dev) { rc = deliver(ctx, d_po, out_points, n * 192); if (rc) return rc; }
+  return B200MSM_OK;
 }
 
 int b200msm_fq_op(b200msm_ctx* ctx, int curve, int op, const void* a, const void* b, void* r, uint64_t count) {
