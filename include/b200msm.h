@@ -79,6 +79,15 @@ int b200msm_free_bases(b200msm_ctx* ctx, uint64_t handle);
 int b200msm_g1_multiexp_resident(b200msm_ctx* ctx, uint64_t handle, const void* scalars, uint32_t scalar_size,
                                  uint64_t n, void* out, b200msm_stats* stats /* nullable */);
 
+/* ---- resident bases WITH a precomputed window table (no counterpart in the reference, which receives its bases with
+ *      every call; fixed-base provers upload once).  Row w of the table holds 2^(bit offset of window w) * P_i, so the digits
+ *      of all windows share one bucket array: no per-window bucket reduction, no window combination, wider windows.
+ *      The table serves MSMs whose scalar_size equals the one given here (other sizes run the ordinary pipeline on the
+ *      same handle); window_bits = 0 chooses the width from n.  Device memory: ceil(8*scalar_size / window_bits) * n * 2*n8 bytes.
+ *      Results are identical to b200msm_upload_bases + b200msm_g1_multiexp_resident. */
+int b200msm_upload_bases_windowed(b200msm_ctx* ctx, int curve, const void* bases, uint64_t n, uint32_t scalar_size,
+                                  uint32_t window_bits, uint64_t* handle);
+
 /* ---- == g1m_normalize + f1m_fromMontgomery(x), f1m_fromMontgomery(y)   src/build_curve_jacobian_a0.js:940-973,
  *      the comparison form of the reference's tests (test/batchAffine.js:1249-1254):
  * count Jacobian Montgomery points -> count canonical affine points x || y as plain LE integers < q; infinity -> zeros. */

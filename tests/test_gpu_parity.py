@@ -420,3 +420,86 @@ def test_glv_msm_equals_plain_msm(eng, n):
     if n <= 1000: assert plain == oracle_msm(cv, bases, sc, 32, n)
     import b200msm
     with pytest.raises(b200msm.B200MsmError): eng.glv_preprocess(curve("bn128").cid, bytes(64), bytes(32), 1)
+
+
+# ---------------------------------------------------------------- resident bases with a precomputed window table
+def _resident(eng, cv, h, sc, ssz, n):
+    return eng.normalize(cv.cid, eng.multiexp_resident(h, sc, ssz, n, cv.cid))
+
+
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+@pytest.mark.parametrize("n,wb", [(1, 0), (37, 3), (1000, 0), (1000, 8), (5000, 13), (5000, 16), (3000, 11)])
+def test_window_table_matches_oracle(eng, cname, n, wb):
+    """b200msm_upload_bases_windowed: all windows share one bucket array fed from the table rows 2^(off_w) * P_i.
+    wb = 8 and 16 divide 256 (the unsigned last digit needs the second slot); 3 / 11 / 13 give mixed window widths."""
+    cv = curve(cname)
+    bases = make_bases(cv, n, 71)
+    h = eng.upload_bases_windowed(cv.cid, bases, n, 32, wb)
+    try:
+        for kind in ("u256", "equal", "small"):
+            sc = make_scalars(n, 72, kind)
+            assert _resident(eng, cv, h, sc, 32, n) == oracle_msm(cv, bases, sc, 32, n), kind
+        assert _resident(eng, cv, h, bytes(32 * n), 32, n) == bytes(2 * cv.n8)               # all-zero scalars
+        sc = b"".join(v.to_bytes(32, "little") for v in ([cv.r - 1, cv.r, (1 << 256) - 1, 1 << 255, 1, 0, (1 << 128) - 1] * n)[:n])
+        assert _resident(eng, cv, h, sc, 32, n) == oracle_msm(cv, bases, sc, 32, n)
+        if n > 100:
+            m = n - 33                                                                        # fewer points than uploaded
+            sc = make_scalars(m, 73, "u256")
+            assert _resident(eng, cv, h, sc, 32, m) == oracle_msm(cv, bases[:m * 2 * cv.n8], sc, 32, m)
+            sc16 = bytes(random.Random(74).getrandbits(8) for _ in range(16 * n))             # other scalar size: ordinary pipeline, same handle
+            assert _resident(eng, cv, h, sc16, 16, n) == oracle_msm(cv, bases, sc16, 16, n)
+            eng.set_option("combine", 1)
+            try:
+                sc = make_scalars(n, 75, "u256")
+                assert _resident(eng, cv, h, sc, 32, n) == oracle_msm(cv, bases, sc, 32, n)
+            finally:
+                eng.set_option("combine", 0)
+    finally:
+        eng.free_bases(h)
+
+
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+def test_window_table_special_points_and_lanes(eng, cname):
+    """duplicate points, P and -P, infinity inputs (their table rows stay infinity), any lane / group split, 16-byte scalars"""
+    cv = curve(cname); n8 = cv.n8
+    g = gen_bytes(cv); ng = pyref.affine_to_bytes(cv, pyref.neg(cv, cv.G)); zero = bytes(2 * n8)
+    pts = (g + g + ng + zero + g + ng + ng + zero) * 40 + make_bases(cv, 3000, 81)
+    m = len(pts) // (2 * n8)
+    h = eng.upload_bases_windowed(cv.cid, pts, m, 32, 10)
+    h16 = eng.upload_bases_windowed(cv.cid, pts, m, 16, 0)
+    try:
+        for lanes, gp in ((1, 0), (4, 0), (3, 7000), (2, 1500)):
+            eng.set_option("lanes", lanes); eng.set_option("group_pairs", gp)
+            for seed, kind in ((1, "equal"), (2, "small"), (3, "u256")):
+                sc = make_scalars(m, seed, kind)
+                assert _resident(eng, cv, h, sc, 32, m) == oracle_msm(cv, pts, sc, 32, m), (lanes, gp, kind)
+        sc16 = bytes(random.Random(82).getrandbits(8) for _ in range(16 * m))
+        assert _resident(eng, cv, h16, sc16, 16, m) == oracle_msm(cv, pts, sc16, 16, m)
+    finally:
+        eng.set_option("lanes", 4); eng.set_option("group_pairs", 0)
+        eng.free_bases(h); eng.free_bases(h16)
+
+
+@pytest.mark.parametrize("cname,lg", [("bls12381", 18), ("bn128", 18)])
+def test_window_table_full_size_known_answer(eng, cname, lg):
+    """2^18 points through the window table against the exact known answer (sum_i s_i k_i mod r) * G and against the ordinary path"""
+    import numpy as np, torch
+    cv = curve(cname); n = 1 << lg; n8 = cv.n8
+    seed = 0xB2000000 + lg
+    d = torch.empty(n * 2 * n8, dtype=torch.uint8, device="cuda")
+    eng.generate_bases(cv.cid, seed, 0, n, d)
+    with np.errstate(over="ignore"):
+        k = _splitmix64_np(np.uint64(seed) + np.arange(n, dtype=np.uint64))
+    k[k == 0] = 1
+    sc = np.random.default_rng(lg + 100).integers(0, 256, size=(n, 32), dtype=np.uint8)
+    sd = torch.from_numpy(sc.reshape(-1).copy()).cuda()
+    words = sc.view("<u8").astype(object)
+    svals = words[:, 0] + (words[:, 1] << 64) + (words[:, 2] << 128) + (words[:, 3] << 192)
+    total = int((svals * k.astype(object)).sum() % cv.r)
+    exp = coracle.normalize(cv.cid, coracle.times_scalar_affine(cv.cid, gen_bytes(cv), total.to_bytes(32, "little")))
+    h = eng.upload_bases_windowed(cv.cid, d, n, 32, 0)
+    try:
+        assert _resident(eng, cv, h, sd, 32, n) == exp
+        assert msm(eng, cv, d, sd, 32, n) == exp
+    finally:
+        eng.free_bases(h)

@@ -7,7 +7,7 @@ import torch, b200msm
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--curve", default="bls12381"); ap.add_argument("--sizes", default="14,16,18,20"); ap.add_argument("--reps", type=int, default=5)
-ap.add_argument("--opt", action="append", default=[]); ap.add_argument("--probe", action="store_true")
+ap.add_argument("--opt", action="append", default=[]); ap.add_argument("--probe", action="store_true"); ap.add_argument("--windowed", type=int, default=-1, help="upload with a precomputed window table of this width (0 = auto)")
 a = ap.parse_args()
 cid = 0 if a.curve == "bls12381" else 1; n8 = b200msm.N8[cid]
 eng = b200msm.Engine(0); dev = torch.device("cuda", 0)
@@ -26,7 +26,7 @@ for lg in [int(x) for x in a.sizes.split(",")]:
     eng.generate_bases(cid, 0xB2000000 + lg, 0, n, bases)
     g = torch.Generator(device=dev); g.manual_seed(lg)
     sc = torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device=dev, generator=g)
-    h = eng.upload_bases(cid, bases, n); out = torch.zeros(3 * n8, dtype=torch.uint8, device=dev)
+    h = eng.upload_bases(cid, bases, n) if a.windowed < 0 else eng.upload_bases_windowed(cid, bases, n, 32, a.windowed); out = torch.zeros(3 * n8, dtype=torch.uint8, device=dev)
     for _ in range(2): eng.multiexp_resident(h, sc, 32, n, cid, out=out)
     eng.multiexp_resident(h, sc, 32, n, cid, out=out, want_stats=True)
     torch.cuda.synchronize()

@@ -63,6 +63,11 @@ class Engine:
         pb, kb = _ptr(bases); h = ctypes.c_uint64()
         self._ck(lib.b200msm_upload_bases(self._ctx, curve, pb, n, ctypes.byref(h))); return h.value
 
+    def upload_bases_windowed(self, curve, bases, n, scalar_size=32, window_bits=0):
+        """resident bases + precomputed window table (rows 2^(c*w) * P_i); use the handle with multiexp_resident"""
+        pb, kb = _ptr(bases); h = ctypes.c_uint64()
+        self._ck(lib.b200msm_upload_bases_windowed(self._ctx, curve, pb, n, scalar_size, window_bits, ctypes.byref(h))); return h.value
+
     def free_bases(self, handle): self._ck(lib.b200msm_free_bases(self._ctx, handle))
 
     def multiexp_resident(self, handle, scalars, scalar_size, n, curve, out=None, want_stats=False):

@@ -42,7 +42,9 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct Resident { int curve; uint64_t n; void* d; };
+struct Resident { int curve; uint64_t n; void* d;                // d: n affine points; with a window table: Wd rows of n points, row 0 = the bases
+                  uint32_t t_nbits = 0, t_c0 = 0, t_rem = 0, t_Wd = 0; };   // window plan the table was built for (t_Wd == 0: no table)
+struct Precomp { uint32_t stride, nbits, c0, rem, Wd; };
 
 // one accumulate lane: a stream with its own tree scratch (see accumulate_batch_affine)
 struct TreeLane {
@@ -61,7 +63,7 @@ struct b200msm_ctx {
   int opt_window_bits = 0, opt_accumulate = 0, opt_tree_rounds = -1;
   DevBuf bases, scalars, canon, counts, offsets, cursors, tiles, sorted, buckets, wsum, out, misc, acc_a, acc_b, acc_c, acc_d, acc_e;
   TreeLane lane[MAX_LANES];                                                   // batch-affine tree lanes
-  int opt_lanes = 4, opt_ba_k = 8, opt_pt_k = 8, opt_persist = 444;
+  int opt_lanes = 4, opt_ba_k = 8, opt_pt_k = 8, opt_persist = 444, opt_subslots = 0;
   bool probe29 = false, probe_sqr = false; int64_t opt_group_pairs = 0;
   cudaEvent_t ev_plan = nullptr, ev_sorted = nullptr, ev_bases = nullptr, ev_done = nullptr;
   cudaStream_t copy_stream = nullptr; bool bases_pending = false;
@@ -266,23 +268,28 @@ int fold_slots(b200msm_ctx* ctx, cudaStream_t s, void* buckets_g, uint32_t slots
 
 // Core pipeline: d_bases (affine Montgomery, device), d_scal (canonical 8-word scalars, device), result -> d_out (device, 3*n8 bytes)
 template <class C>
-int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, uint64_t n64, uint32_t nbits, void* d_out, b200msm_stats* st) {
+int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, uint64_t n64, uint32_t nbits, void* d_out, b200msm_stats* st, const Precomp* pre) {
   cudaStream_t s = ctx->stream;
   const uint32_t n = (uint32_t)n64;
   MsmPlan pl;
-  pl.n = n; pl.nbits = nbits;
+  pl.n = n; pl.nbits = nbits; pl.pre_stride = 0;
+  if (pre) {   // the plan the table was built for; all windows share one bucket array (two slots when the unsigned last digit can reach 2B)
+    pl.Wd = pre->Wd; pl.c0 = pre->c0; pl.rem = pre->rem; pl.c = pl.c0 + (pl.rem ? 1 : 0); pl.B = 1u << (pl.c - 1); pl.logB = pl.c - 1;
+    pl.W = pl.rem == 0 ? 2 : 1; pl.pre_stride = pre->stride;
+  } else
   { // window plan: target width ct, then equalise: Wd windows whose widths differ by at most one bit
     uint32_t ct = ctx->opt_window_bits > 0 ? std::min<uint32_t>((uint32_t)ctx->opt_window_bits, std::min<uint32_t>(nbits, 24)) : auto_window_bits(n, nbits);
     pl.Wd = (nbits + ct - 1) / ct; pl.c0 = nbits / pl.Wd; pl.rem = nbits - pl.c0 * pl.Wd;
     pl.c = pl.c0 + (pl.rem ? 1 : 0); pl.B = 1u << (pl.c - 1); pl.logB = pl.c - 1;
     pl.W = pl.Wd + (pl.rem == 0 ? 1 : 0); }
   const uint32_t nb = pl.W * pl.B;
-  if ((uint64_t)pl.W * pl.B > (1ull << 31) || (uint64_t)n * pl.W >= (1ull << 32)) { ctx->err = "problem too large for 32-bit pair indices"; return B200MSM_E_UNSUPPORTED; }
+  if (pre && (uint64_t)pre->stride * pl.Wd >= (1ull << 31)) { ctx->err = "window table too large for 31-bit point indices"; return B200MSM_E_UNSUPPORTED; }
+  if ((uint64_t)pl.W * pl.B > (1ull << 31) || (uint64_t)n * std::max(pl.W, pl.Wd) >= (1ull << 32)) { ctx->err = "problem too large for 32-bit pair indices"; return B200MSM_E_UNSUPPORTED; }
   if (pl.W > 400) { ctx->err = "too many windows"; return B200MSM_E_UNSUPPORTED; }
 
   if (st) CK(cudaEventRecord(ctx->ev[1], s));
   CK(ctx->counts.ensure((size_t)nb * 4)); CK(ctx->offsets.ensure((size_t)(nb + 1) * 4)); CK(ctx->cursors.ensure((size_t)nb * 4));
-  CK(ctx->sorted.ensure((size_t)n * pl.W * 4 + 16));
+  CK(ctx->sorted.ensure((size_t)n * std::max(pl.W, pl.Wd) * 4 + 16));
   CK(cudaMemsetAsync(ctx->counts.p, 0, (size_t)nb * 4, s));
   const uint32_t tb = 256, gb = (n + tb - 1) / tb;
   k_digits<false><<<gb, tb, 0, s>>>(d_scal, pl, ctx->counts.as<uint32_t>(), nullptr); CKL();
@@ -291,9 +298,20 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   // ---- per-slot pair counts and largest bucket populations go back to the host while the scatter runs
   CK(ctx->misc.ensure(512 * 4));
   CK(cudaMemsetAsync(ctx->misc.p, 0, 512 * 4, s));
-  { dim3 g((pl.B + 255) / 256, pl.W); k_window_max<<<g, 256, 0, s>>>(ctx->counts.as<uint32_t>(), pl.B, ctx->misc.as<uint32_t>()); CKL(); }
-  CK(cudaMemcpyAsync(ctx->h_pinned, ctx->misc.p, pl.W * 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpy2DAsync(ctx->h_pinned + 512, 4, ctx->offsets.as<uint32_t>(), (size_t)pl.B * 4, 4, pl.W + 1, cudaMemcpyDeviceToHost, s));
+  // planning granules: whole slots normally; with a window table (one or two slots only) the slot is cut into up to 64 bucket ranges
+  uint32_t Bg = pl.B;
+  if (pre) {   // sub-slots (see the accumulate block): 8 per slot by default, more when a sub-slot's tree scratch would exceed the memory budget
+    const double per_pair = 8.0 * C::N * 0.75 + 4.0 * C::N * 0.75 + 6;
+    const double budget = ctx->opt_group_pairs > 0 ? (double)ctx->opt_group_pairs : 0.45 * (double)ctx->total_mem / per_pair / MAX_LANES;
+    uint32_t S = ctx->opt_subslots > 0 ? (uint32_t)ctx->opt_subslots : 4;      // measured at 2^20, c = 20: 4 -> 5.86 ms, 8 -> 5.97, 16 -> 5.96, 32 -> 6.23
+    while (S < 256 && (double)n * pl.Wd / S > budget) S *= 2;
+    while (S > 1 && pl.B / S < 64) S /= 2;
+    if (pl.B / S >= 1) Bg = pl.B / S;
+  }
+  const uint32_t G = nb / Bg;
+  { dim3 g((Bg + 255) / 256, G); k_window_max<<<g, 256, 0, s>>>(ctx->counts.as<uint32_t>(), Bg, ctx->misc.as<uint32_t>()); CKL(); }
+  CK(cudaMemcpyAsync(ctx->h_pinned, ctx->misc.p, G * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpy2DAsync(ctx->h_pinned + 512, 4, ctx->offsets.as<uint32_t>(), (size_t)Bg * 4, 4, G + 1, cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(ctx->ev_plan, s));
   k_digits<true><<<gb, tb, 0, s>>>(d_scal, pl, ctx->cursors.as<uint32_t>(), ctx->sorted.as<uint32_t>()); CKL();
   if (st) CK(cudaEventRecord(ctx->ev[2], s));
@@ -307,7 +325,97 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   if (mode == 0) mode = 2;
   uint32_t rounds = 0; uint64_t adds = 0;
   ctx->adds_r0 = 0; ctx->adds_exact = 0; ctx->cur_n = n;
-  if (mode == 2) {
+  if (pre) {
+    // ---- window-table form: the single bucket array is cut into S sub-slots of Bs = Bg buckets (a power of two).  Each sub-slot is a
+    // group: its tree runs on one lane, then it is folded on its own (k_fold sees it as a slot of Bs buckets) while the other lanes still
+    // accumulate, so the latency-bound fold levels are hidden.  With b = s*Bs + l:  sum_b (b+1) T[b] = sum_s [ F_s + s*Bs * T_s ],
+    // F_s = folded value of sub-slot s, T_s = its plain sum = folded entry 0; the host adds these few terms (combine_subslots).
+    const uint64_t mtot = ctx->h_pinned[512 + G];
+    if (mtot == 0) {
+      uint32_t z[3 * C::N]; memset(z, 0, sizeof z); for (int i = 0; i < C::N; i++) z[C::N + i] = C::one(i);
+      memcpy(ctx->h_pinned + 1100, z, sizeof z);
+      CK(cudaMemcpyAsync(d_out, ctx->h_pinned + 1100, sizeof z, cudaMemcpyHostToDevice, s));
+      if (st) { CK(cudaEventRecord(ctx->ev[3], s)); CK(cudaEventRecord(ctx->ev[4], s)); CK(cudaEventRecord(ctx->ev[5], s));
+                st->n = n; st->window_bits = pl.c; st->windows = pl.Wd; st->reserved = pl.W; st->buckets_per_window = pl.B; }
+      return B200MSM_OK;
+    }
+    uint32_t lanes = ctx->prof ? 1u : (uint32_t)std::max(1, std::min(ctx->opt_lanes, (int)MAX_LANES));
+    if (mtot < (1u << 16)) lanes = 1;
+    const bool host_tail = ctx->opt_combine == 0;
+    uint32_t logBs = 0; while ((1u << logBs) < Bg) logBs++;
+    const uint32_t per = logBs + 1;
+    const size_t fbytes = (size_t)G * per * 16 * C::N;
+    if (host_tail) {
+      CK(ctx->wsum.ensure(fbytes));
+      if (ctx->h_folded_cap < fbytes + 4096) { if (ctx->h_folded) cudaFreeHost(ctx->h_folded); ctx->h_folded = nullptr; ctx->h_folded_cap = 0;
+        CK(cudaMallocHost(&ctx->h_folded, fbytes + 4096)); ctx->h_folded_cap = fbytes + 4096; }
+      while (ctx->gev.size() < G) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->gev.push_back(e); }
+    }
+    for (uint32_t l = 0; l < lanes; l++) { rc = lane_init(ctx, ctx->lane[l]); if (rc) return rc; if (lanes > 1) CK(cudaStreamWaitEvent(ctx->lane[l].stream, ctx->ev_sorted, 0)); }
+    // groups = contiguous runs of sub-slots with (nearly) equal pair counts, one tree each; at least one per lane
+    const double per_pair = 8.0 * C::N * 0.75 + 4.0 * C::N * 0.75 + 6;
+    const uint64_t budget_pairs = ctx->opt_group_pairs > 0 ? (uint64_t)ctx->opt_group_pairs : (uint64_t)std::max(1.0, 0.45 * (double)ctx->total_mem / per_pair / lanes);
+    uint32_t ngroups = std::min<uint32_t>(G, std::max<uint32_t>(lanes, (uint32_t)((mtot + budget_pairs - 1) / budget_pairs)));
+    std::vector<uint32_t> cut(ngroups + 1, 0); cut[ngroups] = G;
+    { uint32_t w = 0; for (uint32_t g = 1; g < ngroups; g++) { uint64_t target = mtot * g / ngroups;
+        while (w < G && ctx->h_pinned[512 + w] < target) w++;
+        cut[g] = std::min(std::max(w, cut[g - 1] + 1), G - (ngroups - g)); } }
+    for (uint32_t g = 0; g < ngroups; g++) {
+      TreeLane& ln = ctx->lane[g % lanes];
+      const uint32_t g0 = cut[g], g1 = cut[g + 1];
+      uint32_t mc = 0; for (uint32_t k = g0; k < g1; k++) mc = std::max(mc, ctx->h_pinned[k]);
+      const uint64_t m0 = ctx->h_pinned[512 + g1] - ctx->h_pinned[512 + g0];
+      const uint32_t b0 = g0 * Bg, nbg = (g1 - g0) * Bg;
+      cudaStream_t keep = ln.stream; if (lanes == 1) ln.stream = s;
+      cudaStream_t ls = ln.stream;
+      char* bg = ctx->buckets.as<char>() + (size_t)b0 * 16 * C::N;
+      rc = accumulate_batch_affine<C>(ctx, ln, d_bases, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc, bg, &rounds, &adds);
+      if (!rc && host_tail) {
+        if (st && g + 1 == ngroups) CK(cudaEventRecord(ctx->ev[3], s));
+        rc = fold_slots<C>(ctx, ls, bg, g1 - g0, Bg);
+        if (!rc) {
+          const uint32_t np = (g1 - g0) * per; const size_t o = (size_t)g0 * per * 16 * C::N;
+          k_gather_folded<C><<<(np + 127) / 128, 128, 0, ls>>>(bg, g1 - g0, Bg, logBs, ctx->wsum.as<char>() + o); CKL();
+          CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->h_folded) + o, ctx->wsum.as<char>() + o, (size_t)np * 16 * C::N, cudaMemcpyDeviceToHost, ls));
+          CK(cudaEventRecord(ctx->gev[g], ls));
+        }
+      }
+      ln.stream = keep;
+      if (rc) return rc;
+    }
+    if (host_tail) {
+      if (st) { MARK(T_FOLD); CK(cudaEventRecord(ctx->ev[4], s)); }
+      constexpr int L = C::N / 2;
+      b200host::Field<L> f;
+      for (int i = 0; i < L; i++) { f.q[i] = (uint64_t)C::q(2 * i) | ((uint64_t)C::q(2 * i + 1) << 32); f.one[i] = (uint64_t)C::one(2 * i) | ((uint64_t)C::one(2 * i + 1) << 32); }
+      { uint64_t x = 1; for (int k = 0; k < 6; k++) x *= 2 - f.q[0] * x; f.np = 0 - x; }
+      b200host::SubslotCombiner<L> cb; cb.begin(f, G, logBs);
+      float host_ms = 0;
+      for (uint32_t g = 0; g < ngroups; g++) {          // each group's sub-slots are reduced as soon as they arrive, while the other lanes still run
+        CK(cudaEventSynchronize(ctx->gev[g]));
+        auto t0 = std::chrono::steady_clock::now();
+        cb.feed(reinterpret_cast<const b200host::XYZZ<L>*>(ctx->h_folded), cut[g], cut[g + 1]);
+        host_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      }
+      uint64_t* res = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ctx->h_folded) + fbytes);
+      cb.finish(res);
+      ctx->host_combine_ms = host_ms;
+      if (lanes > 1) for (uint32_t l = 0; l < lanes; l++) { CK(cudaEventRecord(ctx->lane[l].done, ctx->lane[l].stream)); CK(cudaStreamWaitEvent(s, ctx->lane[l].done, 0)); }
+      CK(cudaMemcpyAsync(d_out, res, 12 * C::N, cudaMemcpyHostToDevice, s));
+      MARK(T_HORNER);
+    } else {   // device chain (cross-check form): fold the whole array as pl.W slots of B buckets
+      if (lanes > 1) for (uint32_t l = 0; l < lanes; l++) { CK(cudaEventRecord(ctx->lane[l].done, ctx->lane[l].stream)); CK(cudaStreamWaitEvent(s, ctx->lane[l].done, 0)); }
+      if (st) CK(cudaEventRecord(ctx->ev[3], s));
+      rc = fold_slots<C>(ctx, s, ctx->buckets.p, pl.W, pl.B); if (rc) return rc;
+      MARK(T_FOLD);
+      if (st) CK(cudaEventRecord(ctx->ev[4], s));
+      CK(ctx->wsum.ensure((size_t)pl.W * 16 * C::N));
+      k_window_sums<C><<<(pl.W + 31) / 32, 32, 0, s>>>(ctx->buckets.p, pl.W, 1, pl.B, pl.logB, ctx->wsum.p); CKL();
+      MARK(T_WSUM);
+      k_horner<C><<<1, 32, 0, s>>>(ctx->wsum.p, pl.W, 1, pl.c0, 0, d_out); CKL();
+      MARK(T_HORNER);
+    }
+  } else if (mode == 2) {
     // groups of whole slots: at least `lanes` of them (overlap), more if the tree scratch would not fit in device memory
     const uint64_t mtot = ctx->h_pinned[512 + pl.W];
     uint32_t lanes = ctx->prof ? 1u : (uint32_t)std::max(1, std::min(ctx->opt_lanes, (int)MAX_LANES));
@@ -446,7 +554,7 @@ int stage(b200msm_ctx* ctx, const void* src, size_t bytes, DevBuf& buf, const vo
 }
 
 int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_resident, const void* scalars, uint32_t scalar_size, uint64_t n,
-              uint32_t bit0, uint32_t nbits, void* out, b200msm_stats* st) {
+              uint32_t bit0, uint32_t nbits, void* out, b200msm_stats* st, const Precomp* pre = nullptr) {
   if (!ctx) return B200MSM_E_ARG;
   if (!curve_ok(curve) || !out || (n && (!bases || !scalars)) || scalar_size == 0) { ctx->err = "bad argument"; return B200MSM_E_ARG; }
   if (n >= (1ull << 31)) { ctx->err = "n must be < 2^31"; return B200MSM_E_UNSUPPORTED; }
@@ -491,8 +599,9 @@ int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_residen
     d_scal = ctx->canon.as<uint32_t>();
   }
   MARK(T_NTAGS);
-  rc = curve == 0 ? run_pipeline<BLS12_381>(ctx, d_bases, d_scal, n, nbits, ctx->out.p, st)
-                  : run_pipeline<BN254>(ctx, d_bases, d_scal, n, nbits, ctx->out.p, st);
+  if (pre && (pre->nbits != nbits || bit0 != 0)) pre = nullptr;      // the table serves exactly the bit range it was built for
+  rc = curve == 0 ? run_pipeline<BLS12_381>(ctx, d_bases, d_scal, n, nbits, ctx->out.p, st, pre)
+                  : run_pipeline<BN254>(ctx, d_bases, d_scal, n, nbits, ctx->out.p, st, pre);
   if (rc) { ctx->prof = false; return rc; }
   if (st) CK(cudaEventRecord(ctx->ev[6], ctx->stream));
   rc = deliver(ctx, ctx->out.p, out, 3 * n8); if (rc) return rc;
@@ -517,6 +626,24 @@ int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_residen
     st->launches = ctx->launches - launches0;
     ctx->prof = false;
   }
+  return B200MSM_OK;
+}
+
+// window table for resident bases: rows w = 1..Wd-1 hold 2^(bit offset of window w) * P_i (see k_table_double)
+template <class C>
+int build_window_table(b200msm_ctx* ctx, void* table, uint64_t n, uint32_t c0, uint32_t rem, uint32_t Wd) {
+  const size_t pt = 8 * C::N;
+  CK(ctx->acc_a.ensure(n * 16 * C::N + 16));
+  const uint32_t g = (uint32_t)((n + 127) / 128);
+  constexpr int GROUP = 16;
+  const uint32_t g2 = (uint32_t)(((n + GROUP - 1) / GROUP + 127) / 128);
+  k_table_init<C><<<g, 128, 0, ctx->stream>>>(table, (uint32_t)n, ctx->acc_a.p); CKL();
+  for (uint32_t w = 1; w < Wd; w++) {
+    const uint32_t cw = c0 + ((w - 1) < rem ? 1u : 0u);
+    k_table_double<C><<<g, 128, 0, ctx->stream>>>(ctx->acc_a.p, (uint32_t)n, cw); CKL();
+    k_xyzz_to_affine<C, GROUP><<<g2, 128, 0, ctx->stream>>>(ctx->acc_a.p, (uint32_t)n, reinterpret_cast<char*>(table) + (size_t)w * n * pt); CKL();
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
   return B200MSM_OK;
 }
 
@@ -610,6 +737,7 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "probe_sqr")) { ctx->probe_sqr = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "probe29")) { ctx->probe29 = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "lanes")) { if (v < 1 || v > MAX_LANES) return B200MSM_E_ARG; ctx->opt_lanes = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "subslots")) { if (v < 0 || v > 256 || (v & (v - 1))) return B200MSM_E_ARG; ctx->opt_subslots = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "combine")) { if (v < 0 || v > 1) return B200MSM_E_ARG; ctx->opt_combine = (int)v; return B200MSM_OK; }
   return B200MSM_E_ARG;
 }
@@ -638,6 +766,31 @@ int b200msm_upload_bases(b200msm_ctx* ctx, int curve, const void* bases, uint64_
   *handle = h;
   return B200MSM_OK;
 }
+int b200msm_upload_bases_windowed(b200msm_ctx* ctx, int curve, const void* bases, uint64_t n, uint32_t scalar_size, uint32_t window_bits, uint64_t* handle) {
+  if (!ctx || !handle || !curve_ok(curve) || !n || !bases || scalar_size == 0 || scalar_size > 32 || window_bits > 24) return B200MSM_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const uint32_t nbits = 8 * scalar_size;
+  uint32_t ct = window_bits;
+  if (ct == 0) { uint32_t lg = 0; while ((2ull << lg) <= n) lg++; ct = std::min<uint32_t>(std::max<uint32_t>(lg, 2), 20); }      // one bucket array: wider windows than the per-window plan (measured: 2^18 -> 18, 2^20 -> 20)
+  if (ct < 2) ct = 2;
+  if (ct > nbits) ct = nbits;
+  const uint32_t Wd = (nbits + ct - 1) / ct, c0 = nbits / Wd, rem = nbits - c0 * Wd;
+  if (n * Wd >= (1ull << 31)) { ctx->err = "window table too large for 31-bit point indices"; return B200MSM_E_UNSUPPORTED; }
+  const size_t pt = 2 * (size_t)n8_of(curve);
+  void* d = nullptr;
+  { cudaError_t e = cudaMalloc(&d, (size_t)n * Wd * pt + 16);
+    if (e != cudaSuccess) { cudaGetLastError(); ctx->err = "window table does not fit in device memory"; return B200MSM_E_NOMEM; } }
+  cudaError_t e = cudaMemcpyAsync(d, bases, (size_t)n * pt, cudaMemcpyDefault, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { cudaFree(d); ctx->err = cudaGetErrorString(e); return B200MSM_E_CUDA; }
+  int rc = curve == 0 ? build_window_table<BLS12_381>(ctx, d, n, c0, rem, Wd) : build_window_table<BN254>(ctx, d, n, c0, rem, Wd);
+  if (rc) { cudaFree(d); return rc; }
+  uint64_t h = ctx->next_handle++;
+  Resident r{curve, n, d}; r.t_nbits = nbits; r.t_c0 = c0; r.t_rem = rem; r.t_Wd = Wd;
+  ctx->residents[h] = r;
+  *handle = h;
+  return B200MSM_OK;
+}
 int b200msm_free_bases(b200msm_ctx* ctx, uint64_t handle) {
   if (!ctx) return B200MSM_E_ARG;
   auto it = ctx->residents.find(handle);
@@ -650,7 +803,9 @@ int b200msm_g1_multiexp_resident(b200msm_ctx* ctx, uint64_t handle, const void* 
   if (!ctx) return B200MSM_E_ARG;
   auto it = ctx->residents.find(handle);
   if (it == ctx->residents.end() || n > it->second.n) { ctx->err = "unknown handle or n larger than the uploaded base count"; return B200MSM_E_ARG; }
-  return msm_entry(ctx, it->second.curve, it->second.d, true, scalars, scalar_size, n, 0, scalar_size > 32 ? 257 : 8 * scalar_size, out, stats);
+  const Resident& r = it->second;
+  Precomp pre{(uint32_t)r.n, r.t_nbits, r.t_c0, r.t_rem, r.t_Wd};
+  return msm_entry(ctx, r.curve, r.d, true, scalars, scalar_size, n, 0, scalar_size > 32 ? 257 : 8 * scalar_size, out, stats, r.t_Wd ? &pre : nullptr);
 }
 
 int b200msm_g1_normalize(b200msm_ctx* ctx, int curve, const void* jac, uint64_t count, void* xy) {

@@ -12,6 +12,7 @@
 //
 // Field: Montgomery form, R = 2^(64*L), 64-bit limbs via unsigned __int128 (same values as fp.cuh's 32-bit limbs).
 #pragma once
+#include <vector>
 #include <stdint.h>
 #include <string.h>
 
@@ -162,5 +163,32 @@ template <int L>
 static void combine_windows(const Field<L>& f, const XYZZ<L>* folded, uint32_t W, uint32_t Wd, uint32_t c0, uint32_t rem, uint32_t logB, uint64_t* out_jac) {
   Combiner<L> cb; cb.begin(f, W, Wd, c0, rem, logB); cb.feed(folded, 0, W); cb.finish(out_jac);
 }
+
+// Window-table form (one bucket array cut into S sub-slots of 2^logBs buckets, each folded on its own):
+//   sum_b (b+1) T[b] = sum_s V_s,   V_s = F_s[0] + sum_j 2^j F_s[2^j] + s * 2^logBs * F_s[0]      (F_s[0] = plain sum of sub-slot s)
+// folded: (logBs + 1) XYZZ points per sub-slot as written by k_gather_folded.  Every V_s is one short Horner pass over its
+// exponents (~logBs + log2 S doublings), independent of the other sub-slots, so groups are reduced as they arrive.
+template <int L> struct SubslotCombiner {
+  Field<L> f; uint32_t S, logBs, per, sbits; XYZZ<L> total;
+  void begin(const Field<L>& f_, uint32_t S_, uint32_t logBs_) {
+    f = f_; S = S_; logBs = logBs_; per = logBs + 1; sbits = 0; while ((1u << sbits) < S) sbits++;
+    set_inf<L>(f, total);
+  }
+  void feed(const XYZZ<L>* folded, uint32_t s0, uint32_t s1) {
+    for (uint32_t s = s0; s < s1; s++) {
+      const XYZZ<L>* F = folded + (size_t)s * per;
+      const bool have0 = !is_inf<L>(F[0]);
+      XYZZ<L> acc; set_inf<L>(f, acc);
+      for (int e = (int)(logBs + sbits) - 1; e >= 0; e--) {
+        if (!is_inf<L>(acc)) { XYZZ<L> d; pdbl<L>(f, d, acc); acc = d; }
+        if ((uint32_t)e >= logBs) { if (have0 && ((s >> ((uint32_t)e - logBs)) & 1)) padd<L>(f, acc, F[0]); }
+        else if (!is_inf<L>(F[1 + e])) padd<L>(f, acc, F[1 + e]);
+      }
+      if (have0) padd<L>(f, acc, F[0]);
+      if (!is_inf<L>(acc)) padd<L>(f, total, acc);
+    }
+  }
+  void finish(uint64_t* out_jac) { Combiner<L> cb; cb.f = f; cb.acc = total; cb.cur = 0; cb.finish(out_jac); }
+};
 
 }  // namespace b200host

@@ -30,6 +30,8 @@ struct MsmPlan {
   uint32_t B;          // buckets per slot = 2^(c-1)   (bucket index = |digit| - 1)
   uint32_t nbits;      // scalar bits processed
   uint32_t logB;       // c - 1
+  uint32_t pre_stride; // 0: one bucket array per window, points = bases[i].  > 0 (precomputed window tables, see k_table_double):
+                       // ONE bucket array for all windows, digit w of scalar i selects table[w * pre_stride + i] = 2^(bit offset of w) * P_i
 };
 
 // ------------------------------------------------------------------ scalars
@@ -94,11 +96,13 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
         for (int q = 0; q < 8; q++) { lo = (k == (uint32_t)q) ? sw[q] : lo; hi = (k + 1 == (uint32_t)q) ? sw[q] : hi; }
         const uint32_t raw = __funnelshift_r(lo, hi, r) & ((1u << cw) - 1u);
         const uint32_t d = raw + carry;
-        if (w + 1 == pl.Wd) { if (d) gb[u] = w * pl.B + d - 1; }
+        const uint32_t slot0 = pl.pre_stride ? 0u : w * pl.B;
+        if (pl.pre_stride) val[u] = i + w * pl.pre_stride;
+        if (w + 1 == pl.Wd) { if (d) gb[u] = slot0 + d - 1; }
         else {
           carry = d > (1u << (cw - 1));
           const uint32_t mag = carry ? ((1u << cw) - d) : d;
-          if (mag) { gb[u] = w * pl.B + mag - 1; val[u] = i | (carry << 31); }
+          if (mag) { gb[u] = slot0 + mag - 1; val[u] |= carry << 31; }
         }
       }
     }
@@ -299,6 +303,30 @@ __global__ void k_gather_folded(const void* __restrict__ buckets, uint32_t W, ui
   uint64_t src = (uint64_t)w * B + (k == 0 ? 0u : (1u << (k - 1)));
   XYZZ<C> p; xyzz_load<C>(p, buckets, src);
   xyzz_store<C>(out, t, p);
+}
+
+// ------------------------------------------------------------------ precomputed window tables (resident bases only)
+// table row w holds 2^(bit offset of window w) * P_i for every resident base, so the digits of ALL windows can share ONE
+// bucket array: the per-window bucket reductions and the window combination (W*c doublings) disappear from the MSM, and
+// the window can be wider than a per-window bucket array could afford.  Built once at upload time: the running multiples
+// are kept in XYZZ and doubled in place (g1m_double, build_curve_jacobian_a0.js:291-359), each row is converted to affine
+// with k_xyzz_to_affine.  The reference has no such table (it receives the bases with every call); the sum is unchanged.
+template <class C>
+__global__ void __launch_bounds__(128) k_table_init(const void* __restrict__ bases, uint32_t n, void* __restrict__ cur_xyzz) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<C> p; affine_load<C>(p, bases, i);
+  XYZZ<C> q;
+  if (affine_is_inf<C>(p)) xyzz_set_inf<C>(q); else xyzz_from_affine<C>(q, p);
+  xyzz_store<C>(cur_xyzz, i, q);
+}
+template <class C>
+__global__ void __launch_bounds__(128) k_table_double(void* __restrict__ cur_xyzz, uint32_t n, uint32_t doublings) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  XYZZ<C> p; xyzz_load<C>(p, cur_xyzz, i);
+  for (uint32_t k = 0; k < doublings; k++) { XYZZ<C> d; xyzz_dbl<C>(d, p); p = d; }
+  xyzz_store<C>(cur_xyzz, i, p);
 }
 
 // ------------------------------------------------------------------ small utility kernels behind the C ABI
