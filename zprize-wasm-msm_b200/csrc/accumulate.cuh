@@ -126,57 +126,70 @@ B200_DI bool tree_slot(const TreeRound& tr, uint32_t j, uint32_t& in0, bool& has
   return true;
 }
 
-// forward: denominators, per-slot prefix products, per-thread products.
-// The kernel is gather-bound (two scattered 96-byte points per slot in round 0), so the loads of slot i+1 are issued
-// before the multiplication of slot i (two slots in flight per thread).
-template <class C, bool FIRST>
-struct FwdSlot { Fe<C::N> x1, x2; uint32_t j, in0; bool valid, has2; };
-
-// x coordinate only (the y coordinates are needed only in the rare equal-x / zero-x cases and are fetched then)
-template <class C, bool FIRST>
-B200_DI void tree_load_x(Fe<C::N>& x, const void* __restrict__ bases, const uint32_t* __restrict__ sorted, const void* __restrict__ pin, uint32_t pos) {
-  if (FIRST) fe_load<C>(x, reinterpret_cast<const char*>(bases) + (uint64_t)(__ldg(sorted + pos) & 0x7fffffffu) * (8 * C::N));
-  else fe_load_cg<C>(x, reinterpret_cast<const char*>(pin) + (uint64_t)pos * (8 * C::N));
-}
-
-template <class C, bool FIRST>
-B200_DI void fwd_fetch(FwdSlot<C, FIRST>& sl, const TreeRound& tr, const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                       const void* __restrict__ pin, uint32_t j) {
-  sl.j = j; sl.has2 = false;
-  sl.valid = tree_slot(tr, j, sl.in0, sl.has2, true);
-  if (sl.valid && sl.has2) {
-    tree_load_x<C, FIRST>(sl.x1, bases, sorted, pin, sl.in0);
-    tree_load_x<C, FIRST>(sl.x2, bases, sorted, pin, sl.in0 + 1);
+// Per-slot operand table of a round, written once by k_tree_meta and read (coalesced) by the forward and the backward pass:
+// meta[j] = (a, b): operand references of output slot j -- round 0: the sorted entries (point index | sign << 31), later rounds:
+// positions in the previous round's output; b = NONE: the slot only carries its single input over; a = NONE: padding slot.
+// This takes the dependent lookups (bid -> offsets -> sorted entry) out of the arithmetic kernels, whose gathers then depend
+// on ONE coalesced load that is issued an iteration ahead; the table covers whole tiles, so those kernels need no bounds checks.
+constexpr uint32_t META_NONE = 0xffffffffu;
+template <bool FIRST>
+__global__ void __launch_bounds__(256) k_tree_meta(TreeRound tr, const uint32_t* __restrict__ sorted, uint2* __restrict__ meta, uint32_t nslots) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nslots) return;
+  uint32_t in0; bool has2;
+  uint2 m = make_uint2(META_NONE, META_NONE);
+  if (tree_slot(tr, j, in0, has2, true)) {
+    if (FIRST) { m.x = __ldg(sorted + in0); if (has2) m.y = __ldg(sorted + in0 + 1); }
+    else { m.x = in0; if (has2) m.y = in0 + 1; }
   }
+  meta[j] = m;
 }
 
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, 6) k_tree_fwd(TreeRound tr, const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                            const void* __restrict__ pin, void* __restrict__ prefix, void* __restrict__ prod, int K, uint32_t ntiles) {
+B200_DI void meta_load_point(Affine<C>& p, const void* __restrict__ src, uint32_t ref) {
+  if (FIRST) { affine_load<C>(p, src, ref & 0x7fffffffu); if (ref >> 31) fe_neg<C>(p.y, p.y); }
+  else affine_load_cg<C>(p, src, ref);
+}
+template <class C, bool FIRST>
+B200_DI void meta_load_x(Fe<C::N>& x, const void* __restrict__ src, uint32_t ref) {
+  if (FIRST) fe_load<C>(x, reinterpret_cast<const char*>(src) + (uint64_t)(ref & 0x7fffffffu) * (8 * C::N));
+  else fe_load_cg<C>(x, reinterpret_cast<const char*>(src) + (uint64_t)ref * (8 * C::N));
+}
+
+// forward: denominators, per-slot prefix products, per-thread products.
+// The kernel is gather-bound (two scattered 96-byte points per slot in round 0), so the x coordinates of slot i+1 are requested
+// before the multiplication of slot i and the operand references of slot i+2 before that (only the x coordinates are needed;
+// the y coordinates are fetched in the rare equal-x / zero-x cases).
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(BA_THREADS, 6) k_tree_fwd(const uint2* __restrict__ meta, const void* __restrict__ src,
+                                                            void* __restrict__ prefix, void* __restrict__ prod, int K, uint32_t ntiles) {
  // persistent form: gridDim.x may be smaller than ntiles (leaves SM room for the other lane's latency-bound kernels)
  for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
-  uint32_t tile = tb * (K * BA_THREADS);
+  const uint32_t tile = tb * (K * BA_THREADS) + threadIdx.x;
   Fe<C::N> p; fe_set_one<C>(p);
-  FwdSlot<C, FIRST> cur, nxt;
-  fwd_fetch<C, FIRST>(cur, tr, bases, sorted, pin, tile + threadIdx.x);
+  Fe<C::N> x1, x2, nx1, nx2;
+  uint2 mc = meta[tile], mn = K > 1 ? meta[tile + BA_THREADS] : make_uint2(META_NONE, META_NONE);
+  if (mc.y != META_NONE) { meta_load_x<C, FIRST>(x1, src, mc.x); meta_load_x<C, FIRST>(x2, src, mc.y); }
 #pragma unroll 1
   for (int i = 0; i < K; i++) {
-    if (i + 1 < K) fwd_fetch<C, FIRST>(nxt, tr, bases, sorted, pin, tile + (i + 1) * BA_THREADS + threadIdx.x);
-    if (cur.valid && cur.has2) {
+    uint2 mn2 = make_uint2(META_NONE, META_NONE);
+    if (i + 2 < K) mn2 = meta[tile + (i + 2) * BA_THREADS];
+    if (i + 1 < K && mn.y != META_NONE) { meta_load_x<C, FIRST>(nx1, src, mn.x); meta_load_x<C, FIRST>(nx2, src, mn.y); }
+    if (mc.y != META_NONE) {
       Fe<C::N> d; int kind = 0;
-      fe_sub<C>(d, cur.x2, cur.x1);
-      if (fe_is_zero<C>(d) || fe_is_zero<C>(cur.x1) || fe_is_zero<C>(cur.x2)) {        // rare: decide with the full points
+      fe_sub<C>(d, x2, x1);
+      if (fe_is_zero<C>(d) || fe_is_zero<C>(x1) || fe_is_zero<C>(x2)) {        // rare: decide with the full points
         Affine<C> p1, p2;
-        tree_load_point<C, FIRST>(p1, bases, sorted, pin, cur.in0);
-        tree_load_point<C, FIRST>(p2, bases, sorted, pin, cur.in0 + 1);
+        meta_load_point<C, FIRST>(p1, src, mc.x);
+        meta_load_point<C, FIRST>(p2, src, mc.y);
         kind = affine_add_denominator<C>(d, p1, p2);
       }
       if (kind <= 1) {
-        fe_store<C>(reinterpret_cast<char*>(prefix) + (uint64_t)cur.j * 4 * C::N, p);
+        fe_store<C>(reinterpret_cast<char*>(prefix) + (uint64_t)(tile + i * BA_THREADS) * 4 * C::N, p);
         fe_mul<C>(p, p, d);
       }
     }
-    cur = nxt;
+    mc = mn; mn = mn2; x1 = nx1; x2 = nx2;
   }
   fe_store<C>(reinterpret_cast<char*>(prod) + (uint64_t)(tb * BA_THREADS + threadIdx.x) * 4 * C::N, p);
  }
@@ -184,21 +197,24 @@ __global__ void __launch_bounds__(BA_THREADS, 6) k_tree_fwd(TreeRound tr, const 
 
 // backward: consume the inverse of the thread's product, finish every addition, write the round's output points
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, 4) k_tree_bwd(TreeRound tr, const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                         const void* __restrict__ pin, const void* __restrict__ prefix, const void* __restrict__ inv,
+__global__ void __launch_bounds__(BA_THREADS, 4) k_tree_bwd(const uint2* __restrict__ meta, const void* __restrict__ src,
+                                                         const void* __restrict__ prefix, const void* __restrict__ inv,
                                                          void* __restrict__ pout, int K, uint32_t ntiles) {
  for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
-  uint32_t tile = tb * (K * BA_THREADS);
+  const uint32_t tile = tb * (K * BA_THREADS) + threadIdx.x;
   Fe<C::N> q;
   fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)(tb * BA_THREADS + threadIdx.x) * 4 * C::N);
+  uint2 mn = meta[tile + (K - 1) * BA_THREADS];
 #pragma unroll 1
   for (int i = K - 1; i >= 0; i--) {
-    uint32_t j = tile + i * BA_THREADS + threadIdx.x, in0; bool has2;
-    if (!tree_slot(tr, j, in0, has2, false)) continue;
+    const uint2 m = mn;
+    if (i > 0) mn = meta[tile + (i - 1) * BA_THREADS];
+    if (m.x == META_NONE) continue;
+    const uint32_t j = tile + i * BA_THREADS;
     Affine<C> p1, p2, r;
-    tree_load_point<C, FIRST>(p1, bases, sorted, pin, in0);
-    if (!has2) { affine_store<C>(pout, j, p1); continue; }
-    tree_load_point<C, FIRST>(p2, bases, sorted, pin, in0 + 1);
+    meta_load_point<C, FIRST>(p1, src, m.x);
+    if (m.y == META_NONE) { affine_store<C>(pout, j, p1); continue; }
+    meta_load_point<C, FIRST>(p2, src, m.y);
     Fe<C::N> d, dinv;
     int kind = affine_add_denominator<C>(d, p1, p2);
     if (kind <= 1) {

@@ -49,7 +49,7 @@ struct Precomp { uint32_t stride, nbits, c0, rem, Wd; };
 // one accumulate lane: a stream with its own tree scratch (see accumulate_batch_affine)
 struct TreeLane {
   cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
-  DevBuf offs, tiles, bid, pa, pb, prefix, prod, lvlprefix, others;
+  DevBuf offs, tiles, bid, pa, pb, prefix, prod, lvlprefix, others, meta;
 };
 constexpr int MAX_LANES = 4;
 constexpr uint64_t WARP_LEVEL_MAX = 131072;     // product-tree levels with at most this many values use the warp-assisted kernel (only one such level can occur: 131072 / 128 <= BA_ROOT_MAX)
@@ -191,7 +191,8 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
   const int BK = ctx->opt_ba_k, PK = ctx->opt_pt_k;
   const uint64_t BA_TILE = (uint64_t)BK * BA_THREADS;
   CK(ln_.pa.ensure(U[1] * pt + 16)); if (R > 1) CK(ln_.pb.ensure(U[2] * pt + 16));
-  CK(ln_.prefix.ensure(U[1] * fe + 16));
+  CK(ln_.prefix.ensure((U[1] + BA_TILE) * fe + 16));
+  CK(ln_.meta.ensure((U[1] + BA_TILE) * 8 + 16));
   // product-tree level sizes for the largest round
   { uint64_t n1 = ((U[1] + BA_TILE - 1) / BA_TILE) * BA_THREADS;       // every level above is at least 4x smaller: 2*n1 bounds the sum
     CK(ln_.prod.ensure((2 * n1 + 4096) * fe)); CK(ln_.lvlprefix.ensure((2 * n1 + 4096) * fe)); CK(ln_.others.ensure((WARP_LEVEL_MAX / 4 + 4096) * fe)); }
@@ -203,8 +204,13 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
     if (grid == 0) grid = 1;
     char* prod = ln_.prod.as<char>(); char* lpre = ln_.lvlprefix.as<char>();
     const uint32_t pgrid = (ctx->opt_persist > 0 && ln_.stream != ctx->stream) ? std::min<uint32_t>(grid, (uint32_t)ctx->opt_persist) : grid;   // persistent grid only when lanes overlap
-    if (r == 0) k_tree_fwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(tr, d_bases, sorted, nullptr, ln_.prefix.p, prod, BK, grid);
-    else k_tree_fwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(tr, nullptr, nullptr, pin, ln_.prefix.p, prod, BK, grid);
+    const uint32_t nslots = grid * (uint32_t)BA_TILE;
+    uint2* meta = ln_.meta.as<uint2>();
+    if (r == 0) k_tree_meta<true><<<(nslots + 255) / 256, 256, 0, s>>>(tr, sorted, meta, nslots);
+    else k_tree_meta<false><<<(nslots + 255) / 256, 256, 0, s>>>(tr, nullptr, meta, nslots);
+    CKL();
+    if (r == 0) k_tree_fwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(meta, d_bases, ln_.prefix.p, prod, BK, grid);
+    else k_tree_fwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(meta, pin, ln_.prefix.p, prod, BK, grid);
     CKL(); MARK(T_TREE_FWD);
     // up the product tree: plain K-ary levels while the level is large, one warp-assisted level (arity 32*4) once it is small
     struct Lvl { uint64_t n; char* v; char* p; bool warp; int K; };
@@ -231,8 +237,8 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
       CKL();
     }
     MARK(T_INV_TREE);
-    if (r == 0) k_tree_bwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(tr, d_bases, sorted, nullptr, ln_.prefix.p, prod, pout, BK, grid);
-    else k_tree_bwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(tr, nullptr, nullptr, pin, ln_.prefix.p, prod, pout, BK, grid);
+    if (r == 0) k_tree_bwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(meta, d_bases, ln_.prefix.p, prod, pout, BK, grid);
+    else k_tree_bwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(meta, pin, ln_.prefix.p, prod, pout, BK, grid);
     CKL(); MARK(r == 0 ? T_TREE_BWD0 : T_TREE_BWD);
     pin = pout;
     *adds_out += U[r] - U[r + 1];
@@ -694,7 +700,7 @@ void b200msm_destroy(b200msm_ctx* ctx) {
   for (DevBuf* b : {&ctx->bases, &ctx->scalars, &ctx->canon, &ctx->counts, &ctx->offsets, &ctx->cursors, &ctx->tiles, &ctx->sorted, &ctx->buckets,
                     &ctx->wsum, &ctx->out, &ctx->misc, &ctx->acc_a, &ctx->acc_b, &ctx->acc_c, &ctx->acc_d, &ctx->acc_e}) b->release();
   for (auto& ln : ctx->lane) {
-    for (DevBuf* b : {&ln.offs, &ln.tiles, &ln.bid, &ln.pa, &ln.pb, &ln.prefix, &ln.prod, &ln.lvlprefix, &ln.others}) b->release();
+    for (DevBuf* b : {&ln.offs, &ln.tiles, &ln.bid, &ln.pa, &ln.pb, &ln.prefix, &ln.prod, &ln.lvlprefix, &ln.others, &ln.meta}) b->release();
     if (ln.done) cudaEventDestroy(ln.done);
     if (ln.stream) cudaStreamDestroy(ln.stream);
   }
