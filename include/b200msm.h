@@ -134,6 +134,9 @@ int b200msm_fq_op(b200msm_ctx* ctx, int curve, int op, const void* a, const void
 int b200msm_probe_imad(b200msm_ctx* ctx, double* imad_wide_per_s);
 int b200msm_probe_imad32(b200msm_ctx* ctx, double* imad32_per_s);
 int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s);
+/* dfma_per_s: FP64 fused multiply-adds per second (8 independent chains per thread) -- the second multiplier pipe of the SM, unused by
+ * the integer path; measured to size an FP64-limb multiplier that would run beside the IMAD one. */
+int b200msm_probe_dfma(b200msm_ctx* ctx, double* dfma_per_s);
 
 /* ---- tuning knobs (never change results).  key: "window_bits" (0 = auto), "accumulate" (0 = auto, 1 = serial, 2 = batch-affine),
  * "tree_rounds" (-1 = auto), "combine" (0 = serial tail on the host (default), 1 = device chain k_window_sums + k_horner). */

@@ -132,5 +132,8 @@ class Engine:
     def probe_imad32(self):
         v = ctypes.c_double(); self._ck(lib.b200msm_probe_imad32(self._ctx, ctypes.byref(v))); return v.value
 
+    def probe_dfma(self):
+        v = ctypes.c_double(); self._ck(lib.b200msm_probe_dfma(self._ctx, ctypes.byref(v))); return v.value
+
     def probe_fqmul(self, curve):
         v = ctypes.c_double(); self._ck(lib.b200msm_probe_fqmul(self._ctx, curve, ctypes.byref(v))); return v.value

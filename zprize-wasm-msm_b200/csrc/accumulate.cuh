@@ -94,17 +94,6 @@ __global__ void __launch_bounds__(256) k_fill_bid(const uint32_t* __restrict__ o
 }
 
 // ---- one tree round, level 0 --------------------------------------------------------------------------
-template <class C, bool FIRST>
-B200_DI void tree_load_point(Affine<C>& p, const void* __restrict__ bases, const uint32_t* __restrict__ sorted, const void* __restrict__ pin, uint32_t pos) {
-  if (FIRST) {
-    uint32_t e = __ldg(sorted + pos);
-    affine_load<C>(p, bases, e & 0x7fffffffu);
-    if (e >> 31) fe_neg<C>(p.y, p.y);
-  } else {
-    affine_load_cg<C>(p, pin, pos);
-  }
-}
-
 struct TreeRound {
   const uint32_t* off_in;     // off[r]    (nb + 1)
   const uint32_t* off_out;    // off[r+1]  (nb + 1)
@@ -145,15 +134,21 @@ __global__ void __launch_bounds__(256) k_tree_meta(TreeRound tr, const uint32_t*
   meta[j] = m;
 }
 
+// Round 0 reads the caller's bases (x || y records, 2*n8 bytes apart).  The rounds' own outputs are stored as TWO arrays, all x
+// coordinates then (yoff bytes further) all y coordinates, because the forward pass needs only x: its sequential reads halve.
 template <class C, bool FIRST>
-B200_DI void meta_load_point(Affine<C>& p, const void* __restrict__ src, uint32_t ref) {
+B200_DI void meta_load_point(Affine<C>& p, const void* __restrict__ src, uint64_t yoff, uint32_t ref) {
   if (FIRST) { affine_load<C>(p, src, ref & 0x7fffffffu); if (ref >> 31) fe_neg<C>(p.y, p.y); }
-  else affine_load_cg<C>(p, src, ref);
+  else { const char* b = reinterpret_cast<const char*>(src) + (uint64_t)ref * (4 * C::N); fe_load_cg<C>(p.x, b); fe_load_cg<C>(p.y, b + yoff); }
 }
 template <class C, bool FIRST>
 B200_DI void meta_load_x(Fe<C::N>& x, const void* __restrict__ src, uint32_t ref) {
   if (FIRST) fe_load<C>(x, reinterpret_cast<const char*>(src) + (uint64_t)(ref & 0x7fffffffu) * (8 * C::N));
-  else fe_load_cg<C>(x, reinterpret_cast<const char*>(src) + (uint64_t)ref * (8 * C::N));
+  else fe_load_cg<C>(x, reinterpret_cast<const char*>(src) + (uint64_t)ref * (4 * C::N));
+}
+template <class C>
+B200_DI void soa_store_point(void* __restrict__ dst, uint64_t yoff, uint32_t j, const Affine<C>& p) {
+  char* b = reinterpret_cast<char*>(dst) + (uint64_t)j * (4 * C::N); fe_store<C>(b, p.x); fe_store<C>(b + yoff, p.y);
 }
 
 // forward: denominators, per-slot prefix products, per-thread products.
@@ -161,7 +156,7 @@ B200_DI void meta_load_x(Fe<C::N>& x, const void* __restrict__ src, uint32_t ref
 // before the multiplication of slot i and the operand references of slot i+2 before that (only the x coordinates are needed;
 // the y coordinates are fetched in the rare equal-x / zero-x cases).
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, 6) k_tree_fwd(const uint2* __restrict__ meta, const void* __restrict__ src,
+__global__ void __launch_bounds__(BA_THREADS, 6) k_tree_fwd(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
                                                             void* __restrict__ prefix, void* __restrict__ prod, int K, uint32_t ntiles) {
  // persistent form: gridDim.x may be smaller than ntiles (leaves SM room for the other lane's latency-bound kernels)
  for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
@@ -180,8 +175,8 @@ __global__ void __launch_bounds__(BA_THREADS, 6) k_tree_fwd(const uint2* __restr
       fe_sub<C>(d, x2, x1);
       if (fe_is_zero<C>(d) || fe_is_zero<C>(x1) || fe_is_zero<C>(x2)) {        // rare: decide with the full points
         Affine<C> p1, p2;
-        meta_load_point<C, FIRST>(p1, src, mc.x);
-        meta_load_point<C, FIRST>(p2, src, mc.y);
+        meta_load_point<C, FIRST>(p1, src, yoff, mc.x);
+        meta_load_point<C, FIRST>(p2, src, yoff, mc.y);
         kind = affine_add_denominator<C>(d, p1, p2);
       }
       if (kind <= 1) {
@@ -197,9 +192,9 @@ __global__ void __launch_bounds__(BA_THREADS, 6) k_tree_fwd(const uint2* __restr
 
 // backward: consume the inverse of the thread's product, finish every addition, write the round's output points
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, 4) k_tree_bwd(const uint2* __restrict__ meta, const void* __restrict__ src,
+__global__ void __launch_bounds__(BA_THREADS, 4) k_tree_bwd(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
                                                          const void* __restrict__ prefix, const void* __restrict__ inv,
-                                                         void* __restrict__ pout, int K, uint32_t ntiles) {
+                                                         void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles) {
  for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
   const uint32_t tile = tb * (K * BA_THREADS) + threadIdx.x;
   Fe<C::N> q;
@@ -212,9 +207,9 @@ __global__ void __launch_bounds__(BA_THREADS, 4) k_tree_bwd(const uint2* __restr
     if (m.x == META_NONE) continue;
     const uint32_t j = tile + i * BA_THREADS;
     Affine<C> p1, p2, r;
-    meta_load_point<C, FIRST>(p1, src, m.x);
-    if (m.y == META_NONE) { affine_store<C>(pout, j, p1); continue; }
-    meta_load_point<C, FIRST>(p2, src, m.y);
+    meta_load_point<C, FIRST>(p1, src, yoff, m.x);
+    if (m.y == META_NONE) { soa_store_point<C>(pout, yoff_out, j, p1); continue; }
+    meta_load_point<C, FIRST>(p2, src, yoff, m.y);
     Fe<C::N> d, dinv;
     int kind = affine_add_denominator<C>(d, p1, p2);
     if (kind <= 1) {
@@ -227,8 +222,87 @@ __global__ void __launch_bounds__(BA_THREADS, 4) k_tree_bwd(const uint2* __restr
 #endif
     }
     affine_add_finish<C>(r, p1, p2, dinv, kind);
-    affine_store<C>(pout, j, r);
+    soa_store_point<C>(pout, yoff_out, j, r);
   }
+ }
+}
+
+// backward pass with operand staging: the 2 points + prefix product of the NEXT slot are copied global -> shared with cp.async
+// while the current slot's five multiplications run, so the arithmetic never waits on a gather (the plain kernel above shows
+// 2.3 of its 4 warps per scheduler stalled on the scoreboard).  Each thread stages only its own operands (chunk-major layout:
+// 16-byte chunk c of thread t at sm[c * BA_THREADS + t], conflict-free), so no CTA barrier is involved: cp.async.wait_group
+// orders a thread's own copies, and the next copy is issued only after the registers read from the buffer have been consumed.
+B200_DI void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+B200_DI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+B200_DI void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <class C, bool FIRST>
+B200_DI void bwd_stage(uint4* sm, uint2 m, const void* __restrict__ src, uint64_t yoff, const void* __restrict__ prefix, uint32_t j) {
+  constexpr int FC = C::N / 4, PC = 2 * FC;       // 16-byte chunks per field element / per point
+  if (m.x != META_NONE) {
+    const char* b1 = reinterpret_cast<const char*>(src) + (FIRST ? (uint64_t)(m.x & 0x7fffffffu) * (8 * C::N) : (uint64_t)m.x * (4 * C::N));
+#pragma unroll
+    for (int c = 0; c < PC; c++) cp_async16(sm + c * BA_THREADS + threadIdx.x, (FIRST || c < FC) ? b1 + 16 * c : b1 + yoff + 16 * (c - FC));
+    if (m.y != META_NONE) {
+      const char* b2 = reinterpret_cast<const char*>(src) + (FIRST ? (uint64_t)(m.y & 0x7fffffffu) * (8 * C::N) : (uint64_t)m.y * (4 * C::N));
+      const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(prefix) + (uint64_t)j * (4 * C::N));
+#pragma unroll
+      for (int c = 0; c < PC; c++) cp_async16(sm + (PC + c) * BA_THREADS + threadIdx.x, (FIRST || c < FC) ? b2 + 16 * c : b2 + yoff + 16 * (c - FC));
+#pragma unroll
+      for (int c = 0; c < FC; c++) cp_async16(sm + (2 * PC + c) * BA_THREADS + threadIdx.x, gp + c);
+    }
+  }
+  cp_async_commit();
+}
+template <class C> B200_DI void sm_read_fe(Fe<C::N>& r, const uint4* sm, int chunk0) {
+#pragma unroll
+  for (int c = 0; c < C::N / 4; c++) { const uint4 v = sm[(chunk0 + c) * BA_THREADS + threadIdx.x]; r.l[4 * c] = v.x; r.l[4 * c + 1] = v.y; r.l[4 * c + 2] = v.z; r.l[4 * c + 3] = v.w; }
+}
+
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(BA_THREADS, 4) k_tree_bwd_staged(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
+                                                                const void* __restrict__ prefix, const void* __restrict__ inv,
+                                                                void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles) {
+ extern __shared__ uint4 sm[];
+ constexpr int FC = C::N / 4, PC = 2 * FC;
+ for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
+  const uint32_t tile = tb * (K * BA_THREADS) + threadIdx.x;
+  uint2 mn = meta[tile + (K - 1) * BA_THREADS];
+  bwd_stage<C, FIRST>(sm, mn, src, yoff, prefix, tile + (K - 1) * BA_THREADS);
+  Fe<C::N> q;
+  fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)(tb * BA_THREADS + threadIdx.x) * 4 * C::N);
+#pragma unroll 1
+  for (int i = K - 1; i >= 0; i--) {
+    const uint2 m = mn;
+    mn = make_uint2(META_NONE, META_NONE);
+    if (i > 0) mn = meta[tile + (i - 1) * BA_THREADS];
+    const uint32_t j = tile + i * BA_THREADS;
+    cp_async_wait_all();
+    if (m.x == META_NONE) { bwd_stage<C, FIRST>(sm, mn, src, yoff, prefix, j - BA_THREADS); continue; }
+    Affine<C> p1, p2, r;
+    sm_read_fe<C>(p1.x, sm, 0); sm_read_fe<C>(p1.y, sm, FC);
+    if (FIRST && (m.x >> 31)) fe_neg<C>(p1.y, p1.y);
+    if (m.y == META_NONE) {
+      soa_store_point<C>(pout, yoff_out, j, p1);       // the store consumes the registers read from the buffer
+      bwd_stage<C, FIRST>(sm, mn, src, yoff, prefix, j - BA_THREADS);
+      continue;
+    }
+    sm_read_fe<C>(p2.x, sm, PC); sm_read_fe<C>(p2.y, sm, PC + FC);
+    if (FIRST && (m.y >> 31)) fe_neg<C>(p2.y, p2.y);
+    Fe<C::N> d, dinv, pre;
+    sm_read_fe<C>(pre, sm, 2 * PC);
+    int kind = affine_add_denominator<C>(d, p1, p2);
+    if (kind <= 1) {
+      fe_mul<C>(dinv, q, pre);
+      fe_mul<C>(q, q, d);
+    }
+    bwd_stage<C, FIRST>(sm, mn, src, yoff, prefix, j - BA_THREADS);     // p1, p2, pre are in registers (consumed above): the buffer is free
+    affine_add_finish<C>(r, p1, p2, dinv, kind);
+    soa_store_point<C>(pout, yoff_out, j, r);
+  }
+  cp_async_wait_all();
  }
 }
 
@@ -370,14 +444,15 @@ __global__ void __launch_bounds__(BA_ROOT_THREADS) k_inv_root(void* __restrict__
 
 // ---- finish: one thread per bucket sums what is left of its segment and writes the bucket as XYZZ -------
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(128) k_accum_finish(const void* __restrict__ bases, const uint32_t* __restrict__ sorted, const void* __restrict__ pin,
+__global__ void __launch_bounds__(128) k_accum_finish(const void* __restrict__ bases, const uint32_t* __restrict__ sorted, const void* __restrict__ pin, uint64_t yoff,
                                                       const uint32_t* __restrict__ off, uint32_t nb, void* __restrict__ buckets) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   uint32_t lo = off[b], hi = off[b + 1];
   XYZZ<C> acc; xyzz_set_inf<C>(acc);
   for (uint32_t k = lo; k < hi; k++) {
-    Affine<C> p; tree_load_point<C, FIRST>(p, bases, sorted, pin, k);
+    Affine<C> p;
+    if (FIRST) meta_load_point<C, true>(p, bases, 0, __ldg(sorted + k)); else meta_load_point<C, false>(p, pin, yoff, k);
     xyzz_madd<C>(acc, p);
   }
   xyzz_store<C>(buckets, b, acc);

@@ -63,7 +63,7 @@ struct b200msm_ctx {
   int opt_window_bits = 0, opt_accumulate = 0, opt_tree_rounds = -1;
   DevBuf bases, scalars, canon, counts, offsets, cursors, tiles, sorted, buckets, wsum, out, misc, acc_a, acc_b, acc_c, acc_d, acc_e;
   TreeLane lane[MAX_LANES];                                                   // batch-affine tree lanes
-  int opt_lanes = 4, opt_ba_k = 8, opt_pt_k = 8, opt_persist = 444, opt_subslots = 0;
+  int opt_lanes = 4, opt_ba_k = 0, opt_pt_k = 8, opt_persist = 444, opt_subslots = 0, opt_bwd_staged = 0, opt_probe_smem = 0;
   bool probe29 = false, probe_sqr = false; int64_t opt_group_pairs = 0;
   cudaEvent_t ev_plan = nullptr, ev_sorted = nullptr, ev_bases = nullptr, ev_done = nullptr;
   cudaStream_t copy_stream = nullptr; bool bases_pending = false;
@@ -164,7 +164,7 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
   if (R > 30) R = 30;
   *rounds_out = std::max(*rounds_out, R);
   if (R == 0) {
-    k_accum_finish<C, true><<<(nbg + 127) / 128, 128, 0, s>>>(d_bases, sorted, nullptr, off0, nbg, buckets_g); CKL();
+    k_accum_finish<C, true><<<(nbg + 127) / 128, 128, 0, s>>>(d_bases, sorted, nullptr, 0, off0, nbg, buckets_g); CKL();
     MARK(T_FINISH);
     return B200MSM_OK;
   }
@@ -188,17 +188,18 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
   k_fill_bid<<<(nbg + 255) / 256, 256, 0, s>>>(off[1], nbg, bid[1]); CKL();
   MARK(T_PLAN);
   const size_t fe = 4 * C::N, pt = 8 * C::N;
-  const int BK = ctx->opt_ba_k, PK = ctx->opt_pt_k;
+  const int BK = ctx->opt_ba_k > 0 ? ctx->opt_ba_k : (m0 >= (1u << 22) ? 16 : 8), PK = ctx->opt_pt_k;     // chain length per thread: measured 2^20: 8 -> 6.84, 12 -> 6.76, 16 -> 6.70 ms; 2^18: 2.70 / 2.69 / 2.80
   const uint64_t BA_TILE = (uint64_t)BK * BA_THREADS;
-  CK(ln_.pa.ensure(U[1] * pt + 16)); if (R > 1) CK(ln_.pb.ensure(U[2] * pt + 16));
+  CK(ln_.pa.ensure(U[1] * pt + 1024)); if (R > 1) CK(ln_.pb.ensure(U[2] * pt + 1024));
   CK(ln_.prefix.ensure((U[1] + BA_TILE) * fe + 16));
   CK(ln_.meta.ensure((U[1] + BA_TILE) * 8 + 16));
   // product-tree level sizes for the largest round
   { uint64_t n1 = ((U[1] + BA_TILE - 1) / BA_TILE) * BA_THREADS;       // every level above is at least 4x smaller: 2*n1 bounds the sum
     CK(ln_.prod.ensure((2 * n1 + 4096) * fe)); CK(ln_.lvlprefix.ensure((2 * n1 + 4096) * fe)); CK(ln_.others.ensure((WARP_LEVEL_MAX / 4 + 4096) * fe)); }
-  void* pin = nullptr;
+  void* pin = nullptr; uint64_t yin = 0;
+  const uint64_t ya = ((U[1] * fe + 255) / 256) * 256, yb = R > 1 ? ((U[2] * fe + 255) / 256) * 256 : 0;      // x array, then y array (see meta_load_point)
   for (uint32_t r = 0; r < R; r++) {
-    void* pout = (r & 1) ? ln_.pb.p : ln_.pa.p;
+    void* pout = (r & 1) ? ln_.pb.p : ln_.pa.p; const uint64_t yout = (r & 1) ? yb : ya;
     TreeRound tr{off[r], off[r + 1], (r + 2 <= R) ? off[r + 2] : nullptr, bid[r + 1], (r + 2 <= R) ? bid[r + 2] : nullptr, nbg};
     uint32_t grid = (uint32_t)((U[r + 1] + BA_TILE - 1) / BA_TILE);
     if (grid == 0) grid = 1;
@@ -209,8 +210,8 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
     if (r == 0) k_tree_meta<true><<<(nslots + 255) / 256, 256, 0, s>>>(tr, sorted, meta, nslots);
     else k_tree_meta<false><<<(nslots + 255) / 256, 256, 0, s>>>(tr, nullptr, meta, nslots);
     CKL();
-    if (r == 0) k_tree_fwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(meta, d_bases, ln_.prefix.p, prod, BK, grid);
-    else k_tree_fwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(meta, pin, ln_.prefix.p, prod, BK, grid);
+    if (r == 0) k_tree_fwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(meta, d_bases, 0, ln_.prefix.p, prod, BK, grid);
+    else k_tree_fwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(meta, pin, yin, ln_.prefix.p, prod, BK, grid);
     CKL(); MARK(T_TREE_FWD);
     // up the product tree: plain K-ary levels while the level is large, one warp-assisted level (arity 32*4) once it is small
     struct Lvl { uint64_t n; char* v; char* p; bool warp; int K; };
@@ -237,10 +238,15 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
       CKL();
     }
     MARK(T_INV_TREE);
-    if (r == 0) k_tree_bwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(meta, d_bases, ln_.prefix.p, prod, pout, BK, grid);
-    else k_tree_bwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(meta, pin, ln_.prefix.p, prod, pout, BK, grid);
+    if (ctx->opt_bwd_staged) {
+      const size_t smem = (size_t)(5 * (C::N / 4)) * BA_THREADS * 16;          // 2 points + 1 field element per thread
+      if (r == 0) k_tree_bwd_staged<C, true><<<pgrid, BA_THREADS, smem, s>>>(meta, d_bases, 0, ln_.prefix.p, prod, pout, yout, BK, grid);
+      else k_tree_bwd_staged<C, false><<<pgrid, BA_THREADS, smem, s>>>(meta, pin, yin, ln_.prefix.p, prod, pout, yout, BK, grid);
+    } else
+    if (r == 0) k_tree_bwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(meta, d_bases, 0, ln_.prefix.p, prod, pout, yout, BK, grid);
+    else k_tree_bwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(meta, pin, yin, ln_.prefix.p, prod, pout, yout, BK, grid);
     CKL(); MARK(r == 0 ? T_TREE_BWD0 : T_TREE_BWD);
-    pin = pout;
+    pin = pout; yin = yout;
     *adds_out += U[r] - U[r + 1];
   }
   if (ctx->prof) {   // exact slot counts per round (the U[] are upper bounds): read the scan totals back, stats mode only
@@ -250,7 +256,7 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
     for (uint32_t r = 1; r <= R; r++) { uint64_t cur = ctx->h_pinned[1024 + r]; exact += prev - cur; if (r == 1) ctx->adds_r0 += prev - cur; prev = cur; }
     *adds_out -= 0; ctx->adds_exact += exact;
   }
-  k_accum_finish<C, false><<<(nbg + 127) / 128, 128, 0, s>>>(nullptr, nullptr, pin, off[R], nbg, buckets_g); CKL();
+  k_accum_finish<C, false><<<(nbg + 127) / 128, 128, 0, s>>>(nullptr, nullptr, pin, yin, off[R], nbg, buckets_g); CKL();
   MARK(T_FINISH);
   return B200MSM_OK;
 }
@@ -738,11 +744,13 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "tree_rounds")) { ctx->opt_tree_rounds = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "group_pairs")) { if (v < 0) return B200MSM_E_ARG; ctx->opt_group_pairs = v; return B200MSM_OK; }
   if (!strcmp(key, "persist")) { if (v < 0) return B200MSM_E_ARG; ctx->opt_persist = (int)v; return B200MSM_OK; }
-  if (!strcmp(key, "ba_k")) { if (v < 1 || v > 64) return B200MSM_E_ARG; ctx->opt_ba_k = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "ba_k")) { if (v < 0 || v > 64) return B200MSM_E_ARG; ctx->opt_ba_k = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "pt_k")) { if (v < 2 || v > 64) return B200MSM_E_ARG; ctx->opt_pt_k = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "probe_sqr")) { ctx->probe_sqr = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "probe29")) { ctx->probe29 = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "lanes")) { if (v < 1 || v > MAX_LANES) return B200MSM_E_ARG; ctx->opt_lanes = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "probe_smem")) { if (v < 0 || v > 200 * 1024) return B200MSM_E_ARG; ctx->opt_probe_smem = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "bwd_staged")) { ctx->opt_bwd_staged = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "subslots")) { if (v < 0 || v > 256 || (v & (v - 1))) return B200MSM_E_ARG; ctx->opt_subslots = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "combine")) { if (v < 0 || v > 1) return B200MSM_E_ARG; ctx->opt_combine = (int)v; return B200MSM_OK; }
   return B200MSM_E_ARG;
@@ -975,14 +983,16 @@ int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s) {
   const int n8 = n8_of(curve);
   CK(ctx->acc_a.ensure(1024 * 48)); CK(ctx->acc_b.ensure((size_t)blocks * threads * n8));
   CK(cudaMemsetAsync(ctx->acc_a.p, 0x17, 1024 * 48, ctx->stream));
+  const size_t psm = (size_t)ctx->opt_probe_smem;       // dynamic shared memory per block, only to cap the resident warps per SM (occupancy sensitivity of the multiplier)
+  if (psm) { CK(cudaFuncSetAttribute(k_fpmul_probe<BLS12_381>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm)); CK(cudaFuncSetAttribute(k_fpmul_probe<BN254>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm)); }
   double best = 0;
   for (int rep = 0; rep < 4; rep++) {
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (ctx->probe29) {
       if (curve == 0) k_fpmul29_probe<BLS12_381><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
       else k_fpmul29_probe<BN254><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
-    } else if (curve == 0) k_fpmul_probe<BLS12_381><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
-    else k_fpmul_probe<BN254><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
+    } else if (curve == 0) k_fpmul_probe<BLS12_381><<<blocks, threads, psm, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
+    else k_fpmul_probe<BN254><<<blocks, threads, psm, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
     CKL();
     CK(cudaEventRecord(ctx->ev[1], ctx->stream)); CK(cudaEventSynchronize(ctx->ev[1]));
     float ms; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
@@ -990,6 +1000,24 @@ int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s) {
     if (rep && rate > best) best = rate;
   }
   *fqmul_per_s = best; return B200MSM_OK;
+}
+
+int b200msm_probe_dfma(b200msm_ctx* ctx, double* dfma_per_s) {
+  if (!ctx || !dfma_per_s) return B200MSM_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
+  const uint32_t blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  CK(ctx->acc_b.ensure((size_t)blocks * threads * 8));
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    k_dfma_probe<<<blocks, threads, 0, ctx->stream>>>(iters, 1.000001, ctx->acc_b.as<double>()); CKL();
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream)); CK(cudaEventSynchronize(ctx->ev[1]));
+    float ms; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    double rate = (double)blocks * threads * iters * 8 / (ms * 1e-3);
+    if (rep && rate > best) best = rate;
+  }
+  *dfma_per_s = best; return B200MSM_OK;
 }
 
 int b200msm_get_counter(b200msm_ctx* ctx, const char* key, uint64_t* value) {

@@ -484,6 +484,20 @@ __global__ void __launch_bounds__(256) k_imadx_probe(uint32_t iters, uint32_t se
   if (s == 0x1234567u) sink[0] = s;
 }
 // Field-multiply throughput probe: ITER dependent Montgomery multiplications per thread (2N^2+N limb products each).
+// FP64 pipe probe: 8 independent DFMA chains per thread (the pipe an FP64-based multiplier would run on, beside the integer pipe)
+__global__ void __launch_bounds__(256) k_dfma_probe(uint32_t iters, double seed, double* __restrict__ sink) {
+  double a[8], b = seed * 1.0000001, c = seed * 0.5;
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = seed + k;
+  for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = __fma_rz(a[k], b, c);
+  }
+  double t = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) t += a[k];
+  if (t == 12345.678) sink[blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
 template <class C>
 __global__ void __launch_bounds__(256) k_fpmul_probe(uint32_t iters, const void* __restrict__ in, void* __restrict__ out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
