@@ -31,14 +31,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--log2n", type=int, default=20, help="points per GPU = 2^log2n")
+    ap.add_argument("--log2n", type=int, default=0, help="points per GPU = 2^log2n (default 20; 18 for --workload batched)")
     ap.add_argument("--log2n-total", type=int, default=0, help="strong scaling: total points 2^K split over the GPUs (overrides --log2n)")
     ap.add_argument("--curve", default="bls12381", choices=["bls12381", "bn128"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-log2n", type=int, default=16, help="points per reference step (bounded sample)")
+    ap.add_argument("--workload", default="single", choices=["single", "batched"],
+                    help="single: one MSM of 2^log2n points per GPU per step (default, the headline); batched: BASELINE config 5, --batch independent MSMs of 2^log2n points (default 2^18) spread over the GPUs per step")
+    ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-window-table", action="store_true", help="skip the extra measurement with precomputed window tables")
     ap.add_argument("--table-window-bits", type=int, default=0, help="window width of the precomputed table (0 = auto)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.log2n == 0: a.log2n = 18 if a.workload == "batched" else 20
+    return a
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -167,10 +172,48 @@ def run_reference(a):
             "cpu_baseline": {"value": pps, "unit": "points/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": pps, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def kernel_roofline(eng, handle, scal, n, cid, cname, a, out_dev):
+    """per-phase CUDA-event timings inside the engine (single lane, same inputs) -> (roofline object, averaged stats)"""
+    NSETS = len(scal); n8 = 48 if cid == 0 else 32
+    agg = {}; reps = max(3, min(a.steps, 10))
+    eng.multiexp_resident(handle, scal[0], 32, n, cid, out=out_dev, want_stats=True)      # untimed: grows the single-lane scratch
+    for i in range(reps):
+        _, st = eng.multiexp_resident(handle, scal[i % NSETS], 32, n, cid, out=out_dev, want_stats=True)
+        for k, v in st.items(): agg[k] = agg.get(k, 0) + v
+    st = {k: v / reps for k, v in agg.items()}
+    imad = eng.probe_imad(); fq = eng.probe_fqmul(cid)
+    hbm_peak, hbm_src = measured_peaks()
+    lp = LIMB_PRODUCTS_PER_FQMUL[cname]
+    adds = st["affine_adds"]
+    # dominant kernel: the first (largest) k_tree_bwd launch = the backward pass of tree round 0, which does 5 of the 6
+    # field multiplications of every batch-affine addition of that round
+    bwd0_ms = st["ms_k_tree_bwd_round0"]; adds0 = st["affine_adds_round0"]
+    alg_lp = adds0 * 5 * lp                                   # algorithmic limb products of that launch
+    achieved = alg_lp / (bwd0_ms * 1e-3) if bwd0_ms > 0 else 0.0
+    # algorithmic HBM bytes of that launch per addition: 2 input points + prefix product + share of the thread inverse + output point
+    bytes_per_add = 2 * 2 * n8 + n8 + n8 / 8 + 2 * n8
+    # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture (profiles/), 2^20 BLS12-381 only
+    traffic = 3.04e9 if (cname == "bls12381" and a.log2n == 20) else None      # profiles/r1b_ncu_full_tree_kernels_2p20_bls.csv: 2.236 GB read + 0.804 GB written
+    roof = {"bound": "imad", "kernel": "k_tree_bwd<FIRST=1> (batch-affine backward pass, tree round 0: one launch per step)",
+            "achieved": achieved / 1e12, "peak": imad / 1e12, "unit": "T limb-products/s (32x32+64 IMAD.WIDE.U32)",
+            "frac": (achieved / imad) if imad else None, "traffic": traffic,
+            "avg_launch_ms": bwd0_ms, "algorithmic_units_per_launch": alg_lp, "additions_per_launch": adds0,
+            "peak_source": "measured in this run by b200msm_probe_imad: register-resident IMAD.WIDE.U32 carry chains on all SMs (the instruction the field multiplier is made of); plain 32-bit IMAD runs at twice this rate",
+            "hbm": {"achieved": adds0 * bytes_per_add / (bwd0_ms * 1e-3) / 1e9 if bwd0_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": (adds0 * bytes_per_add / (bwd0_ms * 1e-3) / 1e9 / hbm_peak) if bwd0_ms > 0 else None,
+                    "algorithmic_bytes_per_launch": adds0 * bytes_per_add, "peak_source": hbm_src},
+            "all_rounds": {"kernel_group": "k_tree_bwd, all rounds", "limb_products": adds * 5 * lp, "ms": st["ms_k_tree_bwd"],
+                           "frac_of_imad_peak": (adds * 5 * lp / (st["ms_k_tree_bwd"] * 1e-3) / imad) if imad and st["ms_k_tree_bwd"] > 0 else None},
+            "whole_accumulate": {"limb_products": adds * FQMUL_PER_AFFINE_ADD * lp, "ms": st["ms_accumulate"],
+                                 "frac_of_imad_peak": (adds * FQMUL_PER_AFFINE_ADD * lp / (st["ms_accumulate"] * 1e-3) / imad) if imad and st["ms_accumulate"] > 0 else None},
+            "fqmul_per_s_measured": fq, "fqmul_frac_of_imad_peak": fq * lp / imad if imad else None}
+    return roof, st
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -309,38 +352,8 @@ def run_ours(a):
     # ---- kernel-level timings (per-phase CUDA events inside the engine) for the roofline, same inputs, rank 0 only
     line = None
     if rank == 0:
-        agg = {}; reps = max(3, min(a.steps, 10))
-        eng.multiexp_resident(handle, scal[0], 32, n, cid, out=out_dev, want_stats=True)      # untimed: grows the single-lane scratch
-        for i in range(reps):
-            _, st = eng.multiexp_resident(handle, scal[i % NSETS], 32, n, cid, out=out_dev, want_stats=True)
-            for k, v in st.items(): agg[k] = agg.get(k, 0) + v
-        st = {k: v / reps for k, v in agg.items()}
-        imad = eng.probe_imad(); fq = eng.probe_fqmul(cid)
-        hbm_peak, hbm_src = measured_peaks()
-        lp = LIMB_PRODUCTS_PER_FQMUL[cname]
+        roof, st = kernel_roofline(eng, handle, scal, n, cid, cname, a, out_dev)
         adds = st["affine_adds"]
-        # dominant kernel: the first (largest) k_tree_bwd launch = the backward pass of tree round 0, which does 5 of the 6
-        # field multiplications of every batch-affine addition of that round
-        bwd0_ms = st["ms_k_tree_bwd_round0"]; adds0 = st["affine_adds_round0"]
-        alg_lp = adds0 * 5 * lp                                   # algorithmic limb products of that launch
-        achieved = alg_lp / (bwd0_ms * 1e-3) if bwd0_ms > 0 else 0.0
-        # algorithmic HBM bytes of that launch per addition: 2 input points + prefix product + share of the thread inverse + output point
-        bytes_per_add = 2 * 2 * n8 + n8 + n8 / 8 + 2 * n8
-        # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture (profiles/), 2^20 BLS12-381 only
-        traffic = 3.27e9 if (cname == "bls12381" and a.log2n == 20) else None
-        roof = {"bound": "imad", "kernel": "k_tree_bwd<FIRST=1> (batch-affine backward pass, tree round 0: one launch per step)",
-                "achieved": achieved / 1e12, "peak": imad / 1e12, "unit": "T limb-products/s (32x32+64 IMAD.WIDE.U32)",
-                "frac": (achieved / imad) if imad else None, "traffic": traffic,
-                "avg_launch_ms": bwd0_ms, "algorithmic_units_per_launch": alg_lp, "additions_per_launch": adds0,
-                "peak_source": "measured in this run by b200msm_probe_imad: register-resident IMAD.WIDE.U32 carry chains on all SMs (the instruction the field multiplier is made of); plain 32-bit IMAD runs at twice this rate",
-                "hbm": {"achieved": adds0 * bytes_per_add / (bwd0_ms * 1e-3) / 1e9 if bwd0_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": (adds0 * bytes_per_add / (bwd0_ms * 1e-3) / 1e9 / hbm_peak) if bwd0_ms > 0 else None,
-                        "algorithmic_bytes_per_launch": adds0 * bytes_per_add, "peak_source": hbm_src},
-                "all_rounds": {"kernel_group": "k_tree_bwd, all rounds", "limb_products": adds * 5 * lp, "ms": st["ms_k_tree_bwd"],
-                               "frac_of_imad_peak": (adds * 5 * lp / (st["ms_k_tree_bwd"] * 1e-3) / imad) if imad and st["ms_k_tree_bwd"] > 0 else None},
-                "whole_accumulate": {"limb_products": adds * FQMUL_PER_AFFINE_ADD * lp, "ms": st["ms_accumulate"],
-                                     "frac_of_imad_peak": (adds * FQMUL_PER_AFFINE_ADD * lp / (st["ms_accumulate"] * 1e-3) / imad) if imad and st["ms_accumulate"] > 0 else None},
-                "fqmul_per_s_measured": fq, "fqmul_frac_of_imad_peak": fq * lp / imad if imad else None}
         total_points = (1 << a.log2n_total) if strong else n * world
         line = {"metric": METRIC if cname == "bls12381" else "bn254_g1_msm_points_per_s", "value": total_points / (ms * 1e-3), "unit": "points/s",
                 "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if strong else "weak",
@@ -367,12 +380,104 @@ def run_ours(a):
             line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
     elif rank == 0:
         line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": 0, "kind": "skipped", "sample": "measured at N=1 only"}
-    if rank == 0: print(json.dumps(line), flush=True)
+    if rank == 0: _emit(line)
     eng.free_bases(handle)
     if world > 1: dist.barrier(); dist.destroy_process_group()
 
 
+def run_batched(a):
+    """BASELINE config 5: a.batch independent MSMs of 2^log2n points over the same bases, MSM j on rank j % world (replicas, no collective
+    on the data path; one barrier brackets the step).  value = points of the whole batch / second, scalars resident in HBM;
+    e2e = the same with every MSM's scalars in pinned host memory and results returned to the host."""
+    import torch
+    import torch.distributed as dist
+    import b200msm
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available(): raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    if world > 1: dist.init_process_group("nccl", device_id=dev)
+    cname = a.curve; cid = 0 if cname == "bls12381" else 1; n8 = b200msm.N8[cid]; n = 1 << a.log2n
+    mine = len(range(rank, a.batch, world))                       # MSMs of this rank per step
+    eng = b200msm.Engine(local); stream = torch.cuda.current_stream(dev); eng.set_stream(stream.cuda_stream)
+    bases = torch.empty(n * 2 * n8, dtype=torch.uint8, device=dev); eng.generate_bases(cid, SEED + a.log2n, 0, n, bases)
+    g = torch.Generator(device=dev); g.manual_seed(99 + rank)
+    scal = torch.randint(0, 256, (max(1, mine) * n * 32,), dtype=torch.uint8, device=dev, generator=g)
+    out_dev = torch.zeros(max(1, mine) * 3 * n8, dtype=torch.uint8, device=dev)
+    handle = eng.upload_bases(cid, bases, n)
+    hwin = None if a.no_window_table else eng.upload_bases_windowed(cid, bases, n, 32, a.table_window_bits)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warm):
+        for _ in range(warm): fn()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(steps): fn()
+        sync_all()
+        t = torch.tensor([(time.perf_counter() - t0) * 1e3 / steps], dtype=torch.float64, device=dev)
+        if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_dev(h=None):
+        if mine: eng.multiexp_batch(h or handle, scal, 32, n, mine, cid, out=out_dev)      # returns when all results are in out_dev
+    if rank == 0:       # correctness guard: first MSM of the batch vs a single call
+        one = eng.multiexp_resident(handle, scal[: n * 32], 32, n, cid)
+        step_dev(); torch.cuda.synchronize(dev)
+        assert eng.normalize(cid, out_dev[: 3 * n8]) == eng.normalize(cid, one), "batched result differs from the single-MSM path"
+    sampler = ClockSampler(local)
+    if rank == 0: sampler.start()
+    ms = timed(step_dev, a.steps, max(3, a.warmup))
+    wms = timed(lambda: step_dev(hwin), a.steps, max(3, a.warmup)) if hwin else None
+    hs = torch.empty(max(1, mine) * n * 32, dtype=torch.uint8).pin_memory(); hs.copy_(scal)
+    hout = torch.zeros(max(1, mine) * 3 * n8, dtype=torch.uint8).pin_memory()
+
+    def step_host():
+        if mine: eng.multiexp_batch(handle, hs, 32, n, mine, cid, out=hout)
+    e2e_ms = timed(step_host, max(3, min(a.steps, 10)), 2)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        roof, st = kernel_roofline(eng, handle, [scal[: n * 32]], n, cid, cname, a, out_dev[: 3 * n8])
+        total = a.batch * n
+        line = {"metric": METRIC if cname == "bls12381" else "bn254_g1_msm_points_per_s", "value": total / (ms * 1e-3), "unit": "points/s",
+                "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u32 limbs (Montgomery Fq, 32x32->64 IMAD)", "data": "synthetic",
+                "config": {"workload": "batched: %d independent %s G1 MSMs of 2^%d points per step over one resident base set, MSM j on GPU j %% %d, %d worker contexts per GPU; uniform 256-bit scalars"
+                                       % (a.batch, "BLS12-381" if cid == 0 else "BN254", a.log2n, world, 4),
+                           "curve": cname, "log2n_per_msm": a.log2n, "batch": a.batch, "parallelism": "replicas (independent MSMs), no collective",
+                           "window_bits": int(st["window_bits"]), "windows": int(st["windows"]),
+                           "cache": "no L2 flush: each MSM's working set (bases %d MiB + sort/tree scratch) exceeds the 126 MB L2 and %d MSMs run concurrently" % (n * 2 * n8 >> 20, 4)},
+                "msm_per_s": a.batch / (ms * 1e-3), "ms_per_msm": ms / a.batch,
+                "clocks": clocks,
+                "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": a.batch * n * 32, "d2h_bytes_per_step": a.batch * 3 * n8,
+                        "api": "b200msm_g1_multiexp_batch with pinned host scalars / results, bases resident"},
+                "gpu_launches": int(st["launches"]) * a.batch,
+                "roofline": roof, "phases_ms_single_msm": {k: round(v, 4) for k, v in st.items() if k.startswith("ms_")},
+                "resident_window_table": ({"ms_per_step": wms, "value": total / (wms * 1e-3), "unit": "points/s", "msm_per_s": a.batch / (wms * 1e-3)} if wms else None),
+                "cpu_baseline": {"value": None, "unit": "points/s", "cores": 0, "kind": "skipped", "sample": "see the default (single) workload"}}
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                pps, rms, cores, kind, sample = time_reference(cname, a.ref_log2n, 2, 1)
+                line["cpu_baseline"] = {"value": pps, "unit": "points/s", "cores": cores, "kind": kind, "sample": sample, "ms_per_sample": rms}
+            except Exception as ex:
+                line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+        _emit(line)
+    eng.free_bases(handle)
+    if hwin: eng.free_bases(hwin)
+    if world > 1: dist.barrier(); dist.destroy_process_group()
+
+
+def _emit(line):
+    """the ONE JSON line goes to the real stdout; everything else printed while running (NCCL's version banner, warnings) went to stderr"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1); os.dup2(2, 1)           # library chatter on fd 1 must not break the one-line contract
     args = parse()
     if args.impl == "reference": run_reference(args)
+    elif args.workload == "batched": run_batched(args)
     else: run_ours(args)

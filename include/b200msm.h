@@ -88,6 +88,13 @@ int b200msm_g1_multiexp_resident(b200msm_ctx* ctx, uint64_t handle, const void* 
 int b200msm_upload_bases_windowed(b200msm_ctx* ctx, int curve, const void* bases, uint64_t n, uint32_t scalar_size,
                                   uint32_t window_bits, uint64_t* handle);
 
+/* ---- count independent MSMs of n points each over the same resident bases (a stream of proofs over one proving key; the
+ *      reference runs one WASM instance per worker for this, SURVEY.md 8b "Threading").  scalars: count * n * scalar_size bytes,
+ *      MSM j uses the j-th block; out: count * 3*n8 bytes.  Internally spread over `batch_workers` (option, default 4) sub-contexts
+ *      with their own streams, scratch and host threads.  Returns when all results are in `out`. */
+int b200msm_g1_multiexp_batch(b200msm_ctx* ctx, uint64_t handle, const void* scalars, uint32_t scalar_size, uint64_t n,
+                              uint32_t count, void* out);
+
 /* ---- == g1m_normalize + f1m_fromMontgomery(x), f1m_fromMontgomery(y)   src/build_curve_jacobian_a0.js:940-973,
  *      the comparison form of the reference's tests (test/batchAffine.js:1249-1254):
  * count Jacobian Montgomery points -> count canonical affine points x || y as plain LE integers < q; infinity -> zeros. */

@@ -503,3 +503,30 @@ def test_window_table_full_size_known_answer(eng, cname, lg):
         assert msm(eng, cv, d, sd, 32, n) == exp
     finally:
         eng.free_bases(h)
+
+
+# ---------------------------------------------------------------- batched MSMs over one resident base set (BASELINE config 5)
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+@pytest.mark.parametrize("windowed", [False, True])
+def test_batch_matches_individual_msms(eng, cname, windowed):
+    """b200msm_g1_multiexp_batch: every MSM of the batch equals the oracle's result for its scalar block, for any worker count;
+    device and host buffers."""
+    import torch
+    cv = curve(cname); n = 700; count = 11
+    bases = make_bases(cv, n, 95)
+    sc = b"".join(make_scalars(n, 200 + j, "u256") for j in range(count))
+    exp = [oracle_msm(cv, bases, sc[j * n * 32:(j + 1) * n * 32], 32, n) for j in range(count)]
+    h = eng.upload_bases_windowed(cv.cid, bases, n, 32, 0) if windowed else eng.upload_bases(cv.cid, bases, n)
+    try:
+        for workers in (1, 3, 4):
+            eng.set_option("batch_workers", workers)
+            out = eng.multiexp_batch(h, sc, 32, n, count, cv.cid)
+            sz = 3 * cv.n8
+            assert [eng.normalize(cv.cid, out[j * sz:(j + 1) * sz]) for j in range(count)] == exp, workers
+        import numpy as np
+        sd = torch.from_numpy(np.frombuffer(sc, dtype=np.uint8).copy()).cuda(); od = torch.zeros(count * 3 * cv.n8, dtype=torch.uint8, device="cuda")
+        eng.multiexp_batch(h, sd, 32, n, count, cv.cid, out=od)
+        torch.cuda.synchronize()
+        assert eng.normalize(cv.cid, od, count) == b"".join(exp)
+    finally:
+        eng.set_option("batch_workers", 4); eng.free_bases(h)

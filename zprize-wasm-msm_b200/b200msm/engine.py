@@ -81,6 +81,15 @@ class Engine:
         res = o.raw if out is None else out
         return (res, st.as_dict()) if want_stats else res
 
+    def multiexp_batch(self, handle, scalars, scalar_size, n, count, curve, out=None):
+        """count independent MSMs over the same resident bases; scalars = count blocks of n scalars; -> count * 3*n8 bytes"""
+        ps, ks = _ptr(scalars)
+        if out is None:
+            o = ctypes.create_string_buffer(3 * N8[curve] * count)
+            self._ck(lib.b200msm_g1_multiexp_batch(self._ctx, handle, ps, scalar_size, n, count, o)); return o.raw
+        po, ko = _ptr(out)
+        self._ck(lib.b200msm_g1_multiexp_batch(self._ctx, handle, ps, scalar_size, n, count, po)); return out
+
     def normalize(self, curve, jac, count=1):
         """g1m_normalize + fromMontgomery: canonical x||y bytes (plain LE ints; infinity = zeros)"""
         pj, kj = _ptr(jac); o = ctypes.create_string_buffer(2 * N8[curve] * count)

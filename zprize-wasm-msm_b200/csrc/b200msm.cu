@@ -23,6 +23,7 @@
 #include "glv.cuh"
 #include "host_ec.h"
 #include <chrono>
+#include <thread>
 
 using namespace b200;
 
@@ -78,6 +79,7 @@ struct b200msm_ctx {
   std::vector<cudaEvent_t> pev; std::vector<int> ptag; size_t pused = 0; bool prof = false;
   uint64_t launches = 0, adds_r0 = 0, adds_exact = 0, cur_n = 0;
   size_t total_mem = 0;
+  std::vector<b200msm_ctx*> workers; int opt_batch_workers = 4;            // sub-contexts (own stream + scratch) that run the MSMs of a batch concurrently
 };
 
 namespace {
@@ -701,6 +703,8 @@ int b200msm_create(b200msm_ctx** out, int device_id) {
 
 void b200msm_destroy(b200msm_ctx* ctx) {
   if (!ctx) return;
+  for (b200msm_ctx* w : ctx->workers) b200msm_destroy(w);
+  ctx->workers.clear();
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->bases, &ctx->scalars, &ctx->canon, &ctx->counts, &ctx->offsets, &ctx->cursors, &ctx->tiles, &ctx->sorted, &ctx->buckets,
@@ -751,6 +755,7 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "lanes")) { if (v < 1 || v > MAX_LANES) return B200MSM_E_ARG; ctx->opt_lanes = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "probe_smem")) { if (v < 0 || v > 200 * 1024) return B200MSM_E_ARG; ctx->opt_probe_smem = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "bwd_staged")) { ctx->opt_bwd_staged = v != 0; return B200MSM_OK; }
+  if (!strcmp(key, "batch_workers")) { if (v < 1 || v > 16) return B200MSM_E_ARG; ctx->opt_batch_workers = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "subslots")) { if (v < 0 || v > 256 || (v & (v - 1))) return B200MSM_E_ARG; ctx->opt_subslots = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "combine")) { if (v < 0 || v > 1) return B200MSM_E_ARG; ctx->opt_combine = (int)v; return B200MSM_OK; }
   return B200MSM_E_ARG;
@@ -820,6 +825,48 @@ int b200msm_g1_multiexp_resident(b200msm_ctx* ctx, uint64_t handle, const void* 
   const Resident& r = it->second;
   Precomp pre{(uint32_t)r.n, r.t_nbits, r.t_c0, r.t_rem, r.t_Wd};
   return msm_entry(ctx, r.curve, r.d, true, scalars, scalar_size, n, 0, scalar_size > 32 ? 257 : 8 * scalar_size, out, stats, r.t_Wd ? &pre : nullptr);
+}
+
+// count independent MSMs over the same resident bases (BASELINE config 5: streams of equal-size MSMs).  The MSMs are spread over
+// `batch_workers` sub-contexts -- each with its own stream and scratch, driven by its own host thread -- so that the latency-bound
+// parts of one MSM (sort read-back, inversion tails, host window combination) overlap the throughput-bound kernels of the others.
+int b200msm_g1_multiexp_batch(b200msm_ctx* ctx, uint64_t handle, const void* scalars, uint32_t scalar_size, uint64_t n, uint32_t count, void* out) {
+  if (!ctx) return B200MSM_E_ARG;
+  auto it = ctx->residents.find(handle);
+  if (it == ctx->residents.end() || n > it->second.n || !out || scalar_size == 0 || (n && !scalars)) { ctx->err = "bad handle or argument"; return B200MSM_E_ARG; }
+  if (count == 0) return B200MSM_OK;
+  const Resident r = it->second;
+  const int n8 = n8_of(r.curve);
+  const uint32_t K = std::min<uint32_t>((uint32_t)ctx->opt_batch_workers, count);
+  while (ctx->workers.size() < K) {
+    b200msm_ctx* w = nullptr; int rc = b200msm_create(&w, ctx->device);
+    if (rc) { ctx->err = "cannot create a batch worker context"; return rc; }
+    ctx->workers.push_back(w);
+  }
+  for (uint32_t k = 0; k < K; k++) {      // workers inherit the tuning options of the parent
+    b200msm_ctx* w = ctx->workers[k];
+    w->opt_window_bits = ctx->opt_window_bits; w->opt_accumulate = ctx->opt_accumulate; w->opt_tree_rounds = ctx->opt_tree_rounds; w->opt_lanes = ctx->opt_lanes;
+    w->opt_ba_k = ctx->opt_ba_k; w->opt_pt_k = ctx->opt_pt_k; w->opt_persist = ctx->opt_persist; w->opt_subslots = ctx->opt_subslots; w->opt_combine = ctx->opt_combine;
+    w->opt_group_pairs = ctx->opt_group_pairs;
+  }
+  CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream));       // inputs produced on the caller's stream are complete
+  Precomp pre{(uint32_t)r.n, r.t_nbits, r.t_c0, r.t_rem, r.t_Wd};
+  const uint32_t nbits = scalar_size > 32 ? 257 : 8 * scalar_size;
+  std::vector<int> rcs(K, 0);
+  std::vector<std::thread> th;
+  for (uint32_t k = 0; k < K; k++) th.emplace_back([&, k]() {
+    b200msm_ctx* w = ctx->workers[k];
+    for (uint32_t j = k; j < count; j += K) {
+      const char* sc = reinterpret_cast<const char*>(scalars) + (size_t)j * n * scalar_size;
+      char* o = reinterpret_cast<char*>(out) + (size_t)j * 3 * n8;
+      int rc = msm_entry(w, r.curve, r.d, true, sc, scalar_size, n, 0, nbits, o, nullptr, r.t_Wd ? &pre : nullptr);
+      if (rc) { rcs[k] = rc; return; }
+    }
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) rcs[k] = B200MSM_E_CUDA;
+  });
+  for (auto& t : th) t.join();
+  for (uint32_t k = 0; k < K; k++) if (rcs[k]) { ctx->err = "batch worker " + std::to_string(k) + ": " + ctx->workers[k]->err; return rcs[k]; }
+  return B200MSM_OK;
 }
 
 int b200msm_g1_normalize(b200msm_ctx* ctx, int curve, const void* jac, uint64_t count, void* xy) {
