@@ -30,7 +30,14 @@ extern "C" {
 typedef struct b200msm_ctx b200msm_ctx;
 
 enum { B200MSM_BLS12_381_G1 = 0,   /* src/bls12381/build_bls12381.js:16-125 */
-       B200MSM_BN254_G1 = 1 };     /* src/bn128/build_bn128.js:14-125       */
+       B200MSM_BN254_G1 = 1,       /* src/bn128/build_bn128.js:14-125       */
+       /* G2: the same entry points over the quadratic extension Fq2 = Fq[u]/(u^2+1) (src/build_f2m.js; g2m_* exports,
+        * build_bls12381.js:48-53, build_bn128.js:44-49).  For these ids "n8" below is the size of an Fq2 element, c0 || c1 = 96 / 64
+        * bytes, i.e. an affine point is 192 / 128 bytes and a Jacobian point 288 / 192 bytes -- the g2m layouts.  The MSM entry points
+        * (== g2m_multiexpAffine, g2m_multiexpAffine_chunk), resident / windowed / batched forms, normalize, sum, generate_bases and
+        * fq_op (== f2m_*) accept them; the point codecs, GLV and the radix-2^29 probe are G1 only. */
+       B200MSM_BLS12_381_G2 = 2,
+       B200MSM_BN254_G2 = 3 };
 
 enum { B200MSM_OK = 0, B200MSM_E_ARG = -1, B200MSM_E_CUDA = -2, B200MSM_E_NOMEM = -3, B200MSM_E_UNSUPPORTED = -4 };
 

@@ -279,3 +279,52 @@ def glv_preprocess(points, scalars):
 
 
 GLV_LAMBDA = BLS_LAMBDA      # phi(x, y) = (GLV_BETA * x, y) = GLV_LAMBDA * (x, y); signed halves satisfy k = k1 + k2 * GLV_LAMBDA (mod r)
+
+
+# ---- G2: E'(Fq2), Fq2 = Fq[u]/(u^2 + 1) (build_f2m.js; f1m_neg is the non-residue multiplication on both curves).
+# Elements are pairs (c0, c1) of plain integers; points are (x, y) pairs of such or None.  Used to pin the G2 path on small cases.
+def f2_add(cv, a, b): return ((a[0] + b[0]) % cv.q, (a[1] + b[1]) % cv.q)
+def f2_sub(cv, a, b): return ((a[0] - b[0]) % cv.q, (a[1] - b[1]) % cv.q)
+def f2_mul(cv, a, b): return ((a[0] * b[0] - a[1] * b[1]) % cv.q, (a[0] * b[1] + a[1] * b[0]) % cv.q)        # f2m_mul, build_f2m.js:152-194
+def f2_inv(cv, a):                                                                                            # f2m_inverse, build_f2m.js:402-440
+    t = pow((a[0] * a[0] + a[1] * a[1]) % cv.q, -1, cv.q)
+    return (a[0] * t % cv.q, (-a[1]) * t % cv.q)
+
+
+def g2_add(cv, P, Q):
+    if P is None: return Q
+    if Q is None: return P
+    if P[0] == Q[0]:
+        if f2_add(cv, P[1], Q[1]) == (0, 0): return None
+        lam = f2_mul(cv, f2_mul(cv, (3, 0), f2_mul(cv, P[0], P[0])), f2_inv(cv, f2_add(cv, P[1], P[1])))
+    else:
+        lam = f2_mul(cv, f2_sub(cv, Q[1], P[1]), f2_inv(cv, f2_sub(cv, Q[0], P[0])))
+    x3 = f2_sub(cv, f2_sub(cv, f2_mul(cv, lam, lam), P[0]), Q[0])
+    return (x3, f2_sub(cv, f2_mul(cv, lam, f2_sub(cv, P[0], x3)), P[1]))
+
+
+def g2_mul(cv, k, P):
+    acc = None
+    while k:
+        if k & 1: acc = g2_add(cv, acc, P)
+        P = g2_add(cv, P, P); k >>= 1
+    return acc
+
+
+def g2_msm_naive(cv, points, scalars):
+    acc = None
+    for P, k in zip(points, scalars): acc = g2_add(cv, acc, g2_mul(cv, k, P))
+    return acc
+
+
+def g2_from_bytes(cv, b):
+    """affine Montgomery bytes x0 || x1 || y0 || y1 -> point (or None for all-zero)"""
+    n8 = cv.n8; Ri = pow(cv.R, -1, cv.q)
+    v = [int.from_bytes(b[i * n8:(i + 1) * n8], "little") * Ri % cv.q for i in range(4)]
+    return None if not any(v) else ((v[0], v[1]), (v[2], v[3]))
+
+
+def g2_canonical_bytes(cv, P):
+    n8 = cv.n8
+    if P is None: return bytes(4 * n8)
+    return b"".join(c.to_bytes(n8, "little") for c in (P[0][0], P[0][1], P[1][0], P[1][1]))

@@ -134,3 +134,59 @@ class RefModule:
         out = self.normalize_read(pR)
         self.heap_release(mark)
         return out
+
+
+# ---- G2 (g2m_* exports over f2m, build_bls12381.js:48-53 / build_bn128.js:44-49): same rig, elements are Fq2 = c0 || c1
+class RefG2:
+    """helpers over one RefModule for the G2 exports; all data in the reference's own byte formats"""
+
+    def __init__(self, mod: RefModule):
+        self.m = mod; self.n8 = mod.n8; self.e8 = 2 * mod.n8          # bytes per Fq / per Fq2 element
+
+    def generator_affine(self) -> bytes:
+        return self.m.read(self.m.consts["pG2gen"], 2 * self.e8)
+
+    def times_scalar_affine(self, base_affine: bytes, scalar: bytes) -> bytes:
+        """g2m_timesScalarAffine + g2m_toAffine -> affine Montgomery bytes (2 * e8)"""
+        m = self.m; mark = m.heap_mark()
+        pB = m.alloc(2 * self.e8); pS = m.alloc(len(scalar) + 8); pR = m.alloc(3 * self.e8)
+        m.write(pB, base_affine); m.write(pS, scalar)
+        m.g2m_timesScalarAffine(pB, pS, len(scalar), pR)
+        m.g2m_toAffine(pR, pR)
+        out = m.read(pR, 2 * self.e8); m.heap_release(mark); return out
+
+    def canonical(self, pR) -> bytes:
+        """g2m_normalize + f2m_fromMontgomery on x and y -> x0 || x1 || y0 || y1 as plain LE integers; infinity -> zeros"""
+        m = self.m
+        if m.g2m_isZero(pR): return bytes(2 * self.e8)
+        m.g2m_normalize(pR, pR)
+        m.f2m_fromMontgomery(pR, pR); m.f2m_fromMontgomery(pR + self.e8, pR + self.e8)
+        return m.read(pR, 2 * self.e8)
+
+    def msm_affine(self, bases: bytes, scalars: bytes, scalar_size: int, n: int) -> bytes:
+        m = self.m; mark = m.heap_mark()
+        pB = m.alloc(max(len(bases), 8)); pS = m.alloc(len(scalars) + 8); pR = m.alloc(3 * self.e8)
+        m.write(pB, bases); m.write(pS, scalars)
+        m.g2m_multiexpAffine(pB, pS, scalar_size, n, pR)
+        out = self.canonical(pR); m.heap_release(mark); return out
+
+    def msm_chunk(self, bases, scalars, scalar_size, n, start_bit, chunk_bits) -> bytes:
+        m = self.m; mark = m.heap_mark()
+        pB = m.alloc(max(len(bases), 8)); pS = m.alloc(len(scalars) + 8); pR = m.alloc(3 * self.e8)
+        m.write(pB, bases); m.write(pS, scalars)
+        m.g2m_multiexpAffine_chunk(pB, pS, scalar_size, n, start_bit, chunk_bits, pR)
+        out = self.canonical(pR); m.heap_release(mark); return out
+
+    def canonical_of(self, jac: bytes) -> bytes:
+        m = self.m; mark = m.heap_mark()
+        pR = m.alloc(3 * self.e8); m.write(pR, jac)
+        out = self.canonical(pR); m.heap_release(mark); return out
+
+    def f2m(self, fn: str, a: bytes, b: bytes = None) -> bytes:
+        """one f2m_<fn> call on Montgomery Fq2 operands"""
+        m = self.m; mark = m.heap_mark()
+        pA = m.alloc(self.e8); pB = m.alloc(self.e8); pR = m.alloc(self.e8)
+        m.write(pA, a)
+        if b is not None: m.write(pB, b); getattr(m, "f2m_" + fn)(pA, pB, pR)
+        else: getattr(m, "f2m_" + fn)(pA, pR)
+        out = m.read(pR, self.e8); m.heap_release(mark); return out

@@ -530,3 +530,141 @@ def test_batch_matches_individual_msms(eng, cname, windowed):
         assert eng.normalize(cv.cid, od, count) == b"".join(exp)
     finally:
         eng.set_option("batch_workers", 4); eng.free_bases(h)
+
+
+# ---------------------------------------------------------------- "next" row 3: G2 (g2m_* over Fq2) through the same entry points
+G2ID = {"bls12381": 2, "bn128": 3}
+_M64 = (1 << 64) - 1
+
+
+def _splitmix64(x):
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+@pytest.fixture(scope="module", params=["bls12381", "bn128"])
+def g2ref(request):
+    if not refwasm.available(request.param): pytest.skip("oracle/_ref not built")
+    return request.param, refwasm.RefG2(refwasm.RefModule(request.param))
+
+
+def _g2_bases(ref, n, seed):
+    """P_i = k_i * G2 from the reference's own g2m_timesScalarAffine (k_i = splitmix64(seed + i), the engine's stream)"""
+    G = ref.generator_affine()
+    return b"".join(ref.times_scalar_affine(G, (_splitmix64(seed + i) or 1).to_bytes(8, "little")) for i in range(n))
+
+
+def _g2_msm(eng, cid, bases, sc, ssz, n):
+    return eng.normalize(cid, eng.multiexp_affine(cid, bases, sc, ssz, n))
+
+
+def test_g2_fq2_ops_match_reference(eng, g2ref):
+    """f2m_mul / add / sub / square / inverse / neg / toMontgomery / fromMontgomery (build_f2m.js) through b200msm_fq_op"""
+    cname, ref = g2ref; cv = curve(cname); cid = G2ID[cname]; e8 = 2 * cv.n8
+    rnd = random.Random(41)
+    def el(c0, c1): return c0.to_bytes(cv.n8, "little") + c1.to_bytes(cv.n8, "little")
+    vals = [el(0, 0), el(1, 0), el(0, 1), el(cv.q - 1, cv.q - 1), el(cv.R % cv.q, 0), el(5, 0), el(0, 7)] + [el(rnd.randrange(cv.q), rnd.randrange(cv.q)) for _ in range(60)]
+    a = b"".join(vals); b = b"".join(reversed(vals)); n = len(vals)
+    for op, fn, two in ((0, "mul", True), (1, "add", True), (2, "sub", True), (3, "square", False), (4, "inverse", False), (5, "toMontgomery", False),
+                        (6, "fromMontgomery", False), (7, "neg", False), (8, "inverse", False)):
+        got = eng.fq_op(cid, op, a, b if two else None)
+        for i in range(n):
+            x = a[i * e8:(i + 1) * e8]; y = b[i * e8:(i + 1) * e8]
+            if fn == "inverse" and x == bytes(e8): continue
+            assert got[i * e8:(i + 1) * e8] == ref.f2m(fn, x, y if two else None), (fn, i)
+
+
+def test_g2_generate_bases_matches_reference(eng, g2ref):
+    import torch
+    cname, ref = g2ref; cv = curve(cname); cid = G2ID[cname]; n = 40
+    d = torch.empty(n * 4 * cv.n8, dtype=torch.uint8, device="cuda")
+    eng.generate_bases(cid, 777, 5, n, d)
+    assert bytes(d.cpu().numpy()) == _g2_bases(ref, n, 777 + 5)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 10, 100, 1000])
+def test_g2_msm_matches_reference_wasm(eng, g2ref, n):
+    """g2m_multiexpAffine of the reference module vs the engine, canonical affine output, uniform 256-bit scalars"""
+    cname, ref = g2ref; cv = curve(cname); cid = G2ID[cname]
+    bases = _g2_bases(ref, min(n, 120), 900 + n) * (n // 120 + 1)
+    bases = bases[: n * 4 * cv.n8]
+    sc = make_scalars(n, 901 + n, "u256")
+    assert _g2_msm(eng, cid, bases, sc, 32, n) == ref.msm_affine(bases, sc, 32, n)
+
+
+def test_g2_edge_cases_chunks_and_variants(eng, g2ref):
+    cname, ref = g2ref; cv = curve(cname); cid = G2ID[cname]; pt = 4 * cv.n8
+    zero = bytes(pt)
+    assert _g2_msm(eng, cid, b"", b"", 32, 0) == zero
+    G = ref.generator_affine()
+    Gp = pyref.g2_from_bytes(cv, G); R = cv.R
+    negG = b"".join(((c * R) % cv.q).to_bytes(cv.n8, "little") for c in (Gp[0][0], Gp[0][1], (-Gp[1][0]) % cv.q, (-Gp[1][1]) % cv.q))
+    five = (5).to_bytes(32, "little")
+    assert _g2_msm(eng, cid, G + negG, five * 2, 32, 2) == zero
+    base = _g2_bases(ref, 60, 33)
+    pts = (G + G + negG + zero + G + negG + negG + zero) * 10 + base
+    m = len(pts) // pt
+    for seed, kind in ((1, "equal"), (2, "small"), (3, "u256")):
+        sc = make_scalars(m, seed, kind)
+        assert _g2_msm(eng, cid, pts, sc, 32, m) == ref.msm_affine(pts, sc, 32, m), kind
+    assert _g2_msm(eng, cid, pts, bytes(32 * m), 32, m) == zero
+    special = [cv.r - 1, cv.r, cv.r + 1, (1 << 256) - 1, 1 << 255, 1, 0, (1 << 128) - 1]
+    sc = b"".join(v.to_bytes(32, "little") for v in special)
+    assert _g2_msm(eng, cid, base[: 8 * pt], sc, 32, 8) == ref.msm_affine(base[: 8 * pt], sc, 32, 8)
+    # per-window export and other scalar sizes
+    sc = make_scalars(60, 7, "u256")
+    for start, bits in ((0, 5), (13, 7), (250, 11)):
+        got = eng.normalize(cid, eng.multiexp_affine_chunk(cid, base, sc, 32, 60, start, bits))
+        assert got == ref.msm_chunk(base, sc, 32, 60, start, bits), (start, bits)
+    sc5 = bytes(random.Random(8).getrandbits(8) for _ in range(5 * 60))
+    assert _g2_msm(eng, cid, base, sc5, 5, 60) == ref.msm_affine(base, sc5, 5, 60)
+    # window widths, device window chain, window table, batch, sum of partials
+    sc = make_scalars(60, 9, "u256"); exp = ref.msm_affine(base, sc, 32, 60)
+    try:
+        for wb in (1, 4, 8, 13):
+            eng.set_option("window_bits", wb)
+            assert _g2_msm(eng, cid, base, sc, 32, 60) == exp, wb
+        eng.set_option("window_bits", 0); eng.set_option("combine", 1)
+        assert _g2_msm(eng, cid, base, sc, 32, 60) == exp
+    finally:
+        eng.set_option("window_bits", 0); eng.set_option("combine", 0)
+    for wb in (0, 8, 11):
+        h = eng.upload_bases_windowed(cid, base, 60, 32, wb)
+        try:
+            assert eng.normalize(cid, eng.multiexp_resident(h, sc, 32, 60, cid)) == exp, wb
+            out = eng.multiexp_batch(h, sc + make_scalars(60, 10, "u256"), 32, 60, 2, cid)
+            assert eng.normalize(cid, out[: 3 * 2 * cv.n8]) == exp
+        finally:
+            eng.free_bases(h)
+    a = eng.multiexp_affine(cid, base[: 30 * pt], sc[: 30 * 32], 32, 30); b = eng.multiexp_affine(cid, base[30 * pt:], sc[30 * 32:], 32, 30)
+    assert eng.normalize(cid, eng.sum_points(cid, a + b, 2)) == exp
+
+
+@pytest.mark.parametrize("lg", [14, 16])
+def test_g2_full_size_known_answer(eng, g2ref, lg):
+    """P_i = k_i * G2 generated on the device (stream checked above): sum_i s_i P_i = (sum_i s_i k_i mod r) * G2, the right-hand
+    side from ONE g2m_timesScalarAffine of the reference; ordinary path and window table."""
+    import numpy as np, torch
+    cname, ref = g2ref; cv = curve(cname); cid = G2ID[cname]; n = 1 << lg
+    seed = 0xB2000000 + lg
+    d = torch.empty(n * 4 * cv.n8, dtype=torch.uint8, device="cuda")
+    eng.generate_bases(cid, seed, 0, n, d)
+    with np.errstate(over="ignore"):
+        k = _splitmix64_np(np.uint64(seed) + np.arange(n, dtype=np.uint64))
+    k[k == 0] = 1
+    sc = np.random.default_rng(lg).integers(0, 256, size=(n, 32), dtype=np.uint8)
+    sd = torch.from_numpy(sc.reshape(-1).copy()).cuda()
+    words = sc.view("<u8").astype(object)
+    svals = words[:, 0] + (words[:, 1] << 64) + (words[:, 2] << 128) + (words[:, 3] << 192)
+    total = int((svals * k.astype(object)).sum() % cv.r)
+    m = ref.m; mark = m.heap_mark(); pB = m.alloc(4 * cv.n8); pS = m.alloc(40); pR = m.alloc(6 * cv.n8)
+    m.write(pB, ref.generator_affine()); m.write(pS, total.to_bytes(32, "little")); m.g2m_timesScalarAffine(pB, pS, 32, pR)
+    exp = ref.canonical(pR); m.heap_release(mark)
+    assert _g2_msm(eng, cid, d, sd, 32, n) == exp
+    h = eng.upload_bases_windowed(cid, d, n, 32, 0)
+    try:
+        assert eng.normalize(cid, eng.multiexp_resident(h, sd, 32, n, cid)) == exp
+    finally:
+        eng.free_bases(h)

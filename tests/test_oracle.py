@@ -222,3 +222,22 @@ def test_field_ops_against_python():
         for i, x in enumerate(xs):  # Montgomery-domain inverse: (xR)^-1 * R^2 ... checked via mul == one
             got = pyref.fe_from(cv, inv[i * cv.n8:(i + 1) * cv.n8])
             assert (got == 0) if x == 0 else (got * x * Ri % cv.q == cv.R % cv.q)
+
+
+# ---- G2: the Python restatement over Fq2 against the reference's own g2m exports
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+def test_g2_restatement_matches_reference_wasm(cname):
+    """g2m_multiexpAffine / g2m_timesScalarAffine of the reference module vs affine arithmetic over Fq2 = Fq[u]/(u^2+1)"""
+    if not refwasm.available(cname): pytest.skip("oracle/_ref not built")
+    cv = pyref.CURVES[cname]
+    g2 = refwasm.RefG2(refwasm.RefModule(cname))
+    G = pyref.g2_from_bytes(cv, g2.generator_affine())
+    rnd = random.Random(31)
+    ks = [rnd.getrandbits(64) | 1 for _ in range(6)]
+    bases = [g2.times_scalar_affine(g2.generator_affine(), k.to_bytes(8, "little")) for k in ks]
+    P = [pyref.g2_from_bytes(cv, b) for b in bases]
+    assert P == [pyref.g2_mul(cv, k, G) for k in ks]
+    sc = [rnd.getrandbits(256) for _ in ks]
+    got = g2.msm_affine(b"".join(bases), b"".join(s.to_bytes(32, "little") for s in sc), 32, len(ks))
+    assert got == pyref.g2_canonical_bytes(cv, pyref.g2_msm_naive(cv, P, sc))
+    assert pyref.g2_mul(cv, cv.r, G) is None                                   # test/bls12381.js:349-357 style: r * G2 = 0

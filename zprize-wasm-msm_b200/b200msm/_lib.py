@@ -9,8 +9,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200MSM_LIB") or os.path.join(_HERE, "libb200msm.so")     # B200MSM_LIB: alternative build of the same ABI (A/B experiments)
 
 OK, E_ARG, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4
-BLS12_381_G1, BN254_G1 = 0, 1
-N8 = {BLS12_381_G1: 48, BN254_G1: 32}
+BLS12_381_G1, BN254_G1, BLS12_381_G2, BN254_G2 = 0, 1, 2, 3
+N8 = {BLS12_381_G1: 48, BN254_G1: 32, BLS12_381_G2: 96, BN254_G2: 64}     # bytes per coordinate-field element (Fq / Fq2)
 
 EXPORTS = [  # every symbol include/b200msm.h declares (checked by tests/test_abi.py)
     "b200msm_create", "b200msm_destroy", "b200msm_strerror", "b200msm_last_error", "b200msm_version",

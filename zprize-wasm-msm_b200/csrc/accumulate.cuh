@@ -156,7 +156,7 @@ B200_DI void soa_store_point(void* __restrict__ dst, uint64_t yoff, uint32_t j, 
 // before the multiplication of slot i and the operand references of slot i+2 before that (only the x coordinates are needed;
 // the y coordinates are fetched in the rare equal-x / zero-x cases).
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, 6) k_tree_fwd(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
+__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 3 : 6) k_tree_fwd(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
                                                             void* __restrict__ prefix, void* __restrict__ prod, int K, uint32_t ntiles) {
  // persistent form: gridDim.x may be smaller than ntiles (leaves SM room for the other lane's latency-bound kernels)
  for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(BA_THREADS, 6) k_tree_fwd(const uint2* __restr
 
 // backward: consume the inverse of the thread's product, finish every addition, write the round's output points
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, 4) k_tree_bwd(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
+__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_bwd(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
                                                          const void* __restrict__ prefix, const void* __restrict__ inv,
                                                          void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles) {
  for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
@@ -262,7 +262,7 @@ template <class C> B200_DI void sm_read_fe(Fe<C::N>& r, const uint4* sm, int chu
 }
 
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, 4) k_tree_bwd_staged(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
+__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_bwd_staged(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
                                                                 const void* __restrict__ prefix, const void* __restrict__ inv,
                                                                 void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles) {
  extern __shared__ uint4 sm[];
@@ -380,10 +380,12 @@ __global__ void __launch_bounds__(BA_THREADS) k_prod_bwd(void* __restrict__ vals
 // root: n <= BA_ROOT_MAX values inverted in place by ONE block of BA_ROOT_THREADS threads: each thread forms the running
 // product of up to ROOT_PER values, a binary product tree over the threads lives in shared memory (log depth), thread 0
 // inverts the root once (f1m_inverse at build_batchinverse.js:90), then the tree and the per-thread chains are walked back.
-constexpr uint32_t BA_ROOT_THREADS = 256, ROOT_PER = 4;
+// (256 threads x 4 values; 128 x 8 for the 24-limb Fq2 of BLS12-381 G2, whose tree would not fit in 48 KB of static shared memory otherwise)
+template <class C> struct RootCfg { static constexpr uint32_t THREADS = C::N > 16 ? 128 : 256, PER = BA_ROOT_MAX / THREADS; };
 template <class C>
-__global__ void __launch_bounds__(BA_ROOT_THREADS) k_inv_root(void* __restrict__ vals, uint32_t n) {
+__global__ void __launch_bounds__(RootCfg<C>::THREADS) k_inv_root(void* __restrict__ vals, uint32_t n) {
   constexpr int N = C::N;
+  constexpr uint32_t BA_ROOT_THREADS = RootCfg<C>::THREADS, ROOT_PER = RootCfg<C>::PER;
   __shared__ uint32_t tree[2 * BA_ROOT_THREADS * N];       // node k (1-based heap order): leaves at [BA_ROOT_THREADS, 2*BA_ROOT_THREADS)
   const uint32_t t = threadIdx.x;
   Fe<N> v[ROOT_PER], pre[ROOT_PER], p;

@@ -116,8 +116,31 @@ bool is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-int n8_of(int curve) { return curve == B200MSM_BLS12_381_G1 ? 48 : 32; }
-bool curve_ok(int curve) { return curve == B200MSM_BLS12_381_G1 || curve == B200MSM_BN254_G1; }
+// n8 = bytes per coordinate-field element: Fq for G1 (48 / 32), Fq2 for G2 (96 / 64)
+int n8_of(int curve) { static const int t[4] = {48, 32, 96, 64}; return t[curve & 3]; }
+bool curve_ok(int curve) { return curve >= 0 && curve <= 3; }
+bool curve_g1(int curve) { return curve == B200MSM_BLS12_381_G1 || curve == B200MSM_BN254_G1; }
+// run a statement with C bound to the field class of `curve` (G2 = the same templates over Fq2, see fp.cuh)
+#define B200_CURVE_SWITCH(curve, ...) \
+  switch (curve) { case 0: { using C = BLS12_381; __VA_ARGS__; } break; case 1: { using C = BN254; __VA_ARGS__; } break; \
+                   case 2: { using C = Fq2<BLS12_381>; __VA_ARGS__; } break; default: { using C = Fq2<BN254>; __VA_ARGS__; } break; }
+
+// host-side field descriptor of C for the serial tail (host_ec.h)
+template <class C> struct HostField {
+  static constexpr int L = C::N / 2;
+  using type = b200host::Field<L>;
+  static type make() {
+    type f;
+    for (int i = 0; i < L; i++) { f.q[i] = (uint64_t)C::q(2 * i) | ((uint64_t)C::q(2 * i + 1) << 32); f.one[i] = (uint64_t)C::one(2 * i) | ((uint64_t)C::one(2 * i + 1) << 32); }
+    { uint64_t x = 1; for (int k = 0; k < 6; k++) x *= 2 - f.q[0] * x; f.np = 0 - x; }      // -q^-1 mod 2^64 (Newton)
+    return f;
+  }
+};
+template <class B> struct HostField<Fq2<B>> {
+  static constexpr int L = B::N / 2;
+  using type = b200host::Field2<L>;
+  static type make() { type f; f.b = HostField<B>::make(); for (int i = 0; i < 2 * L; i++) f.one[i] = i < L ? f.b.one[i] : 0; return f; }
+};
 
 uint32_t auto_window_bits(uint64_t n, uint32_t nbits) {
   uint32_t lg = 0; while ((2ull << lg) <= n) lg++;          // floor(log2 n)
@@ -230,7 +253,7 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
       lv.push_back(Lvl{n, cur, curp, warp, K});
       curp += n * fe; cur = nxt; n = warp ? (uint64_t)g2 * (BA_THREADS / 32) : (uint64_t)g2 * BA_THREADS;
     }
-    k_inv_root<C><<<1, BA_ROOT_THREADS, 0, s>>>(cur, (uint32_t)n); CKL();
+    k_inv_root<C><<<1, RootCfg<C>::THREADS, 0, s>>>(cur, (uint32_t)n); CKL();
     // back down
     for (int l = (int)lv.size() - 1; l >= 0; l--) {
       const Lvl& L = lv[l];
@@ -399,16 +422,13 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
     }
     if (host_tail) {
       if (st) { MARK(T_FOLD); CK(cudaEventRecord(ctx->ev[4], s)); }
-      constexpr int L = C::N / 2;
-      b200host::Field<L> f;
-      for (int i = 0; i < L; i++) { f.q[i] = (uint64_t)C::q(2 * i) | ((uint64_t)C::q(2 * i + 1) << 32); f.one[i] = (uint64_t)C::one(2 * i) | ((uint64_t)C::one(2 * i + 1) << 32); }
-      { uint64_t x = 1; for (int k = 0; k < 6; k++) x *= 2 - f.q[0] * x; f.np = 0 - x; }
-      b200host::SubslotCombiner<L> cb; cb.begin(f, G, logBs);
+      using HF = typename HostField<C>::type; const HF f = HostField<C>::make();
+      b200host::SubslotCombiner<HF> cb; cb.begin(f, G, logBs);
       float host_ms = 0;
       for (uint32_t g = 0; g < ngroups; g++) {          // each group's sub-slots are reduced as soon as they arrive, while the other lanes still run
         CK(cudaEventSynchronize(ctx->gev[g]));
         auto t0 = std::chrono::steady_clock::now();
-        cb.feed(reinterpret_cast<const b200host::XYZZ<L>*>(ctx->h_folded), cut[g], cut[g + 1]);
+        cb.feed(reinterpret_cast<const b200host::XYZZ<HF::W>*>(ctx->h_folded), cut[g], cut[g + 1]);
         host_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
       }
       uint64_t* res = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ctx->h_folded) + fbytes);
@@ -492,17 +512,14 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
     }
     if (st) { if (!host_tail) CK(cudaEventRecord(ctx->ev[3], s)); else { MARK(T_FOLD); } CK(cudaEventRecord(ctx->ev[4], s)); }
     if (host_tail) {
-      constexpr int L = C::N / 2;
-      b200host::Field<L> f;
-      for (int i = 0; i < L; i++) { f.q[i] = (uint64_t)C::q(2 * i) | ((uint64_t)C::q(2 * i + 1) << 32); f.one[i] = (uint64_t)C::one(2 * i) | ((uint64_t)C::one(2 * i + 1) << 32); }
-      { uint64_t x = 1; for (int k = 0; k < 6; k++) x *= 2 - f.q[0] * x; f.np = 0 - x; }      // -q^-1 mod 2^64 (Newton)
-      b200host::Combiner<L> cb; cb.begin(f, pl.W, pl.Wd, pl.c0, pl.rem, pl.logB);
+      using HF = typename HostField<C>::type; const HF f = HostField<C>::make();
+      b200host::Combiner<HF> cb; cb.begin(f, pl.W, pl.Wd, pl.c0, pl.rem, pl.logB);
       float host_ms = 0;
       for (uint32_t gi = 0; gi < ngroups; gi++) {
         const uint32_t g = ngroups - 1 - gi;
         CK(cudaEventSynchronize(ctx->gev[gi]));
         auto t0 = std::chrono::steady_clock::now();
-        cb.feed(reinterpret_cast<const b200host::XYZZ<L>*>(ctx->h_folded), cut[g], cut[g + 1]);
+        cb.feed(reinterpret_cast<const b200host::XYZZ<HF::W>*>(ctx->h_folded), cut[g], cut[g + 1]);
         host_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
       }
       auto t0 = std::chrono::steady_clock::now();
@@ -574,7 +591,7 @@ int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_residen
   if (n >= (1ull << 31)) { ctx->err = "n must be < 2^31"; return B200MSM_E_UNSUPPORTED; }
   CK(cudaSetDevice(ctx->device));
   const int n8 = n8_of(curve);
-  CK(ctx->out.ensure(3 * 48));
+  CK(ctx->out.ensure(3 * 96));
   ctx->prof = false;
   if (st) { memset(st, 0, sizeof *st); CK(cudaEventRecord(ctx->ev[0], ctx->stream)); ctx->prof = true; ctx->pused = 0; }
   const uint64_t launches0 = ctx->launches;
@@ -583,7 +600,7 @@ int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_residen
   if (nbits > 256) { ctx->err = "more than 256 scalar bits per call are not supported"; return B200MSM_E_UNSUPPORTED; }
   int rc;
   if (n == 0 || nbits == 0) {
-    rc = curve == 0 ? write_zero<BLS12_381>(ctx, ctx->out.p) : write_zero<BN254>(ctx, ctx->out.p);
+    B200_CURVE_SWITCH(curve, rc = write_zero<C>(ctx, ctx->out.p))
     if (rc) return rc;
     return deliver(ctx, ctx->out.p, out, 3 * n8);
   }
@@ -614,8 +631,7 @@ int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_residen
   }
   MARK(T_NTAGS);
   if (pre && (pre->nbits != nbits || bit0 != 0)) pre = nullptr;      // the table serves exactly the bit range it was built for
-  rc = curve == 0 ? run_pipeline<BLS12_381>(ctx, d_bases, d_scal, n, nbits, ctx->out.p, st, pre)
-                  : run_pipeline<BN254>(ctx, d_bases, d_scal, n, nbits, ctx->out.p, st, pre);
+  B200_CURVE_SWITCH(curve, rc = run_pipeline<C>(ctx, d_bases, d_scal, n, nbits, ctx->out.p, st, pre))
   if (rc) { ctx->prof = false; return rc; }
   if (st) CK(cudaEventRecord(ctx->ev[6], ctx->stream));
   rc = deliver(ctx, ctx->out.p, out, 3 * n8); if (rc) return rc;
@@ -802,7 +818,7 @@ int b200msm_upload_bases_windowed(b200msm_ctx* ctx, int curve, const void* bases
   cudaError_t e = cudaMemcpyAsync(d, bases, (size_t)n * pt, cudaMemcpyDefault, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { cudaFree(d); ctx->err = cudaGetErrorString(e); return B200MSM_E_CUDA; }
-  int rc = curve == 0 ? build_window_table<BLS12_381>(ctx, d, n, c0, rem, Wd) : build_window_table<BN254>(ctx, d, n, c0, rem, Wd);
+  int rc; B200_CURVE_SWITCH(curve, rc = build_window_table<C>(ctx, d, n, c0, rem, Wd))
   if (rc) { cudaFree(d); return rc; }
   uint64_t h = ctx->next_handle++;
   Resident r{curve, n, d}; r.t_nbits = nbits; r.t_c0 = c0; r.t_rem = rem; r.t_Wd = Wd;
@@ -877,8 +893,7 @@ int b200msm_g1_normalize(b200msm_ctx* ctx, int curve, const void* jac, uint64_t 
   const void* d_in; int rc = stage(ctx, jac, (size_t)count * 3 * n8, ctx->misc, &d_in); if (rc) return rc;
   CK(ctx->acc_e.ensure((size_t)count * 2 * n8));
   uint32_t g = (uint32_t)((count + 63) / 64);
-  if (curve == 0) k_normalize<BLS12_381><<<g, 64, 0, ctx->stream>>>(d_in, ctx->acc_e.p, (uint32_t)count);
-  else k_normalize<BN254><<<g, 64, 0, ctx->stream>>>(d_in, ctx->acc_e.p, (uint32_t)count);
+  B200_CURVE_SWITCH(curve, k_normalize<C><<<g, 64, 0, ctx->stream>>>(d_in, ctx->acc_e.p, (uint32_t)count))
   CKL();
   return deliver(ctx, ctx->acc_e.p, xy, (size_t)count * 2 * n8);
 }
@@ -888,9 +903,8 @@ int b200msm_g1_sum(b200msm_ctx* ctx, int curve, const void* pts, uint64_t count,
   CK(cudaSetDevice(ctx->device));
   const int n8 = n8_of(curve);
   const void* d_in; int rc = stage(ctx, pts, (size_t)count * 3 * n8, ctx->misc, &d_in); if (rc) return rc;
-  CK(ctx->out.ensure(3 * 48));
-  if (curve == 0) k_sum_jacobian<BLS12_381><<<1, 32, 0, ctx->stream>>>(d_in, (uint32_t)count, ctx->out.p);
-  else k_sum_jacobian<BN254><<<1, 32, 0, ctx->stream>>>(d_in, (uint32_t)count, ctx->out.p);
+  CK(ctx->out.ensure(3 * 96));
+  B200_CURVE_SWITCH(curve, k_sum_jacobian<C><<<1, 32, 0, ctx->stream>>>(d_in, (uint32_t)count, ctx->out.p))
   CKL();
   return deliver(ctx, ctx->out.p, out, 3 * n8);
 }
@@ -905,25 +919,34 @@ int b200msm_g1_generate_bases(b200msm_ctx* ctx, int curve, uint64_t seed, uint64
                                      0x0ce72271u, 0xbaac93d5u, 0x7918fd8eu, 0x8c22631au, 0x570725ceu, 0xdd595f13u, 0x50405194u, 0x51ac5829u, 0xad0059c0u, 0x0e1c8c3fu, 0x5008a26au, 0x0bbc3efcu};
   static const uint32_t G_BN[16] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u,
                                     0x8b1e1b3au, 0xa6ba871bu, 0xeb8e167bu, 0x14f1d651u, 0xf0f28c58u, 0xccdd46deu, 0x340fbe5eu, 0x1c14ef83u};
+  // G2 generators, x = x0 + x1 u, y = y0 + y1 u as x0 || x1 || y0 || y1 (build_bls12381.js:127-148, build_bn128.js:122-144)
+  static const uint32_t G2_BLS[48] = {
+    0x02940a10u, 0xf5f28fa2u, 0x87b4961au, 0xb3f5fb26u, 0x3e2ae580u, 0xa1a893b5u, 0x1a3caee9u, 0x9894999du, 0x1863366bu, 0x6f67b763u, 0x4350bcd7u, 0x05819192u,
+    0x9e23f606u, 0xa5a9c075u, 0xbccd60c3u, 0xaaa0c59du, 0xe2867806u, 0x3bb17e18u, 0x8541b367u, 0x1b1ab6ccu, 0xf2158547u, 0xc2b6ed0eu, 0x7360edf3u, 0x11922a09u,
+    0x60494c4au, 0x4c730af8u, 0x5e369c5au, 0x597cfa1fu, 0xaa0a635au, 0xe7e6856cu, 0x6e0d495fu, 0xbbefb5e9u, 0xf0ef25a2u, 0x07d3a975u, 0x7e80dae5u, 0x0083fd8eu,
+    0xdf64b05du, 0xadc0fc92u, 0x2b1461dcu, 0x18aa270au, 0x3be4eba0u, 0x86adac6au, 0xc93da33au, 0x79495c4eu, 0xa43ccaedu, 0xe7175850u, 0x63de1bf2u, 0x0b2bc2a1u};
+  static const uint32_t G2_BN[32] = {
+    0x02bc2026u, 0x8e83b5d1u, 0x497b0172u, 0xdceb1935u, 0x97811adfu, 0xfbb82647u, 0xaf96503bu, 0x19573841u,
+    0xa84c6140u, 0xafb4737du, 0x5802d8c4u, 0x6043dd5au, 0x52a02f86u, 0x09e950fcu, 0x3aea7b6bu, 0x14fef083u,
+    0x886be9f6u, 0x619dfa9du, 0xf59e9b78u, 0xfe7fd297u, 0x231b7dfeu, 0xff9e1a62u, 0xae9e4206u, 0x28fd7eebu,
+    0xc71856eeu, 0x64095b56u, 0x327d3cbbu, 0xdc57f922u, 0x33351076u, 0x55f935beu, 0x93fd6482u, 0x0da4a0e6u};
+  const void* gens[4] = {G_BLS, G_BN, G2_BLS, G2_BN};
   CK(ctx->misc.ensure(256));
-  CK(cudaMemcpyAsync(ctx->misc.p, curve == 0 ? (const void*)G_BLS : (const void*)G_BN, 2 * n8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->misc.p, gens[curve], 2 * n8, cudaMemcpyHostToDevice, ctx->stream));
   CK(ctx->acc_a.ensure((size_t)n * 4 * n8));
   uint32_t g = (uint32_t)((n + 127) / 128);
   constexpr int GROUP = 16;
   uint32_t g2 = (uint32_t)(((n + GROUP - 1) / GROUP + 127) / 128);
-  if (curve == 0) {
-    k_generate_xyzz<BLS12_381><<<g, 128, 0, ctx->stream>>>(ctx->misc.p, seed, first, (uint32_t)n, ctx->acc_a.p); CKL();
-    k_xyzz_to_affine<BLS12_381, GROUP><<<g2, 128, 0, ctx->stream>>>(ctx->acc_a.p, (uint32_t)n, device_out); CKL();
-  } else {
-    k_generate_xyzz<BN254><<<g, 128, 0, ctx->stream>>>(ctx->misc.p, seed, first, (uint32_t)n, ctx->acc_a.p); CKL();
-    k_xyzz_to_affine<BN254, GROUP><<<g2, 128, 0, ctx->stream>>>(ctx->acc_a.p, (uint32_t)n, device_out); CKL();
-  }
+  B200_CURVE_SWITCH(curve,
+    k_generate_xyzz<C><<<g, 128, 0, ctx->stream>>>(ctx->misc.p, seed, first, (uint32_t)n, ctx->acc_a.p); CKL();
+    k_xyzz_to_affine<C, GROUP><<<g2, 128, 0, ctx->stream>>>(ctx->acc_a.p, (uint32_t)n, device_out); CKL())
   CK(cudaStreamSynchronize(ctx->stream));
   return B200MSM_OK;
 }
 
 int b200msm_g1_batch_convert(b200msm_ctx* ctx, int curve, int op, const void* in, uint64_t n, void* out) {
   if (!ctx || !curve_ok(curve) || op < 0 || op > 5 || (n && (!in || !out)) || n >= (1ull << 31)) return B200MSM_E_ARG;
+  if (!curve_g1(curve)) { ctx->err = "the point codecs are built for G1"; return B200MSM_E_UNSUPPORTED; }
   if (n == 0) return B200MSM_OK;
   CK(cudaSetDevice(ctx->device));
   const size_t n8 = n8_of(curve);
@@ -991,10 +1014,10 @@ int b200msm_fq_op(b200msm_ctx* ctx, int curve, int op, const void* a, const void
   uint32_t g = (uint32_t)((count + 127) / 128);
   if (op >= 9) {
     if (!db) { ctx->err = "op 9/10 need two operands"; return B200MSM_E_ARG; }
+    if (!curve_g1(curve)) { ctx->err = "radix-2^29 multiplier: prime fields only"; return B200MSM_E_UNSUPPORTED; }
     if (curve == 0) k_fp29_mul<BLS12_381><<<g, 128, 0, ctx->stream>>>(da, db, ctx->acc_c.p, (uint32_t)count, op - 9);
     else k_fp29_mul<BN254><<<g, 128, 0, ctx->stream>>>(da, db, ctx->acc_c.p, (uint32_t)count, op - 9);
-  } else if (curve == 0) k_fp_op<BLS12_381><<<g, 128, 0, ctx->stream>>>(op, da, db, ctx->acc_c.p, (uint32_t)count);
-  else k_fp_op<BN254><<<g, 128, 0, ctx->stream>>>(op, da, db, ctx->acc_c.p, (uint32_t)count);
+  } else { B200_CURVE_SWITCH(curve, k_fp_op<C><<<g, 128, 0, ctx->stream>>>(op, da, db, ctx->acc_c.p, (uint32_t)count)) }
   CKL();
   return deliver(ctx, ctx->acc_c.p, r, bytes);
 }
@@ -1028,8 +1051,9 @@ int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s) {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
   const uint32_t blocks = prop.multiProcessorCount * 4, threads = 256, iters = 512 | (ctx->probe_sqr ? 0x80000000u : 0u);
   const int n8 = n8_of(curve);
-  CK(ctx->acc_a.ensure(1024 * 48)); CK(ctx->acc_b.ensure((size_t)blocks * threads * n8));
-  CK(cudaMemsetAsync(ctx->acc_a.p, 0x17, 1024 * 48, ctx->stream));
+  CK(ctx->acc_a.ensure(1024 * 96)); CK(ctx->acc_b.ensure((size_t)blocks * threads * n8));
+  CK(cudaMemsetAsync(ctx->acc_a.p, 0x17, 1024 * 96, ctx->stream));
+  if (!curve_g1(curve) && (ctx->probe29 || ctx->opt_probe_smem)) { ctx->err = "probe29 / probe_smem: prime fields only"; return B200MSM_E_UNSUPPORTED; }
   const size_t psm = (size_t)ctx->opt_probe_smem;       // dynamic shared memory per block, only to cap the resident warps per SM (occupancy sensitivity of the multiplier)
   if (psm) { CK(cudaFuncSetAttribute(k_fpmul_probe<BLS12_381>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm)); CK(cudaFuncSetAttribute(k_fpmul_probe<BN254>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm)); }
   double best = 0;
@@ -1038,8 +1062,7 @@ int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s) {
     if (ctx->probe29) {
       if (curve == 0) k_fpmul29_probe<BLS12_381><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
       else k_fpmul29_probe<BN254><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
-    } else if (curve == 0) k_fpmul_probe<BLS12_381><<<blocks, threads, psm, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
-    else k_fpmul_probe<BN254><<<blocks, threads, psm, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
+    } else { B200_CURVE_SWITCH(curve, k_fpmul_probe<C><<<blocks, threads, psm, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p)) }
     CKL();
     CK(cudaEventRecord(ctx->ev[1], ctx->stream)); CK(cudaEventSynchronize(ctx->ev[1]));
     float ms; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);

@@ -20,6 +20,7 @@ namespace b200 {
 // ------------------------------------------------------------------ curve / field parameters
 struct BLS12_381 {
   static constexpr int ID = 0;
+  static constexpr int EXT = 1;          // prime field
   static constexpr int N = 12;           // u32 limbs per Fq element (n8 = 48)
   static constexpr uint32_t NP = 0xfffcfffdu;   // -q^-1 mod 2^32   (build_f1m.js:504)
   static constexpr int QBITS = 381;
@@ -47,6 +48,7 @@ struct BLS12_381 {
 
 struct BN254 {
   static constexpr int ID = 1;
+  static constexpr int EXT = 1;
   static constexpr int N = 8;            // n8 = 32
   static constexpr uint32_t NP = 0xe4866389u;
   static constexpr int QBITS = 254;
@@ -68,12 +70,37 @@ struct BN254 {
   }
 };
 
+// Quadratic extension Fq2 = Fq[u]/(u^2 + 1): the coordinate field of G2 on both curves (build_f2m.js; build_bls12381.js:48 and
+// build_bn128.js:44 pass f1m_neg as the multiplication by the non-residue).  An element c0 + c1*u is stored c0 || c1 (the f2m layout)
+// and is, to every template below and to every kernel, ONE field element of N = 2*Nb limbs: the fe_* entry points dispatch on EXT,
+// so the whole G1 pipeline (sort, batch-affine tree, fold, window tables, batches) instantiates unchanged for G2.
+template <class B> struct Fq2 {
+  using Base = B;
+  static constexpr int ID = B::ID + 2;
+  static constexpr int EXT = 2;
+  static constexpr int N = 2 * B::N;
+  static constexpr int QBITS = B::QBITS;
+  __host__ __device__ static constexpr uint32_t one(int i) { return i < B::N ? B::one(i) : 0u; }      // (R mod q) + 0*u
+};
+
 template <int N> struct alignas(16) Fe { uint32_t l[N]; };
+#ifndef B200_DI
+#define B200_DI __device__ __forceinline__
+#endif
+// field interface (dispatching on C::EXT; the *_p functions below are the prime-field implementations)
+template <class C> B200_DI void fe_add(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b);
+template <class C> B200_DI void fe_sub(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b);
+template <class C> B200_DI void fe_neg(Fe<C::N>& r, const Fe<C::N>& a);
+template <class C> B200_DI void fe_mul(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b);
+template <class C> B200_DI void fe_sqr(Fe<C::N>& r, const Fe<C::N>& a);
+template <class C> B200_DI void fe_to_mont(Fe<C::N>& r, const Fe<C::N>& a);
+template <class C> B200_DI void fe_from_mont(Fe<C::N>& r, const Fe<C::N>& a);
+template <class C> B200_DI void fe_inv(Fe<C::N>& r, const Fe<C::N>& a);
+template <class C> B200_DI void fe_inv_fast(Fe<C::N>& r, const Fe<C::N>& a);
 
 // ------------------------------------------------------------------ PTX carry-chain primitives
 // asm volatile keeps the statements in program order; the condition-code register is only written
 // by these instructions, so a chain spread over several statements is safe.
-#define B200_DI __device__ __forceinline__
 B200_DI uint32_t ptx_mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 B200_DI uint32_t ptx_mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 B200_DI void mad_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
@@ -122,7 +149,7 @@ template <class C> B200_DI void fe_reduce_once(Fe<C::N>& a) {
 }
 
 // f1m_add (build_f1m.js:71-89)
-template <class C> B200_DI void fe_add(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
+template <class C> B200_DI void fe_add_p(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
   constexpr int N = C::N;
   add_cc(r.l[0], a.l[0], b.l[0]);
 #pragma unroll
@@ -132,7 +159,7 @@ template <class C> B200_DI void fe_add(Fe<C::N>& r, const Fe<C::N>& a, const Fe<
 }
 
 // f1m_sub (build_f1m.js:91-105)
-template <class C> B200_DI void fe_sub(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
+template <class C> B200_DI void fe_sub_p(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
   constexpr int N = C::N;
   uint32_t borrow;
   sub_cc(r.l[0], a.l[0], b.l[0]);
@@ -146,7 +173,7 @@ template <class C> B200_DI void fe_sub(Fe<C::N>& r, const Fe<C::N>& a, const Fe<
   addc(r.l[N - 1], r.l[N - 1], C::q(N - 1) & borrow);
 }
 
-template <class C> B200_DI void fe_neg(Fe<C::N>& r, const Fe<C::N>& a) {
+template <class C> B200_DI void fe_neg_p(Fe<C::N>& r, const Fe<C::N>& a) {
   constexpr int N = C::N;
   uint32_t nz = 0;
 #pragma unroll
@@ -428,7 +455,7 @@ template <class C> B200_DI void fe_mul_karatsuba(Fe<C::N>& r, const Fe<C::N>& a,
   addc(T[2 * N - 1], T[2 * N - 1], 0);
   mont_reduce<C>(r, T);
 }
-template <class C> B200_DI void fe_mul(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
+template <class C> B200_DI void fe_mul_p(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
 #if defined(B200_KARATSUBA)
   fe_mul_karatsuba<C>(r, a, b);
 #else
@@ -438,7 +465,7 @@ template <class C> B200_DI void fe_mul(Fe<C::N>& r, const Fe<C::N>& a, const Fe<
 
 // f1m_square (build_f1m.js:779-1076): dedicated squaring, N(N-1)/2 + N + N*N + N limb products (234 for BLS12-381, 108 for BN254)
 // instead of the 2N*N + N of a general multiplication.
-template <class C> B200_DI void fe_sqr(Fe<C::N>& r, const Fe<C::N>& a) {
+template <class C> B200_DI void fe_sqr_p(Fe<C::N>& r, const Fe<C::N>& a) {
 #if defined(B200_SQR_AS_MUL)
   fe_mul<C>(r, a, a);
 #else
@@ -449,13 +476,13 @@ template <class C> B200_DI void fe_sqr(Fe<C::N>& r, const Fe<C::N>& a) {
 }
 
 // to / from Montgomery (build_f1m.js:1089,1098)
-template <class C> B200_DI void fe_to_mont(Fe<C::N>& r, const Fe<C::N>& a) {
+template <class C> B200_DI void fe_to_mont_p(Fe<C::N>& r, const Fe<C::N>& a) {
   Fe<C::N> k;
 #pragma unroll
   for (int i = 0; i < C::N; i++) k.l[i] = C::r2(i);
   fe_mul<C>(r, a, k);
 }
-template <class C> B200_DI void fe_from_mont(Fe<C::N>& r, const Fe<C::N>& a) {
+template <class C> B200_DI void fe_from_mont_p(Fe<C::N>& r, const Fe<C::N>& a) {
   Fe<C::N> k;
 #pragma unroll
   for (int i = 0; i < C::N; i++) k.l[i] = (i == 0);
@@ -464,7 +491,7 @@ template <class C> B200_DI void fe_from_mont(Fe<C::N>& r, const Fe<C::N>& a) {
 
 // f1m_inverse (build_f1m.js:1112-1122) by Fermat: a^(q-2).  Montgomery in, Montgomery out; inv(0) = 0.
 // Left-to-right square-and-multiply over the constant exponent; the loop is NOT unrolled (code size).
-template <class C> __device__ __noinline__ void fe_inv(Fe<C::N>& r, const Fe<C::N>& a) {
+template <class C> __device__ __noinline__ void fe_inv_p(Fe<C::N>& r, const Fe<C::N>& a) {
   constexpr int N = C::N;
   uint32_t e[N];
   // e = q - 2 (q is odd and its low limb is >= 2 for both fields)
@@ -508,7 +535,7 @@ template <class C> B200_DI bool limbs_is_one(const uint32_t (&a)[C::N]) {
   for (int i = 1; i < C::N; i++) o |= a[i];
   return o == 0;
 }
-template <class C> __device__ __noinline__ void fe_inv_fast(Fe<C::N>& r, const Fe<C::N>& a) {
+template <class C> __device__ __noinline__ void fe_inv_fast_p(Fe<C::N>& r, const Fe<C::N>& a) {
   constexpr int N = C::N;
   if (fe_is_zero<C>(a)) { fe_set_zero<C>(r); return; }
   uint32_t u[N], v[N];
@@ -543,6 +570,72 @@ template <class C> __device__ __noinline__ void fe_inv_fast(Fe<C::N>& r, const F
 #pragma unroll
   for (int i = 0; i < N; i++) k.l[i] = C::r3(i);
   fe_mul<C>(r, x2, k);
+}
+
+// ------------------------------------------------------------------ Fq2 arithmetic on the halves + the dispatching entry points
+template <class C> B200_DI void fq2_get(Fe<C::Base::N>& a0, Fe<C::Base::N>& a1, const Fe<C::N>& a) {
+#pragma unroll
+  for (int i = 0; i < C::Base::N; i++) { a0.l[i] = a.l[i]; a1.l[i] = a.l[C::Base::N + i]; }
+}
+template <class C> B200_DI void fq2_put(Fe<C::N>& r, const Fe<C::Base::N>& r0, const Fe<C::Base::N>& r1) {
+#pragma unroll
+  for (int i = 0; i < C::Base::N; i++) { r.l[i] = r0.l[i]; r.l[C::Base::N + i] = r1.l[i]; }
+}
+template <class C> B200_DI void fe_add(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
+  if constexpr (C::EXT == 2) { using B = typename C::Base; Fe<B::N> a0, a1, b0, b1; fq2_get<C>(a0, a1, a); fq2_get<C>(b0, b1, b); fe_add_p<B>(a0, a0, b0); fe_add_p<B>(a1, a1, b1); fq2_put<C>(r, a0, a1); }
+  else fe_add_p<C>(r, a, b);
+}
+template <class C> B200_DI void fe_sub(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
+  if constexpr (C::EXT == 2) { using B = typename C::Base; Fe<B::N> a0, a1, b0, b1; fq2_get<C>(a0, a1, a); fq2_get<C>(b0, b1, b); fe_sub_p<B>(a0, a0, b0); fe_sub_p<B>(a1, a1, b1); fq2_put<C>(r, a0, a1); }
+  else fe_sub_p<C>(r, a, b);
+}
+template <class C> B200_DI void fe_neg(Fe<C::N>& r, const Fe<C::N>& a) {
+  if constexpr (C::EXT == 2) { using B = typename C::Base; Fe<B::N> a0, a1; fq2_get<C>(a0, a1, a); fe_neg_p<B>(a0, a0); fe_neg_p<B>(a1, a1); fq2_put<C>(r, a0, a1); }
+  else fe_neg_p<C>(r, a);
+}
+// (a0 + a1 u)(b0 + b1 u) = (a0 b0 - a1 b1) + ((a0 + a1)(b0 + b1) - a0 b0 - a1 b1) u: 3 base multiplications      (f2m_mul, build_f2m.js:152-194)
+template <class C> B200_DI void fe_mul(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
+  if constexpr (C::EXT == 2) {
+    using B = typename C::Base; Fe<B::N> a0, a1, b0, b1, v0, v1, sa, sb;
+    fq2_get<C>(a0, a1, a); fq2_get<C>(b0, b1, b);
+    fe_add_p<B>(sa, a0, a1); fe_add_p<B>(sb, b0, b1);
+    fe_mul_p<B>(v0, a0, b0); fe_mul_p<B>(v1, a1, b1); fe_mul_p<B>(sa, sa, sb);
+    fe_sub_p<B>(sa, sa, v0); fe_sub_p<B>(sa, sa, v1); fe_sub_p<B>(v0, v0, v1);
+    fq2_put<C>(r, v0, sa);
+  } else fe_mul_p<C>(r, a, b);
+}
+// (a0 + a1 u)^2 = (a0 + a1)(a0 - a1) + 2 a0 a1 u: 2 base multiplications                                         (f2m_square, build_f2m.js:290-330)
+template <class C> B200_DI void fe_sqr(Fe<C::N>& r, const Fe<C::N>& a) {
+  if constexpr (C::EXT == 2) {
+    using B = typename C::Base; Fe<B::N> a0, a1, s, d, p;
+    fq2_get<C>(a0, a1, a);
+    fe_add_p<B>(s, a0, a1); fe_sub_p<B>(d, a0, a1); fe_mul_p<B>(p, a0, a1);
+    fe_mul_p<B>(s, s, d); fe_add_p<B>(p, p, p);
+    fq2_put<C>(r, s, p);
+  } else fe_sqr_p<C>(r, a);
+}
+template <class C> B200_DI void fe_to_mont(Fe<C::N>& r, const Fe<C::N>& a) {
+  if constexpr (C::EXT == 2) { using B = typename C::Base; Fe<B::N> a0, a1; fq2_get<C>(a0, a1, a); fe_to_mont_p<B>(a0, a0); fe_to_mont_p<B>(a1, a1); fq2_put<C>(r, a0, a1); }
+  else fe_to_mont_p<C>(r, a);
+}
+template <class C> B200_DI void fe_from_mont(Fe<C::N>& r, const Fe<C::N>& a) {
+  if constexpr (C::EXT == 2) { using B = typename C::Base; Fe<B::N> a0, a1; fq2_get<C>(a0, a1, a); fe_from_mont_p<B>(a0, a0); fe_from_mont_p<B>(a1, a1); fq2_put<C>(r, a0, a1); }
+  else fe_from_mont_p<C>(r, a);
+}
+// 1 / (a0 + a1 u) = (a0 - a1 u) / (a0^2 + a1^2)                                                                  (f2m_inverse, build_f2m.js:402-440)
+template <class C, bool FAST> B200_DI void fq2_inv(Fe<C::N>& r, const Fe<C::N>& a) {
+  using B = typename C::Base; Fe<B::N> a0, a1, t0, t1;
+  fq2_get<C>(a0, a1, a);
+  fe_sqr_p<B>(t0, a0); fe_sqr_p<B>(t1, a1); fe_add_p<B>(t0, t0, t1);
+  if (FAST) fe_inv_fast_p<B>(t1, t0); else fe_inv_p<B>(t1, t0);
+  fe_mul_p<B>(a0, a0, t1); fe_mul_p<B>(a1, a1, t1); fe_neg_p<B>(a1, a1);
+  fq2_put<C>(r, a0, a1);
+}
+template <class C> B200_DI void fe_inv(Fe<C::N>& r, const Fe<C::N>& a) {
+  if constexpr (C::EXT == 2) fq2_inv<C, false>(r, a); else fe_inv_p<C>(r, a);
+}
+template <class C> B200_DI void fe_inv_fast(Fe<C::N>& r, const Fe<C::N>& a) {
+  if constexpr (C::EXT == 2) fq2_inv<C, true>(r, a); else fe_inv_fast_p<C>(r, a);
 }
 
 // ------------------------------------------------------------------ global-memory access helpers
