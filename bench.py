@@ -21,7 +21,14 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "zprize-wasm-ms
 
 METRIC = "bls12381_g1_msm_points_per_s"
 SEED = 0xB2000000
-LIMB_PRODUCTS_PER_FQMUL = {"bls12381": 300, "bn128": 136}     # 2*n32^2 + n32 (build_f1m.js:575-660)
+LIMB_PRODUCTS_PER_FQMUL = {"bls12381": 300, "bn128": 136,      # 2*n32^2 + n32 (build_f1m.js:575-660)
+                           "bls12381_g2": 900, "bn128_g2": 408}   # G2: one Fq2 multiplication = 3 Fq multiplications (f2m_mul, build_f2m.js:152-194)
+CURVE_ID = {"bls12381": 0, "bn128": 1, "bls12381_g2": 2, "bn128_g2": 3}
+CURVE_LABEL = {"bls12381": "BLS12-381 G1", "bn128": "BN254 G1", "bls12381_g2": "BLS12-381 G2", "bn128_g2": "BN254 G2"}
+
+
+def metric_name(cname):
+    return METRIC if cname == "bls12381" else {"bn128": "bn254_g1", "bls12381_g2": "bls12381_g2", "bn128_g2": "bn254_g2"}[cname] + "_msm_points_per_s"
 FQMUL_PER_AFFINE_ADD = 6                                       # build_multiexp_opt.js:1207-1233 + build_batchinverse.js
 
 
@@ -33,7 +40,7 @@ def parse():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--log2n", type=int, default=0, help="points per GPU = 2^log2n (default 20; 18 for --workload batched)")
     ap.add_argument("--log2n-total", type=int, default=0, help="strong scaling: total points 2^K split over the GPUs (overrides --log2n)")
-    ap.add_argument("--curve", default="bls12381", choices=["bls12381", "bn128"])
+    ap.add_argument("--curve", default="bls12381", choices=["bls12381", "bn128", "bls12381_g2", "bn128_g2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-log2n", type=int, default=16, help="points per reference step (bounded sample)")
     ap.add_argument("--workload", default="single", choices=["single", "batched"],
@@ -125,10 +132,29 @@ def reference_msm_parallel(pool, cname, bases, scalars, n, nproc, n8):
 reference_msm_parallel._pb = {}
 
 
+def time_reference_g2(cname, log2n, steps, warmup):
+    """G2: the reference's own g2m_multiexpAffine on ONE host core (one WASM instance), 2^log2n points built from 256 distinct multiples of G2"""
+    import random
+    import refwasm
+    base = cname[:-3]
+    if not refwasm.available(base): raise RuntimeError("oracle/_ref not built")
+    g2 = refwasm.RefG2(refwasm.RefModule(base)); n = 1 << log2n
+    G = g2.generator_affine()
+    distinct = b"".join(g2.times_scalar_affine(G, (0x9E3779B97F4A7C15 * (i + 1) & ((1 << 64) - 1)).to_bytes(8, "little")) for i in range(256))
+    bases = (distinct * (n // 256 + 1))[: n * 2 * g2.e8]
+    scalars = random.Random(log2n).getrandbits(256 * n).to_bytes(32 * n, "little")
+    for _ in range(warmup): g2.msm_affine(bases, scalars, 32, n)
+    t0 = time.perf_counter()
+    for _ in range(steps): g2.msm_affine(bases, scalars, 32, n)
+    dt = (time.perf_counter() - t0) / steps
+    return n / dt, dt * 1e3, 1, "reference", "reference WASM (upstream wasmcurves g2m_multiexpAffine) AOT-compiled via C; one MSM of 2^%d points per step on one host core" % log2n
+
+
 def time_reference(cname, log2n, steps, warmup):
     """returns (points_per_s, ms_per_step, cores, kind, sample description)"""
     import multiprocessing as mp
     import pyref, coracle, refwasm
+    if cname.endswith("_g2"): return time_reference_g2(cname, min(log2n, 12), steps, warmup)
     cv = pyref.CURVES[cname]
     n = 1 << log2n
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -164,10 +190,10 @@ def run_reference(a):
     cname = a.curve
     steps = max(1, min(a.steps, 5)); warm = max(1, min(a.warmup, 1))
     pps, ms, cores, kind, sample = time_reference(cname, a.ref_log2n, steps, warm)
-    line = {"impl": "reference", "metric": METRIC if cname == "bls12381" else "bn254_g1_msm_points_per_s", "value": pps, "unit": "points/s",
+    line = {"impl": "reference", "metric": metric_name(cname), "value": pps, "unit": "points/s",
             "n_gpus": a.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 limbs (Montgomery Fq)", "data": "synthetic",
-            "config": {"workload": "%s G1 MSM, bounded sample 2^%d points per step (of the 2^%d-point workload), uniform 256-bit scalars" % (cname, a.ref_log2n, a.log2n),
+            "config": {"workload": "%s MSM, bounded sample 2^%d points per step (of the 2^%d-point workload), uniform 256-bit scalars" % (cname, a.ref_log2n, a.log2n),
                        "curve": cname, "log2n_per_step": a.ref_log2n},
             "cpu_baseline": {"value": pps, "unit": "points/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": pps, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -178,7 +204,7 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------ our arm
 def kernel_roofline(eng, handle, scal, n, cid, cname, a, out_dev):
     """per-phase CUDA-event timings inside the engine (single lane, same inputs) -> (roofline object, averaged stats)"""
-    NSETS = len(scal); n8 = 48 if cid == 0 else 32
+    NSETS = len(scal); n8 = {0: 48, 1: 32, 2: 96, 3: 64}[cid]
     agg = {}; reps = max(3, min(a.steps, 10))
     eng.multiexp_resident(handle, scal[0], 32, n, cid, out=out_dev, want_stats=True)      # untimed: grows the single-lane scratch
     for i in range(reps):
@@ -225,7 +251,7 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cname = a.curve; cid = 0 if cname == "bls12381" else 1; n8 = b200msm.N8[cid]
+    cname = a.curve; cid = CURVE_ID[cname]; n8 = b200msm.N8[cid]
     strong = a.log2n_total > 0
     if strong:
         from b200msm.sharded import shard_range
@@ -260,12 +286,19 @@ def run_ours(a):
         torch.cuda.synchronize(dev)
 
     # ---- correctness guard on a small prefix (device path vs the oracle) -- not timed
-    if rank == 0:
+    if rank == 0 and cid < 2:
         import pyref, coracle
         cv = pyref.CURVES[cname]; m = 1 << 10
         hb = bytes(bases[: m * 2 * n8].cpu().numpy()); hs = bytes(scal[0][: m * 32].cpu().numpy())
         got = eng.normalize(cid, eng.multiexp_affine(cid, hb, hs, 32, m))
         assert got == coracle.normalize(cid, coracle.multiexp_affine(cid, hb, hs, 32, m)), "GPU result differs from the oracle"
+    elif rank == 0:
+        import refwasm
+        if refwasm.available(cname[:-3]):
+            m = 1 << 8
+            hb = bytes(bases[: m * 2 * n8].cpu().numpy()); hs = bytes(scal[0][: m * 32].cpu().numpy())
+            got = eng.normalize(cid, eng.multiexp_affine(cid, hb, hs, 32, m))
+            assert got == refwasm.RefG2(refwasm.RefModule(cname[:-3])).msm_affine(hb, hs, 32, m), "GPU G2 result differs from the reference"
 
     for i in range(max(3, a.warmup)): step_device(i)
     sync_all()
@@ -355,11 +388,11 @@ def run_ours(a):
         roof, st = kernel_roofline(eng, handle, scal, n, cid, cname, a, out_dev)
         adds = st["affine_adds"]
         total_points = (1 << a.log2n_total) if strong else n * world
-        line = {"metric": METRIC if cname == "bls12381" else "bn254_g1_msm_points_per_s", "value": total_points / (ms * 1e-3), "unit": "points/s",
+        line = {"metric": metric_name(cname), "value": total_points / (ms * 1e-3), "unit": "points/s",
                 "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if strong else "weak",
                 "vs_baseline": None, "dtype": "u32 limbs (Montgomery Fq, 32x32->64 IMAD)", "data": "synthetic",
-                "config": {"workload": ("%s G1 MSM, %d points per GPU (%d points per step), uniform 256-bit scalars, bases P_i = k_i*G resident in HBM"
-                                        % ("BLS12-381" if cid == 0 else "BN254", n, total_points)),
+                "config": {"workload": ("%s MSM, %d points per GPU (%d points per step), uniform 256-bit scalars, bases P_i = k_i*G resident in HBM"
+                                        % (CURVE_LABEL[cname], n, total_points)),
                            "curve": cname, "log2n_per_gpu": a.log2n, "parallelism": "point-range shards x%d + all_gather of partials" % world if world > 1 else "single GPU",
                            "window_bits": int(st["window_bits"]), "windows": int(st["windows"]), "tree_rounds": int(round(st["tree_rounds"])),
                            "cache": "no L2 flush: per-step working set (bases %d MiB + scalars %d MiB + sort/tree scratch > 1 GiB) exceeds the 126 MB L2; %d scalar sets alternate"
@@ -396,7 +429,7 @@ def run_batched(a):
     if not torch.cuda.is_available(): raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     torch.cuda.set_device(local); dev = torch.device("cuda", local)
     if world > 1: dist.init_process_group("nccl", device_id=dev)
-    cname = a.curve; cid = 0 if cname == "bls12381" else 1; n8 = b200msm.N8[cid]; n = 1 << a.log2n
+    cname = a.curve; cid = CURVE_ID[cname]; n8 = b200msm.N8[cid]; n = 1 << a.log2n
     mine = len(range(rank, a.batch, world))                       # MSMs of this rank per step
     eng = b200msm.Engine(local); stream = torch.cuda.current_stream(dev); eng.set_stream(stream.cuda_stream)
     bases = torch.empty(n * 2 * n8, dtype=torch.uint8, device=dev); eng.generate_bases(cid, SEED + a.log2n, 0, n, bases)
@@ -441,11 +474,11 @@ def run_batched(a):
     if rank == 0:
         roof, st = kernel_roofline(eng, handle, [scal[: n * 32]], n, cid, cname, a, out_dev[: 3 * n8])
         total = a.batch * n
-        line = {"metric": METRIC if cname == "bls12381" else "bn254_g1_msm_points_per_s", "value": total / (ms * 1e-3), "unit": "points/s",
+        line = {"metric": metric_name(cname), "value": total / (ms * 1e-3), "unit": "points/s",
                 "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "u32 limbs (Montgomery Fq, 32x32->64 IMAD)", "data": "synthetic",
                 "config": {"workload": "batched: %d independent %s G1 MSMs of 2^%d points per step over one resident base set, MSM j on GPU j %% %d, %d worker contexts per GPU; uniform 256-bit scalars"
-                                       % (a.batch, "BLS12-381" if cid == 0 else "BN254", a.log2n, world, 4),
+                                       % (a.batch, CURVE_LABEL[cname].replace(" G1", ""), a.log2n, world, 4),
                            "curve": cname, "log2n_per_msm": a.log2n, "batch": a.batch, "parallelism": "replicas (independent MSMs), no collective",
                            "window_bits": int(st["window_bits"]), "windows": int(st["windows"]),
                            "cache": "no L2 flush: each MSM's working set (bases %d MiB + sort/tree scratch) exceeds the 126 MB L2 and %d MSMs run concurrently" % (n * 2 * n8 >> 20, 4)},

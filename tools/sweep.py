@@ -9,7 +9,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--curve", default="bls12381"); ap.add_argument("--sizes", default="14,16,18,20"); ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--opt", action="append", default=[]); ap.add_argument("--probe", action="store_true"); ap.add_argument("--windowed", type=int, default=-1, help="upload with a precomputed window table of this width (0 = auto)")
 a = ap.parse_args()
-cid = 0 if a.curve == "bls12381" else 1; n8 = b200msm.N8[cid]
+cid = {"bls12381": 0, "bn128": 1, "bls12381_g2": 2, "bn128_g2": 3}[a.curve]; n8 = b200msm.N8[cid]
 eng = b200msm.Engine(0); dev = torch.device("cuda", 0)
 eng.set_stream(torch.cuda.current_stream(dev).cuda_stream)
 for kv in a.opt:
