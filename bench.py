@@ -43,13 +43,13 @@ def parse():
     ap.add_argument("--curve", default="bls12381", choices=["bls12381", "bn128", "bls12381_g2", "bn128_g2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-log2n", type=int, default=16, help="points per reference step (bounded sample)")
-    ap.add_argument("--workload", default="single", choices=["single", "batched"],
+    ap.add_argument("--workload", default="single", choices=["single", "batched", "ntt"],
                     help="single: one MSM of 2^log2n points per GPU per step (default, the headline); batched: BASELINE config 5, --batch independent MSMs of 2^log2n points (default 2^18) spread over the GPUs per step")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-window-table", action="store_true", help="skip the extra measurement with precomputed window tables")
     ap.add_argument("--table-window-bits", type=int, default=0, help="window width of the precomputed table (0 = auto)")
     a = ap.parse_args()
-    if a.log2n == 0: a.log2n = 18 if a.workload == "batched" else 20
+    if a.log2n == 0: a.log2n = {"batched": 18, "ntt": 24}.get(a.workload, 20)
     return a
 
 
@@ -502,6 +502,105 @@ def run_batched(a):
     if world > 1: dist.barrier(); dist.destroy_process_group()
 
 
+def run_ntt(a):
+    """one Fr NTT (frm_fft) of 2^log2n elements per GPU per step; N > 1 runs independent replicas (the transform does
+    not shard in this design: no collective).  value = elements transformed per second, data resident in HBM; e2e = pinned host in/out."""
+    import torch
+    import torch.distributed as dist
+    import b200msm
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available(): raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local); dev = torch.device("cuda", local)
+    if world > 1: dist.init_process_group("nccl", device_id=dev)
+    cname = a.curve if a.curve in ("bls12381", "bn128") else "bls12381"; cid = CURVE_ID[cname]; lg = a.log2n; n = 1 << lg
+    eng = b200msm.Engine(local); stream = torch.cuda.current_stream(dev); eng.set_stream(stream.cuda_stream)
+    g = torch.Generator(device=dev); g.manual_seed(5 + rank)
+    xs = []
+    for _ in range(2):
+        x = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev, generator=g); x[:, 31] &= 0x0F      # < 2^252 < r: reduced Montgomery elements
+        xs.append(x.reshape(-1).contiguous())
+    out = torch.empty_like(xs[0])
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize(dev)
+    if rank == 0:   # correctness guard (not timed): a 2^12 prefix against the reference module, and the round trip at full size
+        import refwasm
+        if refwasm.available(cname):
+            pb = refwasm.RefModule(cname); m = 1 << 12; hb = bytes(xs[0][: m * 32].cpu().numpy())
+            p = pb.alloc(len(hb) + 64); pb.write(p, hb); pb.frm_fft(p, m)
+            assert eng.fr_fft(cid, hb, 12) == pb.read(p, len(hb)), "GPU NTT differs from the reference's frm_fft"
+        eng.fr_fft(cid, xs[0], lg, out=out); eng.fr_fft(cid, out, lg, inverse=True, out=out); torch.cuda.synchronize(dev)
+        assert torch.equal(out, xs[0]), "ifft(fft(x)) != x"
+    for i in range(max(3, a.warmup)): eng.fr_fft(cid, xs[i % 2], lg, out=out)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0: sampler.start()
+    l0 = eng.counter("launches")
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(a.steps): eng.fr_fft(cid, xs[i % 2], lg, out=out)
+    e1.record(stream); sync_all()
+    ms = e0.elapsed_time(e1) / a.steps
+    launches = (eng.counter("launches") - l0) // max(1, a.steps)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ph = {}
+    for i in range(5):
+        eng.fr_fft(cid, xs[i % 2], lg, out=out)
+        for k, v in eng.fr_fft_last_phases().items(): ph[k] = ph.get(k, 0) + v / 5
+    hin = torch.empty(n * 32, dtype=torch.uint8).pin_memory(); hin.copy_(xs[0]); hout = torch.empty(n * 32, dtype=torch.uint8).pin_memory()
+    for _ in range(2): eng.fr_fft(cid, hin, lg, out=hout)
+    sync_all(); t0 = time.perf_counter()
+    k = max(3, min(a.steps, 10))
+    for _ in range(k): eng.fr_fft(cid, hin, lg, out=hout)
+    sync_all(); e2e_ms = (time.perf_counter() - t0) * 1e3 / k
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        hbm_peak, hbm_src = measured_peaks()
+        passes = int(round(ph["radix4_passes"] + ph["radix2_passes"]))
+        alg_bytes = n * 32 * 2                                     # one global pass reads and writes every element once
+        per_pass_ms = ph["ms_passes"] / max(1, passes)
+        roof = {"bound": "hbm", "kernel": "k_ntt_stage4 (two radix-2 stages per pass over the array; %d radix-4 + %d radix-2 passes per transform)" % (ph["radix4_passes"], ph["radix2_passes"]),
+                "achieved": alg_bytes / (per_pass_ms * 1e-3) / 1e9 if per_pass_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
+                "frac": (alg_bytes / (per_pass_ms * 1e-3) / 1e9 / hbm_peak) if per_pass_ms > 0 else None, "traffic": None,
+                "avg_launch_ms": per_pass_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": hbm_src,
+                "note": "each pass also performs n/2 (radix-2) or n (radix-4) Fr multiplications: %.1f G multiplications/s in the passes"
+                        % ((ph["radix4_passes"] * n + ph["radix2_passes"] * n / 2) / (ph["ms_passes"] * 1e-3) / 1e9 if ph["ms_passes"] > 0 else 0.0)}
+        line = {"metric": ("bls12381" if cid == 0 else "bn254") + "_fr_ntt_elements_per_s", "value": n * world / (ms * 1e-3), "unit": "elements/s",
+                "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u32 limbs (Montgomery Fr, 32x32->64 IMAD)", "data": "synthetic",
+                "config": {"workload": "%s Fr NTT (frm_fft), 2^%d elements per GPU per step, forward transform, data resident in HBM" % ("BLS12-381" if cid == 0 else "BN254", lg),
+                           "curve": cname, "log2n": lg, "parallelism": "replicas only (independent transforms)" if world > 1 else "single GPU",
+                           "cache": "no L2 flush: the array (%d MiB) and its twiddle table (%d MiB) exceed the 126 MB L2; two input arrays alternate" % (n * 32 >> 20, n * 16 >> 20)},
+                "clocks": clocks,
+                "e2e": {"value": n * world / (e2e_ms * 1e-3), "unit": "elements/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32,
+                        "api": "b200msm_fr_fft with pinned host buffers"},
+                "gpu_launches": int(launches), "roofline": roof, "phases_ms": {k: round(v, 4) for k, v in ph.items()}}
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                import refwasm, random
+                pb = refwasm.RefModule(cname); m = 1 << 16
+                hb = random.Random(1).getrandbits(252 * 1).to_bytes(32, "little") * m
+                p = pb.alloc(len(hb) + 64); pb.write(p, hb)
+                t0 = time.perf_counter(); reps = 3
+                for _ in range(reps): pb.frm_fft(p, m)
+                dt = (time.perf_counter() - t0) / reps
+                line["cpu_baseline"] = {"value": m / dt, "unit": "elements/s", "cores": 1, "kind": "reference", "ms_per_sample": dt * 1e3,
+                                        "sample": "reference WASM (wasmcurves frm_fft) AOT-compiled via C, one transform of 2^16 elements per step on one host core"}
+            except Exception as ex:
+                line["cpu_baseline"] = {"value": None, "unit": "elements/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+        else:
+            line["cpu_baseline"] = {"value": None, "unit": "elements/s", "cores": 0, "kind": "skipped", "sample": "measured at N=1 only"}
+        _emit(line)
+    if world > 1: dist.barrier(); dist.destroy_process_group()
+
+
 def _emit(line):
     """the ONE JSON line goes to the real stdout; everything else printed while running (NCCL's version banner, warnings) went to stderr"""
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
@@ -513,4 +612,5 @@ if __name__ == "__main__":
     args = parse()
     if args.impl == "reference": run_reference(args)
     elif args.workload == "batched": run_batched(args)
+    elif args.workload == "ntt": run_ntt(args)
     else: run_ours(args)

@@ -130,6 +130,16 @@ int b200msm_glv_decompose_scalars(b200msm_ctx* ctx, int curve, const void* scala
 int b200msm_g1_glv_preprocess(b200msm_ctx* ctx, int curve, const void* points, const void* scalars, uint64_t n,
                               void* out_points, void* out_scalars);
 
+/* ---- == frm_fft(px, n) / frm_ifft(px, n) with n = 2^log2n                                    src/build_fft.js:178-245
+ * (frm wired at src/bls12381/build_bls12381.js:39-43, src/bn128/build_bn128.js:35-39).  Fr elements: 32 bytes little-endian,
+ * Montgomery form a * 2^256 mod r, reduced.  out[k] = sum_j in[j] * w^(j*k) with w = ROOTs[log2n] (build_fft.js:44-63); the
+ * inverse is the same transform followed by i -> n - i and the factor 1/n (:396-516).  curve: 0 = BLS12-381 Fr (log2n <= 28),
+ * 1 = BN254 Fr (log2n <= 28).  in / out: host or device, n * 32 bytes each; in == out transforms in place. */
+int b200msm_fr_fft(b200msm_ctx* ctx, int curve, const void* in, uint32_t log2n, int inverse, void* out);
+/* measurement hook: CUDA-event times (ms) of the last transform on this context: bit reversal, shared-memory tile stages, global
+ * radix-4/2 passes, inverse finalisation; passes[0] / passes[1] = number of radix-4 / radix-2 global passes it ran. */
+int b200msm_fr_fft_last_phases(b200msm_ctx* ctx, float ms[4], uint32_t passes[2]);
+
 /* ---- synthetic inputs (benchmarks/multiexp.js:16-23 builds bases on the module itself):
  * device_out[i] = k_i * G for i in [0, n), affine Montgomery, k_i = splitmix64(seed + first + i) (0 mapped to 1).
  * device_out must be a device pointer with room for n * 2*n8 bytes. */

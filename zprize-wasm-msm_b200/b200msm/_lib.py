@@ -18,7 +18,7 @@ EXPORTS = [  # every symbol include/b200msm.h declares (checked by tests/test_ab
     "b200msm_upload_bases", "b200msm_free_bases", "b200msm_g1_multiexp_resident", "b200msm_g1_normalize",
     "b200msm_g1_sum", "b200msm_g1_generate_bases", "b200msm_fq_op", "b200msm_probe_imad", "b200msm_probe_imad32", "b200msm_probe_fqmul",
     "b200msm_set_option", "b200msm_constants", "b200msm_get_counter", "b200msm_g1_batch_convert",
-    "b200msm_glv_decompose_scalars", "b200msm_g1_glv_preprocess", "b200msm_upload_bases_windowed", "b200msm_probe_dfma", "b200msm_g1_multiexp_batch",
+    "b200msm_glv_decompose_scalars", "b200msm_g1_glv_preprocess", "b200msm_upload_bases_windowed", "b200msm_probe_dfma", "b200msm_g1_multiexp_batch", "b200msm_fr_fft", "b200msm_fr_fft_last_phases",
 ]
 
 
@@ -64,6 +64,8 @@ lib.b200msm_upload_bases_windowed.argtypes = [_vp, _i, _vp, _u64, _u32, _u32, ct
 lib.b200msm_free_bases.argtypes = [_vp, _u64]
 lib.b200msm_g1_multiexp_resident.argtypes = [_vp, _u64, _vp, _u32, _u64, _vp, ctypes.POINTER(Stats)]
 lib.b200msm_g1_multiexp_batch.argtypes = [_vp, _u64, _vp, _u32, _u64, _u32, _vp]
+lib.b200msm_fr_fft.argtypes = [_vp, _i, _vp, _u32, _i, _vp]
+lib.b200msm_fr_fft_last_phases.argtypes = [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_u32)]
 lib.b200msm_g1_normalize.argtypes = [_vp, _i, _vp, _u64, _vp]
 lib.b200msm_g1_sum.argtypes = [_vp, _i, _vp, _u64, _vp]
 lib.b200msm_g1_generate_bases.argtypes = [_vp, _i, _u64, _u64, _u64, _vp]

@@ -90,6 +90,20 @@ class Engine:
         po, ko = _ptr(out)
         self._ck(lib.b200msm_g1_multiexp_batch(self._ctx, handle, ps, scalar_size, n, count, po)); return out
 
+    def fr_fft(self, curve, data, log2n, inverse=False, out=None):
+        """frm_fft / frm_ifft over 2^log2n Montgomery Fr elements (32 bytes each) -> bytes, or into `out` (host/device buffer)"""
+        pi, ki = _ptr(data)
+        if out is None:
+            o = ctypes.create_string_buffer(32 << log2n)
+            self._ck(lib.b200msm_fr_fft(self._ctx, curve, pi, log2n, 1 if inverse else 0, o)); return o.raw
+        po, ko = _ptr(out)
+        self._ck(lib.b200msm_fr_fft(self._ctx, curve, pi, log2n, 1 if inverse else 0, po)); return out
+
+    def fr_fft_last_phases(self):
+        ms = (ctypes.c_float * 4)(); ps = (ctypes.c_uint32 * 2)()
+        self._ck(lib.b200msm_fr_fft_last_phases(self._ctx, ms, ps))
+        return {"ms_bitrev": ms[0], "ms_tile": ms[1], "ms_passes": ms[2], "ms_final": ms[3], "radix4_passes": ps[0], "radix2_passes": ps[1]}
+
     def normalize(self, curve, jac, count=1):
         """g1m_normalize + fromMontgomery: canonical x||y bytes (plain LE ints; infinity = zeros)"""
         pj, kj = _ptr(jac); o = ctypes.create_string_buffer(2 * N8[curve] * count)

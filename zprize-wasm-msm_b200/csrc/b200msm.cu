@@ -22,6 +22,7 @@
 #include "codecs.cuh"
 #include "glv.cuh"
 #include "host_ec.h"
+#include "internal.h"
 #include <chrono>
 #include <thread>
 
@@ -679,6 +680,12 @@ int build_window_table(b200msm_ctx* ctx, void* table, uint64_t n, uint32_t c0, u
 
 }  // namespace
 
+// =================================================================== internal interface for the library's other translation units (internal.h)
+cudaStream_t b200msm_internal_stream(b200msm_ctx* ctx) { return ctx->stream; }
+int b200msm_internal_device(b200msm_ctx* ctx) { return ctx->device; }
+void b200msm_internal_count_launches(b200msm_ctx* ctx, uint64_t k) { ctx->launches += k; }
+void b200msm_internal_set_error(b200msm_ctx* ctx, const char* msg) { ctx->err = msg ? msg : ""; }
+
 // =================================================================== C ABI
 extern "C" {
 
@@ -719,6 +726,7 @@ int b200msm_create(b200msm_ctx** out, int device_id) {
 
 void b200msm_destroy(b200msm_ctx* ctx) {
   if (!ctx) return;
+  b200ntt_release(ctx);
   for (b200msm_ctx* w : ctx->workers) b200msm_destroy(w);
   ctx->workers.clear();
   cudaSetDevice(ctx->device);
