@@ -5,7 +5,7 @@
 // The result is the DFT  out[k] = sum_j in[j] * w^(j*k),  w = ROOTs[log2 n]  (resp. its inverse), so any exact algorithm gives
 // the same canonical Montgomery bytes; parity is checked against the reference module's own frm_fft / frm_ifft exports.
 //
-// Here: one gather pass for the bit reversal, the first 10 stages of every 1024-element tile in shared memory (one launch),
+// Here: the first 10 stages of every 1024-element tile in shared memory, reading the inputs from their bit-reversed positions (one launch),
 // the remaining stages as radix-4 (two stages per pass over the data) or radix-2 global passes, twiddles w^e from a table of
 // n/2 entries built once per (context, curve, size).  Fr elements are 32 bytes = one DRAM sector.
 #include <cuda_runtime.h>
@@ -60,13 +60,16 @@ __global__ void __launch_bounds__(256) k_ntt_bitrev(const void* __restrict__ in,
   fe_store<F>(reinterpret_cast<char*>(out) + (size_t)i * 4 * F::N, v);
 }
 // stages 1 .. K (K = min(log2n, 10)) of every tile of 2^K consecutive elements, in shared memory (limb-major: conflict-free)
+// The tile reads its inputs straight from their bit-reversed positions (__reversePermutation fused into the load: element i of tile b
+// is in[bitrev(b*T + i)], a gather of whole 32-byte sectors), so the permuted array is never written out and read back.
 template <class F>
-__global__ void __launch_bounds__(TILE / 2) k_ntt_tile(void* __restrict__ x, const void* __restrict__ W, uint32_t log2n, uint32_t K) {
+__global__ void __launch_bounds__(TILE / 2) k_ntt_tile(const void* __restrict__ in, void* __restrict__ x, const void* __restrict__ W, uint32_t log2n, uint32_t K) {
   __shared__ uint32_t sm[F::N][TILE];
   const uint32_t T = 1u << K, half_threads = T >> 1;
   char* base = reinterpret_cast<char*>(x) + (size_t)blockIdx.x * T * 4 * F::N;
   for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
-    Fe<F::N> v; fe_load_cg<F>(v, base + (size_t)i * 4 * F::N);
+    const uint32_t src = __brev(blockIdx.x * T + i) >> (32 - log2n);
+    Fe<F::N> v; fe_load<F>(v, reinterpret_cast<const char*>(in) + (size_t)src * 4 * F::N);
 #pragma unroll
     for (int k = 0; k < F::N; k++) sm[k][i] = v.l[k];
   }
@@ -193,10 +196,10 @@ int run_ntt(b200msm_ctx* ctx, NttState& st, int ci, const void* in, uint32_t L, 
   else { int rc = ensure(ctx, &st.buf2, &st.buf2_cap, bytes); if (rc) return rc; d_x = st.buf2; }
   for (auto& e : st.ev) if (!e) NCK(cudaEventCreate(&e));
   NCK(cudaEventRecord(st.ev[0], s));
-  k_ntt_bitrev<F><<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(d_in, d_x, L); launches++;
-  NCK(cudaEventRecord(st.ev[1], s));
   const uint32_t K = L < (uint32_t)TILE_LOG ? L : (uint32_t)TILE_LOG;
-  if (K >= 1) { k_ntt_tile<F><<<(uint32_t)(n >> K), TILE / 2, 0, s>>>(d_x, st.W[ci], L, K); launches++; }
+  if (K == 0) { k_ntt_bitrev<F><<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(d_in, d_x, L); launches++; }      // n == 1: plain copy
+  NCK(cudaEventRecord(st.ev[1], s));
+  if (K >= 1) { k_ntt_tile<F><<<(uint32_t)(n >> K), TILE / 2, 0, s>>>(d_in, d_x, st.W[ci], L, K); launches++; }
   NCK(cudaEventRecord(st.ev[2], s));
   uint32_t sg = K + 1; st.last_passes4 = st.last_passes2 = 0;
   for (; sg + 1 <= L; sg += 2) { k_ntt_stage4<F><<<(uint32_t)((n / 4 + 255) / 256), 256, 0, s>>>(d_x, st.W[ci], L, sg); launches++; st.last_passes4++; }
