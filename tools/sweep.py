@@ -7,7 +7,7 @@ import torch, b200msm
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--curve", default="bls12381"); ap.add_argument("--sizes", default="14,16,18,20"); ap.add_argument("--reps", type=int, default=5)
-ap.add_argument("--opt", action="append", default=[]); ap.add_argument("--probe", action="store_true"); ap.add_argument("--windowed", type=int, default=-1, help="upload with a precomputed window table of this width (0 = auto)")
+ap.add_argument("--opt", action="append", default=[]); ap.add_argument("--probe", action="store_true"); ap.add_argument("--roofline", action="store_true", help="compact rows with the whole-MSM fraction of the IMAD roofline"); ap.add_argument("--windowed", type=int, default=-1, help="upload with a precomputed window table of this width (0 = auto)")
 a = ap.parse_args()
 cid = {"bls12381": 0, "bn128": 1, "bls12381_g2": 2, "bn128_g2": 3}[a.curve]; n8 = b200msm.N8[cid]
 eng = b200msm.Engine(0); dev = torch.device("cuda", 0)
@@ -42,5 +42,10 @@ for lg in [int(x) for x in a.sizes.split(",")]:
     row = {"log2n": lg, "ms": round(ms, 3), "c": int(agg["window_bits"]), "W": int(agg["windows"]), "rounds": int(agg["tree_rounds"]),
            "pairs": int(agg["pairs"]), "adds": int(agg["affine_adds"]), "launches": int(agg["launches"])}
     row.update({k[3:]: round(v, 3) for k, v in agg.items() if k.startswith("ms_")})
+    if a.roofline:      # whole-MSM fraction of the integer-multiply roofline: 6 field multiplications per batch-affine addition
+        lp = {0: 300, 1: 136, 2: 900, 3: 408}[cid]
+        if "imad" not in globals(): imad = eng.probe_imad()
+        row = {"curve": a.curve, "log2n": lg, "ms": row["ms"], "Mpoints_per_s": round(n / row["ms"] / 1e3, 1), "c": row["c"], "windows": row["W"], "adds": row["adds"],
+               "frac_of_imad_roofline": round(row["adds"] * 6 * lp / (row["ms"] * 1e-3) / imad, 3), "table": a.windowed >= 0}
     print(json.dumps(row), flush=True)
     eng.free_bases(h); del bases, sc

@@ -119,12 +119,21 @@ bool is_device_ptr(const void* p) {
 
 // n8 = bytes per coordinate-field element: Fq for G1 (48 / 32), Fq2 for G2 (96 / 64)
 int n8_of(int curve) { static const int t[4] = {48, 32, 96, 64}; return t[curve & 3]; }
+#if defined(B200_NO_G2)
+bool curve_ok(int curve) { return curve >= 0 && curve <= 1; }
+#else
 bool curve_ok(int curve) { return curve >= 0 && curve <= 3; }
+#endif
 bool curve_g1(int curve) { return curve == B200MSM_BLS12_381_G1 || curve == B200MSM_BN254_G1; }
 // run a statement with C bound to the field class of `curve` (G2 = the same templates over Fq2, see fp.cuh)
+#if defined(B200_NO_G2)      // development builds (B200_DEV_NO_G2=1 in __graft_entry__): the two G2 instantiations are 85 % of the compile time
+#define B200_CURVE_SWITCH(curve, ...) \
+  switch (curve) { case 0: { using C = BLS12_381; __VA_ARGS__; } break; default: { using C = BN254; __VA_ARGS__; } break; }
+#else
 #define B200_CURVE_SWITCH(curve, ...) \
   switch (curve) { case 0: { using C = BLS12_381; __VA_ARGS__; } break; case 1: { using C = BN254; __VA_ARGS__; } break; \
                    case 2: { using C = Fq2<BLS12_381>; __VA_ARGS__; } break; default: { using C = Fq2<BN254>; __VA_ARGS__; } break; }
+#endif
 
 // host-side field descriptor of C for the serial tail (host_ec.h)
 template <class C> struct HostField {

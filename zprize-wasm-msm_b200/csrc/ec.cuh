@@ -57,10 +57,10 @@ template <class C> B200_DI void xyzz_store(void* base, uint64_t idx, const XYZZ<
 // 2*P for affine P != inf  (mdbl-2008-s-1; y != 0 on these curves: no 2-torsion)
 template <class C> __device__ __noinline__ void xyzz_dbl_affine(XYZZ<C>& r, const Affine<C>& p) {
   Fe<C::N> U, V, W, S, M, t;
-  fe_dbl<C>(U, p.y); fe_sqr<C>(V, U); fe_mul<C>(W, U, V); fe_mul<C>(S, p.x, V);
-  fe_sqr<C>(t, p.x); fe_dbl<C>(M, t); fe_add<C>(M, M, t);
-  fe_sqr<C>(r.x, M); fe_sub<C>(r.x, r.x, S); fe_sub<C>(r.x, r.x, S);
-  fe_sub<C>(t, S, r.x); fe_mul<C>(t, M, t); fe_mul<C>(U, W, p.y); fe_sub<C>(r.y, t, U);
+  fe_dbl<C>(U, p.y); fe_sqr_x<C>(V, U); fe_mul_x<C>(W, U, V); fe_mul_x<C>(S, p.x, V);
+  fe_sqr_x<C>(t, p.x); fe_dbl<C>(M, t); fe_add<C>(M, M, t);
+  fe_sqr_x<C>(r.x, M); fe_sub<C>(r.x, r.x, S); fe_sub<C>(r.x, r.x, S);
+  fe_sub<C>(t, S, r.x); fe_mul_x<C>(t, M, t); fe_mul_x<C>(U, W, p.y); fe_sub<C>(r.y, t, U);
   r.zz = V; r.zzz = W;
 }
 
@@ -68,12 +68,12 @@ template <class C> __device__ __noinline__ void xyzz_dbl_affine(XYZZ<C>& r, cons
 template <class C> __device__ __noinline__ void xyzz_dbl(XYZZ<C>& r, const XYZZ<C>& p) {
   if (xyzz_is_inf<C>(p)) { r = p; return; }
   Fe<C::N> U, V, W, S, M, t, X3;
-  fe_dbl<C>(U, p.y); fe_sqr<C>(V, U); fe_mul<C>(W, U, V); fe_mul<C>(S, p.x, V);
-  fe_sqr<C>(t, p.x); fe_dbl<C>(M, t); fe_add<C>(M, M, t);
-  fe_sqr<C>(X3, M); fe_sub<C>(X3, X3, S); fe_sub<C>(X3, X3, S);
-  fe_sub<C>(t, S, X3); fe_mul<C>(t, M, t); fe_mul<C>(U, W, p.y);
+  fe_dbl<C>(U, p.y); fe_sqr_x<C>(V, U); fe_mul_x<C>(W, U, V); fe_mul_x<C>(S, p.x, V);
+  fe_sqr_x<C>(t, p.x); fe_dbl<C>(M, t); fe_add<C>(M, M, t);
+  fe_sqr_x<C>(X3, M); fe_sub<C>(X3, X3, S); fe_sub<C>(X3, X3, S);
+  fe_sub<C>(t, S, X3); fe_mul_x<C>(t, M, t); fe_mul_x<C>(U, W, p.y);
   r.x = X3; fe_sub<C>(r.y, t, U);
-  fe_mul<C>(r.zz, V, p.zz); fe_mul<C>(r.zzz, W, p.zzz);
+  fe_mul_x<C>(r.zz, V, p.zz); fe_mul_x<C>(r.zzz, W, p.zzz);
 }
 
 // acc += P (affine).  g1m_addMixed, build_curve_jacobian_a0.js:661-761 (madd-2008-s in XYZZ)
@@ -81,16 +81,16 @@ template <class C> B200_DI void xyzz_madd(XYZZ<C>& acc, const Affine<C>& p) {
   if (affine_is_inf<C>(p)) return;
   if (xyzz_is_inf<C>(acc)) { acc.x = p.x; acc.y = p.y; fe_set_one<C>(acc.zz); fe_set_one<C>(acc.zzz); return; }
   Fe<C::N> U2, S2, P, R, PP, PPP, Q, t;
-  fe_mul<C>(U2, p.x, acc.zz); fe_mul<C>(S2, p.y, acc.zzz);
+  fe_mul_x<C>(U2, p.x, acc.zz); fe_mul_x<C>(S2, p.y, acc.zzz);
   fe_sub<C>(P, U2, acc.x); fe_sub<C>(R, S2, acc.y);
   if (fe_is_zero<C>(P)) {
     if (fe_is_zero<C>(R)) xyzz_dbl_affine<C>(acc, p); else xyzz_set_inf<C>(acc);
     return;
   }
-  fe_sqr<C>(PP, P); fe_mul<C>(PPP, P, PP); fe_mul<C>(Q, acc.x, PP);
-  fe_sqr<C>(t, R); fe_sub<C>(t, t, PPP); fe_sub<C>(t, t, Q); fe_sub<C>(acc.x, t, Q);
-  fe_sub<C>(t, Q, acc.x); fe_mul<C>(t, R, t); fe_mul<C>(Q, acc.y, PPP); fe_sub<C>(acc.y, t, Q);
-  fe_mul<C>(acc.zz, acc.zz, PP); fe_mul<C>(acc.zzz, acc.zzz, PPP);
+  fe_sqr_x<C>(PP, P); fe_mul_x<C>(PPP, P, PP); fe_mul_x<C>(Q, acc.x, PP);
+  fe_sqr_x<C>(t, R); fe_sub<C>(t, t, PPP); fe_sub<C>(t, t, Q); fe_sub<C>(acc.x, t, Q);
+  fe_sub<C>(t, Q, acc.x); fe_mul_x<C>(t, R, t); fe_mul_x<C>(Q, acc.y, PPP); fe_sub<C>(acc.y, t, Q);
+  fe_mul_x<C>(acc.zz, acc.zz, PP); fe_mul_x<C>(acc.zzz, acc.zzz, PPP);
 }
 
 // acc += Q (XYZZ).  g1m_add, build_curve_jacobian_a0.js:541-658 (add-2008-s)
@@ -98,18 +98,18 @@ template <class C> B200_DI void xyzz_add(XYZZ<C>& acc, const XYZZ<C>& q) {
   if (xyzz_is_inf<C>(q)) return;
   if (xyzz_is_inf<C>(acc)) { acc = q; return; }
   Fe<C::N> U1, U2, S1, S2, P, R, PP, PPP, Q, t;
-  fe_mul<C>(U1, acc.x, q.zz); fe_mul<C>(U2, q.x, acc.zz);
-  fe_mul<C>(S1, acc.y, q.zzz); fe_mul<C>(S2, q.y, acc.zzz);
+  fe_mul_x<C>(U1, acc.x, q.zz); fe_mul_x<C>(U2, q.x, acc.zz);
+  fe_mul_x<C>(S1, acc.y, q.zzz); fe_mul_x<C>(S2, q.y, acc.zzz);
   fe_sub<C>(P, U2, U1); fe_sub<C>(R, S2, S1);
   if (fe_is_zero<C>(P)) {
     if (fe_is_zero<C>(R)) { XYZZ<C> d; xyzz_dbl<C>(d, q); acc = d; } else xyzz_set_inf<C>(acc);
     return;
   }
-  fe_sqr<C>(PP, P); fe_mul<C>(PPP, P, PP); fe_mul<C>(Q, U1, PP);
-  fe_sqr<C>(t, R); fe_sub<C>(t, t, PPP); fe_sub<C>(t, t, Q); fe_sub<C>(acc.x, t, Q);
-  fe_sub<C>(t, Q, acc.x); fe_mul<C>(t, R, t); fe_mul<C>(Q, S1, PPP); fe_sub<C>(acc.y, t, Q);
-  fe_mul<C>(t, acc.zz, q.zz); fe_mul<C>(acc.zz, t, PP);
-  fe_mul<C>(t, acc.zzz, q.zzz); fe_mul<C>(acc.zzz, t, PPP);
+  fe_sqr_x<C>(PP, P); fe_mul_x<C>(PPP, P, PP); fe_mul_x<C>(Q, U1, PP);
+  fe_sqr_x<C>(t, R); fe_sub<C>(t, t, PPP); fe_sub<C>(t, t, Q); fe_sub<C>(acc.x, t, Q);
+  fe_sub<C>(t, Q, acc.x); fe_mul_x<C>(t, R, t); fe_mul_x<C>(Q, S1, PPP); fe_sub<C>(acc.y, t, Q);
+  fe_mul_x<C>(t, acc.zz, q.zz); fe_mul_x<C>(acc.zz, t, PP);
+  fe_mul_x<C>(t, acc.zzz, q.zzz); fe_mul_x<C>(acc.zzz, t, PPP);
 }
 
 // XYZZ -> Jacobian (X', Y', Z') with x = X'/Z'^2, y = Y'/Z'^3, no inversion:
@@ -117,11 +117,11 @@ template <class C> B200_DI void xyzz_add(XYZZ<C>& acc, const XYZZ<C>& q) {
 template <class C> B200_DI void xyzz_to_jacobian(Fe<C::N>& X, Fe<C::N>& Y, Fe<C::N>& Z, const XYZZ<C>& p) {
   if (xyzz_is_inf<C>(p)) { fe_set_zero<C>(X); fe_set_one<C>(Y); fe_set_zero<C>(Z); return; }
   Fe<C::N> t, u;
-  fe_mul<C>(Z, p.zz, p.zzz);            // Z'
-  fe_mul<C>(t, Z, p.zzz);               // ZZ*ZZZ^2
-  fe_mul<C>(X, p.x, t);
-  fe_sqr<C>(u, p.zz); fe_mul<C>(t, t, u);   // ZZ^3*ZZZ^2
-  fe_mul<C>(Y, p.y, t);
+  fe_mul_x<C>(Z, p.zz, p.zzz);            // Z'
+  fe_mul_x<C>(t, Z, p.zzz);               // ZZ*ZZZ^2
+  fe_mul_x<C>(X, p.x, t);
+  fe_sqr_x<C>(u, p.zz); fe_mul_x<C>(t, t, u);   // ZZ^3*ZZZ^2
+  fe_mul_x<C>(Y, p.y, t);
 }
 
 // Decision + denominator for one affine + affine addition that shares a batched inversion

@@ -638,6 +638,14 @@ template <class C> B200_DI void fe_inv_fast(Fe<C::N>& r, const Fe<C::N>& a) {
   if constexpr (C::EXT == 2) fq2_inv<C, true>(r, a); else fe_inv_fast_p<C>(r, a);
 }
 
+// Multiplication / squaring for the XYZZ formulas (ec.cuh).  Over Fq2 they are CALLS: an XYZZ addition is 14 Fq2 = 42 Fq
+// multiplications, and inlining them all pushes the fold / finish / table kernels to 255 registers plus a kilobyte of spill
+// (and the compile of the two G2 instantiations to ten minutes).  The batch-affine tree kernels keep the inlined forms.
+template <class C> __device__ __noinline__ void fe_mul_call(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) { Fe<C::N> t; fe_mul<C>(t, a, b); r = t; }
+template <class C> __device__ __noinline__ void fe_sqr_call(Fe<C::N>& r, const Fe<C::N>& a) { Fe<C::N> t; fe_sqr<C>(t, a); r = t; }
+template <class C> B200_DI void fe_mul_x(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) { if constexpr (C::EXT == 2) fe_mul_call<C>(r, a, b); else fe_mul<C>(r, a, b); }
+template <class C> B200_DI void fe_sqr_x(Fe<C::N>& r, const Fe<C::N>& a) { if constexpr (C::EXT == 2) fe_sqr_call<C>(r, a); else fe_sqr<C>(r, a); }
+
 // ------------------------------------------------------------------ global-memory access helpers
 // Elements are 16-byte aligned in every buffer the engine owns; 128-bit vector loads/stores.
 template <class C> B200_DI void fe_load(Fe<C::N>& r, const void* p) {
