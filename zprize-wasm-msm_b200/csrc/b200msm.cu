@@ -53,7 +53,7 @@ struct TreeLane {
   cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
   DevBuf offs, tiles, bid, pa, pb, prefix, prod, lvlprefix, others, meta;
 };
-constexpr int MAX_LANES = 4;
+constexpr int MAX_LANES = 8;
 constexpr uint64_t WARP_LEVEL_MAX = 131072;     // product-tree levels with at most this many values use the warp-assisted kernel (only one such level can occur: 131072 / 128 <= BA_ROOT_MAX)
 
 }  // namespace
@@ -65,7 +65,7 @@ struct b200msm_ctx {
   int opt_window_bits = 0, opt_accumulate = 0, opt_tree_rounds = -1;
   DevBuf bases, scalars, canon, counts, offsets, cursors, tiles, sorted, buckets, wsum, out, misc, acc_a, acc_b, acc_c, acc_d, acc_e;
   TreeLane lane[MAX_LANES];                                                   // batch-affine tree lanes
-  int opt_lanes = 4, opt_ba_k = 0, opt_pt_k = 8, opt_persist = 444, opt_subslots = 0, opt_bwd_staged = 0, opt_probe_smem = 0;
+  int opt_lanes = 4, opt_ba_k = 0, opt_pt_k = 8, opt_persist = 592, opt_subslots = 0, opt_bwd_staged = 0, opt_probe_smem = 0;
   bool probe29 = false, probe_sqr = false; int64_t opt_group_pairs = 0;
   cudaEvent_t ev_plan = nullptr, ev_sorted = nullptr, ev_bases = nullptr, ev_done = nullptr;
   cudaStream_t copy_stream = nullptr; bool bases_pending = false;
