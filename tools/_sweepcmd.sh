@@ -1,6 +1,6 @@
-for cfg in "lanes=4" "lanes=6" "lanes=8" "lanes=8 persist=296" "lanes=6 persist=592" "lanes=4 persist=592" "lanes=4 persist=296"; do
+for cfg in "lanes=1" "lanes=2" "lanes=3" "lanes=4" "lanes=2 tree_rounds=4" "lanes=2 tree_rounds=5" "lanes=4 tree_rounds=4" "lanes=3 tree_rounds=4"; do
   args=""; for kv in $cfg; do args="$args --opt $kv"; done
-  echo "== $cfg"; python tools/sweep.py --sizes 16,18,20,22 --reps 8 $args 2>&1 | tail -4 | python -c "
+  echo "== $cfg"; python tools/sweep.py --sizes 14,16,18,19 --reps 10 $args 2>&1 | tail -4 | python -c "
 import sys, json
 for l in sys.stdin:
     d = json.loads(l); print({k: d[k] for k in ('log2n','ms')})"

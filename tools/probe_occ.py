@@ -6,6 +6,7 @@ import b200msm
 eng = b200msm.Engine(0)
 imad = eng.probe_imad()
 print(json.dumps({"imad_wide_per_s": imad, "imad32_per_s": eng.probe_imad32(), "dfma_per_s": eng.probe_dfma()}))
+print(json.dumps(eng.probe_dualpipe()))
 for smem, warps in ((0, 32), (56 * 1024, 24), (100 * 1024, 16), (200 * 1024, 8)):
     eng.set_option("probe_smem", smem)
     for sq in (0, 1):

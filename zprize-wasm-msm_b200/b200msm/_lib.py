@@ -18,7 +18,7 @@ EXPORTS = [  # every symbol include/b200msm.h declares (checked by tests/test_ab
     "b200msm_upload_bases", "b200msm_free_bases", "b200msm_g1_multiexp_resident", "b200msm_g1_normalize",
     "b200msm_g1_sum", "b200msm_g1_generate_bases", "b200msm_fq_op", "b200msm_probe_imad", "b200msm_probe_imad32", "b200msm_probe_fqmul",
     "b200msm_set_option", "b200msm_constants", "b200msm_get_counter", "b200msm_g1_batch_convert",
-    "b200msm_glv_decompose_scalars", "b200msm_g1_glv_preprocess", "b200msm_upload_bases_windowed", "b200msm_probe_dfma", "b200msm_g1_multiexp_batch", "b200msm_fr_fft", "b200msm_fr_fft_last_phases",
+    "b200msm_glv_decompose_scalars", "b200msm_g1_glv_preprocess", "b200msm_upload_bases_windowed", "b200msm_probe_dfma", "b200msm_g1_multiexp_batch", "b200msm_fr_fft", "b200msm_fr_fft_last_phases", "b200msm_probe_dualpipe",
 ]
 
 
@@ -74,6 +74,7 @@ lib.b200msm_probe_imad.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
 lib.b200msm_probe_imad32.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
 lib.b200msm_probe_fqmul.argtypes = [_vp, _i, ctypes.POINTER(ctypes.c_double)]
 lib.b200msm_probe_dfma.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
+lib.b200msm_probe_dualpipe.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
 lib.b200msm_set_option.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int64]
 lib.b200msm_g1_batch_convert.argtypes = [_vp, _i, _i, _vp, _u64, _vp]
 lib.b200msm_glv_decompose_scalars.argtypes = [_vp, _i, _vp, _u64, _vp, _vp]
