@@ -163,8 +163,9 @@ int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s);
 int b200msm_probe_dfma(b200msm_ctx* ctx, double* dfma_per_s);
 /* Do the FP64 and the integer-multiply pipes overlap?  ms[0]: 256 BLS12-381 Fq multiplications per thread (IMAD.WIDE), ms[1]: 256 blocks of
  * 690 FP64 operations per thread (the instruction mix of a 48-bit-limb FP64 Montgomery multiplication), ms[2]: both in the same thread,
- * ms[3] = 256.  ms[2] ~ max(ms[0], ms[1]) means a second multiplier can run beside the first (csrc/probes.cu). */
-int b200msm_probe_dualpipe(b200msm_ctx* ctx, double ms[4]);
+ * ms[3] = 256, ms[4]: odd warps do the integer work and even warps the FP64 work (half of each).  ms[2] ~ max(ms[0], ms[1]) would mean a
+ * second multiplier can run beside the first (csrc/probes.cu). */
+int b200msm_probe_dualpipe(b200msm_ctx* ctx, double ms[5]);
 
 /* ---- tuning knobs (never change results).  key: "window_bits" (0 = auto), "accumulate" (0 = auto, 1 = serial, 2 = batch-affine),
  * "tree_rounds" (-1 = auto), "combine" (0 = serial tail on the host (default), 1 = device chain k_window_sums + k_horner). */

@@ -159,8 +159,8 @@ class Engine:
         v = ctypes.c_double(); self._ck(lib.b200msm_probe_dfma(self._ctx, ctypes.byref(v))); return v.value
 
     def probe_dualpipe(self):
-        v = (ctypes.c_double * 4)(); self._ck(lib.b200msm_probe_dualpipe(self._ctx, v))
-        return {"ms_imad_only": v[0], "ms_fp64_only": v[1], "ms_both": v[2], "mults_per_thread": int(v[3])}
+        v = (ctypes.c_double * 5)(); self._ck(lib.b200msm_probe_dualpipe(self._ctx, v))
+        return {"ms_imad_only": v[0], "ms_fp64_only": v[1], "ms_both": v[2], "mults_per_thread": int(v[3]), "ms_warp_specialised_half_each": v[4]}
 
     def probe_fqmul(self, curve):
         v = ctypes.c_double(); self._ck(lib.b200msm_probe_fqmul(self._ctx, curve, ctypes.byref(v))); return v.value

@@ -25,7 +25,7 @@ constexpr int F64_ACC = 32;            // column accumulators of the FP64 multip
 constexpr int F64_OPS = 690;           // FP64 operations per multiplication (see above)
 static_assert(21 * F64_ACC + 18 == F64_OPS, "the unrolled block below issues F64_OPS operations");
 
-template <int MODE>   // 1: integer only, 2: FP64 only, 3: both
+template <int MODE>   // 1: integer only, 2: FP64 only, 3: both in every thread, 4: odd warps integer, even warps FP64 (warp-specialised)
 __global__ void __launch_bounds__(256) k_dualpipe(uint32_t iters, const void* __restrict__ in, void* __restrict__ out, double seed) {
   using C = BLS12_381;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -35,9 +35,10 @@ __global__ void __launch_bounds__(256) k_dualpipe(uint32_t iters, const void* __
   double acc[F64_ACC], a = seed + (double)(i & 7), b = seed * 1.000001;
 #pragma unroll
   for (int k = 0; k < F64_ACC; k++) acc[k] = seed + k;
+  const bool do_int = MODE == 4 ? ((threadIdx.x >> 5) & 1) : (MODE & 1), do_f64 = MODE == 4 ? !((threadIdx.x >> 5) & 1) : (MODE & 2);
   for (uint32_t it = 0; it < iters; it++) {
-    if (MODE & 1) fe_mul<C>(y, y, x);
-    if (MODE & 2) {
+    if (do_int) fe_mul<C>(y, y, x);
+    if (do_f64) {
       // 690 operations: 21 sweeps over the 32 accumulators (alternating fma, fma, add) + 18 more
 #pragma unroll
       for (int r = 0; r < 21; r++) {
@@ -61,8 +62,9 @@ __global__ void __launch_bounds__(256) k_dualpipe(uint32_t iters, const void* __
 
 }  // namespace
 
-// out[0] = integer-only ms, out[1] = FP64-only ms, out[2] = both in one thread ms, out[3] = multiplications per thread
-extern "C" int b200msm_probe_dualpipe(b200msm_ctx* ctx, double out[4]) {
+// out[0] = integer-only ms, out[1] = FP64-only ms, out[2] = both in one thread ms, out[3] = multiplications per thread,
+// out[4] = warp-specialised ms (half of the warps do the integer work, the other half the FP64 work: half of each pipe's load)
+extern "C" int b200msm_probe_dualpipe(b200msm_ctx* ctx, double out[5]) {
   if (!ctx || !out) return B200MSM_E_ARG;
   if (cudaSetDevice(b200msm_internal_device(ctx)) != cudaSuccess) return B200MSM_E_CUDA;
   cudaStream_t s = b200msm_internal_stream(ctx);
@@ -72,18 +74,19 @@ extern "C" int b200msm_probe_dualpipe(b200msm_ctx* ctx, double out[4]) {
   if (cudaMalloc(&din, 1024 * 48) != cudaSuccess || cudaMalloc(&dout, (size_t)blocks * threads * 48) != cudaSuccess) { cudaFree(din); return B200MSM_E_NOMEM; }
   cudaMemsetAsync(din, 0x17, 1024 * 48, s);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int mode = 1; mode <= 3; mode++) {
+  for (int mode = 1; mode <= 4; mode++) {
     float best = 1e30f;
     for (int rep = 0; rep < 4; rep++) {
       cudaEventRecord(e0, s);
       if (mode == 1) k_dualpipe<1><<<blocks, threads, 0, s>>>(iters, din, dout, 1.000001);
       else if (mode == 2) k_dualpipe<2><<<blocks, threads, 0, s>>>(iters, din, dout, 1.000001);
-      else k_dualpipe<3><<<blocks, threads, 0, s>>>(iters, din, dout, 1.000001);
+      else if (mode == 3) k_dualpipe<3><<<blocks, threads, 0, s>>>(iters, din, dout, 1.000001);
+      else k_dualpipe<4><<<blocks, threads, 0, s>>>(iters, din, dout, 1.000001);
       cudaEventRecord(e1, s); cudaEventSynchronize(e1);
       float ms; cudaEventElapsedTime(&ms, e0, e1);
       if (rep && ms < best) best = ms;
     }
-    out[mode - 1] = best;
+    out[mode == 4 ? 4 : mode - 1] = best;
   }
   out[3] = iters;
   b200msm_internal_count_launches(ctx, 12);
