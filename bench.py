@@ -87,6 +87,15 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
+def _splitmix64(x):
+    """the engine's base-point stream (b200msm_g1_generate_bases): P_i = splitmix64(seed + first + i) * G"""
+    M = (1 << 64) - 1
+    x = (x + 0x9E3779B97F4A7C15) & M
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M
+    return x ^ (x >> 31)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -285,20 +294,19 @@ def run_ours(a):
         if world > 1: dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- correctness guard on a small prefix (device path vs the oracle) -- not timed
-    if rank == 0 and cid < 2:
-        import pyref, coracle
-        cv = pyref.CURVES[cname]; m = 1 << 10
-        hb = bytes(bases[: m * 2 * n8].cpu().numpy()); hs = bytes(scal[0][: m * 32].cpu().numpy())
-        got = eng.normalize(cid, eng.multiexp_affine(cid, hb, hs, 32, m))
-        assert got == coracle.normalize(cid, coracle.multiexp_affine(cid, hb, hs, 32, m)), "GPU result differs from the oracle"
-    elif rank == 0:
-        import refwasm
-        if refwasm.available(cname[:-3]):
-            m = 1 << 8
-            hb = bytes(bases[: m * 2 * n8].cpu().numpy()); hs = bytes(scal[0][: m * 32].cpu().numpy())
-            got = eng.normalize(cid, eng.multiexp_affine(cid, hb, hs, 32, m))
-            assert got == refwasm.RefG2(refwasm.RefModule(cname[:-3])).msm_affine(hb, hs, 32, m), "GPU G2 result differs from the reference"
+    # ---- correctness guard, oracle-free (the oracle is test infrastructure; in this file only the cpu_baseline leg touches it): the bases
+    # are P_i = k_i*G with a known splitmix64 stream, so  sum_i s_i*P_i = (sum_i s_i*k_i mod r)*G = t*P_0  with  t = (sum_i s_i*k_i)*k_0^-1 mod r.
+    # Left side: the full pipeline on a 2^12-point prefix; right side: a one-point MSM.  Not timed.
+    if rank == 0:
+        R_ORDER = {0: 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001, 1: 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001}[cid & 1]
+        m = 1 << 12
+        hs = bytes(scal[0][: m * 32].cpu().numpy())
+        ks = [(_splitmix64(SEED + a.log2n + first_pt + i) or 1) for i in range(m)]
+        tot = sum(int.from_bytes(hs[32 * i: 32 * i + 32], "little") * ks[i] for i in range(m)) % R_ORDER
+        t = tot * pow(ks[0], -1, R_ORDER) % R_ORDER
+        lhs = eng.normalize(cid, eng.multiexp_affine(cid, bases[: m * 2 * n8], scal[0][: m * 32], 32, m))
+        rhs = eng.normalize(cid, eng.multiexp_affine(cid, bases[: 2 * n8], t.to_bytes(32, "little"), 32, 1))
+        assert lhs == rhs and any(lhs), "GPU MSM fails the known-answer identity sum_i s_i*k_i*G"
 
     for i in range(max(3, a.warmup)): step_device(i)
     sync_all()
@@ -525,12 +533,7 @@ def run_ntt(a):
         torch.cuda.synchronize(dev)
         if world > 1: dist.barrier()
         torch.cuda.synchronize(dev)
-    if rank == 0:   # correctness guard (not timed): a 2^12 prefix against the reference module, and the round trip at full size
-        import refwasm
-        if refwasm.available(cname):
-            pb = refwasm.RefModule(cname); m = 1 << 12; hb = bytes(xs[0][: m * 32].cpu().numpy())
-            p = pb.alloc(len(hb) + 64); pb.write(p, hb); pb.frm_fft(p, m)
-            assert eng.fr_fft(cid, hb, 12) == pb.read(p, len(hb)), "GPU NTT differs from the reference's frm_fft"
+    if rank == 0:   # correctness guard (not timed, oracle-free): ifft(fft(x)) == x at full size; byte parity with frm_fft is tests/test_gpu_parity.py
         eng.fr_fft(cid, xs[0], lg, out=out); eng.fr_fft(cid, out, lg, inverse=True, out=out); torch.cuda.synchronize(dev)
         assert torch.equal(out, xs[0]), "ifft(fft(x)) != x"
     for i in range(max(3, a.warmup)): eng.fr_fft(cid, xs[i % 2], lg, out=out)
