@@ -19,4 +19,28 @@ for cname in ("bls12381", "bn128"):
     ch = eng.multiexp_affine_chunk(cv.cid, bases, sc, 32, 500, 250, 11)
     assert eng.normalize(cv.cid, ch) == coracle.normalize(cv.cid, coracle.multiexp_affine_chunk(cv.cid, bases, sc, 32, 500, 250, 11))
     c = eng.batch_convert(cv.cid, "LEMtoC", bases, 500); assert eng.batch_convert(cv.cid, "CtoLEM", c, 500) == bases
+# window table, batch, GLV, G2 and NTT entry points on small inputs
+cv = pyref.BLS12_381
+bases = make_bases(cv, 3000, 7); sc = make_scalars(3000, 8, "u256")
+exp = oracle_msm(cv, bases, sc, 32, 3000)
+for wb in (0, 8):
+    h = eng.upload_bases_windowed(cv.cid, bases, 3000, 32, wb)
+    assert eng.normalize(cv.cid, eng.multiexp_resident(h, sc, 32, 3000, cv.cid)) == exp
+    out = eng.multiexp_batch(h, sc * 3, 32, 3000, 3, cv.cid); assert eng.normalize(cv.cid, out[:144]) == exp
+    eng.free_bases(h)
+p2, s2 = eng.glv_preprocess(cv.cid, bases, sc, 3000)
+assert eng.normalize(cv.cid, eng.multiexp_affine(cv.cid, p2, s2, 32, 6000)) == exp
+import torch
+for cid, n8 in ((2, 96), (3, 64)):
+    d = torch.empty(2000 * 2 * n8, dtype=torch.uint8, device="cuda"); eng.generate_bases(cid, 11, 0, 2000, d)
+    sd = torch.randint(0, 256, (2000 * 32,), dtype=torch.uint8, device="cuda")
+    a = eng.normalize(cid, eng.multiexp_affine(cid, d, sd, 32, 2000))
+    h = eng.upload_bases_windowed(cid, d, 2000, 32, 0)
+    assert eng.normalize(cid, eng.multiexp_resident(h, sd, 32, 2000, cid)) == a
+    eng.free_bases(h)
+for cid in (0, 1):
+    for lg in (0, 1, 5, 11, 13):
+        x = torch.randint(0, 256, (32 << lg,), dtype=torch.uint8, device="cuda"); x.view(-1, 32)[:, 31] &= 0x0F
+        y = torch.empty_like(x); eng.fr_fft(cid, x, lg, out=y); eng.fr_fft(cid, y, lg, inverse=True, out=y); eng.synchronize()
+        assert torch.equal(x, y), (cid, lg)
 print("sanitizer case ok")
