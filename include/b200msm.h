@@ -79,6 +79,14 @@ int b200msm_g1_multiexp_affine(b200msm_ctx* ctx, int curve, const void* bases, c
 int b200msm_g1_multiexp_affine_chunk(b200msm_ctx* ctx, int curve, const void* bases, const void* scalars,
                                      uint32_t scalar_size, uint64_t n, uint32_t start_bit, uint32_t chunk_bits, void* out);
 
+/* ---- == g1m_multiexp(pBases, pScalars, scalarSize, n, pr) / g1m_multiexp_chunk(..., startBit, chunkSize, pr): the same two functions
+ *      over JACOBIAN bases of 3*n8 bytes each (n8b = 3*n8: src/build_curve_jacobian_a0.js:1429, src/build_multiexp.js:8-16); bases with
+ *      z == 0 are the point at infinity and contribute nothing.  Also for the G2 curve ids (== g2m_multiexp). */
+int b200msm_g1_multiexp(b200msm_ctx* ctx, int curve, const void* bases_jacobian, const void* scalars,
+                        uint32_t scalar_size, uint64_t n, void* out);
+int b200msm_g1_multiexp_chunk(b200msm_ctx* ctx, int curve, const void* bases_jacobian, const void* scalars,
+                              uint32_t scalar_size, uint64_t n, uint32_t start_bit, uint32_t chunk_bits, void* out);
+
 /* ---- resident bases: upload once (pb.alloc + pb.set of pBases in the reference rig, benchmarks/multiexp.js:16-23),
  *      then run any number of MSMs against them.  n in the MSM call may be <= the uploaded count. */
 int b200msm_upload_bases(b200msm_ctx* ctx, int curve, const void* bases, uint64_t n, uint64_t* handle);

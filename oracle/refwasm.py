@@ -190,3 +190,15 @@ class RefG2:
         if b is not None: m.write(pB, b); getattr(m, "f2m_" + fn)(pA, pB, pR)
         else: getattr(m, "f2m_" + fn)(pA, pR)
         out = m.read(pR, self.e8); m.heap_release(mark); return out
+
+
+def msm_jacobian(mod: RefModule, group: str, bases_jac: bytes, scalars: bytes, scalar_size: int, n: int, chunk=None) -> bytes:
+    """<group>_multiexp / <group>_multiexp_chunk of the reference module over JACOBIAN bases -> raw Jacobian result bytes.
+    group = "g1m" (elements of n8 bytes) or "g2m" (2*n8)."""
+    e8 = mod.n8 * (2 if group == "g2m" else 1)
+    mark = mod.heap_mark()
+    pB = mod.alloc(max(len(bases_jac), 8)); pS = mod.alloc(len(scalars) + 8); pR = mod.alloc(3 * e8)
+    mod.write(pB, bases_jac); mod.write(pS, scalars)
+    if chunk is None: getattr(mod, group + "_multiexp")(pB, pS, scalar_size, n, pR)
+    else: getattr(mod, group + "_multiexp_chunk")(pB, pS, scalar_size, n, chunk[0], chunk[1], pR)
+    out = mod.read(pR, 3 * e8); mod.heap_release(mark); return out

@@ -734,3 +734,36 @@ def test_fr_fft_large_properties(eng, cname, lg):
     Ri = pow(R, -1, cv.r)
     w0, w1, w2, w3 = [int.from_bytes(fd[i * 32:(i + 1) * 32], "little") * Ri % cv.r for i in range(4)]
     assert w0 == 1 and w2 == w1 * w1 % cv.r and w3 == w2 * w1 % cv.r and pow(w1, n, cv.r) == 1 and pow(w1, n // 2, cv.r) == cv.r - 1
+
+
+# ---------------------------------------------------------------- Jacobian bases: g1m_multiexp / g2m_multiexp (n8b = 3*n8)
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+def test_jacobian_bases_match_reference_wasm(eng, cname):
+    """b200msm_g1_multiexp[_chunk] vs the reference module's g1m_multiexp / g2m_multiexp on bases (X, Y, Z) with random Z, Z = 1 and Z = 0"""
+    if not refwasm.available(cname): pytest.skip("oracle/_ref not built")
+    cv = curve(cname); n8 = cv.n8; q = cv.q; R = cv.R; rnd = random.Random(77)
+    pb = refwasm.RefModule(cname)
+    n = 300
+    aff = make_bases(cv, n, 123)
+    jac = bytearray()
+    for i in range(n):
+        x = int.from_bytes(aff[i * 2 * n8: i * 2 * n8 + n8], "little"); y = int.from_bytes(aff[i * 2 * n8 + n8: (i + 1) * 2 * n8], "little")   # Montgomery
+        if i % 7 == 3: jac += bytes(3 * n8); continue                                             # infinity (z = 0)
+        z = 1 if i % 5 == 0 else rnd.randrange(1, q)
+        Ri = pow(R, -1, q); xs = x * Ri % q; ys = y * Ri % q
+        for c in (xs * z * z % q, ys * z * z * z % q, z): jac += (c * R % q).to_bytes(n8, "little")
+    jac = bytes(jac); sc = make_scalars(n, 124, "u256")
+    want = pb.normalize_bytes(refwasm.msm_jacobian(pb, "g1m", jac, sc, 32, n))
+    assert eng.normalize(cv.cid, eng.multiexp_jacobian(cv.cid, jac, sc, 32, n)) == pyref.canonical_bytes(cv, want)
+    for ch in ((0, 7), (100, 13), (250, 11)):
+        want = pb.normalize_bytes(refwasm.msm_jacobian(pb, "g1m", jac, sc, 32, n, ch))
+        assert eng.normalize(cv.cid, eng.multiexp_jacobian(cv.cid, jac, sc, 32, n, ch)) == pyref.canonical_bytes(cv, want), ch
+    assert eng.normalize(cv.cid, eng.multiexp_jacobian(cv.cid, b"", b"", 32, 0)) == bytes(2 * n8)
+    # G2: bases k_i * G2 with Z = 1 (and two infinities)
+    g2 = refwasm.RefG2(pb); cid2 = G2ID[cname]; e8 = 2 * n8; m = 40
+    base = _g2_bases(g2, m, 55)
+    one2 = (R % q).to_bytes(n8, "little") + bytes(n8)
+    jac2 = b"".join((bytes(3 * e8) if i in (4, 17) else base[i * 2 * e8:(i + 1) * 2 * e8] + one2) for i in range(m))
+    sc2 = make_scalars(m, 56, "u256")
+    want2 = g2.canonical_of(refwasm.msm_jacobian(pb, "g2m", jac2, sc2, 32, m))
+    assert eng.normalize(cid2, eng.multiexp_jacobian(cid2, jac2, sc2, 32, m)) == want2

@@ -15,6 +15,7 @@ N8 = {BLS12_381_G1: 48, BN254_G1: 32, BLS12_381_G2: 96, BN254_G2: 64}     # byte
 EXPORTS = [  # every symbol include/b200msm.h declares (checked by tests/test_abi.py)
     "b200msm_create", "b200msm_destroy", "b200msm_strerror", "b200msm_last_error", "b200msm_version",
     "b200msm_set_stream", "b200msm_synchronize", "b200msm_g1_multiexp_affine", "b200msm_g1_multiexp_affine_chunk",
+    "b200msm_g1_multiexp", "b200msm_g1_multiexp_chunk",
     "b200msm_upload_bases", "b200msm_free_bases", "b200msm_g1_multiexp_resident", "b200msm_g1_normalize",
     "b200msm_g1_sum", "b200msm_g1_generate_bases", "b200msm_fq_op", "b200msm_probe_imad", "b200msm_probe_imad32", "b200msm_probe_fqmul",
     "b200msm_set_option", "b200msm_constants", "b200msm_get_counter", "b200msm_g1_batch_convert",
@@ -59,6 +60,8 @@ lib.b200msm_set_stream.argtypes = [_vp, _vp]
 lib.b200msm_synchronize.argtypes = [_vp]
 lib.b200msm_g1_multiexp_affine.argtypes = [_vp, _i, _vp, _vp, _u32, _u64, _vp]
 lib.b200msm_g1_multiexp_affine_chunk.argtypes = [_vp, _i, _vp, _vp, _u32, _u64, _u32, _u32, _vp]
+lib.b200msm_g1_multiexp.argtypes = [_vp, _i, _vp, _vp, _u32, _u64, _vp]
+lib.b200msm_g1_multiexp_chunk.argtypes = [_vp, _i, _vp, _vp, _u32, _u64, _u32, _u32, _vp]
 lib.b200msm_upload_bases.argtypes = [_vp, _i, _vp, _u64, ctypes.POINTER(_u64)]
 lib.b200msm_upload_bases_windowed.argtypes = [_vp, _i, _vp, _u64, _u32, _u32, ctypes.POINTER(_u64)]
 lib.b200msm_free_bases.argtypes = [_vp, _u64]

@@ -59,6 +59,14 @@ class Engine:
         o = ctypes.create_string_buffer(3 * N8[curve])
         self._ck(lib.b200msm_g1_multiexp_affine_chunk(self._ctx, curve, pb, ps, scalar_size, n, start_bit, chunk_bits, o)); return o.raw
 
+    def multiexp_jacobian(self, curve, bases_jac, scalars, scalar_size, n, chunk=None):
+        """g1m_multiexp / g1m_multiexp_chunk: Jacobian bases (3*n8 bytes each); chunk = (start_bit, chunk_bits) or None"""
+        pb, kb = _ptr(bases_jac); ps, ks = _ptr(scalars)
+        o = ctypes.create_string_buffer(3 * N8[curve])
+        if chunk is None: self._ck(lib.b200msm_g1_multiexp(self._ctx, curve, pb, ps, scalar_size, n, o))
+        else: self._ck(lib.b200msm_g1_multiexp_chunk(self._ctx, curve, pb, ps, scalar_size, n, chunk[0], chunk[1], o))
+        return o.raw
+
     def upload_bases(self, curve, bases, n):
         pb, kb = _ptr(bases); h = ctypes.c_uint64()
         self._ck(lib.b200msm_upload_bases(self._ctx, curve, pb, n, ctypes.byref(h))); return h.value

@@ -63,7 +63,7 @@ struct b200msm_ctx {
   cudaStream_t stream = nullptr; bool own_stream = false;
   std::string err;
   int opt_window_bits = 0, opt_accumulate = 0, opt_tree_rounds = -1;
-  DevBuf bases, scalars, canon, counts, offsets, cursors, tiles, sorted, buckets, wsum, out, misc, acc_a, acc_b, acc_c, acc_d, acc_e;
+  DevBuf bases, scalars, canon, counts, offsets, cursors, tiles, sorted, buckets, wsum, out, misc, acc_a, acc_b, acc_c, acc_d, acc_e, jac_in, jac_affine;
   TreeLane lane[MAX_LANES];                                                   // batch-affine tree lanes
   int opt_lanes = 4, opt_ba_k = 0, opt_pt_k = 8, opt_persist = 592, opt_subslots = 0, opt_bwd_staged = 0, opt_probe_smem = 0;
   bool probe29 = false, probe_sqr = false; int64_t opt_group_pairs = 0;
@@ -741,7 +741,7 @@ void b200msm_destroy(b200msm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->bases, &ctx->scalars, &ctx->canon, &ctx->counts, &ctx->offsets, &ctx->cursors, &ctx->tiles, &ctx->sorted, &ctx->buckets,
-                    &ctx->wsum, &ctx->out, &ctx->misc, &ctx->acc_a, &ctx->acc_b, &ctx->acc_c, &ctx->acc_d, &ctx->acc_e}) b->release();
+                    &ctx->wsum, &ctx->out, &ctx->misc, &ctx->acc_a, &ctx->acc_b, &ctx->acc_c, &ctx->acc_d, &ctx->acc_e, &ctx->jac_in, &ctx->jac_affine}) b->release();
   for (auto& ln : ctx->lane) {
     for (DevBuf* b : {&ln.offs, &ln.tiles, &ln.bid, &ln.pa, &ln.pb, &ln.prefix, &ln.prod, &ln.lvlprefix, &ln.others, &ln.meta}) b->release();
     if (ln.done) cudaEventDestroy(ln.done);
@@ -802,6 +802,31 @@ int b200msm_g1_multiexp_affine_chunk(b200msm_ctx* ctx, int curve, const void* ba
                                      uint32_t start_bit, uint32_t chunk_bits, void* out) {
   if (ctx && (chunk_bits == 0 || chunk_bits > 32)) { ctx->err = "chunk_bits must be in [1, 32]"; return B200MSM_E_ARG; }
   return msm_entry(ctx, curve, bases, false, scalars, scalar_size, n, start_bit, chunk_bits, out, nullptr);
+}
+
+// Jacobian bases (n8b = 3*n8, build_curve_jacobian_a0.js:1429): one batched conversion to affine on the device, then the affine pipeline
+static int msm_jacobian(b200msm_ctx* ctx, int curve, const void* bases_jac, const void* scalars, uint32_t scalar_size, uint64_t n,
+                        uint32_t bit0, uint32_t nbits, void* out) {
+  if (!ctx) return B200MSM_E_ARG;
+  if (!curve_ok(curve) || !out || (n && (!bases_jac || !scalars)) || scalar_size == 0 || n >= (1ull << 31)) { ctx->err = "bad argument"; return B200MSM_E_ARG; }
+  if (n == 0) return msm_entry(ctx, curve, bases_jac, false, scalars, scalar_size, 0, bit0, nbits, out, nullptr);
+  CK(cudaSetDevice(ctx->device));
+  const size_t n8 = n8_of(curve);
+  const void* d_in; int rc = stage(ctx, bases_jac, n * 3 * n8, ctx->jac_in, &d_in); if (rc) return rc;
+  CK(ctx->jac_affine.ensure(n * 2 * n8 + 16));
+  constexpr int GROUP = 8;
+  const uint32_t g2 = (uint32_t)(((n + GROUP - 1) / GROUP + 127) / 128);
+  B200_CURVE_SWITCH(curve, k_jacobian_to_affine<C, GROUP><<<g2, 128, 0, ctx->stream>>>((const uint8_t*)d_in, (uint32_t)n, ctx->jac_affine.as<uint8_t>()))
+  CKL();
+  return msm_entry(ctx, curve, ctx->jac_affine.p, false, scalars, scalar_size, n, bit0, nbits, out, nullptr);
+}
+int b200msm_g1_multiexp(b200msm_ctx* ctx, int curve, const void* bases_jac, const void* scalars, uint32_t scalar_size, uint64_t n, void* out) {
+  return msm_jacobian(ctx, curve, bases_jac, scalars, scalar_size, n, 0, scalar_size > 32 ? 257 : 8 * scalar_size, out);
+}
+int b200msm_g1_multiexp_chunk(b200msm_ctx* ctx, int curve, const void* bases_jac, const void* scalars, uint32_t scalar_size, uint64_t n,
+                              uint32_t start_bit, uint32_t chunk_bits, void* out) {
+  if (ctx && (chunk_bits == 0 || chunk_bits > 32)) { ctx->err = "chunk_bits must be in [1, 32]"; return B200MSM_E_ARG; }
+  return msm_jacobian(ctx, curve, bases_jac, scalars, scalar_size, n, start_bit, chunk_bits, out);
 }
 
 int b200msm_upload_bases(b200msm_ctx* ctx, int curve, const void* bases, uint64_t n, uint64_t* handle) {
