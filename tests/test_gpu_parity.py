@@ -736,6 +736,22 @@ def test_fr_fft_large_properties(eng, cname, lg):
     assert w0 == 1 and w2 == w1 * w1 % cv.r and w3 == w2 * w1 % cv.r and pow(w1, n, cv.r) == 1 and pow(w1, n // 2, cv.r) == cv.r - 1
 
 
+def test_ffjavascript_style_g2_surface(eng, g2ref):
+    """b200msm.G2: curve.G2.multiExpAffine / multiExp / add / eq / zero over byte buffers"""
+    import b200msm
+    cname, ref = g2ref; cv = curve(cname); e8 = 2 * cv.n8; n = 50
+    G2 = b200msm.G2(eng, cname)
+    bases = _g2_bases(ref, n, 301); sc = make_scalars(n, 302, "u256")
+    exp = ref.msm_affine(bases, sc, 32, n)
+    r = G2.multiExpAffine(bases, sc)
+    assert len(r) == 3 * e8 and eng.normalize(G2.curve, r) == exp
+    one2 = (cv.R % cv.q).to_bytes(cv.n8, "little") + bytes(cv.n8)
+    jac = b"".join(bases[i * 2 * e8:(i + 1) * 2 * e8] + one2 for i in range(n))
+    assert eng.normalize(G2.curve, G2.multiExp(jac, sc)) == exp
+    assert G2.isZero(G2.multiExpAffine(b"", b"")) and G2.eq(G2.add(r, G2.zero()), r)
+    with pytest.raises(ValueError, match="Base size does not match"): G2.multiExpAffine(bases[:-1], sc)
+
+
 # ---------------------------------------------------------------- Jacobian bases: g1m_multiexp / g2m_multiexp (n8b = 3*n8)
 @pytest.mark.parametrize("cname", ["bls12381", "bn128"])
 def test_jacobian_bases_match_reference_wasm(eng, cname):

@@ -8,7 +8,7 @@ wasmcurves/src/build_multiexp.js:96-249 and build_curve_jacobian_a0.js:1040-1328
 This class offers the same method names, argument meaning and error behaviour over byte buffers; the slicing and the
 worker pool disappear because one engine call does the whole MSM on the GPU.
 """
-from ._lib import BLS12_381_G1, BN254_G1, N8
+from ._lib import BLS12_381_G1, BN254_G1, BLS12_381_G2, BN254_G2, N8
 
 
 class G1:
@@ -35,11 +35,10 @@ class G1:
         return self.engine.multiexp_affine(self.curve, buffBases, buffScalars, sScalar, nPoints)
 
     def multiExp(self, buffBases, buffScalars):
-        """Same with Jacobian bases (3*n8 bytes each): normalised on the GPU first (g1m_batchToAffine)."""
+        """Same with Jacobian bases (3*n8 bytes each): g1m_multiexp (converted to affine on the GPU, then the same pipeline)."""
         nPoints, sScalar = self._split(buffBases, buffScalars, 3 * self.n8)
         if nPoints == 0: return self.zero()
-        aff = self.engine.batch_convert(self.curve, "toAffine", buffBases, nPoints)
-        return self.engine.multiexp_affine(self.curve, aff, buffScalars, sScalar, nPoints)
+        return self.engine.multiexp_jacobian(self.curve, buffBases, buffScalars, sScalar, nPoints)
 
     # ---- engine_batchconvert.js
     def _conv(self, op, buff, in_sz):
@@ -65,3 +64,23 @@ class G1:
     def add(self, a, b): return self.engine.sum_points(self.curve, bytes(a) + bytes(b), 2)
     def eq(self, a, b): return self.engine.normalize(self.curve, a) == self.engine.normalize(self.curve, b)
     def isZero(self, p): return bytes(p[2 * self.n8:3 * self.n8]) == bytes(self.n8)
+
+
+class G2(G1):
+    """curve.G2 of ffjavascript: the same multiexp surface over the G2 exports (g2m_multiexpAffine / g2m_multiexp); elements are
+    Fq2 = c0 || c1, so n8 here is 96 / 64 bytes.  The wire codecs (batchLEMtoU ...) exist for G1 only in this engine."""
+
+    def __init__(self, engine, curve):
+        self.engine = engine
+        self.curve = BLS12_381_G2 if curve in ("bls12381", BLS12_381_G2) else BN254_G2
+        self.n8 = N8[self.curve]
+
+    def zero(self):
+        """g2m_zero: (0, (R mod q) + 0u, 0)"""
+        from . import constants
+        _, _, one, _, _ = constants(self.curve - 2)
+        h = self.n8 // 2
+        return bytes(self.n8) + one.to_bytes(h, "little") + bytes(h) + bytes(self.n8)
+
+    def _conv(self, op, buff, in_sz): raise NotImplementedError("point codecs are built for G1")
+    def toAffine(self, p): raise NotImplementedError("use Engine.normalize for G2")
