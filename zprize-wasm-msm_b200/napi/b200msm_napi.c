@@ -45,8 +45,9 @@ static napi_value Create(napi_env env, napi_callback_info info) {
   return ext;
 }
 
-/* shared body of g1m_multiexpAffine (chunk = 0) and g1m_multiexpAffine_chunk (chunk = 1) */
-static napi_value Multiexp(napi_env env, napi_callback_info info, int chunk) {
+/* shared body of g1m_/g2m_ multiexpAffine[_chunk] and multiexp[_chunk]: chunk = per-window form, g2 = G2 exports (Fq2 elements),
+ * jac = Jacobian bases (3 elements per point instead of 2) */
+static napi_value Multiexp(napi_env env, napi_callback_info info, int chunk, int g2, int jac) {
   size_t argc = 8; napi_value argv[8];
   NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
   if (argc < (size_t)(chunk ? 8 : 6)) { napi_throw_type_error(env, NULL, "too few arguments"); return NULL; }
@@ -58,16 +59,43 @@ static napi_value Multiexp(napi_env env, napi_callback_info info, int chunk) {
   NAPI_CALL(env, napi_get_value_uint32(env, argv[4], &ssz));
   NAPI_CALL(env, napi_get_value_int64(env, argv[5], &n));
   if (chunk) { NAPI_CALL(env, napi_get_value_uint32(env, argv[6], &start)); NAPI_CALL(env, napi_get_value_uint32(env, argv[7], &bits)); }
-  const size_t n8 = curve == B200MSM_BLS12_381_G1 ? 48 : 32;
-  if (n < 0 || nb < (size_t)n * 2 * n8 || ns < (size_t)n * ssz) { napi_throw_range_error(env, NULL, "buffers shorter than n points / scalars"); return NULL; }
+  const size_t n8 = (curve == B200MSM_BLS12_381_G1 ? 48 : 32) * (g2 ? 2 : 1);      /* bytes per coordinate-field element */
+  const int cid = curve + (g2 ? 2 : 0);                                            /* B200MSM_*_G2 = G1 id + 2 */
+  if (n < 0 || nb < (size_t)n * (jac ? 3 : 2) * n8 || ns < (size_t)n * ssz) { napi_throw_range_error(env, NULL, "buffers shorter than n points / scalars"); return NULL; }
   void* out; napi_value res; NAPI_CALL(env, napi_create_buffer(env, 3 * n8, &out, &res));
-  int rc = chunk ? b200msm_g1_multiexp_affine_chunk(ctx, curve, bases, scalars, ssz, (uint64_t)n, start, bits, out)
-                 : b200msm_g1_multiexp_affine(ctx, curve, bases, scalars, ssz, (uint64_t)n, out);
+  int rc;
+  if (jac) rc = chunk ? b200msm_g1_multiexp_chunk(ctx, cid, bases, scalars, ssz, (uint64_t)n, start, bits, out)
+                      : b200msm_g1_multiexp(ctx, cid, bases, scalars, ssz, (uint64_t)n, out);
+  else rc = chunk ? b200msm_g1_multiexp_affine_chunk(ctx, cid, bases, scalars, ssz, (uint64_t)n, start, bits, out)
+                  : b200msm_g1_multiexp_affine(ctx, cid, bases, scalars, ssz, (uint64_t)n, out);
   if (rc) return throw_status(env, ctx, rc);
   return res;
 }
-static napi_value MultiexpAffine(napi_env env, napi_callback_info info) { return Multiexp(env, info, 0); }
-static napi_value MultiexpAffineChunk(napi_env env, napi_callback_info info) { return Multiexp(env, info, 1); }
+static napi_value MultiexpAffine(napi_env env, napi_callback_info info) { return Multiexp(env, info, 0, 0, 0); }
+static napi_value MultiexpAffineChunk(napi_env env, napi_callback_info info) { return Multiexp(env, info, 1, 0, 0); }
+static napi_value MultiexpJac(napi_env env, napi_callback_info info) { return Multiexp(env, info, 0, 0, 1); }
+static napi_value MultiexpJacChunk(napi_env env, napi_callback_info info) { return Multiexp(env, info, 1, 0, 1); }
+static napi_value G2MultiexpAffine(napi_env env, napi_callback_info info) { return Multiexp(env, info, 0, 1, 0); }
+static napi_value G2MultiexpAffineChunk(napi_env env, napi_callback_info info) { return Multiexp(env, info, 1, 1, 0); }
+static napi_value G2MultiexpJac(napi_env env, napi_callback_info info) { return Multiexp(env, info, 0, 1, 1); }
+
+/* frm_fft(ctx, curve, buffer) / frm_ifft: n = buffer length / 32 must be a power of two; returns a new Buffer */
+static napi_value FrFft(napi_env env, napi_callback_info info, int inverse) {
+  size_t argc = 3; napi_value argv[3];
+  NAPI_CALL(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+  if (argc < 3) { napi_throw_type_error(env, NULL, "too few arguments"); return NULL; }
+  b200msm_ctx* ctx; NAPI_CALL(env, napi_get_value_external(env, argv[0], (void**)&ctx));
+  int curve = curve_of(env, argv[1]); if (curve < 0) { napi_throw_type_error(env, NULL, "bad curve"); return NULL; }
+  void* in; size_t len; NAPI_CALL(env, napi_get_buffer_info(env, argv[2], &in, &len));
+  size_t n = len / 32; uint32_t lg = 0; while (((size_t)1 << lg) < n) lg++;
+  if (n == 0 || len != n * 32 || ((size_t)1 << lg) != n) { napi_throw_range_error(env, NULL, "buffer must hold a power-of-two number of 32-byte elements"); return NULL; }
+  void* out; napi_value res; NAPI_CALL(env, napi_create_buffer(env, len, &out, &res));
+  int rc = b200msm_fr_fft(ctx, curve, in, lg, inverse, out);
+  if (rc) return throw_status(env, ctx, rc);
+  return res;
+}
+static napi_value FrmFft(napi_env env, napi_callback_info info) { return FrFft(env, info, 0); }
+static napi_value FrmIfft(napi_env env, napi_callback_info info) { return FrFft(env, info, 1); }
 
 static napi_value Normalize(napi_env env, napi_callback_info info) {
   size_t argc = 3; napi_value argv[3];
@@ -89,6 +117,13 @@ static napi_value Init(napi_env env, napi_value exports) {
     {"g1m_multiexpAffine", NULL, MultiexpAffine, NULL, NULL, NULL, napi_default, NULL},
     {"g1m_multiexpAffine_chunk", NULL, MultiexpAffineChunk, NULL, NULL, NULL, napi_default, NULL},
     {"g1m_normalize", NULL, Normalize, NULL, NULL, NULL, napi_default, NULL},
+    {"g1m_multiexp", NULL, MultiexpJac, NULL, NULL, NULL, napi_default, NULL},
+    {"g1m_multiexp_chunk", NULL, MultiexpJacChunk, NULL, NULL, NULL, napi_default, NULL},
+    {"g2m_multiexpAffine", NULL, G2MultiexpAffine, NULL, NULL, NULL, napi_default, NULL},
+    {"g2m_multiexpAffine_chunk", NULL, G2MultiexpAffineChunk, NULL, NULL, NULL, napi_default, NULL},
+    {"g2m_multiexp", NULL, G2MultiexpJac, NULL, NULL, NULL, napi_default, NULL},
+    {"frm_fft", NULL, FrmFft, NULL, NULL, NULL, napi_default, NULL},
+    {"frm_ifft", NULL, FrmIfft, NULL, NULL, NULL, napi_default, NULL},
   };
   napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
   return exports;
