@@ -783,3 +783,44 @@ def test_jacobian_bases_match_reference_wasm(eng, cname):
     sc2 = make_scalars(m, 56, "u256")
     want2 = g2.canonical_of(refwasm.msm_jacobian(pb, "g2m", jac2, sc2, 32, m))
     assert eng.normalize(cid2, eng.multiexp_jacobian(cid2, jac2, sc2, 32, m)) == want2
+
+
+# ---------------------------------------------------------------- the reference's own test bodies through the Protoboard mirror
+def test_reference_fft_and_glv_tests_through_protoboard(eng):
+    """test/fft.js:14-33 ("fft / ifft of N values gives the values back") and test/glv.js:50-65, 103-192 written against
+    b200msm.Protoboard exactly as the reference writes them against its WASM protoboard."""
+    import b200msm
+    pb = b200msm.Protoboard("bls12381", engine=eng)
+    n8r = 32; n8q = 48
+    # --- test/fft.js: N = 1024 values i+1 in Montgomery form, fft then ifft, compare
+    N = 1024
+    p = pb.alloc(n8r * N)
+    r = pyref.BLS12_381.r; R = 1 << 256
+    for i in range(N): pb.set(p + i * n8r, (i + 1) * R % r, n8r)           # frm_toMontgomery(i + 1)
+    before = pb.read(p, n8r * N)
+    pb.frm_fft(p, N)
+    assert pb.read(p, n8r * N) != before
+    pb.frm_ifft(p, N)
+    assert pb.read(p, n8r * N) == before
+    # --- test/glv.js:50-65
+    v = GLV_KAT["decomposeScalar is correct."]["values"]
+    pScalar = pb.alloc(32); pb.set(pScalar, int(v["scalar"], 16), 32)
+    pScalarRes = pb.alloc(64)
+    sign = pb.g1m_glv_decomposeScalar(pScalar, pScalarRes)
+    assert pb.get(pScalarRes, 2, 32) == [int(x, 16) for x in v["expectedOutput"]] and sign == 1
+    # --- test/glv.js:103-192
+    v = GLV_KAT["preprocessEndomorphism is correct."]["values"]
+    numPoints = int(v["numPoints"], 16)
+    pPoints = pb.alloc(numPoints * n8q * 2); pScalars = pb.alloc(numPoints * n8r)
+    pPre = pb.alloc(numPoints * n8q * 4); pPreS = pb.alloc(numPoints * n8r * 2); pRes = pb.alloc(n8q * 3); pExp = pb.alloc(n8q * 3)
+    for i in range(numPoints):
+        pb.set(pPoints + 96 * i, int(v["inputPoints"][2 * i], 16), 48); pb.set(pPoints + 96 * i + 48, int(v["inputPoints"][2 * i + 1], 16), 48)
+        pb.f1m_toMontgomery(pPoints + 96 * i, pPoints + 96 * i); pb.f1m_toMontgomery(pPoints + 96 * i + 48, pPoints + 96 * i + 48)
+        pb.set(pScalars + n8r * i, int(v["inputScalars"][i], 16), n8r)
+    pb.g1m_glv_preprocessEndomorphism(pPoints, pScalars, numPoints, pPre, pPreS)
+    pb.g1m_multiexp_multiExp(pPre, pPreS, numPoints * 2, pRes)
+    pb.g1m_normalize(pRes, pRes)
+    assert pb.get(pPreS, numPoints * 2, n8r) == [int(x, 16) for x in v["expectedScalarOutput"][: 2 * numPoints]]
+    pb.g1m_multiexpAffine(pPoints, pScalars, n8r, numPoints, pExp)
+    pb.g1m_normalize(pExp, pExp)
+    assert pb.get(pRes, 2, 48) == pb.get(pExp, 2, 48)

@@ -69,6 +69,40 @@ class Protoboard:
 
     g1m_multiexpAffine_multiExp = g1m_multiexp_multiExp
 
+    # ---- Jacobian bases (n8b = 3*n8, build_curve_jacobian_a0.js:1429) and the G2 exports (Fq2 elements of 2*n8 bytes)
+    def g1m_multiexp(self, pBases, pScalars, scalarSize, n, pr):
+        self.write(pr, self.engine.multiexp_jacobian(self.curve, self.read(pBases, n * 3 * self.n8), self.read(pScalars, n * scalarSize), scalarSize, n))
+
+    def g1m_multiexp_chunk(self, pBases, pScalars, scalarSize, n, startBit, chunkSize, pr):
+        self.write(pr, self.engine.multiexp_jacobian(self.curve, self.read(pBases, n * 3 * self.n8), self.read(pScalars, n * scalarSize), scalarSize, n, (startBit, chunkSize)))
+
+    def g2m_multiexpAffine(self, pBases, pScalars, scalarSize, n, pr):
+        self.engine.multiexp_affine(self.curve + 2, self._p(pBases), self._p(pScalars), scalarSize, n, out=self._p(pr))
+
+    def g2m_multiexpAffine_chunk(self, pBases, pScalars, scalarSize, n, startBit, chunkSize, pr):
+        self.write(pr, self.engine.multiexp_affine_chunk(self.curve + 2, self._p(pBases), self._p(pScalars), scalarSize, n, startBit, chunkSize))
+
+    def g2m_multiexp(self, pBases, pScalars, scalarSize, n, pr):
+        self.write(pr, self.engine.multiexp_jacobian(self.curve + 2, self.read(pBases, n * 6 * self.n8), self.read(pScalars, n * scalarSize), scalarSize, n))
+
+    # ---- Fr transforms (wasmcurves/src/build_fft.js:178-245): in place on n Montgomery elements of 32 bytes
+    def frm_fft(self, px, n): self._fft(px, n, False)
+    def frm_ifft(self, px, n): self._fft(px, n, True)
+
+    def _fft(self, px, n, inverse):
+        lg = n.bit_length() - 1
+        if n <= 0 or (1 << lg) != n: raise B200MsmError(-1, "frm_fft: n must be a power of two")
+        self.engine.fr_fft(self.curve, self._p(px), lg, inverse=inverse, out=self._p(px))
+
+    # ---- GLV pre-pass (wasmcurves/src/build_glv.js:53-146, 178-263; BLS12-381 only, like the reference)
+    def g1m_glv_decomposeScalar(self, pScalar, pScalarRes):
+        out, signs = self.engine.glv_decompose_scalars(self.curve, self.read(pScalar, 32), 1)
+        self.write(pScalarRes, out); return signs[0]
+
+    def g1m_glv_preprocessEndomorphism(self, pPoints, pScalars, numPoints, pPointsRes, pScalarsRes):
+        pts, scs = self.engine.glv_preprocess(self.curve, self.read(pPoints, numPoints * 2 * self.n8), self.read(pScalars, numPoints * 32), numPoints)
+        self.write(pPointsRes, pts); self.write(pScalarsRes, scs)
+
     # ---- batch conversions / codecs (wasmcurves/src/build_curve_jacobian_a0.js:1040-1328,1413-1418): (pIn, n, pOut)
     def _batch(self, op, pIn, n, pOut, in_sz, out_sz):
         self.write(pOut, self.engine.batch_convert(self.curve, op, self.read(pIn, n * in_sz), n))
