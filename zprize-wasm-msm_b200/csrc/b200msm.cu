@@ -155,6 +155,11 @@ template <class B> struct HostField<Fq2<B>> {
 uint32_t auto_window_bits(uint64_t n, uint32_t nbits) {
   uint32_t lg = 0; while ((2ull << lg) <= n) lg++;          // floor(log2 n)
   int c = (int)lg - 4;
+  // Small problems skip the batch-affine tree (see accumulate_batch_affine): every round costs a latency-bound inversion tail (~0.2 ms),
+  // more than the whole XYZZ accumulation of 2^14 points.  Without the tree a bucket is one thread's serial chain, so the window is chosen
+  // for ~4 points per bucket.  Measured (BLS12-381, tree / no tree): 2^10 1.24 / 0.74 ms, 2^12 1.19 / 0.79, 2^14 1.41 / 1.01, 2^16 1.70 / 1.55 (one round).
+  if (lg <= 13) c = std::min(12, std::max(8, (int)lg + 1));
+  else if (lg <= 16) c = 13;
   if (c > 16 && n < (1ull << 22)) c = 16;
   if (c > 20) c = 20;
   if (c < 2) c = 2;
@@ -188,11 +193,12 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
   else {
     // full tree: until the largest segment is <= 3 points.  Every round ends in a latency-bound tail (product tree + one
     // inversion, ~0.2 ms), so small problems stop earlier and let k_accum_finish sum up to 16 leftover points per bucket
-    // serially (measured optimum: 2 rounds up to 2^16 pairs-per-window-scale inputs, 3 up to 2^18, 4 up to 2^19).
+    // serially (measured optimum: no round below 2^16 points, one at 2^16, 3 up to 2^18, 4 up to 2^19); buckets above 16 points still get
+    // their rounds (need16), so skewed inputs keep the parallel tree.
     uint32_t full = 0, need16 = 0, mc = maxcnt;
     while (mc > 3) { if (mc > 16) need16++; mc = (mc + 1) >> 1; full++; }
     const uint64_t npts = ctx->cur_n;
-    const uint32_t pref = npts <= (1u << 16) ? 2u : npts <= (1u << 18) ? 3u : npts <= (1u << 19) ? 4u : 99u;
+    const uint32_t pref = npts < (1u << 16) ? 0u : npts < (1u << 17) ? 1u : npts <= (1u << 18) ? 3u : npts <= (1u << 19) ? 4u : 99u;
     R = std::min(full, std::max(pref, need16));
   }
   if (m0 < 2) R = 0;
