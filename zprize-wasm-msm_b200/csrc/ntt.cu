@@ -60,10 +60,25 @@ __global__ void __launch_bounds__(256) k_ntt_bitrev(const void* __restrict__ in,
   fe_store<F>(reinterpret_cast<char*>(out) + (size_t)i * 4 * F::N, v);
 }
 // stages 1 .. K (K = min(log2n, 10)) of every tile of 2^K consecutive elements, in shared memory (limb-major: conflict-free)
+// two consecutive radix-2 stages s and s + 1 on the four elements i0, i0 + h, i0 + 2h, i0 + 3h of one block of 4h (h = 2^(s-1), j = i0 mod h)
+template <class F>
+__device__ __forceinline__ void butterfly4(Fe<F::N>& a0, Fe<F::N>& a1, Fe<F::N>& a2, Fe<F::N>& a3, const char* __restrict__ tw, uint32_t log2n, uint32_t s, uint32_t j, uint32_t h) {
+  Fe<F::N> w, t;
+  // stage s: pairs (a0, a1) and (a2, a3), both with twiddle w_(2^s)^j
+  fe_load<F>(w, tw + ((size_t)j << (log2n - s)) * 4 * F::N);
+  fe_mul<F>(t, a1, w); fe_sub<F>(a1, a0, t); fe_add<F>(a0, a0, t);
+  fe_mul<F>(t, a3, w); fe_sub<F>(a3, a2, t); fe_add<F>(a2, a2, t);
+  // stage s + 1: pairs (a0, a2) with w_(2^(s+1))^j and (a1, a3) with w_(2^(s+1))^(j + h)
+  fe_load<F>(w, tw + ((size_t)j << (log2n - s - 1)) * 4 * F::N);
+  fe_mul<F>(t, a2, w); fe_sub<F>(a2, a0, t); fe_add<F>(a0, a0, t);
+  fe_load<F>(w, tw + ((size_t)(j + h) << (log2n - s - 1)) * 4 * F::N);
+  fe_mul<F>(t, a3, w); fe_sub<F>(a3, a1, t); fe_add<F>(a1, a1, t);
+}
+
 // The tile reads its inputs straight from their bit-reversed positions (__reversePermutation fused into the load: element i of tile b
 // is in[bitrev(b*T + i)], a gather of whole 32-byte sectors), so the permuted array is never written out and read back.
 template <class F>
-__global__ void __launch_bounds__(TILE / 2) k_ntt_tile(const void* __restrict__ in, void* __restrict__ x, const void* __restrict__ W, uint32_t log2n, uint32_t K) {
+__global__ void __launch_bounds__(TILE / 4) k_ntt_tile(const void* __restrict__ in, void* __restrict__ x, const void* __restrict__ W, uint32_t log2n, uint32_t K) {
   __shared__ uint32_t sm[F::N][TILE];
   const uint32_t T = 1u << K, half_threads = T >> 1;
   char* base = reinterpret_cast<char*>(x) + (size_t)blockIdx.x * T * 4 * F::N;
@@ -74,17 +89,30 @@ __global__ void __launch_bounds__(TILE / 2) k_ntt_tile(const void* __restrict__ 
     for (int k = 0; k < F::N; k++) sm[k][i] = v.l[k];
   }
   __syncthreads();
-  for (uint32_t s = 1; s <= K; s++) {
-    const uint32_t half = 1u << (s - 1);
+  uint32_t s = 1;
+  if (K & 1) {                                   // odd number of stages: stage 1 alone (all its twiddles are 1)
     for (uint32_t b = threadIdx.x; b < half_threads; b += blockDim.x) {
-      const uint32_t j = b & (half - 1), i1 = ((b >> (s - 1)) << s) + j, i2 = i1 + half;
-      Fe<F::N> u, v, w, t;
+      const uint32_t i1 = 2 * b, i2 = i1 + 1;
+      Fe<F::N> u, v, w;
 #pragma unroll
       for (int k = 0; k < F::N; k++) { u.l[k] = sm[k][i1]; v.l[k] = sm[k][i2]; }
-      if (j) { fe_load<F>(w, reinterpret_cast<const char*>(W) + ((size_t)j << (log2n - s)) * 4 * F::N); fe_mul<F>(t, v, w); } else t = v;
-      fe_add<F>(v, u, t); fe_sub<F>(w, u, t);
+      fe_add<F>(w, u, v); fe_sub<F>(v, u, v);
 #pragma unroll
-      for (int k = 0; k < F::N; k++) { sm[k][i1] = v.l[k]; sm[k][i2] = w.l[k]; }
+      for (int k = 0; k < F::N; k++) { sm[k][i1] = w.l[k]; sm[k][i2] = v.l[k]; }
+    }
+    __syncthreads();
+    s = 2;
+  }
+  for (; s + 1 <= K; s += 2) {                   // two stages per barrier: each thread owns the four elements of a radix-4 butterfly
+    const uint32_t h = 1u << (s - 1);
+    for (uint32_t b = threadIdx.x; b < (T >> 2); b += blockDim.x) {
+      const uint32_t j = b & (h - 1), i0 = ((b >> (s - 1)) << (s + 1)) + j;
+      Fe<F::N> a0, a1, a2, a3;
+#pragma unroll
+      for (int k = 0; k < F::N; k++) { a0.l[k] = sm[k][i0]; a1.l[k] = sm[k][i0 + h]; a2.l[k] = sm[k][i0 + 2 * h]; a3.l[k] = sm[k][i0 + 3 * h]; }
+      butterfly4<F>(a0, a1, a2, a3, reinterpret_cast<const char*>(W), log2n, s, j, h);
+#pragma unroll
+      for (int k = 0; k < F::N; k++) { sm[k][i0] = a0.l[k]; sm[k][i0 + h] = a1.l[k]; sm[k][i0 + 2 * h] = a2.l[k]; sm[k][i0 + 3 * h] = a3.l[k]; }
     }
     __syncthreads();
   }
@@ -117,18 +145,10 @@ __global__ void __launch_bounds__(256) k_ntt_stage4(void* __restrict__ x, const 
   const uint32_t h = 1u << (s - 1), j = b & (h - 1), i0 = ((b >> (s - 1)) << (s + 1)) + j;
   char* p = reinterpret_cast<char*>(x);
   const char* tw = reinterpret_cast<const char*>(W);
-  Fe<F::N> a0, a1, a2, a3, w, t;
+  Fe<F::N> a0, a1, a2, a3;
   fe_load_cg<F>(a0, p + (size_t)i0 * 4 * F::N); fe_load_cg<F>(a1, p + (size_t)(i0 + h) * 4 * F::N);
   fe_load_cg<F>(a2, p + (size_t)(i0 + 2 * h) * 4 * F::N); fe_load_cg<F>(a3, p + (size_t)(i0 + 3 * h) * 4 * F::N);
-  // stage s: pairs (a0, a1) and (a2, a3), both with twiddle w_(2^s)^j
-  fe_load<F>(w, tw + ((size_t)j << (log2n - s)) * 4 * F::N);
-  fe_mul<F>(t, a1, w); fe_sub<F>(a1, a0, t); fe_add<F>(a0, a0, t);
-  fe_mul<F>(t, a3, w); fe_sub<F>(a3, a2, t); fe_add<F>(a2, a2, t);
-  // stage s + 1: pairs (a0, a2) with w_(2^(s+1))^j and (a1, a3) with w_(2^(s+1))^(j + h)
-  fe_load<F>(w, tw + ((size_t)j << (log2n - s - 1)) * 4 * F::N);
-  fe_mul<F>(t, a2, w); fe_sub<F>(a2, a0, t); fe_add<F>(a0, a0, t);
-  fe_load<F>(w, tw + ((size_t)(j + h) << (log2n - s - 1)) * 4 * F::N);
-  fe_mul<F>(t, a3, w); fe_sub<F>(a3, a1, t); fe_add<F>(a1, a1, t);
+  butterfly4<F>(a0, a1, a2, a3, tw, log2n, s, j, h);
   fe_store<F>(p + (size_t)i0 * 4 * F::N, a0); fe_store<F>(p + (size_t)(i0 + h) * 4 * F::N, a1);
   fe_store<F>(p + (size_t)(i0 + 2 * h) * 4 * F::N, a2); fe_store<F>(p + (size_t)(i0 + 3 * h) * 4 * F::N, a3);
 }
@@ -199,7 +219,7 @@ int run_ntt(b200msm_ctx* ctx, NttState& st, int ci, const void* in, uint32_t L, 
   const uint32_t K = L < (uint32_t)TILE_LOG ? L : (uint32_t)TILE_LOG;
   if (K == 0) { k_ntt_bitrev<F><<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(d_in, d_x, L); launches++; }      // n == 1: plain copy
   NCK(cudaEventRecord(st.ev[1], s));
-  if (K >= 1) { k_ntt_tile<F><<<(uint32_t)(n >> K), TILE / 2, 0, s>>>(d_in, d_x, st.W[ci], L, K); launches++; }
+  if (K >= 1) { k_ntt_tile<F><<<(uint32_t)(n >> K), TILE / 4, 0, s>>>(d_in, d_x, st.W[ci], L, K); launches++; }
   NCK(cudaEventRecord(st.ev[2], s));
   uint32_t sg = K + 1; st.last_passes4 = st.last_passes2 = 0;
   for (; sg + 1 <= L; sg += 2) { k_ntt_stage4<F><<<(uint32_t)((n / 4 + 255) / 256), 256, 0, s>>>(d_x, st.W[ci], L, sg); launches++; st.last_passes4++; }
