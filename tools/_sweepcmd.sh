@@ -1,7 +1,5 @@
-for cfg in "lanes=1" "lanes=2" "lanes=4"; do
-  args=""; for kv in $cfg; do args="$args --opt $kv"; done
-  echo "== $cfg"; python tools/sweep.py --sizes 10,12,13,14,15,16 --reps 20 $args 2>&1 | tail -6 | python -c "
+python -m pytest tests -m gpu -x -q -k "window_table or batch or g2_edge or g2_full" 2>&1 | tail -2
+python tools/sweep.py --sizes 8,10,12,14,16,17,18,20 --reps 10 --windowed 0 2>&1 | tail -8 | python -c "
 import sys, json
 for l in sys.stdin:
-    d = json.loads(l); print({k: d[k] for k in ('log2n','ms','rounds')})"
-done
+    d = json.loads(l); print({k: d[k] for k in ('log2n','ms','c','W','rounds')})"
