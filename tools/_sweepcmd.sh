@@ -1,5 +1,4 @@
-python -m pytest tests -m gpu -x -q -k "window_table or batch or g2_edge or g2_full" 2>&1 | tail -2
-python tools/sweep.py --sizes 8,10,12,14,16,17,18,20 --reps 10 --windowed 0 2>&1 | tail -8 | python -c "
-import sys, json
-for l in sys.stdin:
-    d = json.loads(l); print({k: d[k] for k in ('log2n','ms','c','W','rounds')})"
+for cv in bls12381 bn128; do
+  python tools/sweep.py --curve $cv --sizes 10,12,14,16,18,20,22,24,26 --reps 3 --roofline 2>&1 | grep '^{' 
+  python tools/sweep.py --curve $cv --sizes 10,12,14,16,18,20,22,24 --reps 3 --roofline --windowed 0 2>&1 | grep '^{'
+done
