@@ -10,7 +10,10 @@ A "step" is one complete MSM (g1m_multiexpAffine semantics) over one batch of sy
 `value`  = points of the whole job / second with bases and scalars already resident in HBM (device pointers through the
            C ABI, result left on the device);  `e2e` = the same through b200msm_g1_multiexp_affine with pinned HOST
            buffers for bases, scalars and result (H2D and D2H inside the timed region).
-`--impl reference` times the reference's own WASM MSM (compiled natively, oracle/_ref) on the host cores.
+`--impl reference` times the reference's own WASM MSM (compiled natively, oracle/_ref) on the host cores, on the SAME workload
+(one MSM of 2^log2n points per step, one WASM instance per host core; jobs above 2^20 points are sampled at 2^20 points per step and say so).
+With N > 1 the line also carries `strong_2p24` (BASELINE config 4: one MSM of 2^24 points on 1 and on N GPUs, both results checked) and
+`abi_multi` (the same workload through ONE multi-device context, b200msm_create_multi, driven by rank 0).
 Prints ONE JSON line (rank 0).
 """
 import argparse, json, os, subprocess, sys, threading, time
@@ -42,7 +45,11 @@ def parse():
     ap.add_argument("--log2n-total", type=int, default=0, help="strong scaling: total points 2^K split over the GPUs (overrides --log2n)")
     ap.add_argument("--curve", default="bls12381", choices=["bls12381", "bn128", "bls12381_g2", "bn128_g2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-log2n", type=int, default=16, help="points per reference step (bounded sample)")
+    ap.add_argument("--ref-log2n", type=int, default=0, help="points per reference step (0 = the workload itself, bounded at 2^20 points per step)")
+    ap.add_argument("--ref-budget-s", type=float, default=200.0, help="wall-clock cap of the reference arm's timed run (steps are clamped to fit, and the clamp is reported)")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling block (one MSM of 2^--strong-log2n points on 1 and on N GPUs)")
+    ap.add_argument("--strong-log2n", type=int, default=24)
+    ap.add_argument("--no-abi-multi", action="store_true", help="N > 1: skip the measurement of the same workload through ONE multi-device context (b200msm_create_multi) on rank 0")
     ap.add_argument("--workload", default="single", choices=["single", "batched", "ntt"],
                     help="single: one MSM of 2^log2n points per GPU per step (default, the headline); batched: BASELINE config 5, --batch independent MSMs of 2^log2n points (default 2^18) spread over the GPUs per step")
     ap.add_argument("--batch", type=int, default=64)
@@ -106,39 +113,82 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# ------------------------------------------------------------------------------------------------ workload description shared by both arms
+def workload_config(cname, log2n_per_gpu, world, strong_total=0):
+    """`config` of the JSON line: identical for `--impl ours` and `--impl reference` on the same flags"""
+    n = (1 << strong_total) // world if strong_total else 1 << log2n_per_gpu
+    total = (1 << strong_total) if strong_total else n * world
+    n8 = {"bls12381": 48, "bn128": 32, "bls12381_g2": 96, "bn128_g2": 64}[cname]
+    return {"workload": "%s MSM (g1m_multiexpAffine semantics), %d points per GPU, one MSM of %d points per step, uniform 256-bit scalars, bases P_i = k_i*G"
+                        % (CURVE_LABEL[cname], n, total),
+            "curve": cname, "log2n_per_gpu": log2n_per_gpu, "points_per_step": total,
+            "cache": "no cache flush: the per-step working set (bases %d MiB + scalars %d MiB per GPU, plus sort/tree scratch > 1 GiB) exceeds the 126 MB L2 (and any host cache); 2 scalar sets alternate"
+                     % (n * 2 * n8 >> 20, n * 32 >> 20)}
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
-def _ref_worker(args):
-    cname, bases, scalars, n = args
-    import refwasm
-    pb = refwasm.RefModule(cname)
-    return pb.msm_affine_raw(bases, scalars, 32, n)
+def _ref_proc(conn, cname, seed, lo, cnt):
+    """One host process = one instance of the reference's WASM module (as one ffjavascript worker) owning the point range [lo, lo + cnt):
+    bases P_i = splitmix64(seed + i) * G generated once, two scalar sets; every command runs g1m_multiexpAffine on the slice."""
+    try:
+        import numpy as np
+        import pyref, coracle, refwasm
+        cv = pyref.CURVES[cname]
+        bases = coracle.generate_bases(cv.cid, pyref.affine_to_bytes(cv, cv.G), seed, lo, cnt)
+        sets = [np.random.default_rng([seed & 0xffffffff, lo, k]).integers(0, 256, size=cnt * 32, dtype=np.uint8).tobytes() for k in range(2)]
+        pb = refwasm.RefModule(cname)
+        conn.send(("ready", cnt))
+        while True:
+            cmd = conn.recv()
+            if cmd is None: break
+            conn.send(pb.msm_affine_raw(bases, sets[cmd % 2], 32, cnt))
+    except Exception as ex:      # surfaced by the parent
+        conn.send(("error", repr(ex)))
 
 
-def reference_msm_parallel(pool, cname, bases, scalars, n, nproc, n8):
-    """One MSM of n points on nproc host processes: point-range slices, each through the reference's own
-    g1m_multiexpAffine (one WASM instance per worker, as ffjavascript's worker pool does), partials summed with g1m_add."""
-    import refwasm
-    per = (n + nproc - 1) // nproc
-    jobs = []
-    for k in range(nproc):
-        lo, hi = k * per, min(n, (k + 1) * per)
-        if lo >= hi: break
-        jobs.append((cname, bases[lo * 2 * n8: hi * 2 * n8], scalars[lo * 32: hi * 32], hi - lo))
-    parts = pool.map(_ref_worker, jobs)
-    pb = reference_msm_parallel._pb.get(cname)
-    if pb is None:
-        pb = reference_msm_parallel._pb[cname] = refwasm.RefModule(cname)
-    mark = pb.heap_mark()
-    pacc = pb.alloc(3 * n8); pt = pb.alloc(3 * n8)
-    pb.write(pacc, parts[0])
-    for part in parts[1:]:
-        pb.write(pt, part); pb.g1m_add(pacc, pt, pacc)
-    out = pb.normalize_read(pacc)
-    pb.heap_release(mark)
-    return out
+class ReferencePool:
+    """n points over `procs` host processes, point-range slices, partial results added with the reference's own g1m_add"""
+    def __init__(self, cname, n, procs, seed):
+        import multiprocessing as mp
+        import refwasm
+        ctx = mp.get_context("fork")
+        self.cname = cname; self.n = n; self.workers = []
+        per = (n + procs - 1) // procs
+        for k in range(procs):
+            lo, hi = k * per, min(n, (k + 1) * per)
+            if lo >= hi: break
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_ref_proc, args=(b, cname, seed, lo, hi - lo), daemon=True); p.start()
+            self.workers.append((p, a))
+        for p, c in self.workers:
+            msg = c.recv()
+            if msg[0] != "ready": raise RuntimeError("reference worker failed: %r" % (msg,))
+        self.pb = refwasm.RefModule(cname); self.n8 = self.pb.n8
+
+    def step(self, i):
+        for p, c in self.workers: c.send(i)
+        parts = [c.recv() for p, c in self.workers]
+        for part in parts:
+            if isinstance(part, tuple): raise RuntimeError("reference worker failed: %r" % (part,))
+        pb = self.pb; n8 = self.n8
+        mark = pb.heap_mark()
+        pacc = pb.alloc(3 * n8); pt = pb.alloc(3 * n8)
+        pb.write(pacc, parts[0])
+        for part in parts[1:]:
+            pb.write(pt, part); pb.g1m_add(pacc, pt, pacc)
+        out = pb.normalize_read(pacc)
+        pb.heap_release(mark)
+        return out
+
+    def close(self):
+        for p, c in self.workers:
+            try: c.send(None)
+            except Exception: pass
+        for p, c in self.workers: p.join(timeout=5)
 
 
-reference_msm_parallel._pb = {}
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
 def time_reference_g2(cname, log2n, steps, warmup):
@@ -156,63 +206,122 @@ def time_reference_g2(cname, log2n, steps, warmup):
     t0 = time.perf_counter()
     for _ in range(steps): g2.msm_affine(bases, scalars, 32, n)
     dt = (time.perf_counter() - t0) / steps
-    return n / dt, dt * 1e3, 1, "reference", "reference WASM (upstream wasmcurves g2m_multiexpAffine) AOT-compiled via C; one MSM of 2^%d points per step on one host core" % log2n
+    return {"pps": n / dt, "ms": dt * 1e3, "cores": 1, "kind": "reference", "steps": steps, "warmup": warmup, "n": n,
+            "sample": "reference WASM (upstream wasmcurves g2m_multiexpAffine) AOT-compiled via C; one MSM of 2^%d points per step on one host core" % log2n}
 
 
-def time_reference(cname, log2n, steps, warmup):
-    """returns (points_per_s, ms_per_step, cores, kind, sample description)"""
-    import multiprocessing as mp
+def time_reference(cname, n, steps, warmup, budget_s, procs=0):
+    """The reference's own MSM on the host cores: one MSM of n points per step, one WASM instance per core on n/cores points each
+    (ffjavascript's worker sharding), steps clamped so that the run fits budget_s.  -> dict"""
     import pyref, coracle, refwasm
-    if cname.endswith("_g2"): return time_reference_g2(cname, min(log2n, 12), steps, warmup)
+    if cname.endswith("_g2"): return time_reference_g2(cname, min(max(1, n.bit_length() - 1), 12), max(1, min(steps, 3)), min(warmup, 1))
     cv = pyref.CURVES[cname]
-    n = 1 << log2n
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    bases = coracle.generate_bases(cv.cid, pyref.affine_to_bytes(cv, cv.G), SEED + log2n, 0, n)
-    import random
-    rnd = random.Random(log2n)
-    scalars = rnd.getrandbits(256 * n).to_bytes(32 * n, "little")
-    if refwasm.available(cname):
-        kind = "reference"
-        ctx = mp.get_context("fork")
-        with ctx.Pool(cores) as pool:
-            for _ in range(warmup): reference_msm_parallel(pool, cname, bases, scalars, n, cores, cv.n8)
-            t0 = time.perf_counter()
-            for _ in range(steps): res = reference_msm_parallel(pool, cname, bases, scalars, n, cores, cv.n8)
-            dt = (time.perf_counter() - t0) / steps
-        check = coracle.normalize(cv.cid, coracle.multiexp_affine(cv.cid, bases, scalars, 32, n))
-        assert pyref.canonical_bytes(cv, res) == check, "reference arm result differs from the C oracle"
-        what = "reference WASM (upstream wasmcurves g1m_multiexpAffine) AOT-compiled via C"
-    else:
-        kind = "port"; cores = 1
-        for _ in range(warmup): coracle.multiexp_affine(cv.cid, bases, scalars, 32, n)
+    cores = procs or host_cores()
+    seed = SEED + 977
+    if not refwasm.available(cname):      # the reference did not compile here: time the C port of its algorithm on one core
+        bases = coracle.generate_bases(cv.cid, pyref.affine_to_bytes(cv, cv.G), seed, 0, n)
+        import random
+        scalars = random.Random(n).getrandbits(256 * n).to_bytes(32 * n, "little")
+        t0 = time.perf_counter(); coracle.multiexp_affine(cv.cid, bases, scalars, 32, n); dt = time.perf_counter() - t0
+        return {"pps": n / dt, "ms": dt * 1e3, "cores": 1, "kind": "port", "steps": 1, "warmup": 0, "n": n,
+                "sample": "C port of the upstream algorithm (oracle/msm_oracle.c); one MSM of %d points on one host core" % n}
+    pool = ReferencePool(cname, n, cores, seed)
+    try:
+        t0 = time.perf_counter(); first = pool.step(0); t1 = time.perf_counter() - t0          # first (warm-up) step also sizes the run
+        w_done = 1
+        steps_fit = max(1, int((budget_s - t1 * max(warmup, 1)) / max(t1, 1e-9)))
+        k = max(1, min(steps, steps_fit))
+        for i in range(1, warmup): pool.step(i); w_done += 1
         t0 = time.perf_counter()
-        for _ in range(steps): coracle.multiexp_affine(cv.cid, bases, scalars, 32, n)
-        dt = (time.perf_counter() - t0) / steps
-        what = "C port of the upstream algorithm (oracle/msm_oracle.c)"
-    sample = "%s; one MSM of 2^%d points per step, point-range slices over %d host processes, partials summed with g1m_add" % (what, log2n, cores)
-    return n / dt, dt * 1e3, cores, kind, sample
+        for i in range(k): res = pool.step(i)
+        dt = (time.perf_counter() - t0) / k
+        # the two runs of scalar set 0 agree (deterministic), and the result is a point: normalize_read returned canonical (x, y)
+        if k >= 1 and pool.step(0) != first: raise RuntimeError("reference arm is not deterministic")
+    finally:
+        pool.close()
+    return {"pps": n / dt, "ms": dt * 1e3, "cores": len(pool.workers), "kind": "reference", "steps": k, "warmup": w_done, "n": n,
+            "steps_clamped": k < steps,
+            "sample": ("reference WASM (upstream wasmcurves g1m_multiexpAffine) AOT-compiled via C; one MSM of %d points per step, one instance per host core on "
+                       "%d points each (%d processes), partial results added with g1m_add" % (n, (n + len(pool.workers) - 1) // len(pool.workers), len(pool.workers)))}
+
+
+def time_reference_single(cname, log2n=16):
+    """ONE instance, the whole N, one host core -- the recipe of wasmcurves/benchmarks/multiexp.js:7-42"""
+    import pyref, coracle, refwasm, random
+    cv = pyref.CURVES[cname]; n = 1 << log2n
+    bases = coracle.generate_bases(cv.cid, pyref.affine_to_bytes(cv, cv.G), SEED + log2n, 0, n)
+    scalars = random.Random(log2n).getrandbits(256 * n).to_bytes(32 * n, "little")
+    pb = refwasm.RefModule(cname)
+    t0 = time.perf_counter(); pb.msm_affine_raw(bases, scalars, 32, n); dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "points/s", "cores": 1, "ms_per_sample": dt * 1e3,
+            "sample": "one reference WASM instance, one MSM of the whole 2^%d points on one host core (wasmcurves/benchmarks/multiexp.js:7-42)" % log2n}
 
 
 def run_reference(a):
-    rank = int(os.environ.get("RANK", "0"))
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0: return
     cname = a.curve
-    steps = max(1, min(a.steps, 5)); warm = max(1, min(a.warmup, 1))
-    pps, ms, cores, kind, sample = time_reference(cname, a.ref_log2n, steps, warm)
-    line = {"impl": "reference", "metric": metric_name(cname), "value": pps, "unit": "points/s",
-            "n_gpus": a.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+    total = (1 << a.log2n_total) if a.log2n_total else (1 << a.log2n) * max(1, a.gpus)
+    cap = 1 << (a.ref_log2n if a.ref_log2n else 20)
+    n = min(total, cap)                                    # a bounded sample of the workload when the job is larger than 2^20 points
+    r = time_reference(cname, n, a.steps, a.warmup, a.ref_budget_s)
+    cfg = workload_config(cname, a.log2n, max(1, a.gpus), a.log2n_total)
+    line = {"impl": "reference", "metric": metric_name(cname), "value": r["pps"], "unit": "points/s",
+            "n_gpus": a.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "strong" if a.log2n_total else "weak",
             "vs_baseline": None, "dtype": "u32 limbs (Montgomery Fq)", "data": "synthetic",
-            "config": {"workload": "%s MSM, bounded sample 2^%d points per step (of the 2^%d-point workload), uniform 256-bit scalars" % (cname, a.ref_log2n, a.log2n),
-                       "curve": cname, "log2n_per_step": a.ref_log2n},
-            "cpu_baseline": {"value": pps, "unit": "points/s", "cores": cores, "kind": kind, "sample": sample},
-            "e2e": {"value": pps, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": cfg,
+            "sample_points_per_step": r["n"], "sample_is_whole_workload": r["n"] == total, "steps_requested": a.steps, "steps_clamped_to_budget": bool(r.get("steps_clamped")),
+            "cpu_baseline": {"value": r["pps"], "unit": "points/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["pps"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+R_ORDER = {0: 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001, 1: 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001}
+
+
+def scalar_dot(seed, first, sc_dev, n, cid):
+    """sum_i s_i * k_i mod r for this rank's points: k_i = splitmix64(seed + first + i) is the multiplier of base i (P_i = k_i * G), s_i the
+    256-bit scalars in the device tensor.  Host big integers (numpy object arrays), chunked: the oracle-free known answer of the MSM."""
+    import numpy as np
+    r = R_ORDER[cid & 1]; total = 0; CH = 1 << 19
+
+    def sm(x):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+    with np.errstate(over="ignore"):
+        for lo in range(0, n, CH):
+            m = min(CH, n - lo)
+            k = sm(np.uint64(seed) + np.arange(first + lo, first + lo + m, dtype=np.uint64)); k[k == 0] = 1
+            w = sc_dev[lo * 32:(lo + m) * 32].cpu().numpy().view("<u8").reshape(m, 4).astype(object)
+            sv = w[:, 0] + (w[:, 1] << 64) + (w[:, 2] << 128) + (w[:, 3] << 192)
+            total = (total + int((sv * k.astype(object)).sum())) % r
+    return total
+
+
+def known_answer_point(eng, cid, gen_base_dev, k0, total):
+    """canonical affine bytes of total * G, computed as (total / k0) * P_0 by a ONE-point MSM on the first base of the stream (P_0 = k0 * G)"""
+    r = R_ORDER[cid & 1]; n8 = {0: 48, 1: 32, 2: 96, 3: 64}[cid]
+    t = total * pow(k0, -1, r) % r
+    return eng.normalize(cid, eng.multiexp_affine(cid, gen_base_dev[: 2 * n8], t.to_bytes(32, "little"), 32, 1))
+
+
+def profile_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full capture of the CURRENT
+    kernels (profiles/r2_ncu_traffic.json, written by tools/ncu_extract.py); None when no capture of this build exists"""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    try:
+        d = json.load(open(p)); e = d.get(kernel_key)
+        return (float(e["dram_bytes_read"]) + float(e["dram_bytes_write"])) if e else None
+    except Exception:
+        return None
+
+
 def kernel_roofline(eng, handle, scal, n, cid, cname, a, out_dev):
-    """per-phase CUDA-event timings inside the engine (single lane, same inputs) -> (roofline object, averaged stats)"""
+    """per-phase CUDA-event timings inside the engine (a separate single-lane stats loop over the same inputs, NOT the timed loop) -> (roofline object, averaged stats)"""
     NSETS = len(scal); n8 = {0: 48, 1: 32, 2: 96, 3: 64}[cid]
     agg = {}; reps = max(3, min(a.steps, 10))
     eng.multiexp_resident(handle, scal[0], 32, n, cid, out=out_dev, want_stats=True)      # untimed: grows the single-lane scratch
@@ -224,29 +333,58 @@ def kernel_roofline(eng, handle, scal, n, cid, cname, a, out_dev):
     hbm_peak, hbm_src = measured_peaks()
     lp = LIMB_PRODUCTS_PER_FQMUL[cname]
     adds = st["affine_adds"]
-    # dominant kernel: the first (largest) k_tree_bwd launch = the backward pass of tree round 0, which does 5 of the 6
-    # field multiplications of every batch-affine addition of that round
-    bwd0_ms = st["ms_k_tree_bwd_round0"]; adds0 = st["affine_adds_round0"]
-    alg_lp = adds0 * 5 * lp                                   # algorithmic limb products of that launch
-    achieved = alg_lp / (bwd0_ms * 1e-3) if bwd0_ms > 0 else 0.0
-    # algorithmic HBM bytes of that launch per addition: 2 input points + prefix product + share of the thread inverse + output point
-    bytes_per_add = 2 * 2 * n8 + n8 + n8 / 8 + 2 * n8
-    # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture (profiles/), 2^20 BLS12-381 only
-    traffic = 3.04e9 if (cname == "bls12381" and a.log2n == 20) else None      # profiles/r1b_ncu_full_tree_kernels_2p20_bls.csv: 2.236 GB read + 0.804 GB written
-    roof = {"bound": "imad", "kernel": "k_tree_bwd<FIRST=1> (batch-affine backward pass, tree round 0: one launch per step)",
+    fused = cid < 2          # prime fields: the whole tree round (forward pass, product tree, inversion, backward pass) is ONE kernel, k_tree_round
+    # dominant kernel: the tree round 0 launch.  Fused form: all 6 field multiplications of every batch-affine addition of that round;
+    # G2 (separate kernels): k_tree_bwd of round 0, 5 of the 6.
+    mults = 6 if fused else 5
+    r0_ms = st["ms_k_tree_bwd_round0"]; adds0 = st["affine_adds_round0"]
+    alg_lp = adds0 * mults * lp                               # algorithmic limb products of that launch
+    achieved = alg_lp / (r0_ms * 1e-3) if r0_ms > 0 else 0.0
+    # algorithmic HBM bytes of that launch per addition: forward pass 2 x-coordinates + prefix product written; backward pass 2 points + prefix + result
+    bytes_per_add = (2 * n8 + n8) + (2 * 2 * n8 + n8 + 2 * n8) if fused else 2 * 2 * n8 + n8 + n8 / 8 + 2 * n8
+    kname = "k_tree_round<FIRST=1>" if fused else "k_tree_bwd<FIRST=1>"
+    traffic = profile_traffic("%s|%s|2^%d" % (kname, cname, a.log2n))
+    roof = {"bound": "imad", "kernel": kname + (" (tree round 0 as one persistent launch: forward pass + in-kernel batch inversion + backward pass; one launch per window group per step)" if fused
+                                                else " (batch-affine backward pass, tree round 0)"),
             "achieved": achieved / 1e12, "peak": imad / 1e12, "unit": "T limb-products/s (32x32+64 IMAD.WIDE.U32)",
             "frac": (achieved / imad) if imad else None, "traffic": traffic,
-            "avg_launch_ms": bwd0_ms, "algorithmic_units_per_launch": alg_lp, "additions_per_launch": adds0,
+            "avg_launch_ms": r0_ms, "algorithmic_units_per_launch": alg_lp, "additions_per_launch": adds0, "field_multiplications_per_addition": mults,
+            "measured_in": "a separate single-lane stats loop of the engine (CUDA events around every kernel group on the launching stream), same inputs, not the timed loop",
             "peak_source": "measured in this run by b200msm_probe_imad: register-resident IMAD.WIDE.U32 carry chains on all SMs (the instruction the field multiplier is made of); plain 32-bit IMAD runs at twice this rate",
-            "hbm": {"achieved": adds0 * bytes_per_add / (bwd0_ms * 1e-3) / 1e9 if bwd0_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": (adds0 * bytes_per_add / (bwd0_ms * 1e-3) / 1e9 / hbm_peak) if bwd0_ms > 0 else None,
+            "hbm": {"achieved": adds0 * bytes_per_add / (r0_ms * 1e-3) / 1e9 if r0_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": (adds0 * bytes_per_add / (r0_ms * 1e-3) / 1e9 / hbm_peak) if r0_ms > 0 else None,
                     "algorithmic_bytes_per_launch": adds0 * bytes_per_add, "peak_source": hbm_src},
-            "all_rounds": {"kernel_group": "k_tree_bwd, all rounds", "limb_products": adds * 5 * lp, "ms": st["ms_k_tree_bwd"],
-                           "frac_of_imad_peak": (adds * 5 * lp / (st["ms_k_tree_bwd"] * 1e-3) / imad) if imad and st["ms_k_tree_bwd"] > 0 else None},
+            "all_rounds": {"kernel_group": ("k_tree_round" if fused else "k_tree_bwd") + ", all rounds", "limb_products": adds * mults * lp, "ms": st["ms_k_tree_bwd"],
+                           "frac_of_imad_peak": (adds * mults * lp / (st["ms_k_tree_bwd"] * 1e-3) / imad) if imad and st["ms_k_tree_bwd"] > 0 else None},
             "whole_accumulate": {"limb_products": adds * FQMUL_PER_AFFINE_ADD * lp, "ms": st["ms_accumulate"],
                                  "frac_of_imad_peak": (adds * FQMUL_PER_AFFINE_ADD * lp / (st["ms_accumulate"] * 1e-3) / imad) if imad and st["ms_accumulate"] > 0 else None},
             "fqmul_per_s_measured": fq, "fqmul_frac_of_imad_peak": fq * lp / imad if imad else None}
     return roof, st
+
+
+class Timer:
+    """K steps between two CUDA events on the launching stream, bracketed by barrier + synchronize, max over ranks"""
+    def __init__(self, torch, dist, dev, stream, world):
+        self.torch, self.dist, self.dev, self.stream, self.world = torch, dist, dev, stream, world
+        self.e0 = torch.cuda.Event(enable_timing=True); self.e1 = torch.cuda.Event(enable_timing=True)
+
+    def sync_all(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1: self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def run(self, fn, steps, warmup, wall=False):
+        for i in range(warmup): fn(i)
+        self.sync_all()
+        t0 = time.perf_counter(); self.e0.record(self.stream)
+        for i in range(steps): fn(i)
+        self.e1.record(self.stream)
+        self.sync_all()
+        ms = self.e0.elapsed_time(self.e1)
+        if wall: ms = max(ms, (time.perf_counter() - t0) * 1e3)
+        t = self.torch.tensor([ms / steps], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1: self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
 
 def run_ours(a):
@@ -258,22 +396,28 @@ def run_ours(a):
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")            # host-side barriers / object exchange (an NCCL barrier would spin on the GPUs while rank 0 measures alone)
     cname = a.curve; cid = CURVE_ID[cname]; n8 = b200msm.N8[cid]
     strong = a.log2n_total > 0
+    from b200msm.sharded import shard_range
     if strong:
-        from b200msm.sharded import shard_range
         lo_, hi_ = shard_range(1 << a.log2n_total, rank, world); n = hi_ - lo_; first_pt = lo_
     else:
         n = 1 << a.log2n; first_pt = rank * n
+    total_points = (1 << a.log2n_total) if strong else n * world
+    seed = SEED + a.log2n
     eng = b200msm.Engine(local)
     stream = torch.cuda.current_stream(dev)
     eng.set_stream(stream.cuda_stream)
+    T = Timer(torch, dist, dev, stream, world)
+    warm = max(3, a.warmup)
 
     # ---- synthetic inputs, generated on the device: bases P_i = k_i * G (global index range of this rank), uniform 256-bit scalars
     bases = torch.empty(n * 2 * n8, dtype=torch.uint8, device=dev)
-    eng.generate_bases(cid, SEED + a.log2n, first_pt, n, bases)
+    eng.generate_bases(cid, seed, first_pt, n, bases)
     g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
     NSETS = 2
     scal = [torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device=dev, generator=g) for _ in range(NSETS)]
@@ -282,48 +426,38 @@ def run_ours(a):
     gathered = torch.zeros(world * 3 * n8, dtype=torch.uint8, device=dev) if world > 1 else None
     total_dev = torch.zeros(3 * n8, dtype=torch.uint8, device=dev)
 
+    def combine(src_dev, dst):
+        """N > 1: one all_gather of the N partial points (N * 3*n8 bytes over NCCL / NVLink), summed on every rank (b200msm_g1_sum)"""
+        dist.all_gather_into_tensor(gathered, src_dev)
+        rc = b200msm.lib.b200msm_g1_sum(eng._ctx, cid, gathered.data_ptr(), world, dst.data_ptr())
+        assert rc == 0, rc
+
     def step_device(i):
         eng.multiexp_resident(handle, scal[i % NSETS], 32, n, cid, out=out_dev)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out_dev)
-            rc = b200msm.lib.b200msm_g1_sum(eng._ctx, cid, gathered.data_ptr(), world, total_dev.data_ptr())
-            assert rc == 0, rc
+        if world > 1: combine(out_dev, total_dev)
 
-    def sync_all():
-        torch.cuda.synchronize(dev)
-        if world > 1: dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    # ---- correctness guard, oracle-free (the oracle is test infrastructure; in this file only the cpu_baseline leg touches it): the bases
-    # are P_i = k_i*G with a known splitmix64 stream, so  sum_i s_i*P_i = (sum_i s_i*k_i mod r)*G = t*P_0  with  t = (sum_i s_i*k_i)*k_0^-1 mod r.
-    # Left side: the full pipeline on a 2^12-point prefix; right side: a one-point MSM.  Not timed.
+    # ---- correctness of the EXACT timed path on the FULL workload, oracle-free (the oracle is test infrastructure; in this file only the cpu_baseline leg
+    # touches it): bases are P_i = k_i*G with a known splitmix64 stream, so sum_i s_i*P_i = (sum_i s_i*k_i mod r)*G.  Every rank adds up its own
+    # s_i*k_i with host integers, the N sums are exchanged (gloo), and rank 0 compares the all-gathered + summed device result of one step with a one-point MSM.
+    step_device(0); T.sync_all()
+    mine = scalar_dot(seed, first_pt, scal[0], n, cid)
+    sums = [mine]
+    if world > 1:
+        sums = [None] * world; dist.all_gather_object(sums, mine, group=cpu_group)
+    k0 = _splitmix64(seed) or 1
+    checked = None
     if rank == 0:
-        R_ORDER = {0: 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001, 1: 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001}[cid & 1]
-        m = 1 << 12
-        hs = bytes(scal[0][: m * 32].cpu().numpy())
-        ks = [(_splitmix64(SEED + a.log2n + first_pt + i) or 1) for i in range(m)]
-        tot = sum(int.from_bytes(hs[32 * i: 32 * i + 32], "little") * ks[i] for i in range(m)) % R_ORDER
-        t = tot * pow(ks[0], -1, R_ORDER) % R_ORDER
-        lhs = eng.normalize(cid, eng.multiexp_affine(cid, bases[: m * 2 * n8], scal[0][: m * 32], 32, m))
-        rhs = eng.normalize(cid, eng.multiexp_affine(cid, bases[: 2 * n8], t.to_bytes(32, "little"), 32, 1))
-        assert lhs == rhs and any(lhs), "GPU MSM fails the known-answer identity sum_i s_i*k_i*G"
+        g0 = torch.empty(2 * n8, dtype=torch.uint8, device=dev); eng.generate_bases(cid, seed, 0, 1, g0)
+        expect = known_answer_point(eng, cid, g0, k0, sum(sums) % R_ORDER[cid & 1])
+        got = eng.normalize(cid, total_dev if world > 1 else out_dev)
+        assert got == expect and any(got), "GPU MSM (all ranks combined) fails the known-answer identity sum_i s_i*k_i*G on the full workload"
+        checked = True
 
-    for i in range(max(3, a.warmup)): step_device(i)
-    sync_all()
     sampler = ClockSampler(local)
     if rank == 0: sampler.start()
     launches0 = eng.counter("launches")
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record(stream)
-    for i in range(a.steps): step_device(i)
-    e1.record(stream)
-    sync_all()
-    ms = e0.elapsed_time(e1) / a.steps
-    launches = (eng.counter("launches") - launches0) // max(1, a.steps)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = T.run(step_device, a.steps, warm)
+    launches = (eng.counter("launches") - launches0) // max(1, a.steps + warm)
 
     # ---- same workload against resident bases WITH the precomputed window table (b200msm_upload_bases_windowed): the table is a
     # function of the fixed bases only, built once outside the timed region like the upload itself; reported beside `value`, never as it
@@ -336,29 +470,19 @@ def run_ours(a):
 
         def step_win(i):
             eng.multiexp_resident(hwin, scal[i % NSETS], 32, n, cid, out=outw)
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, outw)
-                rc = b200msm.lib.b200msm_g1_sum(eng._ctx, cid, gathered.data_ptr(), world, total_dev.data_ptr())
-                assert rc == 0, rc
-        for i in range(max(3, a.warmup)): step_win(i)
-        eng.multiexp_resident(handle, scal[(max(3, a.warmup) - 1) % NSETS], 32, n, cid, out=out_dev)
-        sync_all()
+            if world > 1: combine(outw, total_dev)
+        l0 = eng.counter("launches")
+        wms = T.run(step_win, a.steps, warm)
+        wl = (eng.counter("launches") - l0) // max(1, a.steps + warm)
+        eng.multiexp_resident(hwin, scal[0], 32, n, cid, out=outw); eng.multiexp_resident(handle, scal[0], 32, n, cid, out=out_dev)
+        T.sync_all()
         same = eng.normalize(cid, outw) == eng.normalize(cid, out_dev)
         assert same, "window-table result differs from the ordinary pipeline"
-        l0 = eng.counter("launches")
-        e0.record(stream)
-        for i in range(a.steps): step_win(i)
-        e1.record(stream)
-        sync_all()
-        wms = e0.elapsed_time(e1) / a.steps
-        t = torch.tensor([wms], dtype=torch.float64, device=dev)
-        if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        wms = float(t.item())
         _, wst = eng.multiexp_resident(hwin, scal[0], 32, n, cid, out=outw, want_stats=True)
-        win = {"ms_per_step": wms, "value": ((1 << a.log2n_total) if strong else n * world) / (wms * 1e-3), "unit": "points/s",
+        win = {"ms_per_step": wms, "value": total_points / (wms * 1e-3), "unit": "points/s",
                "window_bits": int(wst["window_bits"]), "windows": int(wst["windows"]), "affine_adds": int(wst["affine_adds"]),
                "table_bytes_per_gpu": int(wst["windows"]) * n * 2 * n8, "table_build_ms": build_ms,
-               "gpu_launches": int((eng.counter("launches") - l0) // max(1, a.steps + 1)), "result_equals_ordinary_path": bool(same),
+               "gpu_launches": int(wl), "result_equals_ordinary_path": bool(same),
                "api": "b200msm_upload_bases_windowed + b200msm_g1_multiexp_resident (rows 2^(window offset) * P_i precomputed once per base set; all windows share one bucket array)"}
         eng.free_bases(hwin)
 
@@ -367,7 +491,6 @@ def run_ours(a):
     hs = [torch.empty(n * 32, dtype=torch.uint8).pin_memory() for _ in range(NSETS)]
     for k in range(NSETS): hs[k].copy_(scal[k])
     hout = torch.zeros(3 * n8, dtype=torch.uint8).pin_memory()
-    gout = [torch.zeros(3 * n8, dtype=torch.uint8) for _ in range(world)] if world > 1 else None
 
     def step_host(i):
         eng.multiexp_affine(cid, hb, hs[i % NSETS], 32, n, out=hout)          # synchronous: result is in host memory on return
@@ -377,46 +500,51 @@ def run_ours(a):
             rc = b200msm.lib.b200msm_g1_sum(eng._ctx, cid, gathered.data_ptr(), world, hout.data_ptr())
             assert rc == 0, rc
 
-    for i in range(2): step_host(i)
-    sync_all()
-    e2e_steps = max(3, min(a.steps, 10))
-    t0 = time.perf_counter(); e0.record(stream)
-    for i in range(e2e_steps): step_host(i)
-    e1.record(stream)
-    sync_all()
-    e2e_ms = max((time.perf_counter() - t0) * 1e3, e0.elapsed_time(e1)) / e2e_steps
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    e2e_ms = T.run(step_host, max(3, min(a.steps, 10)), 2, wall=True)
+    e2e_ok = None
+    if rank == 0:
+        step_host(0)
+        e2e_ok = eng.normalize(cid, bytes(hout.numpy())) == expect
+        assert e2e_ok, "e2e (host buffers) result fails the known-answer identity"
+    T.sync_all()
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- N > 1 only: (1) strong scaling on BASELINE config 4 (one MSM of 2^24 points on ONE GPU, then sharded over the N ranks), both results checked against
+    # the known answer; (2) the weak workload through ONE multi-device context behind the C ABI (b200msm_create_multi) driven by rank 0 alone.
+    strong_blk = None; abi_blk = None
+    if world > 1 and not strong and cid < 2:
+        if not a.no_strong: strong_blk = strong_scaling_block(a, torch, dist, b200msm, eng, T, cpu_group, rank, world, dev, cid, n8)
+        if not a.no_abi_multi: abi_blk = abi_multi_block(a, torch, dist, b200msm, cpu_group, rank, world, cid, n8, hb, hs, n, seed, sums, k0, eng)
 
     # ---- kernel-level timings (per-phase CUDA events inside the engine) for the roofline, same inputs, rank 0 only
     line = None
     if rank == 0:
         roof, st = kernel_roofline(eng, handle, scal, n, cid, cname, a, out_dev)
         adds = st["affine_adds"]
-        total_points = (1 << a.log2n_total) if strong else n * world
+        cfg = workload_config(cname, a.log2n, world, a.log2n_total)
         line = {"metric": metric_name(cname), "value": total_points / (ms * 1e-3), "unit": "points/s",
-                "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+                "n_gpus": world, "steps": a.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if strong else "weak",
                 "vs_baseline": None, "dtype": "u32 limbs (Montgomery Fq, 32x32->64 IMAD)", "data": "synthetic",
-                "config": {"workload": ("%s MSM, %d points per GPU (%d points per step), uniform 256-bit scalars, bases P_i = k_i*G resident in HBM"
-                                        % (CURVE_LABEL[cname], n, total_points)),
-                           "curve": cname, "log2n_per_gpu": a.log2n, "parallelism": "point-range shards x%d + all_gather of partials" % world if world > 1 else "single GPU",
-                           "window_bits": int(st["window_bits"]), "windows": int(st["windows"]), "tree_rounds": int(round(st["tree_rounds"])),
-                           "cache": "no L2 flush: per-step working set (bases %d MiB + scalars %d MiB + sort/tree scratch > 1 GiB) exceeds the 126 MB L2; %d scalar sets alternate"
-                                    % (n * 2 * n8 >> 20, n * 32 >> 20, NSETS)},
+                "config": cfg,
+                "plan": {"parallelism": "point-range shards x%d + all_gather of partials" % world if world > 1 else "single GPU", "inputs": "bases and scalars resident in HBM (device pointers through the C ABI), result left on the device",
+                         "window_bits": int(st["window_bits"]), "windows": int(st["windows"]), "tree_rounds": int(round(st["tree_rounds"]))},
+                "result_checked": bool(checked), "multi_gpu_result_checked": bool(checked) if world > 1 else None,
+                "result_check": "one full step of the timed path (%d points over %d GPU(s), all-gathered and summed) equals (sum_i s_i*k_i mod r)*G from host integers" % (total_points, world),
                 "clocks": clocks,
                 "e2e": {"value": total_points / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": n * (2 * n8 + 32), "d2h_bytes_per_step": 3 * n8, "api": "b200msm_g1_multiexp_affine with pinned host buffers"},
+                        "h2d_bytes_per_step": n * (2 * n8 + 32), "d2h_bytes_per_step": 3 * n8, "api": "b200msm_g1_multiexp_affine with pinned host buffers", "result_checked": bool(e2e_ok)},
                 "gpu_launches": int(launches),
                 "roofline": roof,
                 "phases_ms": {k: round(v, 4) for k, v in st.items() if k.startswith("ms_")},
                 "pairs": st["pairs"], "affine_adds": adds, "resident_window_table": win}
-    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own code on the host cores, bounded sample
+        if strong_blk is not None: line["strong_2p%d" % a.strong_log2n] = strong_blk
+        if abi_blk is not None: line["abi_multi"] = abi_blk
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own code on the host cores, the SAME workload for one step, plus the single-instance row
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
-            pps, rms, cores, kind, sample = time_reference(cname, a.ref_log2n, 2, 1)
-            line["cpu_baseline"] = {"value": pps, "unit": "points/s", "cores": cores, "kind": kind, "sample": sample, "ms_per_sample": rms}
+            r = time_reference(cname, min(total_points, 1 << 20), 1, 0, 60.0)
+            line["cpu_baseline"] = {"value": r["pps"], "unit": "points/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"] + "; 1 step", "ms_per_sample": r["ms"]}
+            if cid < 2: line["cpu_baseline"]["single_thread"] = time_reference_single(cname, 16)
         except Exception as ex:  # the baseline must never take the GPU number down with it
             line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
     elif rank == 0:
@@ -424,6 +552,94 @@ def run_ours(a):
     if rank == 0: _emit(line)
     eng.free_bases(handle)
     if world > 1: dist.barrier(); dist.destroy_process_group()
+
+
+def strong_scaling_block(a, torch, dist, b200msm, eng, T, cpu_group, rank, world, dev, cid, n8):
+    """BASELINE config 4 inside the driver's own --gpus N run: one MSM of 2^K points (K = --strong-log2n, default 24) timed on rank 0's GPU alone
+    and then sharded by point range over all N ranks (NCCL all_gather + sum in the step); both results compared with the known answer."""
+    K = a.strong_log2n; ntot = 1 << K; sseed = SEED + K
+    from b200msm.sharded import shard_range
+    lo, hi = shard_range(ntot, rank, world); m = hi - lo
+    g = torch.Generator(device=dev); g.manual_seed(777)
+    gathered = torch.zeros(world * 3 * n8, dtype=torch.uint8, device=dev); tot = torch.zeros(3 * n8, dtype=torch.uint8, device=dev); part = torch.zeros(3 * n8, dtype=torch.uint8, device=dev)
+    res = {"log2n_total": K}
+    # (1) one GPU: rank 0 holds the whole problem; the other ranks wait on a host-side barrier
+    full_sc = None; expect = None
+    if rank == 0:
+        fb = torch.empty(ntot * 2 * n8, dtype=torch.uint8, device=dev); eng.generate_bases(cid, sseed, 0, ntot, fb)
+        full_sc = torch.randint(0, 256, (ntot * 32,), dtype=torch.uint8, device=dev, generator=g)
+        h = eng.upload_bases(cid, fb, ntot); del fb
+        for i in range(2): eng.multiexp_resident(h, full_sc, 32, ntot, cid, out=part)
+        torch.cuda.synchronize(dev)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); k1 = 5
+        e0.record(T.stream)
+        for i in range(k1): eng.multiexp_resident(h, full_sc, 32, ntot, cid, out=part)
+        e1.record(T.stream); torch.cuda.synchronize(dev)
+        res["ms_1gpu"] = e0.elapsed_time(e1) / k1
+        g0 = torch.empty(2 * n8, dtype=torch.uint8, device=dev); eng.generate_bases(cid, sseed, 0, 1, g0)
+        expect = known_answer_point(eng, cid, g0, _splitmix64(sseed) or 1, scalar_dot(sseed, 0, full_sc, ntot, cid))
+        res["result_1gpu_checked"] = eng.normalize(cid, part) == expect
+        eng.free_bases(h)
+    # every rank needs ITS slice of the same scalars: rank 0 broadcasts them over NCCL (outside any timed region)
+    dist.barrier(group=cpu_group)
+    if rank != 0: full_sc = torch.empty(ntot * 32, dtype=torch.uint8, device=dev)
+    dist.broadcast(full_sc, src=0)
+    my_sc = full_sc[lo * 32: hi * 32].clone(); del full_sc
+    mb = torch.empty(m * 2 * n8, dtype=torch.uint8, device=dev); eng.generate_bases(cid, sseed, lo, m, mb)
+    h = eng.upload_bases(cid, mb, m); del mb
+
+    def step(i):
+        eng.multiexp_resident(h, my_sc, 32, m, cid, out=part)
+        dist.all_gather_into_tensor(gathered, part)
+        rc = b200msm.lib.b200msm_g1_sum(eng._ctx, cid, gathered.data_ptr(), world, tot.data_ptr())
+        assert rc == 0, rc
+    res["ms_Ngpu"] = T.run(step, 10, 3)
+    eng.free_bases(h)
+    if rank == 0:
+        res["n_gpus"] = world; res["speedup"] = res["ms_1gpu"] / res["ms_Ngpu"]
+        res["result_Ngpu_checked"] = eng.normalize(cid, tot) == expect
+        res["points_per_s_Ngpu"] = ntot / (res["ms_Ngpu"] * 1e-3)
+        assert res["result_1gpu_checked"] and res["result_Ngpu_checked"], "strong-scaling MSM fails the known-answer identity"
+        return res
+    return None
+
+
+def abi_multi_block(a, torch, dist, b200msm, cpu_group, rank, world, cid, n8, hb, hs, n, seed, sums, k0, eng0):
+    """The weak workload (N * 2^log2n points) through ONE context over all N GPUs (b200msm_create_multi): what a JS / C / Rust host that binds
+    include/b200msm.h gets.  Rank 0 drives it alone (the other ranks idle on a host-side barrier; their GPUs keep their memory but run nothing):
+    host buffers in, result to the host; then resident shards.  Checked against the same known answer as the torchrun path."""
+    # rank 0 needs every rank's host inputs: gather them through gloo (outside any timed region)
+    nb = n * 2 * n8
+    allb = [torch.empty(nb, dtype=torch.uint8) for _ in range(world)] if rank == 0 else None
+    alls = [torch.empty(n * 32, dtype=torch.uint8) for _ in range(world)] if rank == 0 else None
+    dist.gather(hb.clone(), allb, dst=0, group=cpu_group); dist.gather(hs[0].clone(), alls, dst=0, group=cpu_group)
+    res = None
+    if rank == 0:
+        tb = torch.cat(allb).pin_memory(); ts = torch.cat(alls).pin_memory(); del allb, alls
+        tot = n * world
+        me = b200msm.Engine(devices=list(range(world)))
+        out = torch.zeros(3 * n8, dtype=torch.uint8).pin_memory()
+        for i in range(3): me.multiexp_affine(cid, tb, ts, 32, tot, out=out)
+        k = 10; t0 = time.perf_counter()
+        for i in range(k): me.multiexp_affine(cid, tb, ts, 32, tot, out=out)
+        e2e = (time.perf_counter() - t0) * 1e3 / k
+        g0 = torch.empty(2 * n8, dtype=torch.uint8, device=torch.device("cuda", 0)); eng0.generate_bases(cid, seed, 0, 1, g0)
+        expect = known_answer_point(eng0, cid, g0, k0, sum(sums) % R_ORDER[cid & 1])
+        ok1 = eng0.normalize(cid, bytes(out.numpy())) == expect
+        h = me.upload_bases(cid, tb, tot)
+        for i in range(3): me.multiexp_resident(h, ts, 32, tot, cid, out=out)
+        t0 = time.perf_counter()
+        for i in range(k): me.multiexp_resident(h, ts, 32, tot, cid, out=out)
+        resid = (time.perf_counter() - t0) * 1e3 / k
+        ok2 = eng0.normalize(cid, bytes(out.numpy())) == expect
+        me.free_bases(h); me.close()
+        assert ok1 and ok2, "multi-device context result fails the known-answer identity"
+        res = {"api": "b200msm_create_multi over %d devices, one host process; b200msm_g1_multiexp_affine (pinned host buffers) / b200msm_upload_bases + b200msm_g1_multiexp_resident (host scalars)" % world,
+               "points_per_step": tot, "e2e_ms_per_step": e2e, "e2e_points_per_s": tot / (e2e * 1e-3), "h2d_bytes_per_step": tot * (2 * n8 + 32),
+               "resident_bases_ms_per_step": resid, "resident_bases_points_per_s": tot / (resid * 1e-3), "h2d_bytes_per_step_resident": tot * 32,
+               "result_checked": True, "timing": "wall clock around synchronous calls (results are in host memory on return), 10 steps after 3 warm-up"}
+    dist.barrier(group=cpu_group)
+    return res
 
 
 def run_batched(a):
@@ -500,8 +716,8 @@ def run_batched(a):
                 "cpu_baseline": {"value": None, "unit": "points/s", "cores": 0, "kind": "skipped", "sample": "see the default (single) workload"}}
         if world == 1 and not a.no_cpu_baseline:
             try:
-                pps, rms, cores, kind, sample = time_reference(cname, a.ref_log2n, 2, 1)
-                line["cpu_baseline"] = {"value": pps, "unit": "points/s", "cores": cores, "kind": kind, "sample": sample, "ms_per_sample": rms}
+                r = time_reference(cname, 1 << min(a.log2n, 20), 1, 0, 60.0)
+                line["cpu_baseline"] = {"value": r["pps"], "unit": "points/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"] + "; 1 step (one MSM of the batch)", "ms_per_sample": r["ms"]}
             except Exception as ex:
                 line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
         _emit(line)

@@ -11,8 +11,8 @@
  *                 n8 = 48 for BLS12-381, 32 for BN254 ("bn128")
  *   affine point: x || y (2*n8 bytes); infinity = all zero                             (src/build_curve_jacobian_a0.js:55-77)
  *   Jacobian    : x || y || z (3*n8 bytes), (X/Z^2, Y/Z^3); infinity: z == 0, written as (0, R mod q, 0)  (:124-150)
- *   scalar      : scalar_size bytes, plain unsigned little-endian integer, NOT Montgomery, NOT required < r
- *                                                                                       (src/build_multiexp.js:73-92)
+ *   scalar      : scalar_size bytes (any size >= 1, as in the reference), plain unsigned little-endian integer, NOT Montgomery,
+ *                 NOT required < r.  More than 32 bytes run as 256-bit slices combined by Horner.   (src/build_multiexp.js:73-92)
  * All `const void*` inputs and `void*` outputs may be HOST or DEVICE pointers (detected with
  * cudaPointerGetAttributes); device buffers must be 16-byte aligned.  There is no CPU fallback:
  * every compute entry point fails with B200MSM_E_CUDA when no usable GPU is present.
@@ -35,7 +35,7 @@ enum { B200MSM_BLS12_381_G1 = 0,   /* src/bls12381/build_bls12381.js:16-125 */
         * build_bls12381.js:48-53, build_bn128.js:44-49).  For these ids "n8" below is the size of an Fq2 element, c0 || c1 = 96 / 64
         * bytes, i.e. an affine point is 192 / 128 bytes and a Jacobian point 288 / 192 bytes -- the g2m layouts.  The MSM entry points
         * (== g2m_multiexpAffine, g2m_multiexpAffine_chunk), resident / windowed / batched forms, normalize, sum, generate_bases and
-        * fq_op (== f2m_*) accept them; the point codecs, GLV and the radix-2^29 probe are G1 only. */
+        * fq_op (== f2m_*) accept them; the point codecs and GLV are G1 only. */
        B200MSM_BLS12_381_G2 = 2,
        B200MSM_BN254_G2 = 3 };
 
@@ -57,11 +57,24 @@ typedef struct b200msm_stats {
 
 /* ---- life cycle.  device_id < 0 selects the current CUDA device. */
 int  b200msm_create(b200msm_ctx** out, int device_id);
+/* One context over n_devices GPUs of this node (device_ids[0] is the "home" device that holds device-resident
+ * outputs).  It owns one stream set, scratch pool and host thread per device.  Every MSM entry point below, called on such a context,
+ * (ordinals may repeat: each entry is one shard with its own context) shards the points by contiguous range over the devices -- the counterpart of ffjavascript running g1m_multiexpAffine on a slice of
+ * the inputs in each worker and adding the partial results (src/build_multiexp.js:319-369 is the per-worker part):
+ * device g pulls ITS slice of the caller's (host) bases and scalars over its own PCIe link, runs the single-GPU pipeline, and the
+ * n_devices partial points are added on the host.  Nothing but those 3*n8-byte partials is exchanged: there is no collective on the
+ * data path.  b200msm_upload_bases[_windowed] on such a context shards the resident set the same way (option "multi_replicate" = 1
+ * keeps a full copy on every device instead, which lets b200msm_g1_multiexp_batch run MSM j on device j mod n_devices).
+ * Problems smaller than "multi_min_points" (default 2^15) per device use fewer devices.  Results are the same group element as on
+ * one device.  n_devices == 1 is b200msm_create. */
+int  b200msm_create_multi(b200msm_ctx** out, const int* device_ids, int n_devices);
+int  b200msm_device_count(const b200msm_ctx* ctx);            /* devices behind this context (1 for b200msm_create) */
 void b200msm_destroy(b200msm_ctx* ctx);
 const char* b200msm_strerror(int status);
 const char* b200msm_last_error(const b200msm_ctx* ctx);      /* detail string of the last failure */
 const char* b200msm_version(void);
-/* Run on an externally owned CUDA stream (cudaStream_t passed as void*), e.g. torch's current stream. */
+/* Run on an externally owned CUDA stream (cudaStream_t passed as void*), e.g. torch's current stream.  Work already issued on the
+ * previous stream is drained first.  Multi-device contexts own their streams: B200MSM_E_UNSUPPORTED. */
 int  b200msm_set_stream(b200msm_ctx* ctx, void* cuda_stream);
 int  b200msm_synchronize(b200msm_ctx* ctx);
 
@@ -154,32 +167,18 @@ int b200msm_fr_fft_last_phases(b200msm_ctx* ctx, float ms[4], uint32_t passes[2]
 int b200msm_g1_generate_bases(b200msm_ctx* ctx, int curve, uint64_t seed, uint64_t first, uint64_t n, void* device_out);
 
 /* ---- kernel-level parity hooks: r[i] = op(a[i], b[i]) on Montgomery Fq elements
- * op: 0 f1m_mul  1 f1m_add  2 f1m_sub  3 f1m_square  4 f1m_inverse  5 f1m_toMontgomery  6 f1m_fromMontgomery  7 f1m_neg
- * (src/build_f1m.js:71-105, 466-777, 779-1076, 1089-1122) */
+ * op: 0 f1m_mul  1 f1m_add  2 f1m_sub  3 f1m_square  4 f1m_inverse (the engine's: optimised binary GCD)  5 f1m_toMontgomery
+ *     6 f1m_fromMontgomery  7 f1m_neg  8 f1m_inverse by Fermat (cross-check)       (src/build_f1m.js:71-105, 466-777, 779-1076, 1089-1122) */
 int b200msm_fq_op(b200msm_ctx* ctx, int curve, int op, const void* a, const void* b, void* r, uint64_t count);
 
-/* ---- measurement hooks: integer-multiply roofline denominators and the field-multiply rate, measured on this GPU.
- * imad_wide_per_s: 32x32+64 -> 64 multiply-adds per second in the form the field multiplier uses (IMAD.WIDE.U32 carry
- *                  chains, register-resident, all SMs) -- the roofline peak for the accumulate phase;
- * imad32_per_s   : plain 32-bit IMAD per second, for context (twice the wide rate on B200);
- * fqmul_per_s    : dependent Montgomery multiplications per second for the given curve. */
-int b200msm_probe_imad(b200msm_ctx* ctx, double* imad_wide_per_s);
-int b200msm_probe_imad32(b200msm_ctx* ctx, double* imad32_per_s);
-int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s);
-/* dfma_per_s: FP64 fused multiply-adds per second (8 independent chains per thread) -- the second multiplier pipe of the SM, unused by
- * the integer path; measured to size an FP64-limb multiplier that would run beside the IMAD one. */
-int b200msm_probe_dfma(b200msm_ctx* ctx, double* dfma_per_s);
-/* Do the FP64 and the integer-multiply pipes overlap?  ms[0]: 256 BLS12-381 Fq multiplications per thread (IMAD.WIDE), ms[1]: 256 blocks of
- * 690 FP64 operations per thread (the instruction mix of a 48-bit-limb FP64 Montgomery multiplication), ms[2]: both in the same thread,
- * ms[3] = 256, ms[4]: odd warps do the integer work and even warps the FP64 work (half of each).  ms[2] ~ max(ms[0], ms[1]) would mean a
- * second multiplier can run beside the first (csrc/probes.cu). */
-int b200msm_probe_dualpipe(b200msm_ctx* ctx, double ms[5]);
-
 /* ---- tuning knobs (never change results).  key: "window_bits" (0 = auto), "accumulate" (0 = auto, 1 = serial, 2 = batch-affine),
- * "tree_rounds" (-1 = auto), "combine" (0 = serial tail on the host (default), 1 = device chain k_window_sums + k_horner). */
+ * "tree_rounds" (-1 = auto), "combine" (0 = serial tail on the host (default), 1 = device chain k_window_sums + k_horner),
+ * "lanes" (1..8 overlapping accumulate streams), "batch_workers", "multi_min_points", "multi_replicate" (multi-device contexts, see
+ * b200msm_create_multi).
+ * On a multi-device context an option applies to every device. */
 int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t value);
 
-/* ---- counters since context creation.  key: "launches" (kernel launches issued by this context). */
+/* ---- counters since context creation.  key: "launches" (kernel launches issued by this context, all its devices and batch workers). */
 int b200msm_get_counter(b200msm_ctx* ctx, const char* key, uint64_t* value);
 
 /* ---- host-only: field constants as the engine uses them (q, R mod q, R^2 mod q as n8-byte LE; np32). No GPU needed. */

@@ -10,10 +10,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_header_symbols_are_exported():
     import b200msm
     hdr = open(os.path.join(ROOT, "include", "b200msm.h")).read()
-    declared = set(re.findall(r"\b(b200msm_\w+)\s*\(", hdr))
+    probes = open(os.path.join(ROOT, "include", "b200msm_probes.h")).read()
+    shipped, experiments = probes.split("#ifdef B200_EXPERIMENTS")
+    declared = set(re.findall(r"\b(b200msm_\w+)\s*\(", hdr)) | set(re.findall(r"\b(b200msm_\w+)\s*\(", shipped))
     assert declared == set(b200msm.EXPORTS), declared ^ set(b200msm.EXPORTS)
     for sym in declared:
         assert hasattr(b200msm.lib, sym), sym
+    # measurement hooks are not part of the drop-in boundary, and exploratory probes are not in the shipped library
+    assert "probe" not in hdr
+    assert set(re.findall(r"\b(b200msm_\w+)\s*\(", experiments)) == set(b200msm._lib.EXPERIMENT_EXPORTS)
 
 
 def test_no_torch_types_in_abi():
@@ -24,7 +29,7 @@ def test_no_torch_types_in_abi():
 def test_constants_match_reference_fields():
     """q, R mod q, R^2 mod q, -q^-1 mod 2^32 (build_bls12381.js:22, build_bn128.js:20, build_f1m.js:30-43,504)"""
     import b200msm
-    for cid, cv in ((0, pyref.BLS12_381), (1, pyref.BN254)):
+    for cid, cv in ((0, pyref.BLS12_381), (1, pyref.BN254), (2, pyref.BLS12_381), (3, pyref.BN254)):      # G2 ids answer with their base field Fq
         n8, q, one, r2, np32 = b200msm.constants(cid)
         assert (n8, q, one, r2) == (cv.n8, cv.q, cv.R % cv.q, cv.R * cv.R % cv.q)
         assert np32 == (-pow(cv.q, -1, 1 << 32)) % (1 << 32)

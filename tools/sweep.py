@@ -16,7 +16,8 @@ for kv in a.opt:
     k, v = kv.split("="); eng.set_option(k, int(v))
 if a.probe:
     imad = eng.probe_imad(); fq = eng.probe_fqmul(cid); im32 = eng.probe_imad32()
-    eng.set_option("probe29", 1); fq29 = eng.probe_fqmul(cid); eng.set_option("probe29", 0)
+    try: eng.set_option("probe29", 1); fq29 = eng.probe_fqmul(cid); eng.set_option("probe29", 0)      # -DB200_EXPERIMENTS builds only
+    except Exception: fq29 = None
     eng.set_option("probe_sqr", 1); fsq = eng.probe_fqmul(cid); eng.set_option("probe_sqr", 0)
     print(json.dumps({"imad_wide_per_s": imad, "imad32_per_s": im32, "fqmul_per_s": fq, "fqmul29_per_s": fq29, "fqsqr_per_s": fsq, "sqr_over_mul": fsq / fq,
                       "fqmul_frac_of_imad_wide_peak": fq * (300 if cid == 0 else 136) / imad}))

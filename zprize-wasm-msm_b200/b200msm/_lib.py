@@ -12,15 +12,16 @@ OK, E_ARG, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4
 BLS12_381_G1, BN254_G1, BLS12_381_G2, BN254_G2 = 0, 1, 2, 3
 N8 = {BLS12_381_G1: 48, BN254_G1: 32, BLS12_381_G2: 96, BN254_G2: 64}     # bytes per coordinate-field element (Fq / Fq2)
 
-EXPORTS = [  # every symbol include/b200msm.h declares (checked by tests/test_abi.py)
-    "b200msm_create", "b200msm_destroy", "b200msm_strerror", "b200msm_last_error", "b200msm_version",
+EXPORTS = [  # every symbol include/b200msm.h and include/b200msm_probes.h declare (checked by tests/test_abi.py)
+    "b200msm_create", "b200msm_create_multi", "b200msm_device_count", "b200msm_destroy", "b200msm_strerror", "b200msm_last_error", "b200msm_version",
     "b200msm_set_stream", "b200msm_synchronize", "b200msm_g1_multiexp_affine", "b200msm_g1_multiexp_affine_chunk",
     "b200msm_g1_multiexp", "b200msm_g1_multiexp_chunk",
     "b200msm_upload_bases", "b200msm_free_bases", "b200msm_g1_multiexp_resident", "b200msm_g1_normalize",
     "b200msm_g1_sum", "b200msm_g1_generate_bases", "b200msm_fq_op", "b200msm_probe_imad", "b200msm_probe_imad32", "b200msm_probe_fqmul",
     "b200msm_set_option", "b200msm_constants", "b200msm_get_counter", "b200msm_g1_batch_convert",
-    "b200msm_glv_decompose_scalars", "b200msm_g1_glv_preprocess", "b200msm_upload_bases_windowed", "b200msm_probe_dfma", "b200msm_g1_multiexp_batch", "b200msm_fr_fft", "b200msm_fr_fft_last_phases", "b200msm_probe_dualpipe",
+    "b200msm_glv_decompose_scalars", "b200msm_g1_glv_preprocess", "b200msm_upload_bases_windowed", "b200msm_g1_multiexp_batch", "b200msm_fr_fft", "b200msm_fr_fft_last_phases",
 ]
+EXPERIMENT_EXPORTS = ["b200msm_probe_dfma", "b200msm_probe_dualpipe"]      # only in -DB200_EXPERIMENTS builds (include/b200msm_probes.h)
 
 
 class Stats(ctypes.Structure):
@@ -52,6 +53,8 @@ if not os.path.exists(LIB_PATH):
 lib = ctypes.CDLL(LIB_PATH)
 _vp, _u32, _u64, _i = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int
 lib.b200msm_create.argtypes = [ctypes.POINTER(_vp), _i]
+lib.b200msm_create_multi.argtypes = [ctypes.POINTER(_vp), ctypes.POINTER(_i), _i]
+lib.b200msm_device_count.argtypes = [_vp]
 lib.b200msm_destroy.argtypes = [_vp]; lib.b200msm_destroy.restype = None
 lib.b200msm_strerror.argtypes = [_i]; lib.b200msm_strerror.restype = ctypes.c_char_p
 lib.b200msm_last_error.argtypes = [_vp]; lib.b200msm_last_error.restype = ctypes.c_char_p
@@ -76,8 +79,9 @@ lib.b200msm_fq_op.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _u64]
 lib.b200msm_probe_imad.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
 lib.b200msm_probe_imad32.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
 lib.b200msm_probe_fqmul.argtypes = [_vp, _i, ctypes.POINTER(ctypes.c_double)]
-lib.b200msm_probe_dfma.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
-lib.b200msm_probe_dualpipe.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
+if hasattr(lib, "b200msm_probe_dfma"):
+    lib.b200msm_probe_dfma.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
+    lib.b200msm_probe_dualpipe.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
 lib.b200msm_set_option.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int64]
 lib.b200msm_g1_batch_convert.argtypes = [_vp, _i, _i, _vp, _u64, _vp]
 lib.b200msm_glv_decompose_scalars.argtypes = [_vp, _i, _vp, _u64, _vp, _vp]

@@ -24,10 +24,19 @@ def _ptr(x):
 
 
 class Engine:
-    def __init__(self, device=-1):
+    def __init__(self, device=-1, devices=None):
+        """device: one GPU ordinal (-1 = current).  devices: a list of ordinals -> ONE multi-device context (b200msm_create_multi):
+        every MSM call on it shards the points over those GPUs behind the same entry points."""
         self._ctx = ctypes.c_void_p()
-        rc = lib.b200msm_create(ctypes.byref(self._ctx), device)
+        if devices is not None and len(devices) > 1:
+            ids = (ctypes.c_int * len(devices))(*devices)
+            rc = lib.b200msm_create_multi(ctypes.byref(self._ctx), ids, len(devices))
+        else:
+            rc = lib.b200msm_create(ctypes.byref(self._ctx), device if devices is None else devices[0])
         if rc: raise B200MsmError(rc, "b200msm_create failed: is a B200 visible? (no CPU fallback)")
+
+    @property
+    def device_count(self): return lib.b200msm_device_count(self._ctx)
 
     def close(self):
         if self._ctx: lib.b200msm_destroy(self._ctx); self._ctx = ctypes.c_void_p()

@@ -27,11 +27,6 @@ constexpr int BA_THREADS = 128;     // threads per block in the tree kernels; a 
                                     // K = additions per thread per inversion chain (level 0) or product-tree arity (levels >= 1): run-time parameters
 constexpr uint32_t BA_ROOT_MAX = 1024;   // = BA_ROOT_THREADS * ROOT_PER   // the product tree is reduced until at most this many values remain
 
-// n_{r+1}[b] = ceil(n_r[b] / 2)
-__global__ void k_halve_counts(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (in[i] + 1) >> 1;
-}
 // All rounds' segment offsets in one three-phase scan: off[r][b] = exclusive scan over b of ceil(n_0[b] / 2^r), r = 1..R.
 // offs: R arrays of (n + 1) words; tile_sums: R arrays of (ntiles + 1) words.
 __global__ void __launch_bounds__(SCAN_THREADS) k_mscan_tiles(const uint32_t* __restrict__ cnt0, uint32_t n, uint32_t R,
@@ -155,13 +150,11 @@ B200_DI void soa_store_point(void* __restrict__ dst, uint64_t yoff, uint32_t j, 
 // The kernel is gather-bound (two scattered 96-byte points per slot in round 0), so the x coordinates of slot i+1 are requested
 // before the multiplication of slot i and the operand references of slot i+2 before that (only the x coordinates are needed;
 // the y coordinates are fetched in the rare equal-x / zero-x cases).
+// One tile (K * BA_THREADS consecutive slots, thread t owns slots t, t + 128, ...): returns the thread's running product in p.
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 3 : 6) k_tree_fwd(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
-                                                            void* __restrict__ prefix, void* __restrict__ prod, int K, uint32_t ntiles) {
- // persistent form: gridDim.x may be smaller than ntiles (leaves SM room for the other lane's latency-bound kernels)
- for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
+B200_DI void tree_fwd_tile(Fe<C::N>& p, const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff, void* __restrict__ prefix, int K, uint32_t tb) {
   const uint32_t tile = tb * (K * BA_THREADS) + threadIdx.x;
-  Fe<C::N> p; fe_set_one<C>(p);
+  fe_set_one<C>(p);
   Fe<C::N> x1, x2, nx1, nx2;
   uint2 mc = meta[tile], mn = K > 1 ? meta[tile + BA_THREADS] : make_uint2(META_NONE, META_NONE);
   if (mc.y != META_NONE) { meta_load_x<C, FIRST>(x1, src, mc.x); meta_load_x<C, FIRST>(x2, src, mc.y); }
@@ -186,19 +179,23 @@ __global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 3 : 6) k_tree_fwd(cons
     }
     mc = mn; mn = mn2; x1 = nx1; x2 = nx2;
   }
+}
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 3 : 6) k_tree_fwd(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
+                                                            void* __restrict__ prefix, void* __restrict__ prod, int K, uint32_t ntiles) {
+ // persistent form: gridDim.x may be smaller than ntiles (leaves SM room for the other lane's latency-bound kernels)
+ for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
+  Fe<C::N> p;
+  tree_fwd_tile<C, FIRST>(p, meta, src, yoff, prefix, K, tb);
   fe_store<C>(reinterpret_cast<char*>(prod) + (uint64_t)(tb * BA_THREADS + threadIdx.x) * 4 * C::N, p);
  }
 }
 
-// backward: consume the inverse of the thread's product, finish every addition, write the round's output points
+// backward: consume the inverse q of the thread's product, finish every addition, write the round's output points
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_bwd(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
-                                                         const void* __restrict__ prefix, const void* __restrict__ inv,
-                                                         void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles) {
- for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
+B200_DI void tree_bwd_tile(Fe<C::N>& q, const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff, const void* __restrict__ prefix,
+                           void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t tb) {
   const uint32_t tile = tb * (K * BA_THREADS) + threadIdx.x;
-  Fe<C::N> q;
-  fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)(tb * BA_THREADS + threadIdx.x) * 4 * C::N);
   uint2 mn = meta[tile + (K - 1) * BA_THREADS];
 #pragma unroll 1
   for (int i = K - 1; i >= 0; i--) {
@@ -214,19 +211,194 @@ __global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_bwd(cons
     int kind = affine_add_denominator<C>(d, p1, p2);
     if (kind <= 1) {
       Fe<C::N> pre; fe_load_cg<C>(pre, reinterpret_cast<const char*>(prefix) + (uint64_t)j * 4 * C::N);
-#if defined(B200_MUL2)
-      Fe<C::N> qn; fe_mul2<C>(dinv, q, pre, qn, q, d); q = qn;
-#else
-      fe_mul<C>(dinv, q, pre);
-      fe_mul<C>(q, q, d);
-#endif
+      // the two multiplications of the inverse-sharing step are independent: their rows are interleaved (fe_mul2), which doubles the
+      // work between dependent carry-chain instructions (measured: k_tree_bwd 3.46 -> 3.39 ms at 2^20, profiles/README.md r2)
+      if constexpr (C::EXT == 1) { Fe<C::N> qn; fe_mul2<C>(dinv, q, pre, qn, q, d); q = qn; }
+      else { fe_mul<C>(dinv, q, pre); fe_mul<C>(q, q, d); }
     }
     affine_add_finish<C>(r, p1, p2, dinv, kind);
     soa_store_point<C>(pout, yoff_out, j, r);
   }
+}
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_bwd(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
+                                                         const void* __restrict__ prefix, const void* __restrict__ inv,
+                                                         void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles) {
+ for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
+  Fe<C::N> q;
+  fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)(tb * BA_THREADS + threadIdx.x) * 4 * C::N);
+  tree_bwd_tile<C, FIRST>(q, meta, src, yoff, prefix, pout, yoff_out, K, tb);
  }
 }
 
+// ---- one tree round in ONE persistent launch ------------------------------------------------------------------------------------
+// k_tree_fwd, the product-tree levels, the root inversion and k_tree_bwd of a round as a single kernel of G co-resident CTAs.
+// CTA c owns the tiles c, c + G, c + 2G, ... ("wave" w = the G tiles w*G .. w*G + G - 1).  Every wave is one batch inversion
+// (f1m_batchInverse, build_batchinverse.js:4-140) of its own: a thread's running product goes up a 128-leaf tree in shared memory,
+// the CTA's product goes to global memory, and one extra CTA (the "root CTA", which owns no tiles) multiplies the <= G CTA products of a
+// wave together as soon as all of them are there (one chain per thread + the same shared-memory tree), inverts the single root (bingcd.h),
+// walks back down and releases the wave.  (A first version let the LAST-arriving worker run the root: that worker then fell one root behind
+// per wave and every wave waited for it -- 3.8 instead of 2.1 ms for round 0 at 2^20.)
+// The waves are software-pipelined: a CTA runs the forward passes of waves w+1 and w+2 BEFORE it waits for the inverse of wave w, so the
+// latency of a wave's root (tree + one inversion, ~70 us) is covered by forward work and by the other CTAs of
+// the SM, which drift out of phase -- gather-bound forward tiles and multiplier-bound backward tiles then share an SM, instead of
+// running as separate kernels one after the other.  Launched cooperatively (all G CTAs resident: the waits below cannot starve), with
+// a clock-bounded spin as a backstop that raises sy.error instead of hanging the device.
+struct RoundSync {
+  uint32_t* arrive;      // [waves]      CTAs that have published their product of wave w
+  uint32_t* ready;       // [waves]      1 once cta_inv[w][*] is complete
+  void* cta_prod;        // [waves][G]   CTA products
+  void* cta_inv;         // [waves][G]   their inverses (scratch for the prefix products of the root's chains before that)
+  uint32_t* error;       // [1]          a spin wait timed out (results invalid)
+};
+constexpr long long ROUND_SPIN_LIMIT = 4000000000ll;      // ~2 s at 1.9 GHz
+
+B200_DI uint32_t ld_volatile_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+// 128-leaf product tree in shared memory, heap order (node 1 = root, leaves at [T, 2T)); all threads of the CTA call these
+template <class C> B200_DI void cta_tree_up(uint32_t* __restrict__ tree, const Fe<C::N>& leaf) {
+  constexpr int N = C::N; const uint32_t t = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < N; k++) tree[(BA_THREADS + t) * N + k] = leaf.l[k];
+  __syncthreads();
+#pragma unroll 1
+  for (uint32_t width = BA_THREADS / 2; width >= 1; width >>= 1) {
+    if (t < width) {
+      Fe<N> a, b, c; const uint32_t node = width + t;
+#pragma unroll
+      for (int k = 0; k < N; k++) { a.l[k] = tree[(2 * node) * N + k]; b.l[k] = tree[(2 * node + 1) * N + k]; }
+      fe_mul<C>(c, a, b);
+#pragma unroll
+      for (int k = 0; k < N; k++) tree[node * N + k] = c.l[k];
+    }
+    __syncthreads();
+  }
+}
+// node 1 holds the inverse of the root on entry; on exit q = inverse of this thread's leaf
+template <class C> B200_DI void cta_tree_down(uint32_t* __restrict__ tree, Fe<C::N>& q) {
+  constexpr int N = C::N; const uint32_t t = threadIdx.x;
+#pragma unroll 1
+  for (uint32_t width = 1; width < BA_THREADS; width <<= 1) {
+    if (t < width) {
+      Fe<N> a, b, ip, ia, ib; const uint32_t node = width + t;
+#pragma unroll
+      for (int k = 0; k < N; k++) { ip.l[k] = tree[node * N + k]; a.l[k] = tree[(2 * node) * N + k]; b.l[k] = tree[(2 * node + 1) * N + k]; }
+      fe_mul<C>(ia, ip, b); fe_mul<C>(ib, ip, a);
+#pragma unroll
+      for (int k = 0; k < N; k++) { tree[(2 * node) * N + k] = ia.l[k]; tree[(2 * node + 1) * N + k] = ib.l[k]; }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < N; k++) q.l[k] = tree[(BA_THREADS + t) * N + k];
+}
+// the wave's root, run by the whole CTA that arrived last: cnt CTA products -> their inverses
+template <class C> __device__ __noinline__ void round_root(uint32_t* __restrict__ tree, const void* __restrict__ prods, void* __restrict__ invs, uint32_t cnt) {
+  constexpr int N = C::N; const uint32_t t = threadIdx.x;
+  Fe<N> p; fe_set_one<C>(p);
+#pragma unroll 1
+  for (uint32_t e = t; e < cnt; e += BA_THREADS) {       // chain of this thread; its prefix products wait in invs[]
+    Fe<N> v; fe_load_l2<C>(v, reinterpret_cast<const char*>(prods) + (uint64_t)e * 4 * N);
+    fe_store<C>(reinterpret_cast<char*>(invs) + (uint64_t)e * 4 * N, p);
+    fe_mul<C>(p, p, v);
+  }
+  cta_tree_up<C>(tree, p);
+  if (t == 0) {
+    Fe<N> r, ri;
+#pragma unroll
+    for (int k = 0; k < N; k++) r.l[k] = tree[1 * N + k];
+    fe_inv_fast<C>(ri, r);
+#pragma unroll
+    for (int k = 0; k < N; k++) tree[1 * N + k] = ri.l[k];
+  }
+  __syncthreads();
+  Fe<N> q; cta_tree_down<C>(tree, q);
+  if (cnt > 0) {
+    const uint32_t last = t + ((cnt - 1 - t) / BA_THREADS) * BA_THREADS;      // largest e = t (mod 128) below cnt (t < cnt)
+    if (t < cnt) {
+#pragma unroll 1
+      for (int64_t e = last; e >= (int64_t)t; e -= BA_THREADS) {
+        Fe<N> v, pre, r;
+        fe_load_l2<C>(v, reinterpret_cast<const char*>(prods) + (uint64_t)e * 4 * N);
+        fe_load_l2<C>(pre, reinterpret_cast<const char*>(invs) + (uint64_t)e * 4 * N);
+        fe_mul<C>(r, q, pre); fe_mul<C>(q, q, v);
+        fe_store<C>(reinterpret_cast<char*>(invs) + (uint64_t)e * 4 * N, r);
+      }
+    }
+  }
+}
+
+constexpr uint32_t ROUND_DEPTH = 2;       // waves whose forward pass runs ahead of the backward pass (tree buffers: ROUND_DEPTH + 1)
+
+// gridDim.x = G + 1: CTAs 0..G-1 are the workers, the last CTA only runs the waves' roots (so that no worker falls behind by a root per wave)
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(BA_THREADS, 4) k_tree_round(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff, void* __restrict__ prefix,
+                                                              void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles, RoundSync sy) {
+  constexpr int N = C::N;
+  __shared__ uint32_t trees[ROUND_DEPTH + 1][2 * BA_THREADS * N];       // the trees of the waves in flight (the root CTA uses the first)
+  __shared__ uint32_t s_stop;
+  const uint32_t G = gridDim.x - 1, c = blockIdx.x, t = threadIdx.x;
+  const uint32_t nw = (ntiles + G - 1) / G;
+  auto spin_until = [&](const uint32_t* flag, uint32_t want) {          // thread 0 only; false = gave up (error raised by this or another CTA)
+    const long long t0 = clock64();
+    while (ld_volatile_u32(flag) < want) {
+      __nanosleep(64);
+      if (ld_volatile_u32(sy.error) != 0u) return false;
+      if (clock64() - t0 > ROUND_SPIN_LIMIT) { atomicExch(sy.error, 1u); return false; }
+    }
+    return true;
+  };
+  if (c == G) {
+    // ---- root CTA: wave after wave, wait until all its CTAs have published, invert, release
+#pragma unroll 1
+    for (uint32_t w = 0; w < nw; w++) {
+      const uint32_t cnt = min(G, ntiles - w * G);
+      if (t == 0) { s_stop = spin_until(sy.arrive + w, cnt) ? 0u : 1u; __threadfence(); }
+      __syncthreads();
+      if (s_stop) return;
+      round_root<C>(trees[0], reinterpret_cast<const char*>(sy.cta_prod) + (uint64_t)w * G * 4 * N, reinterpret_cast<char*>(sy.cta_inv) + (uint64_t)w * G * 4 * N, cnt);
+      __threadfence();
+      __syncthreads();
+      if (t == 0) atomicExch(sy.ready + w, 1u);
+    }
+    return;
+  }
+  if (c >= ntiles) return;
+  const uint32_t mine = (ntiles - c + G - 1) / G;          // waves this CTA takes part in (>= 1)
+#pragma unroll 1
+  for (uint32_t it = 0; it < mine + ROUND_DEPTH; it++) {   // iteration `it`: forward pass of wave `it`, then wait + backward pass of wave `it - ROUND_DEPTH`
+    if (it < mine) {
+      Fe<N> p;
+      tree_fwd_tile<C, FIRST>(p, meta, src, yoff, prefix, K, it * G + c);
+      uint32_t* tr = trees[it % (ROUND_DEPTH + 1)];
+      cta_tree_up<C>(tr, p);
+      if (t == 0) {
+        Fe<N> r;
+#pragma unroll
+        for (int k = 0; k < N; k++) r.l[k] = tr[1 * N + k];
+        fe_store<C>(reinterpret_cast<char*>(sy.cta_prod) + ((uint64_t)it * G + c) * 4 * N, r);
+        __threadfence();
+        atomicAdd(sy.arrive + it, 1u);
+      }
+    }
+    if (it < ROUND_DEPTH) continue;
+    const uint32_t w = it - ROUND_DEPTH;
+    uint32_t* tr = trees[w % (ROUND_DEPTH + 1)];
+    if (t == 0) {
+      spin_until(sy.ready + w, 1u);
+      __threadfence();
+      Fe<N> r; fe_load_l2<C>(r, reinterpret_cast<const char*>(sy.cta_inv) + ((uint64_t)w * G + c) * 4 * N);
+#pragma unroll
+      for (int k = 0; k < N; k++) tr[1 * N + k] = r.l[k];
+    }
+    __syncthreads();
+    Fe<N> q; cta_tree_down<C>(tr, q);
+    tree_bwd_tile<C, FIRST>(q, meta, src, yoff, prefix, pout, yoff_out, K, w * G + c);
+    __syncthreads();                                       // the tree buffer of wave w is free for wave w + ROUND_DEPTH + 1
+  }
+}
+
+#if defined(B200_EXPERIMENTS)      // measured 0-8 % slower than k_tree_bwd (profiles/README.md): not in the shipped library
 // backward pass with operand staging: the 2 points + prefix product of the NEXT slot are copied global -> shared with cp.async
 // while the current slot's five multiplications run, so the arithmetic never waits on a gather (the plain kernel above shows
 // 2.3 of its 4 warps per scheduler stalled on the scoreboard).  Each thread stages only its own operands (chunk-major layout:
@@ -305,6 +477,8 @@ __global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_bwd_stag
   cp_async_wait_all();
  }
 }
+
+#endif  // B200_EXPERIMENTS
 
 // ---- product tree, levels >= 1: plain arrays of field elements -----------------------------------------
 // A level reduces n values by K per thread (serial running product, prefixes stored) and, when WARP is set, by a further

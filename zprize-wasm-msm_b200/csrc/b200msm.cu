@@ -16,9 +16,12 @@
 #include <algorithm>
 
 #include "../../include/b200msm.h"
+#include "../../include/b200msm_probes.h"
 #include "msm_kernels.cuh"
 #include "accumulate.cuh"
+#if defined(B200_EXPERIMENTS)
 #include "fp29.cuh"
+#endif
 #include "codecs.cuh"
 #include "glv.cuh"
 #include "host_ec.h"
@@ -34,11 +37,18 @@ struct DevBuf {
   void* p = nullptr; size_t cap = 0;
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
-    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    // the new block is obtained BEFORE the old one is released: a failed allocation leaves the buffer as it was.  Only when the two
+    // do not fit side by side is the old block given up first (grow-only scratch holds no data across calls).
     size_t want = bytes + (bytes >> 3) + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) { p = nullptr; return e; }
-    cap = want; return cudaSuccess;
+    void* np_ = nullptr;
+    cudaError_t e = cudaMalloc(&np_, want);
+    if (e != cudaSuccess && p) {
+      cudaGetLastError(); cudaFree(p); p = nullptr; cap = 0;
+      e = cudaMalloc(&np_, want);
+    }
+    if (e != cudaSuccess) return e;
+    if (p) cudaFree(p);
+    p = np_; cap = want; return cudaSuccess;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
@@ -47,11 +57,14 @@ struct DevBuf {
 struct Resident { int curve; uint64_t n; void* d;                // d: n affine points; with a window table: Wd rows of n points, row 0 = the bases
                   uint32_t t_nbits = 0, t_c0 = 0, t_rem = 0, t_Wd = 0; };   // window plan the table was built for (t_Wd == 0: no table)
 struct Precomp { uint32_t stride, nbits, c0, rem, Wd; };
+// one base set spread over the devices of a multi context: device g holds points [lo[g], lo[g] + cnt[g]) under its own handle h[g]
+// (sharded: disjoint ranges; replicated: every device holds [0, n))
+struct MultiResident { int curve; uint64_t n; bool replicated; std::vector<uint64_t> h, lo, cnt; };
 
 // one accumulate lane: a stream with its own tree scratch (see accumulate_batch_affine)
 struct TreeLane {
   cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
-  DevBuf offs, tiles, bid, pa, pb, prefix, prod, lvlprefix, others, meta;
+  DevBuf offs, tiles, bid, pa, pb, prefix, prod, lvlprefix, others, meta, sync;      // sync: wave counters / flags / CTA products of the fused round kernel
 };
 constexpr int MAX_LANES = 8;
 constexpr uint64_t WARP_LEVEL_MAX = 131072;     // product-tree levels with at most this many values use the warp-assisted kernel (only one such level can occur: 131072 / 128 <= BA_ROOT_MAX)
@@ -63,8 +76,9 @@ struct b200msm_ctx {
   cudaStream_t stream = nullptr; bool own_stream = false;
   std::string err;
   int opt_window_bits = 0, opt_accumulate = 0, opt_tree_rounds = -1;
-  DevBuf bases, scalars, canon, counts, offsets, cursors, tiles, sorted, buckets, wsum, out, misc, acc_a, acc_b, acc_c, acc_d, acc_e, jac_in, jac_affine;
+  DevBuf bases, scalars, canon, counts, offsets, ranks, tiles, sorted, buckets, wsum, out, misc, acc_a, acc_b, acc_c, acc_d, acc_e, jac_in, jac_affine;
   TreeLane lane[MAX_LANES];                                                   // batch-affine tree lanes
+  int opt_fused = 0, round_slots[4] = {0, 0, 0, 0};      // fused round kernel (k_tree_round): on for the prime fields; co-resident CTAs per device for each curve (0 = not queried yet)
   int opt_lanes = 4, opt_ba_k = 0, opt_pt_k = 8, opt_persist = 592, opt_subslots = 0, opt_bwd_staged = 0, opt_probe_smem = 0;
   bool probe29 = false, probe_sqr = false; int64_t opt_group_pairs = 0;
   cudaEvent_t ev_plan = nullptr, ev_sorted = nullptr, ev_bases = nullptr, ev_done = nullptr;
@@ -78,8 +92,10 @@ struct b200msm_ctx {
   cudaEvent_t ev[8] = {};
   // fine-grained phase profiler (active only while a stats struct is being filled)
   std::vector<cudaEvent_t> pev; std::vector<int> ptag; size_t pused = 0; bool prof = false;
-  uint64_t launches = 0, adds_r0 = 0, adds_exact = 0, cur_n = 0;
+  uint64_t launches = 0, adds_r0 = 0, adds_exact = 0, cur_n = 0; uint32_t fused_groups = 0;
   size_t total_mem = 0;
+  // multi-device context (b200msm_create_multi): devs[0] == this, devs[g] = the single-device context of device g; mres = handles of sharded / replicated base sets
+  std::vector<b200msm_ctx*> devs; std::map<uint64_t, MultiResident> mres; int64_t opt_multi_min = 1 << 15; int opt_multi_replicate = 0;
   std::vector<b200msm_ctx*> workers; int opt_batch_workers = 4;            // sub-contexts (own stream + scratch) that run the MSMs of a batch concurrently
 };
 
@@ -90,6 +106,12 @@ namespace {
 #define CKL() do { ctx->launches++; CK(cudaGetLastError()); } while (0)
 enum { T_SORT = 0, T_PLAN, T_TREE_FWD, T_INV_TREE, T_TREE_BWD, T_FINISH, T_FOLD, T_WSUM, T_HORNER, T_TREE_BWD0, T_NTAGS };
 #define MARK(tag) do { if (ctx->prof) { int rc_ = prof_mark(ctx, tag); if (rc_) return rc_; } } while (0)
+
+void copy_options(b200msm_ctx* w, const b200msm_ctx* ctx) {
+  w->opt_window_bits = ctx->opt_window_bits; w->opt_accumulate = ctx->opt_accumulate; w->opt_tree_rounds = ctx->opt_tree_rounds; w->opt_lanes = ctx->opt_lanes;
+  w->opt_ba_k = ctx->opt_ba_k; w->opt_pt_k = ctx->opt_pt_k; w->opt_persist = ctx->opt_persist; w->opt_subslots = ctx->opt_subslots; w->opt_combine = ctx->opt_combine;
+  w->opt_group_pairs = ctx->opt_group_pairs; w->opt_fused = ctx->opt_fused; w->opt_batch_workers = ctx->opt_batch_workers;
+}
 
 int lane_init(b200msm_ctx* ctx, TreeLane& ln) {
   if (!ln.stream) {
@@ -110,12 +132,14 @@ int prof_mark(b200msm_ctx* ctx, int tag) {
   return B200MSM_OK;
 }
 
-bool is_device_ptr(const void* p) {
-  if (!p) return false;
+// device ordinal a pointer lives on, -1 for host memory (pageable, pinned or unknown)
+int ptr_device(const void* p) {
+  if (!p) return -1;
   cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
 }
+bool is_device_ptr(const void* p) { return ptr_device(p) >= 0; }
 
 // n8 = bytes per coordinate-field element: Fq for G1 (48 / 32), Fq2 for G2 (96 / 64)
 int n8_of(int curve) { static const int t[4] = {48, 32, 96, 64}; return t[curve & 3]; }
@@ -183,9 +207,11 @@ int exclusive_scan(b200msm_ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t
 // off0 = sort offsets (absolute positions in sorted[]), cnt0 = bucket counts of the range,
 // m0 = pairs in the range, maxcnt = largest bucket population in the range.  Writes buckets_g[0 .. nbg) as XYZZ.
 template <class C>
-int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases, const uint32_t* off0, const uint32_t* cnt0, uint32_t nbg, uint64_t m0,
+int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, uint32_t share, const void* d_bases, const uint32_t* off0, const uint32_t* cnt0, uint32_t nbg, uint64_t m0,
                             uint32_t maxcnt, void* buckets_g, uint32_t* rounds_out, uint64_t* adds_out) {
-  cudaStream_t s = ln_.stream;
+  const bool overlapped = share > 1;
+  // s = the stream this group is issued on: the lane's own stream when several lanes overlap, the context's stream otherwise
+  // (the lane then only lends its scratch; nothing in the lane is modified, so every error return leaves the context intact)
   const uint32_t* sorted = ctx->sorted.as<uint32_t>();
   // number of tree rounds: until the largest segment is <= 3 points (the finish kernel sums the rest serially)
   uint32_t R = 0;
@@ -229,6 +255,23 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
   k_fill_bid<<<(nbg + 255) / 256, 256, 0, s>>>(off[1], nbg, bid[1]); CKL();
   MARK(T_PLAN);
   const size_t fe = 4 * C::N, pt = 8 * C::N;
+  bool fused = false;
+  if constexpr (C::EXT == 1) {
+    fused = ctx->opt_fused != 0;
+    if (fused && ctx->round_slots[C::ID & 3] == 0) {      // co-resident CTAs of the round kernel on this device (once per context and curve)
+      cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
+      // shared-memory carve-out: exactly what 4 CTAs need (3 product trees each); the rest of the 228 KB stays L1 for the 16-byte gathers
+      cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_tree_round<C, true>));
+      const int carve = std::min<int>(100, (int)((4 * (fa.sharedSizeBytes + 1024) * 100) / (228 * 1024)) + 2);
+      CK(cudaFuncSetAttribute(k_tree_round<C, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+      CK(cudaFuncSetAttribute(k_tree_round<C, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+      int o1 = 0, o2 = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_tree_round<C, true>, BA_THREADS, 0));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_tree_round<C, false>, BA_THREADS, 0));
+      ctx->round_slots[C::ID & 3] = std::max(1, std::min(o1, o2)) * prop.multiProcessorCount;
+      if (!prop.cooperativeLaunch) { ctx->round_slots[C::ID & 3] = 0; fused = false; ctx->opt_fused = 0; }
+    }
+  }
   const int BK = ctx->opt_ba_k > 0 ? ctx->opt_ba_k : (m0 >= (1u << 22) ? 16 : 8), PK = ctx->opt_pt_k;     // chain length per thread: measured 2^20: 8 -> 6.84, 12 -> 6.76, 16 -> 6.70 ms; 2^18: 2.70 / 2.69 / 2.80
   const uint64_t BA_TILE = (uint64_t)BK * BA_THREADS;
   CK(ln_.pa.ensure(U[1] * pt + 1024)); if (R > 1) CK(ln_.pb.ensure(U[2] * pt + 1024));
@@ -245,12 +288,31 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
     uint32_t grid = (uint32_t)((U[r + 1] + BA_TILE - 1) / BA_TILE);
     if (grid == 0) grid = 1;
     char* prod = ln_.prod.as<char>(); char* lpre = ln_.lvlprefix.as<char>();
-    const uint32_t pgrid = (ctx->opt_persist > 0 && ln_.stream != ctx->stream) ? std::min<uint32_t>(grid, (uint32_t)ctx->opt_persist) : grid;   // persistent grid only when lanes overlap
+    const uint32_t pgrid = (ctx->opt_persist > 0 && overlapped) ? std::min<uint32_t>(grid, (uint32_t)ctx->opt_persist) : grid;   // persistent grid only when lanes overlap
     const uint32_t nslots = grid * (uint32_t)BA_TILE;
     uint2* meta = ln_.meta.as<uint2>();
     if (r == 0) k_tree_meta<true><<<(nslots + 255) / 256, 256, 0, s>>>(tr, sorted, meta, nslots);
     else k_tree_meta<false><<<(nslots + 255) / 256, 256, 0, s>>>(tr, nullptr, meta, nslots);
     CKL();
+    if constexpr (C::EXT == 1) if (fused) {
+      // ---- the whole round (forward pass, product tree, root inversion, backward pass) as ONE cooperative launch of G co-resident CTAs
+      const uint32_t slots = (uint32_t)ctx->round_slots[C::ID & 3] / std::max<uint32_t>(1, share);        // co-resident CTAs this lane may use; one of them is the root CTA
+      const uint32_t G = std::max<uint32_t>(1, std::min<uint32_t>(grid, slots > 1 ? slots - 1 : 1));
+      const uint32_t nw = (grid + G - 1) / G;
+      const size_t ctr = (((size_t)2 * nw * 4 + 255) / 256) * 256, arr = (size_t)nw * G * fe;
+      CK(ln_.sync.ensure(256 + ctr + 2 * arr + 256));
+      char* sb = ln_.sync.as<char>();
+      if (r == 0) CK(cudaMemsetAsync(sb, 0, 256 + ctr, s)); else CK(cudaMemsetAsync(sb + 256, 0, ctr, s));      // the error word survives the rounds of a group
+      RoundSync sy{reinterpret_cast<uint32_t*>(sb + 256), reinterpret_cast<uint32_t*>(sb + 256) + nw, sb + 256 + ctr, sb + 256 + ctr + arr, reinterpret_cast<uint32_t*>(sb)};
+      const void* a_src = r == 0 ? d_bases : pin; uint64_t a_yin = r == 0 ? 0 : yin; void* a_prefix = ln_.prefix.p; int a_K = BK; uint32_t a_nt = grid; uint64_t a_yout = yout; void* a_pout = pout;
+      void* args[] = {&meta, &a_src, &a_yin, &a_prefix, &a_pout, &a_yout, &a_K, &a_nt, &sy};
+      const void* fn = r == 0 ? (const void*)k_tree_round<C, true> : (const void*)k_tree_round<C, false>;
+      CK(cudaLaunchCooperativeKernel(fn, dim3(G + 1), dim3(BA_THREADS), args, 0, s));
+      CKL(); MARK(r == 0 ? T_TREE_BWD0 : T_TREE_BWD);
+      pin = pout; yin = yout;
+      *adds_out += U[r] - U[r + 1];
+      continue;
+    }
     if (r == 0) k_tree_fwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(meta, d_bases, 0, ln_.prefix.p, prod, BK, grid);
     else k_tree_fwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(meta, pin, yin, ln_.prefix.p, prod, BK, grid);
     CKL(); MARK(T_TREE_FWD);
@@ -279,11 +341,13 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
       CKL();
     }
     MARK(T_INV_TREE);
+#if defined(B200_EXPERIMENTS)
     if (ctx->opt_bwd_staged) {
       const size_t smem = (size_t)(5 * (C::N / 4)) * BA_THREADS * 16;          // 2 points + 1 field element per thread
       if (r == 0) k_tree_bwd_staged<C, true><<<pgrid, BA_THREADS, smem, s>>>(meta, d_bases, 0, ln_.prefix.p, prod, pout, yout, BK, grid);
       else k_tree_bwd_staged<C, false><<<pgrid, BA_THREADS, smem, s>>>(meta, pin, yin, ln_.prefix.p, prod, pout, yout, BK, grid);
     } else
+#endif
     if (r == 0) k_tree_bwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(meta, d_bases, 0, ln_.prefix.p, prod, pout, yout, BK, grid);
     else k_tree_bwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(meta, pin, yin, ln_.prefix.p, prod, pout, yout, BK, grid);
     CKL(); MARK(r == 0 ? T_TREE_BWD0 : T_TREE_BWD);
@@ -297,6 +361,7 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, const void* d_bases
     for (uint32_t r = 1; r <= R; r++) { uint64_t cur = ctx->h_pinned[1024 + r]; exact += prev - cur; if (r == 1) ctx->adds_r0 += prev - cur; prev = cur; }
     *adds_out -= 0; ctx->adds_exact += exact;
   }
+  if (fused) CK(cudaMemcpyAsync(ctx->h_pinned + 1900 + (ctx->fused_groups++ & 63), ln_.sync.p, 4, cudaMemcpyDeviceToHost, s));      // wave-wait time-outs of this group (checked with the result)
   k_accum_finish<C, false><<<(nbg + 127) / 128, 128, 0, s>>>(nullptr, nullptr, pin, yin, off[R], nbg, buckets_g); CKL();
   MARK(T_FINISH);
   return B200MSM_OK;
@@ -341,12 +406,13 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   if (pl.W > 400) { ctx->err = "too many windows"; return B200MSM_E_UNSUPPORTED; }
 
   if (st) CK(cudaEventRecord(ctx->ev[1], s));
-  CK(ctx->counts.ensure((size_t)nb * 4)); CK(ctx->offsets.ensure((size_t)(nb + 1) * 4)); CK(ctx->cursors.ensure((size_t)nb * 4));
+  CK(ctx->counts.ensure((size_t)nb * 4)); CK(ctx->offsets.ensure((size_t)(nb + 1) * 4));
   CK(ctx->sorted.ensure((size_t)n * std::max(pl.W, pl.Wd) * 4 + 16));
   CK(cudaMemsetAsync(ctx->counts.p, 0, (size_t)nb * 4, s));
   const uint32_t tb = 256, gb = (n + tb - 1) / tb;
-  k_digits<false><<<gb, tb, 0, s>>>(d_scal, pl, ctx->counts.as<uint32_t>(), nullptr); CKL();
-  int rc = exclusive_scan(ctx, ctx->counts.as<uint32_t>(), ctx->offsets.as<uint32_t>(), nb, ctx->cursors.as<uint32_t>());
+  CK(ctx->ranks.ensure((size_t)n * pl.Wd * 4 + 16));
+  k_digits<false><<<gb, tb, 0, s>>>(d_scal, pl, ctx->counts.as<uint32_t>(), nullptr, ctx->ranks.as<uint32_t>(), nullptr); CKL();
+  int rc = exclusive_scan(ctx, ctx->counts.as<uint32_t>(), ctx->offsets.as<uint32_t>(), nb, nullptr);
   if (rc) return rc;
   // ---- per-slot pair counts and largest bucket populations go back to the host while the scatter runs
   CK(ctx->misc.ensure(512 * 4));
@@ -366,7 +432,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   CK(cudaMemcpyAsync(ctx->h_pinned, ctx->misc.p, G * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpy2DAsync(ctx->h_pinned + 512, 4, ctx->offsets.as<uint32_t>(), (size_t)Bg * 4, 4, G + 1, cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(ctx->ev_plan, s));
-  k_digits<true><<<gb, tb, 0, s>>>(d_scal, pl, ctx->cursors.as<uint32_t>(), ctx->sorted.as<uint32_t>()); CKL();
+  k_digits<true><<<gb, tb, 0, s>>>(d_scal, pl, nullptr, ctx->offsets.as<uint32_t>(), ctx->ranks.as<uint32_t>(), ctx->sorted.as<uint32_t>()); CKL();
   if (st) CK(cudaEventRecord(ctx->ev[2], s));
   CK(cudaEventRecord(ctx->ev_sorted, s));
   CK(cudaEventSynchronize(ctx->ev_plan));
@@ -377,7 +443,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   int mode = ctx->opt_accumulate;
   if (mode == 0) mode = 2;
   uint32_t rounds = 0; uint64_t adds = 0;
-  ctx->adds_r0 = 0; ctx->adds_exact = 0; ctx->cur_n = n;
+  ctx->adds_r0 = 0; ctx->adds_exact = 0; ctx->cur_n = n; ctx->fused_groups = 0;
   if (pre) {
     // ---- window-table form: the single bucket array is cut into S sub-slots of Bs = Bg buckets (a power of two).  Each sub-slot is a
     // group: its tree runs on one lane, then it is folded on its own (k_fold sees it as a slot of Bs buckets) while the other lanes still
@@ -419,10 +485,9 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
       uint32_t mc = 0; for (uint32_t k = g0; k < g1; k++) mc = std::max(mc, ctx->h_pinned[k]);
       const uint64_t m0 = ctx->h_pinned[512 + g1] - ctx->h_pinned[512 + g0];
       const uint32_t b0 = g0 * Bg, nbg = (g1 - g0) * Bg;
-      cudaStream_t keep = ln.stream; if (lanes == 1) ln.stream = s;
-      cudaStream_t ls = ln.stream;
+      cudaStream_t ls = lanes == 1 ? s : ln.stream;
       char* bg = ctx->buckets.as<char>() + (size_t)b0 * 16 * C::N;
-      rc = accumulate_batch_affine<C>(ctx, ln, d_bases, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc, bg, &rounds, &adds);
+      rc = accumulate_batch_affine<C>(ctx, ln, ls, lanes, d_bases, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc, bg, &rounds, &adds);
       if (!rc && host_tail) {
         if (st && g + 1 == ngroups) CK(cudaEventRecord(ctx->ev[3], s));
         rc = fold_slots<C>(ctx, ls, bg, g1 - g0, Bg);
@@ -433,7 +498,6 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
           CK(cudaEventRecord(ctx->gev[g], ls));
         }
       }
-      ln.stream = keep;
       if (rc) return rc;
     }
     if (host_tail) {
@@ -449,6 +513,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
       }
       uint64_t* res = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ctx->h_folded) + fbytes);
       cb.finish(res);
+      for (uint32_t k = 0; k < std::min<uint32_t>(ctx->fused_groups, 64u); k++) if (ctx->h_pinned[1900 + k]) { ctx->err = "k_tree_round: a wave wait timed out (CTAs not co-resident?)"; return B200MSM_E_CUDA; }
       ctx->host_combine_ms = host_ms;
       if (lanes > 1) for (uint32_t l = 0; l < lanes; l++) { CK(cudaEventRecord(ctx->lane[l].done, ctx->lane[l].stream)); CK(cudaStreamWaitEvent(s, ctx->lane[l].done, 0)); }
       CK(cudaMemcpyAsync(d_out, res, 12 * C::N, cudaMemcpyHostToDevice, s));
@@ -510,10 +575,9 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
       uint32_t mc = 0; for (uint32_t w = w0; w < w1; w++) mc = std::max(mc, ctx->h_pinned[w]);
       uint64_t m0 = ctx->h_pinned[512 + w1] - ctx->h_pinned[512 + w0];
       uint32_t b0 = w0 * pl.B, nbg = (w1 - w0) * pl.B;
-      cudaStream_t keep = ln.stream; if (lanes == 1) ln.stream = s;
-      cudaStream_t ls = ln.stream;
+      cudaStream_t ls = lanes == 1 ? s : ln.stream;
       char* bg = ctx->buckets.as<char>() + (size_t)b0 * 16 * C::N;
-      rc = accumulate_batch_affine<C>(ctx, ln, d_bases, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc, bg, &rounds, &adds);
+      rc = accumulate_batch_affine<C>(ctx, ln, ls, lanes, d_bases, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc, bg, &rounds, &adds);
       if (!rc && (lanes > 1 || host_tail)) {
         if (st && gi + 1 == ngroups) CK(cudaEventRecord(ctx->ev[3], s));          // stats mode is single-lane: accumulate ends here
         rc = fold_slots<C>(ctx, ls, bg, w1 - w0, pl.B); }
@@ -523,7 +587,6 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
         CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->h_folded) + o, ctx->wsum.as<char>() + o, (size_t)np * 16 * C::N, cudaMemcpyDeviceToHost, ls));
         CK(cudaEventRecord(ctx->gev[gi], ls));
       }
-      ln.stream = keep;
       if (rc) return rc;
     }
     if (st) { if (!host_tail) CK(cudaEventRecord(ctx->ev[3], s)); else { MARK(T_FOLD); } CK(cudaEventRecord(ctx->ev[4], s)); }
@@ -541,6 +604,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
       auto t0 = std::chrono::steady_clock::now();
       uint64_t* res = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ctx->h_folded) + fbytes);   // 3*n8 bytes in the pinned tail
       cb.finish(res);
+      for (uint32_t k = 0; k < std::min<uint32_t>(ctx->fused_groups, 64u); k++) if (ctx->h_pinned[1900 + k]) { ctx->err = "k_tree_round: a wave wait timed out (CTAs not co-resident?)"; return B200MSM_E_CUDA; }
       ctx->host_combine_ms = host_ms + std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
       if (lanes > 1) for (uint32_t l = 0; l < lanes; l++) { CK(cudaEventRecord(ctx->lane[l].done, ctx->lane[l].stream)); CK(cudaStreamWaitEvent(s, ctx->lane[l].done, 0)); }
       CK(cudaMemcpyAsync(d_out, res, 12 * C::N, cudaMemcpyHostToDevice, s));
@@ -559,7 +623,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
     }
   } else {
     // serial accumulate (one thread per bucket): small problems / cross-check; device-side combination
-    k_accum_serial<C><<<(nb + 127) / 128, 128, 0, s>>>(d_bases, ctx->sorted.as<uint32_t>(), ctx->offsets.as<uint32_t>(), nb, ctx->buckets.p); CKL();
+    k_accum_finish<C, true><<<(nb + 127) / 128, 128, 0, s>>>(d_bases, ctx->sorted.as<uint32_t>(), nullptr, 0, ctx->offsets.as<uint32_t>(), nb, ctx->buckets.p); CKL();
     if (st) CK(cudaEventRecord(ctx->ev[3], s));
     rc = fold_slots<C>(ctx, s, ctx->buckets.p, pl.W, pl.B); if (rc) return rc;
     MARK(T_FOLD);
@@ -586,7 +650,7 @@ template <class C> int write_zero(b200msm_ctx* ctx, void* d_out) {
 }
 
 int deliver(b200msm_ctx* ctx, const void* d_src, void* user_out, size_t bytes) {
-  if (is_device_ptr(user_out)) { CK(cudaMemcpyAsync(user_out, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream)); }
+  if (is_device_ptr(user_out)) { CK(cudaMemcpyAsync(user_out, d_src, bytes, cudaMemcpyDefault, ctx->stream)); }      // any device (UVA); stays asynchronous
   else { CK(cudaMemcpyAsync(user_out, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
   return B200MSM_OK;
 }
@@ -594,14 +658,14 @@ int deliver(b200msm_ctx* ctx, const void* d_src, void* user_out, size_t bytes) {
 // stage an input: returns a device pointer (the user's if already on device and aligned, else a copy in `buf`)
 int stage(b200msm_ctx* ctx, const void* src, size_t bytes, DevBuf& buf, const void** d) {
   if (bytes == 0) { CK(buf.ensure(16)); *d = buf.p; return B200MSM_OK; }
-  if (is_device_ptr(src) && (reinterpret_cast<uintptr_t>(src) & 15) == 0) { *d = src; return B200MSM_OK; }
+  if (ptr_device(src) == ctx->device && (reinterpret_cast<uintptr_t>(src) & 15) == 0) { *d = src; return B200MSM_OK; }      // another device's memory is copied (UVA)
   CK(buf.ensure(bytes + 16));
   CK(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyDefault, ctx->stream));
   *d = buf.p; return B200MSM_OK;
 }
 
-int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_resident, const void* scalars, uint32_t scalar_size, uint64_t n,
-              uint32_t bit0, uint32_t nbits, void* out, b200msm_stats* st, const Precomp* pre = nullptr) {
+int msm_entry_impl(b200msm_ctx* ctx, int curve, const void* bases, bool bases_resident, const void* scalars, uint32_t scalar_size, uint64_t n,
+                   uint32_t bit0, uint32_t nbits, void* out, b200msm_stats* st, const Precomp* pre) {
   if (!ctx) return B200MSM_E_ARG;
   if (!curve_ok(curve) || !out || (n && (!bases || !scalars)) || scalar_size == 0) { ctx->err = "bad argument"; return B200MSM_E_ARG; }
   if (n >= (1ull << 31)) { ctx->err = "n must be < 2^31"; return B200MSM_E_UNSUPPORTED; }
@@ -613,7 +677,7 @@ int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_residen
   const uint64_t launches0 = ctx->launches;
   // clip the processed bit range at the scalar end (getChunk's bitsToEnd mask, build_multiexp.js:38-72)
   if (bit0 >= 8 * scalar_size) nbits = 0; else if (bit0 + nbits > 8 * scalar_size) nbits = 8 * scalar_size - bit0;
-  if (nbits > 256) { ctx->err = "more than 256 scalar bits per call are not supported"; return B200MSM_E_UNSUPPORTED; }
+  if (nbits > 256) { ctx->err = "internal: more than 256 scalar bits per pipeline pass"; return B200MSM_E_UNSUPPORTED; }
   int rc;
   if (n == 0 || nbits == 0) {
     B200_CURVE_SWITCH(curve, rc = write_zero<C>(ctx, ctx->out.p))
@@ -627,7 +691,7 @@ int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_residen
   ctx->bases_pending = false;
   if (!bases_resident) {
     const size_t bytes = (size_t)n * 2 * n8;
-    if (is_device_ptr(bases) && (reinterpret_cast<uintptr_t>(bases) & 15) == 0) d_bases = bases;
+    if (ptr_device(bases) == ctx->device && (reinterpret_cast<uintptr_t>(bases) & 15) == 0) d_bases = bases;
     else {
       CK(ctx->bases.ensure(bytes + 16));
       if (!ctx->copy_stream) { CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&ctx->ev_bases, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming)); }
@@ -673,6 +737,66 @@ int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_residen
     ctx->prof = false;
   }
   return B200MSM_OK;
+}
+
+// acc = 2^shift * acc + part on Jacobian Montgomery points (device buffers of 3*n8 bytes): the Horner step between two 256-bit scalar slices
+template <class C>
+__global__ void k_shift_add_jacobian(void* __restrict__ acc_jac, const void* __restrict__ part_jac, uint32_t shift) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  XYZZ<C> a, p;
+  { const char* s = reinterpret_cast<const char*>(acc_jac); Fe<C::N> X, Y, Z; fe_load_cg<C>(X, s); fe_load_cg<C>(Y, s + 4 * C::N); fe_load_cg<C>(Z, s + 8 * C::N);
+    if (fe_is_zero<C>(Z)) xyzz_set_inf<C>(a); else { a.x = X; a.y = Y; fe_sqr<C>(a.zz, Z); fe_mul<C>(a.zzz, a.zz, Z); } }
+  { const char* s = reinterpret_cast<const char*>(part_jac); Fe<C::N> X, Y, Z; fe_load_cg<C>(X, s); fe_load_cg<C>(Y, s + 4 * C::N); fe_load_cg<C>(Z, s + 8 * C::N);
+    if (fe_is_zero<C>(Z)) xyzz_set_inf<C>(p); else { p.x = X; p.y = Y; fe_sqr<C>(p.zz, Z); fe_mul<C>(p.zzz, p.zz, Z); } }
+  for (uint32_t k = 0; k < shift; k++) { XYZZ<C> d; xyzz_dbl<C>(d, a); a = d; }
+  xyzz_add<C>(a, p);
+  Fe<C::N> X, Y, Z; xyzz_to_jacobian<C>(X, Y, Z, a);
+  char* o = reinterpret_cast<char*>(acc_jac);
+  fe_store<C>(o, X); fe_store<C>(o + 4 * C::N, Y); fe_store<C>(o + 8 * C::N, Z);
+}
+
+// One MSM over scalar bits [bit0, bit0 + nbits).  Bit ranges wider than 256 bits (scalar_size > 32: the reference's g1m_multiexpAffine takes any
+// scalarSize, build_multiexp.js:251-371) run as 256-bit slices from the top down, combined by Horner: result = 2^256 * result + slice.
+int msm_entry(b200msm_ctx* ctx, int curve, const void* bases, bool bases_resident, const void* scalars, uint32_t scalar_size, uint64_t n,
+              uint32_t bit0, uint32_t nbits, void* out, b200msm_stats* st, const Precomp* pre = nullptr) {
+  if (!ctx) return B200MSM_E_ARG;
+  uint32_t eff = nbits;
+  if (scalar_size && bit0 < 8ull * scalar_size && (uint64_t)bit0 + nbits > 8ull * scalar_size) eff = 8 * scalar_size - bit0;
+  int rc;
+  if (eff <= 256 || !curve_ok(curve) || !out || n == 0 || !bases || !scalars) rc = msm_entry_impl(ctx, curve, bases, bases_resident, scalars, scalar_size, n, bit0, nbits, out, st, pre);
+  else {
+    // keep the bases on the device across the slices
+    cudaError_t ce = cudaSetDevice(ctx->device);
+    const int n8 = n8_of(curve);
+    const void* d_bases = bases;
+    rc = B200MSM_OK;
+    if (ce != cudaSuccess) { ctx->err = "cudaSetDevice failed"; rc = B200MSM_E_CUDA; }
+    DevBuf keep_bases, acc, part;
+    if (!rc && !bases_resident && !(ptr_device(bases) == ctx->device && (reinterpret_cast<uintptr_t>(bases) & 15) == 0)) {
+      ce = keep_bases.ensure((size_t)n * 2 * n8 + 16);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(keep_bases.p, bases, (size_t)n * 2 * n8, cudaMemcpyDefault, ctx->stream);
+      if (ce != cudaSuccess) { ctx->err = std::string("staging bases: ") + cudaGetErrorString(ce); rc = ce == cudaErrorMemoryAllocation ? B200MSM_E_NOMEM : B200MSM_E_CUDA; }
+      d_bases = keep_bases.p;
+    }
+    if (!rc && (acc.ensure(3 * 96) != cudaSuccess || part.ensure(3 * 96) != cudaSuccess)) { ctx->err = "out of device memory"; rc = B200MSM_E_NOMEM; }
+    const uint32_t slices = (eff + 255) / 256;
+    for (int k = (int)slices - 1; k >= 0 && !rc; k--) {
+      const uint32_t b0 = bit0 + 256u * (uint32_t)k, nb = std::min<uint32_t>(256u, eff - 256u * (uint32_t)k);
+      rc = msm_entry_impl(ctx, curve, d_bases, true, scalars, scalar_size, n, b0, nb, k == (int)slices - 1 ? acc.p : part.p, nullptr, nullptr);
+      if (!rc && k != (int)slices - 1) {
+        B200_CURVE_SWITCH(curve, k_shift_add_jacobian<C><<<1, 32, 0, ctx->stream>>>(acc.p, part.p, 256u))
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) { ctx->err = "k_shift_add_jacobian launch failed"; rc = B200MSM_E_CUDA; }
+      }
+    }
+    if (!rc) rc = deliver(ctx, acc.p, out, 3 * (size_t)n8);
+    if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = "stream synchronize failed"; rc = B200MSM_E_CUDA; }
+    cudaStreamSynchronize(ctx->stream);
+    keep_bases.release(); acc.release(); part.release();
+    if (st) memset(st, 0, sizeof *st);
+  }
+  ctx->prof = false;                     // the phase profiler never stays armed after an error return
+  return rc;
 }
 
 // window table for resident bases: rows w = 1..Wd-1 hold 2^(bit offset of window w) * P_i (see k_table_double)
@@ -741,15 +865,17 @@ int b200msm_create(b200msm_ctx** out, int device_id) {
 
 void b200msm_destroy(b200msm_ctx* ctx) {
   if (!ctx) return;
+  for (size_t g = 1; g < ctx->devs.size(); g++) b200msm_destroy(ctx->devs[g]);      // a multi context owns the contexts of its other devices
+  ctx->devs.clear(); ctx->mres.clear();
   b200ntt_release(ctx);
   for (b200msm_ctx* w : ctx->workers) b200msm_destroy(w);
   ctx->workers.clear();
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (DevBuf* b : {&ctx->bases, &ctx->scalars, &ctx->canon, &ctx->counts, &ctx->offsets, &ctx->cursors, &ctx->tiles, &ctx->sorted, &ctx->buckets,
+  for (DevBuf* b : {&ctx->bases, &ctx->scalars, &ctx->canon, &ctx->counts, &ctx->offsets, &ctx->ranks, &ctx->tiles, &ctx->sorted, &ctx->buckets,
                     &ctx->wsum, &ctx->out, &ctx->misc, &ctx->acc_a, &ctx->acc_b, &ctx->acc_c, &ctx->acc_d, &ctx->acc_e, &ctx->jac_in, &ctx->jac_affine}) b->release();
   for (auto& ln : ctx->lane) {
-    for (DevBuf* b : {&ln.offs, &ln.tiles, &ln.bid, &ln.pa, &ln.pb, &ln.prefix, &ln.prod, &ln.lvlprefix, &ln.others, &ln.meta}) b->release();
+    for (DevBuf* b : {&ln.offs, &ln.tiles, &ln.bid, &ln.pa, &ln.pb, &ln.prefix, &ln.prod, &ln.lvlprefix, &ln.others, &ln.meta, &ln.sync}) b->release();
     if (ln.done) cudaEventDestroy(ln.done);
     if (ln.stream) cudaStreamDestroy(ln.stream);
   }
@@ -770,18 +896,24 @@ void b200msm_destroy(b200msm_ctx* ctx) {
 
 int b200msm_set_stream(b200msm_ctx* ctx, void* cuda_stream) {
   if (!ctx) return B200MSM_E_ARG;
+  if (ctx->devs.size() > 1) { ctx->err = "a multi-device context owns its streams (one per device)"; return B200MSM_E_UNSUPPORTED; }
   cudaSetDevice(ctx->device);
-  if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);       // work issued on the old stream (cached NTT twiddle tables, resident uploads) completes before the switch
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream); ctx->own_stream = false;
   return B200MSM_OK;
 }
 int b200msm_synchronize(b200msm_ctx* ctx) {
   if (!ctx) return B200MSM_E_ARG;
+  for (size_t g = 1; g < ctx->devs.size(); g++) { CK(cudaSetDevice(ctx->devs[g]->device)); CK(cudaStreamSynchronize(ctx->devs[g]->stream)); }
   CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return B200MSM_OK;
 }
 
 int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!ctx || !key) return B200MSM_E_ARG;
+  for (size_t g = 1; g < ctx->devs.size(); g++) { int rc = b200msm_set_option(ctx->devs[g], key, v); if (rc) return rc; }
+  if (!strcmp(key, "multi_min_points")) { if (v < 1) return B200MSM_E_ARG; ctx->opt_multi_min = v; return B200MSM_OK; }
+  if (!strcmp(key, "multi_replicate")) { ctx->opt_multi_replicate = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "window_bits")) { if (v < 0 || v > 24) return B200MSM_E_ARG; ctx->opt_window_bits = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "accumulate")) { if (v < 0 || v > 2) return B200MSM_E_ARG; ctx->opt_accumulate = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "tree_rounds")) { ctx->opt_tree_rounds = (int)v; return B200MSM_OK; }
@@ -790,25 +922,21 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "ba_k")) { if (v < 0 || v > 64) return B200MSM_E_ARG; ctx->opt_ba_k = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "pt_k")) { if (v < 2 || v > 64) return B200MSM_E_ARG; ctx->opt_pt_k = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "probe_sqr")) { ctx->probe_sqr = v != 0; return B200MSM_OK; }
+#if defined(B200_EXPERIMENTS)
   if (!strcmp(key, "probe29")) { ctx->probe29 = v != 0; return B200MSM_OK; }
+  if (!strcmp(key, "bwd_staged")) { ctx->opt_bwd_staged = v != 0; return B200MSM_OK; }
+#endif
+  if (!strcmp(key, "fused")) { ctx->opt_fused = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "lanes")) { if (v < 1 || v > MAX_LANES) return B200MSM_E_ARG; ctx->opt_lanes = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "probe_smem")) { if (v < 0 || v > 200 * 1024) return B200MSM_E_ARG; ctx->opt_probe_smem = (int)v; return B200MSM_OK; }
-  if (!strcmp(key, "bwd_staged")) { ctx->opt_bwd_staged = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "batch_workers")) { if (v < 1 || v > 16) return B200MSM_E_ARG; ctx->opt_batch_workers = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "subslots")) { if (v < 0 || v > 256 || (v & (v - 1))) return B200MSM_E_ARG; ctx->opt_subslots = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "combine")) { if (v < 0 || v > 1) return B200MSM_E_ARG; ctx->opt_combine = (int)v; return B200MSM_OK; }
   return B200MSM_E_ARG;
 }
 
-int b200msm_g1_multiexp_affine(b200msm_ctx* ctx, int curve, const void* bases, const void* scalars, uint32_t scalar_size, uint64_t n, void* out) {
-  return msm_entry(ctx, curve, bases, false, scalars, scalar_size, n, 0, scalar_size > 32 ? 257 : 8 * scalar_size, out, nullptr);
-}
-
-int b200msm_g1_multiexp_affine_chunk(b200msm_ctx* ctx, int curve, const void* bases, const void* scalars, uint32_t scalar_size, uint64_t n,
-                                     uint32_t start_bit, uint32_t chunk_bits, void* out) {
-  if (ctx && (chunk_bits == 0 || chunk_bits > 32)) { ctx->err = "chunk_bits must be in [1, 32]"; return B200MSM_E_ARG; }
-  return msm_entry(ctx, curve, bases, false, scalars, scalar_size, n, start_bit, chunk_bits, out, nullptr);
-}
+// =================================================================== single-device cores of the MSM entry points
+// (the public functions below dispatch: a context made by b200msm_create_multi shards the same calls over its devices)
 
 // Jacobian bases (n8b = 3*n8, build_curve_jacobian_a0.js:1429): one batched conversion to affine on the device, then the affine pipeline
 static int msm_jacobian(b200msm_ctx* ctx, int curve, const void* bases_jac, const void* scalars, uint32_t scalar_size, uint64_t n,
@@ -826,16 +954,8 @@ static int msm_jacobian(b200msm_ctx* ctx, int curve, const void* bases_jac, cons
   CKL();
   return msm_entry(ctx, curve, ctx->jac_affine.p, false, scalars, scalar_size, n, bit0, nbits, out, nullptr);
 }
-int b200msm_g1_multiexp(b200msm_ctx* ctx, int curve, const void* bases_jac, const void* scalars, uint32_t scalar_size, uint64_t n, void* out) {
-  return msm_jacobian(ctx, curve, bases_jac, scalars, scalar_size, n, 0, scalar_size > 32 ? 257 : 8 * scalar_size, out);
-}
-int b200msm_g1_multiexp_chunk(b200msm_ctx* ctx, int curve, const void* bases_jac, const void* scalars, uint32_t scalar_size, uint64_t n,
-                              uint32_t start_bit, uint32_t chunk_bits, void* out) {
-  if (ctx && (chunk_bits == 0 || chunk_bits > 32)) { ctx->err = "chunk_bits must be in [1, 32]"; return B200MSM_E_ARG; }
-  return msm_jacobian(ctx, curve, bases_jac, scalars, scalar_size, n, start_bit, chunk_bits, out);
-}
 
-int b200msm_upload_bases(b200msm_ctx* ctx, int curve, const void* bases, uint64_t n, uint64_t* handle) {
+static int single_upload(b200msm_ctx* ctx, int curve, const void* bases, uint64_t n, uint64_t* handle) {
   if (!ctx || !handle || !curve_ok(curve) || (n && !bases)) return B200MSM_E_ARG;
   CK(cudaSetDevice(ctx->device));
   size_t bytes = (size_t)n * 2 * n8_of(curve);
@@ -849,7 +969,7 @@ int b200msm_upload_bases(b200msm_ctx* ctx, int curve, const void* bases, uint64_
   *handle = h;
   return B200MSM_OK;
 }
-int b200msm_upload_bases_windowed(b200msm_ctx* ctx, int curve, const void* bases, uint64_t n, uint32_t scalar_size, uint32_t window_bits, uint64_t* handle) {
+static int single_upload_windowed(b200msm_ctx* ctx, int curve, const void* bases, uint64_t n, uint32_t scalar_size, uint32_t window_bits, uint64_t* handle) {
   if (!ctx || !handle || !curve_ok(curve) || !n || !bases || scalar_size == 0 || scalar_size > 32 || window_bits > 24) return B200MSM_E_ARG;
   CK(cudaSetDevice(ctx->device));
   const uint32_t nbits = 8 * scalar_size;
@@ -874,53 +994,50 @@ int b200msm_upload_bases_windowed(b200msm_ctx* ctx, int curve, const void* bases
   *handle = h;
   return B200MSM_OK;
 }
-int b200msm_free_bases(b200msm_ctx* ctx, uint64_t handle) {
-  if (!ctx) return B200MSM_E_ARG;
+static int single_free(b200msm_ctx* ctx, uint64_t handle) {
   auto it = ctx->residents.find(handle);
   if (it == ctx->residents.end()) return B200MSM_E_ARG;
   cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+  for (b200msm_ctx* w : ctx->workers) cudaStreamSynchronize(w->stream);
   cudaFree(it->second.d); ctx->residents.erase(it);
   return B200MSM_OK;
 }
-int b200msm_g1_multiexp_resident(b200msm_ctx* ctx, uint64_t handle, const void* scalars, uint32_t scalar_size, uint64_t n, void* out, b200msm_stats* stats) {
-  if (!ctx) return B200MSM_E_ARG;
+// MSM over the resident points [first, first + n) of a handle (first > 0: one device's share of a replicated base set)
+static int single_resident(b200msm_ctx* ctx, uint64_t handle, uint64_t first, const void* scalars, uint32_t scalar_size, uint64_t n, void* out, b200msm_stats* stats) {
   auto it = ctx->residents.find(handle);
-  if (it == ctx->residents.end() || n > it->second.n) { ctx->err = "unknown handle or n larger than the uploaded base count"; return B200MSM_E_ARG; }
+  if (it == ctx->residents.end() || first + n > it->second.n) { ctx->err = "unknown handle or n larger than the uploaded base count"; return B200MSM_E_ARG; }
   const Resident& r = it->second;
-  Precomp pre{(uint32_t)r.n, r.t_nbits, r.t_c0, r.t_rem, r.t_Wd};
-  return msm_entry(ctx, r.curve, r.d, true, scalars, scalar_size, n, 0, scalar_size > 32 ? 257 : 8 * scalar_size, out, stats, r.t_Wd ? &pre : nullptr);
+  Precomp pre{(uint32_t)r.n, r.t_nbits, r.t_c0, r.t_rem, r.t_Wd};          // a table row is r.n points long whatever the offset
+  const char* d = reinterpret_cast<const char*>(r.d) + first * 2 * (size_t)n8_of(r.curve);
+  return msm_entry(ctx, r.curve, d, true, scalars, scalar_size, n, 0, 8 * scalar_size, out, stats, r.t_Wd ? &pre : nullptr);
 }
 
-// count independent MSMs over the same resident bases (BASELINE config 5: streams of equal-size MSMs).  The MSMs are spread over
-// `batch_workers` sub-contexts -- each with its own stream and scratch, driven by its own host thread -- so that the latency-bound
+// MSMs j = first, first + stride, ... < count of a batch over the same resident bases (BASELINE config 5: streams of equal-size MSMs).  They are
+// spread over `batch_workers` sub-contexts -- each with its own stream and scratch, driven by its own host thread -- so that the latency-bound
 // parts of one MSM (sort read-back, inversion tails, host window combination) overlap the throughput-bound kernels of the others.
-int b200msm_g1_multiexp_batch(b200msm_ctx* ctx, uint64_t handle, const void* scalars, uint32_t scalar_size, uint64_t n, uint32_t count, void* out) {
-  if (!ctx) return B200MSM_E_ARG;
+static int single_batch(b200msm_ctx* ctx, uint64_t handle, const void* scalars, uint32_t scalar_size, uint64_t n, uint32_t count, uint32_t first, uint32_t stride, void* out) {
   auto it = ctx->residents.find(handle);
   if (it == ctx->residents.end() || n > it->second.n || !out || scalar_size == 0 || (n && !scalars)) { ctx->err = "bad handle or argument"; return B200MSM_E_ARG; }
-  if (count == 0) return B200MSM_OK;
+  if (first >= count) return B200MSM_OK;
   const Resident r = it->second;
   const int n8 = n8_of(r.curve);
-  const uint32_t K = std::min<uint32_t>((uint32_t)ctx->opt_batch_workers, count);
+  const uint32_t mine = (count - first + stride - 1) / stride;
+  const uint32_t K = std::min<uint32_t>((uint32_t)ctx->opt_batch_workers, mine);
   while (ctx->workers.size() < K) {
     b200msm_ctx* w = nullptr; int rc = b200msm_create(&w, ctx->device);
     if (rc) { ctx->err = "cannot create a batch worker context"; return rc; }
     ctx->workers.push_back(w);
   }
-  for (uint32_t k = 0; k < K; k++) {      // workers inherit the tuning options of the parent
-    b200msm_ctx* w = ctx->workers[k];
-    w->opt_window_bits = ctx->opt_window_bits; w->opt_accumulate = ctx->opt_accumulate; w->opt_tree_rounds = ctx->opt_tree_rounds; w->opt_lanes = ctx->opt_lanes;
-    w->opt_ba_k = ctx->opt_ba_k; w->opt_pt_k = ctx->opt_pt_k; w->opt_persist = ctx->opt_persist; w->opt_subslots = ctx->opt_subslots; w->opt_combine = ctx->opt_combine;
-    w->opt_group_pairs = ctx->opt_group_pairs;
-  }
+  for (uint32_t k = 0; k < K; k++) copy_options(ctx->workers[k], ctx);      // workers inherit the tuning options of the parent
   CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream));       // inputs produced on the caller's stream are complete
   Precomp pre{(uint32_t)r.n, r.t_nbits, r.t_c0, r.t_rem, r.t_Wd};
-  const uint32_t nbits = scalar_size > 32 ? 257 : 8 * scalar_size;
+  const uint32_t nbits = 8 * scalar_size;
   std::vector<int> rcs(K, 0);
   std::vector<std::thread> th;
   for (uint32_t k = 0; k < K; k++) th.emplace_back([&, k]() {
     b200msm_ctx* w = ctx->workers[k];
-    for (uint32_t j = k; j < count; j += K) {
+    for (uint32_t t = k; t < mine; t += K) {
+      const uint64_t j = first + (uint64_t)t * stride;
       const char* sc = reinterpret_cast<const char*>(scalars) + (size_t)j * n * scalar_size;
       char* o = reinterpret_cast<char*>(out) + (size_t)j * 3 * n8;
       int rc = msm_entry(w, r.curve, r.d, true, sc, scalar_size, n, 0, nbits, o, nullptr, r.t_Wd ? &pre : nullptr);
@@ -929,8 +1046,225 @@ int b200msm_g1_multiexp_batch(b200msm_ctx* ctx, uint64_t handle, const void* sca
     if (cudaStreamSynchronize(w->stream) != cudaSuccess) rcs[k] = B200MSM_E_CUDA;
   });
   for (auto& t : th) t.join();
-  for (uint32_t k = 0; k < K; k++) if (rcs[k]) { ctx->err = "batch worker " + std::to_string(k) + ": " + ctx->workers[k]->err; return rcs[k]; }
+  int first_rc = 0; std::string msg;                                    // every failing worker is reported, not only the first
+  for (uint32_t k = 0; k < K; k++) if (rcs[k]) { if (!first_rc) first_rc = rcs[k]; msg += (msg.empty() ? "" : "; ") + ("batch worker " + std::to_string(k) + ": " + ctx->workers[k]->err); }
+  if (first_rc) { ctx->err = msg; return first_rc; }
   return B200MSM_OK;
+}
+
+// =================================================================== multi-device contexts
+// b200msm_create_multi makes ONE context that owns G single-device contexts (device g: its own streams, scratch and host thread).  An MSM is a sum
+// over independent (point, scalar) pairs, so the calls shard by POINT RANGE exactly as ffjavascript shards g1m_multiexpAffine over its workers
+// (slices of the inputs per worker, partial results added: wasmcurves/src/build_multiexp.js:319-369 is the per-worker part): device g pulls its
+// slice of the caller's host buffers over its own PCIe link, runs the whole single-GPU pipeline and returns ONE partial G1 point (3*n8 bytes);
+// the G partials are added on the host (host_ec.h, ~1 us each).  No bases or scalars ever cross NVLink, so there is no collective on the data path.
+}  // extern "C"  (the templates below need C++ linkage)
+namespace {
+
+void shard_of(uint64_t n, uint32_t g, uint32_t G, uint64_t* lo, uint64_t* cnt) {      // contiguous, balanced: the first n % G devices get one extra point
+  const uint64_t base = n / G, extra = n % G;
+  *lo = g * base + std::min<uint64_t>(g, extra); *cnt = base + (g < extra ? 1 : 0);
+}
+
+// f(g) -> status, run for g = 0..G-1 concurrently (g = 0 on the calling thread); every failing device is reported
+template <class F> int multi_run(b200msm_ctx* ctx, uint32_t G, F&& f) {
+  std::vector<int> rcs(G, 0);
+  std::vector<std::thread> th;
+  for (uint32_t g = 1; g < G; g++) th.emplace_back([&, g]() { rcs[g] = f(g); });
+  rcs[0] = f(0);
+  for (auto& t : th) t.join();
+  int first_rc = 0; std::string msg;
+  for (uint32_t g = 0; g < G; g++) if (rcs[g]) { if (!first_rc) first_rc = rcs[g];
+    msg += (msg.empty() ? "" : "; ") + ("device " + std::to_string(ctx->devs[g]->device) + ": " + (g ? ctx->devs[g]->err : ctx->err)); }
+  if (first_rc) ctx->err = msg;
+  cudaSetDevice(ctx->device);
+  return first_rc;
+}
+
+// out (3*n8 bytes, host) = sum of G Jacobian Montgomery points (g1m_add chain, build_curve_jacobian_a0.js:541-658) on the host
+template <class C> void host_sum_jacobian(const uint8_t* parts, uint32_t G, uint8_t* out) {
+  using HF = typename HostField<C>::type; const HF f = HostField<C>::make();
+  constexpr int W = HF::W;
+  b200host::XYZZ<W> acc; b200host::set_inf(f, acc);
+  for (uint32_t g = 0; g < G; g++) {
+    b200host::Fe<W> X, Y, Z;
+    memcpy(X.l, parts + (size_t)g * 24 * W, 8 * W); memcpy(Y.l, parts + (size_t)g * 24 * W + 8 * W, 8 * W); memcpy(Z.l, parts + (size_t)g * 24 * W + 16 * W, 8 * W);
+    if (b200host::is_zero<W>(Z)) continue;
+    b200host::XYZZ<W> p; p.x = X; p.y = Y; b200host::sqr(f, p.zz, Z); b200host::mul(f, p.zzz, p.zz, Z);
+    b200host::padd(f, acc, p);
+  }
+  b200host::Combiner<HF> cb; cb.f = f; cb.acc = acc; cb.cur = 0;
+  cb.finish(reinterpret_cast<uint64_t*>(out));
+}
+
+int multi_deliver(b200msm_ctx* ctx, int curve, const std::vector<uint8_t>& parts, uint32_t G, void* out) {
+  const size_t sz = 3 * (size_t)n8_of(curve);
+  std::vector<uint64_t> res(sz / 8);
+  B200_CURVE_SWITCH(curve, host_sum_jacobian<C>(parts.data(), G, reinterpret_cast<uint8_t*>(res.data())))
+  if (is_device_ptr(out)) { CK(cudaSetDevice(ctx->device)); CK(cudaMemcpy(out, res.data(), sz, cudaMemcpyDefault)); }
+  else memcpy(out, res.data(), sz);
+  return B200MSM_OK;
+}
+
+// devices that take part in an MSM of n points: small problems stay on fewer devices (sharding a latency-bound MSM only adds the slowest tail)
+uint32_t multi_width(const b200msm_ctx* ctx, uint64_t n) {
+  const uint64_t G = ctx->devs.size(), m = (uint64_t)std::max<int64_t>(1, ctx->opt_multi_min);
+  return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(G, n / m));
+}
+
+int multi_msm(b200msm_ctx* ctx, int curve, const void* bases, bool jacobian, const void* scalars, uint32_t scalar_size, uint64_t n, uint32_t bit0, uint32_t nbits, void* out) {
+  if (!curve_ok(curve) || !out || (n && (!bases || !scalars)) || scalar_size == 0) { ctx->err = "bad argument"; return B200MSM_E_ARG; }
+  const uint32_t G = multi_width(ctx, n);
+  if (G <= 1) return jacobian ? msm_jacobian(ctx, curve, bases, scalars, scalar_size, n, bit0, nbits, out) : msm_entry(ctx, curve, bases, false, scalars, scalar_size, n, bit0, nbits, out, nullptr);
+  const size_t n8 = n8_of(curve), pt = (jacobian ? 3 : 2) * n8;
+  std::vector<uint8_t> parts((size_t)G * 3 * n8);
+  int rc = multi_run(ctx, G, [&](uint32_t g) {
+    uint64_t lo, cnt; shard_of(n, g, G, &lo, &cnt);
+    const char* b = reinterpret_cast<const char*>(bases) + lo * pt; const char* sc = reinterpret_cast<const char*>(scalars) + lo * scalar_size;
+    uint8_t* o = parts.data() + (size_t)g * 3 * n8;
+    return jacobian ? msm_jacobian(ctx->devs[g], curve, b, sc, scalar_size, cnt, bit0, nbits, o) : msm_entry(ctx->devs[g], curve, b, false, sc, scalar_size, cnt, bit0, nbits, o, nullptr);
+  });
+  if (rc) return rc;
+  return multi_deliver(ctx, curve, parts, G, out);
+}
+
+int multi_upload(b200msm_ctx* ctx, int curve, const void* bases, uint64_t n, bool windowed, uint32_t scalar_size, uint32_t window_bits, uint64_t* handle) {
+  if (!handle || !curve_ok(curve) || (n && !bases)) return B200MSM_E_ARG;
+  const uint32_t G = (uint32_t)ctx->devs.size();
+  MultiResident mr; mr.curve = curve; mr.n = n; mr.replicated = ctx->opt_multi_replicate != 0; mr.h.assign(G, 0); mr.lo.assign(G, 0); mr.cnt.assign(G, 0);
+  const size_t pt = 2 * (size_t)n8_of(curve);
+  for (uint32_t g = 0; g < G; g++) { if (mr.replicated) { mr.lo[g] = 0; mr.cnt[g] = n; } else shard_of(n, g, G, &mr.lo[g], &mr.cnt[g]); }
+  int rc = multi_run(ctx, G, [&](uint32_t g) {
+    if (mr.cnt[g] == 0) return (int)B200MSM_OK;
+    const char* b = reinterpret_cast<const char*>(bases) + mr.lo[g] * pt;
+    return windowed ? single_upload_windowed(ctx->devs[g], curve, b, mr.cnt[g], scalar_size, window_bits, &mr.h[g]) : single_upload(ctx->devs[g], curve, b, mr.cnt[g], &mr.h[g]);
+  });
+  if (rc) { for (uint32_t g = 0; g < G; g++) if (mr.h[g]) single_free(ctx->devs[g], mr.h[g]); return rc; }
+  const uint64_t h = ctx->next_handle++;
+  ctx->mres[h] = mr; *handle = h;
+  return B200MSM_OK;
+}
+
+int multi_resident(b200msm_ctx* ctx, uint64_t handle, const void* scalars, uint32_t scalar_size, uint64_t n, void* out, b200msm_stats* stats) {
+  auto it = ctx->mres.find(handle);
+  if (it == ctx->mres.end() || n > it->second.n || !out || scalar_size == 0 || (n && !scalars)) { ctx->err = "unknown handle, or n larger than the uploaded base count"; return B200MSM_E_ARG; }
+  const MultiResident& mr = it->second;
+  const uint32_t Gall = (uint32_t)ctx->devs.size(), G = mr.replicated ? multi_width(ctx, n) : Gall;
+  const size_t n8 = n8_of(mr.curve);
+  std::vector<uint8_t> parts((size_t)G * 3 * n8);
+  int rc = multi_run(ctx, G, [&](uint32_t g) {
+    uint64_t lo, cnt, first;
+    if (mr.replicated) { shard_of(n, g, G, &lo, &cnt); first = lo; }                    // every device holds all points: balanced shares of the first n
+    else { lo = mr.lo[g]; cnt = n > lo ? std::min<uint64_t>(mr.cnt[g], n - lo) : 0; first = 0; }
+    uint8_t* o = parts.data() + (size_t)g * 3 * n8;
+    if (cnt == 0 || !mr.h[g]) {          // nothing of this MSM lives on device g: its partial is the canonical zero (0, R mod q, 0)
+      uint32_t one[24] = {0};
+      B200_CURVE_SWITCH(mr.curve, for (int i = 0; i < C::N; i++) one[i] = C::one(i))
+      memset(o, 0, 3 * n8); memcpy(o + n8, one, n8); return (int)B200MSM_OK; }
+    const char* sc = reinterpret_cast<const char*>(scalars) + lo * scalar_size;
+    return single_resident(ctx->devs[g], mr.h[g], first, sc, scalar_size, cnt, o, g == 0 ? stats : nullptr);
+  });
+  if (rc) return rc;
+  return multi_deliver(ctx, mr.curve, parts, G, out);
+}
+
+int multi_batch(b200msm_ctx* ctx, uint64_t handle, const void* scalars, uint32_t scalar_size, uint64_t n, uint32_t count, void* out) {
+  auto it = ctx->mres.find(handle);
+  if (it == ctx->mres.end() || n > it->second.n || !out || scalar_size == 0 || (n && !scalars)) { ctx->err = "bad handle or argument"; return B200MSM_E_ARG; }
+  const MultiResident mr = it->second;
+  if (!mr.replicated) {      // sharded bases: every MSM of the batch runs across all devices, one after the other
+    const size_t n8 = n8_of(mr.curve);
+    for (uint32_t j = 0; j < count; j++) {
+      int rc = multi_resident(ctx, handle, reinterpret_cast<const char*>(scalars) + (size_t)j * n * scalar_size, scalar_size, n, reinterpret_cast<char*>(out) + (size_t)j * 3 * n8, nullptr);
+      if (rc) return rc;
+    }
+    return B200MSM_OK;
+  }
+  const uint32_t G = std::min<uint32_t>((uint32_t)ctx->devs.size(), std::max<uint32_t>(1, count));      // replicated bases: MSM j on device j mod G (replicas, no exchange)
+  return multi_run(ctx, G, [&](uint32_t g) { return single_batch(ctx->devs[g], mr.h[g], scalars, scalar_size, n, count, g, G, out); });
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200msm_create_multi(b200msm_ctx** out, const int* device_ids, int n_devices) {
+  if (!out || !device_ids || n_devices < 1 || n_devices > 64) return B200MSM_E_ARG;
+  *out = nullptr;
+  for (int i = 0; i < n_devices; i++) if (device_ids[i] < 0) return B200MSM_E_ARG;      // an ordinal may repeat: every entry gets its own context (two shards on one GPU, used by the tests)
+  b200msm_ctx* ctx = nullptr;
+  int rc = b200msm_create(&ctx, device_ids[0]);
+  if (rc) return rc;
+  if (n_devices > 1) {
+    ctx->devs.push_back(ctx);
+    for (int i = 1; i < n_devices; i++) {
+      b200msm_ctx* c = nullptr; rc = b200msm_create(&c, device_ids[i]);
+      if (rc) { b200msm_destroy(ctx); return rc; }
+      ctx->devs.push_back(c);
+    }
+    cudaSetDevice(ctx->device);
+  }
+  *out = ctx;
+  return B200MSM_OK;
+}
+int b200msm_device_count(const b200msm_ctx* ctx) { return ctx ? (int)std::max<size_t>(1, ctx->devs.size()) : 0; }
+
+// =================================================================== the MSM entry points
+int b200msm_g1_multiexp_affine(b200msm_ctx* ctx, int curve, const void* bases, const void* scalars, uint32_t scalar_size, uint64_t n, void* out) {
+  if (ctx && ctx->devs.size() > 1) return multi_msm(ctx, curve, bases, false, scalars, scalar_size, n, 0, 8 * scalar_size, out);
+  return msm_entry(ctx, curve, bases, false, scalars, scalar_size, n, 0, 8 * scalar_size, out, nullptr);
+}
+
+int b200msm_g1_multiexp_affine_chunk(b200msm_ctx* ctx, int curve, const void* bases, const void* scalars, uint32_t scalar_size, uint64_t n,
+                                     uint32_t start_bit, uint32_t chunk_bits, void* out) {
+  if (ctx && (chunk_bits == 0 || chunk_bits > 32)) { ctx->err = "chunk_bits must be in [1, 32]"; return B200MSM_E_ARG; }
+  if (ctx && ctx->devs.size() > 1) return multi_msm(ctx, curve, bases, false, scalars, scalar_size, n, start_bit, chunk_bits, out);
+  return msm_entry(ctx, curve, bases, false, scalars, scalar_size, n, start_bit, chunk_bits, out, nullptr);
+}
+
+int b200msm_g1_multiexp(b200msm_ctx* ctx, int curve, const void* bases_jac, const void* scalars, uint32_t scalar_size, uint64_t n, void* out) {
+  if (ctx && ctx->devs.size() > 1) return multi_msm(ctx, curve, bases_jac, true, scalars, scalar_size, n, 0, 8 * scalar_size, out);
+  return msm_jacobian(ctx, curve, bases_jac, scalars, scalar_size, n, 0, 8 * scalar_size, out);
+}
+int b200msm_g1_multiexp_chunk(b200msm_ctx* ctx, int curve, const void* bases_jac, const void* scalars, uint32_t scalar_size, uint64_t n,
+                              uint32_t start_bit, uint32_t chunk_bits, void* out) {
+  if (ctx && (chunk_bits == 0 || chunk_bits > 32)) { ctx->err = "chunk_bits must be in [1, 32]"; return B200MSM_E_ARG; }
+  if (ctx && ctx->devs.size() > 1) return multi_msm(ctx, curve, bases_jac, true, scalars, scalar_size, n, start_bit, chunk_bits, out);
+  return msm_jacobian(ctx, curve, bases_jac, scalars, scalar_size, n, start_bit, chunk_bits, out);
+}
+
+int b200msm_upload_bases(b200msm_ctx* ctx, int curve, const void* bases, uint64_t n, uint64_t* handle) {
+  if (!ctx) return B200MSM_E_ARG;
+  if (ctx->devs.size() > 1) return multi_upload(ctx, curve, bases, n, false, 0, 0, handle);
+  return single_upload(ctx, curve, bases, n, handle);
+}
+int b200msm_upload_bases_windowed(b200msm_ctx* ctx, int curve, const void* bases, uint64_t n, uint32_t scalar_size, uint32_t window_bits, uint64_t* handle) {
+  if (!ctx) return B200MSM_E_ARG;
+  if (ctx->devs.size() > 1) { if (!n || !bases || scalar_size == 0 || scalar_size > 32 || window_bits > 24) return B200MSM_E_ARG; return multi_upload(ctx, curve, bases, n, true, scalar_size, window_bits, handle); }
+  return single_upload_windowed(ctx, curve, bases, n, scalar_size, window_bits, handle);
+}
+int b200msm_free_bases(b200msm_ctx* ctx, uint64_t handle) {
+  if (!ctx) return B200MSM_E_ARG;
+  auto it = ctx->mres.find(handle);
+  if (it != ctx->mres.end()) {
+    for (size_t g = 0; g < ctx->devs.size(); g++) if (it->second.h[g]) single_free(ctx->devs[g], it->second.h[g]);
+    ctx->mres.erase(it); cudaSetDevice(ctx->device);
+    return B200MSM_OK;
+  }
+  return single_free(ctx, handle);
+}
+int b200msm_g1_multiexp_resident(b200msm_ctx* ctx, uint64_t handle, const void* scalars, uint32_t scalar_size, uint64_t n, void* out, b200msm_stats* stats) {
+  if (!ctx) return B200MSM_E_ARG;
+  if (ctx->mres.count(handle)) return multi_resident(ctx, handle, scalars, scalar_size, n, out, stats);
+  return single_resident(ctx, handle, 0, scalars, scalar_size, n, out, stats);
+}
+
+// count independent MSMs over the same resident bases (see single_batch / multi_batch)
+int b200msm_g1_multiexp_batch(b200msm_ctx* ctx, uint64_t handle, const void* scalars, uint32_t scalar_size, uint64_t n, uint32_t count, void* out) {
+  if (!ctx) return B200MSM_E_ARG;
+  if (count == 0) return B200MSM_OK;
+  if (ctx->mres.count(handle)) return multi_batch(ctx, handle, scalars, scalar_size, n, count, out);
+  return single_batch(ctx, handle, scalars, scalar_size, n, count, 0, 1, out);
 }
 
 int b200msm_g1_normalize(b200msm_ctx* ctx, int curve, const void* jac, uint64_t count, void* xy) {
@@ -1061,10 +1395,14 @@ int b200msm_fq_op(b200msm_ctx* ctx, int curve, int op, const void* a, const void
   CK(ctx->acc_c.ensure(bytes));
   uint32_t g = (uint32_t)((count + 127) / 128);
   if (op >= 9) {
+#if defined(B200_EXPERIMENTS)
     if (!db) { ctx->err = "op 9/10 need two operands"; return B200MSM_E_ARG; }
     if (!curve_g1(curve)) { ctx->err = "radix-2^29 multiplier: prime fields only"; return B200MSM_E_UNSUPPORTED; }
     if (curve == 0) k_fp29_mul<BLS12_381><<<g, 128, 0, ctx->stream>>>(da, db, ctx->acc_c.p, (uint32_t)count, op - 9);
     else k_fp29_mul<BN254><<<g, 128, 0, ctx->stream>>>(da, db, ctx->acc_c.p, (uint32_t)count, op - 9);
+#else
+    ctx->err = "ops 9/10 (radix-2^29 multiplier) exist only in -DB200_EXPERIMENTS builds"; return B200MSM_E_UNSUPPORTED;
+#endif
   } else { B200_CURVE_SWITCH(curve, k_fp_op<C><<<g, 128, 0, ctx->stream>>>(op, da, db, ctx->acc_c.p, (uint32_t)count)) }
   CKL();
   return deliver(ctx, ctx->acc_c.p, r, bytes);
@@ -1107,10 +1445,13 @@ int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s) {
   double best = 0;
   for (int rep = 0; rep < 4; rep++) {
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+#if defined(B200_EXPERIMENTS)
     if (ctx->probe29) {
       if (curve == 0) k_fpmul29_probe<BLS12_381><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
       else k_fpmul29_probe<BN254><<<blocks, threads, 0, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p);
-    } else { B200_CURVE_SWITCH(curve, k_fpmul_probe<C><<<blocks, threads, psm, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p)) }
+    } else
+#endif
+    { B200_CURVE_SWITCH(curve, k_fpmul_probe<C><<<blocks, threads, psm, ctx->stream>>>(iters, ctx->acc_a.p, ctx->acc_b.p)) }
     CKL();
     CK(cudaEventRecord(ctx->ev[1], ctx->stream)); CK(cudaEventSynchronize(ctx->ev[1]));
     float ms; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
@@ -1120,6 +1461,7 @@ int b200msm_probe_fqmul(b200msm_ctx* ctx, int curve, double* fqmul_per_s) {
   *fqmul_per_s = best; return B200MSM_OK;
 }
 
+#if defined(B200_EXPERIMENTS)
 int b200msm_probe_dfma(b200msm_ctx* ctx, double* dfma_per_s) {
   if (!ctx || !dfma_per_s) return B200MSM_E_ARG;
   CK(cudaSetDevice(ctx->device));
@@ -1138,16 +1480,20 @@ int b200msm_probe_dfma(b200msm_ctx* ctx, double* dfma_per_s) {
   *dfma_per_s = best; return B200MSM_OK;
 }
 
+#endif  // B200_EXPERIMENTS
+
 int b200msm_get_counter(b200msm_ctx* ctx, const char* key, uint64_t* value) {
   if (!ctx || !key || !value) return B200MSM_E_ARG;
-  if (!strcmp(key, "launches")) { *value = ctx->launches; return B200MSM_OK; }
+  if (!strcmp(key, "launches")) { uint64_t t = ctx->launches; for (size_t g = 1; g < ctx->devs.size(); g++) t += ctx->devs[g]->launches;      // all devices of a multi context
+    for (b200msm_ctx* w : ctx->workers) t += w->launches; *value = t; return B200MSM_OK; }
   return B200MSM_E_ARG;
 }
 
 int b200msm_constants(int curve, uint32_t* n8, uint8_t* q, uint8_t* r_mod_q, uint8_t* r2_mod_q, uint32_t* np32) {
   if (!curve_ok(curve)) return B200MSM_E_ARG;
   auto put = [](uint8_t* d, int i, uint32_t v) { if (d) memcpy(d + 4 * i, &v, 4); };
-  if (curve == 0) {
+  // G2 ids describe their BASE field Fq (an Fq2 element is two of these): ids 0 and 2 -> BLS12-381, 1 and 3 -> BN254
+  if ((curve & 1) == 0) {
     if (n8) *n8 = 48; if (np32) *np32 = BLS12_381::NP;
     for (int i = 0; i < BLS12_381::N; i++) { put(q, i, BLS12_381::q(i)); put(r_mod_q, i, BLS12_381::one(i)); put(r2_mod_q, i, BLS12_381::r2(i)); }
   } else {

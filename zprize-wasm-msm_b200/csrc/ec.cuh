@@ -133,7 +133,9 @@ template <class C> B200_DI int affine_add_denominator(Fe<C::N>& d, const Affine<
   if (affine_is_inf<C>(p2)) { fe_set_one<C>(d); return 3; }
   fe_sub<C>(d, p2.x, p1.x);
   if (fe_is_zero<C>(d)) {
-    if (fe_eq<C>(p1.y, p2.y)) { fe_dbl<C>(d, p1.y); return 1; }
+    // P + P with y == 0 (a 2-torsion point: impossible in the prime-order groups, possible for unchecked input) doubles to infinity;
+    // it must stay out of the shared product -- d = 2y = 0 would zero the whole batch inversion
+    if (fe_eq<C>(p1.y, p2.y) && !fe_is_zero<C>(p1.y)) { fe_dbl<C>(d, p1.y); return 1; }
     fe_set_one<C>(d); return 4;
   }
   return 0;

@@ -14,61 +14,10 @@
 // algorithmic figure the reference's CIOS has (build_f1m.js:575-660).
 #pragma once
 #include <stdint.h>
+#include "field_params.h"
+#include "bingcd.h"
 
 namespace b200 {
-
-// ------------------------------------------------------------------ curve / field parameters
-struct BLS12_381 {
-  static constexpr int ID = 0;
-  static constexpr int EXT = 1;          // prime field
-  static constexpr int N = 12;           // u32 limbs per Fq element (n8 = 48)
-  static constexpr uint32_t NP = 0xfffcfffdu;   // -q^-1 mod 2^32   (build_f1m.js:504)
-  static constexpr int QBITS = 381;
-  __host__ __device__ static constexpr uint32_t q(int i) {      // build_bls12381.js:22
-    constexpr uint32_t t[N] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
-                               0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
-    return t[i];
-  }
-  __host__ __device__ static constexpr uint32_t one(int i) {    // R mod q
-    constexpr uint32_t t[N] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
-                               0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
-    return t[i];
-  }
-  __host__ __device__ static constexpr uint32_t r2(int i) {     // R^2 mod q
-    constexpr uint32_t t[N] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu,
-                               0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
-    return t[i];
-  }
-  __host__ __device__ static constexpr uint32_t r3(int i) {     // R^3 mod q
-    constexpr uint32_t t[N] = {0xd94ca1e0u, 0xed48ac6bu, 0x03a7adf8u, 0x315f831eu, 0x615e29ddu, 0x9a53352au,
-                               0x921e1761u, 0x34c04e5eu, 0x65724728u, 0x2512d435u, 0x91755d4du, 0x0aa63460u};
-    return t[i];
-  }
-};
-
-struct BN254 {
-  static constexpr int ID = 1;
-  static constexpr int EXT = 1;
-  static constexpr int N = 8;            // n8 = 32
-  static constexpr uint32_t NP = 0xe4866389u;
-  static constexpr int QBITS = 254;
-  __host__ __device__ static constexpr uint32_t q(int i) {      // build_bn128.js:20
-    constexpr uint32_t t[N] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
-    return t[i];
-  }
-  __host__ __device__ static constexpr uint32_t one(int i) {
-    constexpr uint32_t t[N] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
-    return t[i];
-  }
-  __host__ __device__ static constexpr uint32_t r2(int i) {
-    constexpr uint32_t t[N] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
-    return t[i];
-  }
-  __host__ __device__ static constexpr uint32_t r3(int i) {
-    constexpr uint32_t t[N] = {0xda1530dfu, 0xb1cd6dafu, 0xa7283db6u, 0x62f210e6u, 0x0ada0afbu, 0xef7f0b0cu, 0x2d592544u, 0x20fd6e90u};
-    return t[i];
-  }
-};
 
 // Quadratic extension Fq2 = Fq[u]/(u^2 + 1): the coordinate field of G2 on both curves (build_f2m.js; build_bls12381.js:48 and
 // build_bn128.js:44 pass f1m_neg as the multiplication by the non-residue).  An element c0 + c1*u is stored c0 || c1 (the f2m layout)
@@ -371,6 +320,7 @@ template <class C> B200_DI void sqr_product(uint32_t (&T)[2 * C::N], const uint3
   madc_lo_cc(T[2 * N - 2], a[N - 1], a[N - 1], T[2 * N - 2]);
   madc_hi(T[2 * N - 1], a[N - 1], a[N - 1], T[2 * N - 1]);
 }
+#if defined(B200_EXPERIMENTS)      // measured alternative (no gain): kept out of the shipped library
 // H x H limb product (2H limbs) in the same two-accumulator carry-chain form: every row x*y_i is two chains of H/2 wide
 // multiply-adds (even j, odd j); the word after a chain's end has not been touched by earlier rows, so its carry just lands.
 template <int H> B200_DI void half_product(uint32_t (&T)[2 * H], const uint32_t* x, const uint32_t* y) {
@@ -455,8 +405,9 @@ template <class C> B200_DI void fe_mul_karatsuba(Fe<C::N>& r, const Fe<C::N>& a,
   addc(T[2 * N - 1], T[2 * N - 1], 0);
   mont_reduce<C>(r, T);
 }
+#endif
 template <class C> B200_DI void fe_mul_p(Fe<C::N>& r, const Fe<C::N>& a, const Fe<C::N>& b) {
-#if defined(B200_KARATSUBA)
+#if defined(B200_EXPERIMENTS) && defined(B200_KARATSUBA)
   fe_mul_karatsuba<C>(r, a, b);
 #else
   fe_mul_cios<C>(r, a, b);
@@ -509,6 +460,22 @@ template <class C> __device__ __noinline__ void fe_inv_p(Fe<C::N>& r, const Fe<C
   r = acc;
 }
 
+// f1m_inverse for the latency-critical call sites (the root of every batch inversion, k_normalize, the codecs): Pornin's optimised
+// binary GCD (bingcd.h: 31 shift/subtract steps at a time on 64-bit approximations, ~5x fewer instructions than the plain binary
+// Euclid below and an order of magnitude fewer than Fermat).  The reference also uses an extended Euclid here
+// (build_int.js:922-1064).  Variable time; inv(0) = 0.  Montgomery in, Montgomery out.
+template <class C> __device__ __noinline__ void fe_inv_fast_p(Fe<C::N>& r, const Fe<C::N>& a) {
+  constexpr int N = C::N;
+  uint32_t x[N];
+  bingcd_inverse<C>(x, a.l);
+  // x = (aR)^-1 as a plain residue; a^-1 R = x * R^2 = montmul(x, R^3)
+  Fe<N> t, k;
+#pragma unroll
+  for (int i = 0; i < N; i++) { t.l[i] = x[i]; k.l[i] = C::r3(i); }
+  fe_mul<C>(r, t, k);
+}
+
+#if defined(B200_EXPERIMENTS)
 // f1m_inverse by the binary extended Euclidean algorithm (right-shift form): ~2*log2(q) shift/subtract
 // steps on N-limb integers instead of ~1.5*log2(q) field multiplications -- an order of magnitude fewer
 // instructions than Fermat, which matters because the batch inversion's root is a single serial chain.
@@ -535,7 +502,7 @@ template <class C> B200_DI bool limbs_is_one(const uint32_t (&a)[C::N]) {
   for (int i = 1; i < C::N; i++) o |= a[i];
   return o == 0;
 }
-template <class C> __device__ __noinline__ void fe_inv_fast_p(Fe<C::N>& r, const Fe<C::N>& a) {
+template <class C> __device__ __noinline__ void fe_inv_euclid_p(Fe<C::N>& r, const Fe<C::N>& a) {
   constexpr int N = C::N;
   if (fe_is_zero<C>(a)) { fe_set_zero<C>(r); return; }
   uint32_t u[N], v[N];
@@ -571,6 +538,8 @@ template <class C> __device__ __noinline__ void fe_inv_fast_p(Fe<C::N>& r, const
   for (int i = 0; i < N; i++) k.l[i] = C::r3(i);
   fe_mul<C>(r, x2, k);
 }
+
+#endif  // B200_EXPERIMENTS
 
 // ------------------------------------------------------------------ Fq2 arithmetic on the halves + the dispatching entry points
 template <class C> B200_DI void fq2_get(Fe<C::Base::N>& a0, Fe<C::Base::N>& a1, const Fe<C::N>& a) {
@@ -657,6 +626,11 @@ template <class C> B200_DI void fe_load_cg(Fe<C::N>& r, const void* p) {      //
   const uint4* s = reinterpret_cast<const uint4*>(p);
 #pragma unroll
   for (int i = 0; i < C::N / 4; i++) { uint4 v = s[i]; r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w; }
+}
+template <class C> B200_DI void fe_load_l2(Fe<C::N>& r, const void* p) {      // ld.global.cg: served by L2, never by a (possibly stale) L1 line -- values another CTA wrote during this launch
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < C::N / 4; i++) { uint4 v = __ldcg(s + i); r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w; }
 }
 template <class C> B200_DI void fe_store(void* p, const Fe<C::N>& a) {
   uint4* d = reinterpret_cast<uint4*>(p);

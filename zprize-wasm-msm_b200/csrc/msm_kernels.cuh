@@ -70,11 +70,15 @@ __global__ void k_canon_scalars(const uint8_t* __restrict__ in, uint32_t scalar_
 // Digit recoding.  Windows below the last one use signed digits with a carry into the next window; the last window keeps
 // its digit unsigned (it may reach 2^c0 and then indexes into the extra slot), so no carry ever leaves the scalar and no
 // "carry-only" window exists.  A non-zero digit d of window w lands in global bucket w*B + |d| - 1 with its sign.
-// Digits of 8 consecutive windows at a time: the recoding is a serial carry chain, but the 8 atomics (and, when scattering,
-// the 8 dependent stores) that follow are independent, so they are issued back to back instead of one L2 round trip per window.
+// Digits of 8 consecutive windows at a time: the recoding is a serial carry chain, but the 8 atomics that follow are independent,
+// so they are issued back to back instead of one L2 round trip per window.
+// Two passes over the scalars (computeSchedule + organizeBuckets, build_multiexp_opt.js:175-633):
+//   COUNT   : histogram of (window, |digit|); the value each atomicAdd returns is the pair's RANK inside its bucket and is kept
+//             (ranks[w * n + i], coalesced per window), so that
+//   SCATTER : needs no second round of atomics: position = offsets[bucket] + rank, one L2-resident table lookup per pair.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ counters,
-                                                uint32_t* __restrict__ sorted) {
+                                                const uint32_t* __restrict__ offsets, uint32_t* __restrict__ ranks, uint32_t* __restrict__ sorted) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pl.n) return;
   const uint32_t* s = scalars + (uint64_t)i * 8;
@@ -106,12 +110,18 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
         }
       }
     }
-    uint32_t slot[8];
+    if (!SCATTER) {
+      uint32_t rk[8];
 #pragma unroll
-    for (int u = 0; u < 8; u++) if (gb[u] != 0xffffffffu) slot[u] = atomicAdd(&counters[gb[u]], 1u);
-    if (SCATTER) {
+      for (int u = 0; u < 8; u++) if (gb[u] != 0xffffffffu) rk[u] = atomicAdd(&counters[gb[u]], 1u);
 #pragma unroll
-      for (int u = 0; u < 8; u++) if (gb[u] != 0xffffffffu) sorted[slot[u]] = val[u];
+      for (int u = 0; u < 8; u++) if (gb[u] != 0xffffffffu) ranks[(uint64_t)(w0 + u) * pl.n + i] = rk[u];
+    } else {
+      uint32_t pos[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) if (gb[u] != 0xffffffffu) pos[u] = __ldg(offsets + gb[u]) + ranks[(uint64_t)(w0 + u) * pl.n + i];
+#pragma unroll
+      for (int u = 0; u < 8; u++) if (gb[u] != 0xffffffffu) sorted[pos[u]] = val[u];
     }
   }
 }
@@ -184,24 +194,6 @@ __global__ void k_window_max(const uint32_t* __restrict__ counts, uint32_t B, ui
 #pragma unroll
   for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
   if ((threadIdx.x & 31) == 0 && v) atomicMax(out + w, v);
-}
-
-// ------------------------------------------------------------------ accumulate, serial form (one thread per bucket)
-// Correct for any input; used for tiny problems and as the fallback when the batch-affine tree is disabled.
-template <class C>
-__global__ void __launch_bounds__(128) k_accum_serial(const void* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                      const uint32_t* __restrict__ offsets, uint32_t nbuckets, void* __restrict__ buckets) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nbuckets) return;
-  uint32_t lo = offsets[b], hi = offsets[b + 1];
-  XYZZ<C> acc; xyzz_set_inf<C>(acc);
-  for (uint32_t k = lo; k < hi; k++) {
-    uint32_t e = sorted[k];
-    Affine<C> p; affine_load<C>(p, bases, e & 0x7fffffffu);
-    if (e >> 31) fe_neg<C>(p.y, p.y);
-    xyzz_madd<C>(acc, p);
-  }
-  xyzz_store<C>(buckets, b, acc);
 }
 
 // ------------------------------------------------------------------ bucket reduction by in-place folding
@@ -484,6 +476,7 @@ __global__ void __launch_bounds__(256) k_imadx_probe(uint32_t iters, uint32_t se
   if (s == 0x1234567u) sink[0] = s;
 }
 // Field-multiply throughput probe: ITER dependent Montgomery multiplications per thread (2N^2+N limb products each).
+#if defined(B200_EXPERIMENTS)
 // FP64 pipe probe: 8 independent DFMA chains per thread (the pipe an FP64-based multiplier would run on, beside the integer pipe)
 __global__ void __launch_bounds__(256) k_dfma_probe(uint32_t iters, double seed, double* __restrict__ sink) {
   double a[8], b = seed * 1.0000001, c = seed * 0.5;
@@ -498,6 +491,7 @@ __global__ void __launch_bounds__(256) k_dfma_probe(uint32_t iters, double seed,
   for (int k = 0; k < 8; k++) t += a[k];
   if (t == 12345.678) sink[blockIdx.x * blockDim.x + threadIdx.x] = t;
 }
+#endif
 template <class C>
 __global__ void __launch_bounds__(256) k_fpmul_probe(uint32_t iters, const void* __restrict__ in, void* __restrict__ out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

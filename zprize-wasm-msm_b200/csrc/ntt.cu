@@ -169,6 +169,8 @@ __global__ void __launch_bounds__(256) k_ntt_final_inverse(void* __restrict__ x,
 
 struct NttState {
   void* roots[2] = {nullptr, nullptr};         // per curve: (MAXBITS + 1) roots + 1/n slot
+  uint32_t setup_log2n[2] = {~0u, ~0u};        // the size the roots' 1/n slot was computed for (the setup kernel is a serial chain of ~32 squarings + one inversion:
+                                               // run once per (curve, size), not once per transform)
   void* W[2] = {nullptr, nullptr}; uint32_t W_log2n[2] = {0, 0}; size_t W_cap[2] = {0, 0};
   void* buf = nullptr; size_t buf_cap = 0;     // staging / ping buffer
   void* buf2 = nullptr; size_t buf2_cap = 0;
@@ -201,7 +203,8 @@ int run_ntt(b200msm_ctx* ctx, NttState& st, int ci, const void* in, uint32_t L, 
   uint64_t launches = 0;
   if (!st.roots[ci]) NCK(cudaMalloc(&st.roots[ci], (F::MAXBITS + 2) * fe));
   char* aux = reinterpret_cast<char*>(st.roots[ci]) + (size_t)(F::MAXBITS + 1) * fe;
-  k_ntt_setup<F><<<1, 32, 0, s>>>(st.roots[ci], aux, L); launches++;
+  if (st.setup_log2n[ci] != L) { k_ntt_setup<F><<<1, 32, 0, s>>>(st.roots[ci], aux, L); launches++; st.setup_log2n[ci] = L; }
+  // (tables built on the stream of an earlier call stay valid across b200msm_set_stream, which drains the old stream before switching)
   if (L >= 1 && st.W_log2n[ci] != L) {
     int rc = ensure(ctx, &st.W[ci], &st.W_cap[ci], (n / 2 + 1) * fe); if (rc) return rc;
     const uint32_t cnt = (uint32_t)(n / 2);

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "internal.h"
+#include "../../include/b200msm_probes.h"
 #include "fp.cuh"
 
 using namespace b200;
