@@ -231,6 +231,86 @@ __global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_bwd(cons
  }
 }
 
+#if defined(B200_EXPERIMENTS)      // round-2 measured alternatives (profiles/README.md r2): a register-lean backward pass and a single-launch tree round -- both slower, not shipped
+// ---- backward pass, register-lean form ------------------------------------------------------------------------------------------
+// The multiplier runs at the IMAD.WIDE peak from 8 warps per SM upwards, but a batch-affine addition is more than its five multiplications:
+// gathers, carry chains of additions, stores.  While a warp is in those parts another must feed the pipe, and at 128 registers only four warps
+// per scheduler are resident.  This form keeps NO operand alive across a multiplication: x1, x2 are loaded for the denominator and dropped,
+// y1, y2 for the slope's numerator and dropped, and x1, x2, y1 are loaded AGAIN (L1 hits: the lines were touched moments ago) for x3 and y3.
+// Live across the multiplications: q and the multiplication's own operands.  The rare cases (an operand at infinity, P + P, P + (-P)) go
+// through the general code out of line.
+template <class C, bool FIRST>
+__device__ __noinline__ void bwd_slot_general(Fe<C::N>& q, uint2 m, const void* __restrict__ src, uint64_t yoff, const void* __restrict__ prefix,
+                                              void* __restrict__ pout, uint64_t yoff_out, uint32_t j) {
+  Affine<C> p1, p2, r;
+  meta_load_point<C, FIRST>(p1, src, yoff, m.x);
+  meta_load_point<C, FIRST>(p2, src, yoff, m.y);
+  Fe<C::N> d, dinv;
+  int kind = affine_add_denominator<C>(d, p1, p2);
+  if (kind <= 1) {
+    Fe<C::N> pre; fe_load_cg<C>(pre, reinterpret_cast<const char*>(prefix) + (uint64_t)j * 4 * C::N);
+    fe_mul<C>(dinv, q, pre); fe_mul<C>(q, q, d);
+  }
+  affine_add_finish<C>(r, p1, p2, dinv, kind);
+  soa_store_point<C>(pout, yoff_out, j, r);
+}
+template <class C, bool FIRST>
+B200_DI void meta_load_y(Fe<C::N>& y, const void* __restrict__ src, uint64_t yoff, uint32_t ref) {
+  if (FIRST) { fe_load<C>(y, reinterpret_cast<const char*>(src) + (uint64_t)(ref & 0x7fffffffu) * (8 * C::N) + 4 * C::N); if (ref >> 31) fe_neg<C>(y, y); }
+  else fe_load_cg<C>(y, reinterpret_cast<const char*>(src) + (uint64_t)ref * (4 * C::N) + yoff);
+}
+B200_DI void reg_fence() { asm volatile("" ::: "memory"); }       // keeps the compiler from hoisting the later loads above the multiplications
+
+template <class C, bool FIRST>
+B200_DI void tree_bwd_tile_lean(Fe<C::N>& q, const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff, const void* __restrict__ prefix,
+                                void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t tb) {
+  const uint32_t tile = tb * (K * BA_THREADS) + threadIdx.x;
+  uint2 mn = meta[tile + (K - 1) * BA_THREADS];
+#pragma unroll 1
+  for (int i = K - 1; i >= 0; i--) {
+    const uint2 m = mn;
+    if (i > 0) mn = meta[tile + (i - 1) * BA_THREADS];
+    if (m.x == META_NONE) continue;
+    const uint32_t j = tile + i * BA_THREADS;
+    char* ox = reinterpret_cast<char*>(pout) + (uint64_t)j * (4 * C::N);
+    if (m.y == META_NONE) { Affine<C> p1; meta_load_point<C, FIRST>(p1, src, yoff, m.x); soa_store_point<C>(pout, yoff_out, j, p1); continue; }
+    Fe<C::N> d, t;
+    { Fe<C::N> x1, x2; meta_load_x<C, FIRST>(x1, src, m.x); meta_load_x<C, FIRST>(x2, src, m.y);
+      fe_sub<C>(d, x2, x1);
+      if (fe_is_zero<C>(d) || fe_is_zero<C>(x1) || fe_is_zero<C>(x2)) { bwd_slot_general<C, FIRST>(q, m, src, yoff, prefix, pout, yoff_out, j); continue; } }
+    { Fe<C::N> pre; fe_load_cg<C>(pre, reinterpret_cast<const char*>(prefix) + (uint64_t)j * 4 * C::N);
+      fe_mul<C>(t, q, pre); }                        // t = 1 / d
+    fe_mul<C>(q, q, d);
+    reg_fence();
+    { Fe<C::N> y1, y2; meta_load_y<C, FIRST>(y1, src, yoff, m.x); meta_load_y<C, FIRST>(y2, src, yoff, m.y);
+      fe_sub<C>(d, y2, y1); }
+    fe_mul<C>(t, d, t);                              // lambda
+    fe_sqr<C>(d, t);
+    reg_fence();
+    { Fe<C::N> x1, x2; meta_load_x<C, FIRST>(x1, src, m.x); meta_load_x<C, FIRST>(x2, src, m.y);
+      fe_sub<C>(d, d, x1); fe_sub<C>(d, d, x2);      // x3
+      fe_store<C>(ox, d);
+      fe_sub<C>(d, x1, d); }
+    fe_mul<C>(t, t, d);
+    reg_fence();
+    { Fe<C::N> y1; meta_load_y<C, FIRST>(y1, src, yoff, m.x); fe_sub<C>(t, t, y1); }
+    fe_store<C>(ox + yoff_out, t);
+  }
+}
+#ifndef B200_BWD_LEAN_CTAS
+#define B200_BWD_LEAN_CTAS 5
+#endif
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(BA_THREADS, B200_BWD_LEAN_CTAS) k_tree_bwd_lean(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
+                                                         const void* __restrict__ prefix, const void* __restrict__ inv,
+                                                         void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles) {
+ for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
+  Fe<C::N> q;
+  fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)(tb * BA_THREADS + threadIdx.x) * 4 * C::N);
+  tree_bwd_tile_lean<C, FIRST>(q, meta, src, yoff, prefix, pout, yoff_out, K, tb);
+ }
+}
+
 // ---- one tree round in ONE persistent launch ------------------------------------------------------------------------------------
 // k_tree_fwd, the product-tree levels, the root inversion and k_tree_bwd of a round as a single kernel of G co-resident CTAs.
 // CTA c owns the tiles c, c + G, c + 2G, ... ("wave" w = the G tiles w*G .. w*G + G - 1).  Every wave is one batch inversion
@@ -397,6 +477,8 @@ __global__ void __launch_bounds__(BA_THREADS, 4) k_tree_round(const uint2* __res
     __syncthreads();                                       // the tree buffer of wave w is free for wave w + ROUND_DEPTH + 1
   }
 }
+
+#endif  // B200_EXPERIMENTS
 
 #if defined(B200_EXPERIMENTS)      // measured 0-8 % slower than k_tree_bwd (profiles/README.md): not in the shipped library
 // backward pass with operand staging: the 2 points + prefix product of the NEXT slot are copied global -> shared with cp.async

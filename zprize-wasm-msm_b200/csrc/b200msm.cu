@@ -78,6 +78,8 @@ struct b200msm_ctx {
   int opt_window_bits = 0, opt_accumulate = 0, opt_tree_rounds = -1;
   DevBuf bases, scalars, canon, counts, offsets, ranks, tiles, sorted, buckets, wsum, out, misc, acc_a, acc_b, acc_c, acc_d, acc_e, jac_in, jac_affine;
   TreeLane lane[MAX_LANES];                                                   // batch-affine tree lanes
+  int opt_sort_groups = 1;                                // sort the window slots group by group on the lanes' streams (run_grouped)
+  int opt_bwd_lean = 0;                                   // register-lean backward pass (k_tree_bwd_lean)
   int opt_fused = 0, round_slots[4] = {0, 0, 0, 0};      // fused round kernel (k_tree_round): on for the prime fields; co-resident CTAs per device for each curve (0 = not queried yet)
   int opt_lanes = 4, opt_ba_k = 0, opt_pt_k = 8, opt_persist = 592, opt_subslots = 0, opt_bwd_staged = 0, opt_probe_smem = 0;
   bool probe29 = false, probe_sqr = false; int64_t opt_group_pairs = 0;
@@ -110,7 +112,7 @@ enum { T_SORT = 0, T_PLAN, T_TREE_FWD, T_INV_TREE, T_TREE_BWD, T_FINISH, T_FOLD,
 void copy_options(b200msm_ctx* w, const b200msm_ctx* ctx) {
   w->opt_window_bits = ctx->opt_window_bits; w->opt_accumulate = ctx->opt_accumulate; w->opt_tree_rounds = ctx->opt_tree_rounds; w->opt_lanes = ctx->opt_lanes;
   w->opt_ba_k = ctx->opt_ba_k; w->opt_pt_k = ctx->opt_pt_k; w->opt_persist = ctx->opt_persist; w->opt_subslots = ctx->opt_subslots; w->opt_combine = ctx->opt_combine;
-  w->opt_group_pairs = ctx->opt_group_pairs; w->opt_fused = ctx->opt_fused; w->opt_batch_workers = ctx->opt_batch_workers;
+  w->opt_group_pairs = ctx->opt_group_pairs; w->opt_fused = ctx->opt_fused; w->opt_bwd_lean = ctx->opt_bwd_lean; w->opt_sort_groups = ctx->opt_sort_groups; w->opt_batch_workers = ctx->opt_batch_workers;
 }
 
 int lane_init(b200msm_ctx* ctx, TreeLane& ln) {
@@ -192,12 +194,13 @@ uint32_t auto_window_bits(uint64_t n, uint32_t nbits) {
   return (uint32_t)c;
 }
 
-int exclusive_scan(b200msm_ctx* ctx, const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* cursors) {
+// out[i] = base + sum of in[0..i), out[n] = base + total, on stream s with `tiles` as scratch
+int exclusive_scan(b200msm_ctx* ctx, cudaStream_t s, DevBuf& tiles, const uint32_t* in, uint32_t* out, uint32_t n, uint32_t base) {
   uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  CK(ctx->tiles.ensure((size_t)(ntiles + 1) * 4));
-  k_scan_tiles<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, ctx->tiles.as<uint32_t>()); CKL();
-  k_scan_sums<<<1, 1024, 0, ctx->stream>>>(ctx->tiles.as<uint32_t>(), ntiles); CKL();
-  k_scan_apply<<<(n + 255) / 256, 256, 0, ctx->stream>>>(out, n, ctx->tiles.as<uint32_t>(), ntiles, cursors); CKL();
+  CK(tiles.ensure((size_t)(ntiles + 1) * 4));
+  k_scan_tiles<<<ntiles, SCAN_THREADS, 0, s>>>(in, out, n, tiles.as<uint32_t>()); CKL();
+  k_scan_sums<<<1, 1024, 0, s>>>(tiles.as<uint32_t>(), ntiles, base); CKL();
+  k_scan_apply<<<(n + 255) / 256, 256, 0, s>>>(out, n, tiles.as<uint32_t>(), ntiles, nullptr); CKL();
   return B200MSM_OK;
 }
 
@@ -256,6 +259,7 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, uin
   MARK(T_PLAN);
   const size_t fe = 4 * C::N, pt = 8 * C::N;
   bool fused = false;
+#if defined(B200_EXPERIMENTS)
   if constexpr (C::EXT == 1) {
     fused = ctx->opt_fused != 0;
     if (fused && ctx->round_slots[C::ID & 3] == 0) {      // co-resident CTAs of the round kernel on this device (once per context and curve)
@@ -272,6 +276,7 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, uin
       if (!prop.cooperativeLaunch) { ctx->round_slots[C::ID & 3] = 0; fused = false; ctx->opt_fused = 0; }
     }
   }
+#endif
   const int BK = ctx->opt_ba_k > 0 ? ctx->opt_ba_k : (m0 >= (1u << 22) ? 16 : 8), PK = ctx->opt_pt_k;     // chain length per thread: measured 2^20: 8 -> 6.84, 12 -> 6.76, 16 -> 6.70 ms; 2^18: 2.70 / 2.69 / 2.80
   const uint64_t BA_TILE = (uint64_t)BK * BA_THREADS;
   CK(ln_.pa.ensure(U[1] * pt + 1024)); if (R > 1) CK(ln_.pb.ensure(U[2] * pt + 1024));
@@ -294,6 +299,7 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, uin
     if (r == 0) k_tree_meta<true><<<(nslots + 255) / 256, 256, 0, s>>>(tr, sorted, meta, nslots);
     else k_tree_meta<false><<<(nslots + 255) / 256, 256, 0, s>>>(tr, nullptr, meta, nslots);
     CKL();
+#if defined(B200_EXPERIMENTS)
     if constexpr (C::EXT == 1) if (fused) {
       // ---- the whole round (forward pass, product tree, root inversion, backward pass) as ONE cooperative launch of G co-resident CTAs
       const uint32_t slots = (uint32_t)ctx->round_slots[C::ID & 3] / std::max<uint32_t>(1, share);        // co-resident CTAs this lane may use; one of them is the root CTA
@@ -313,6 +319,7 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, uin
       *adds_out += U[r] - U[r + 1];
       continue;
     }
+#endif
     if (r == 0) k_tree_fwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(meta, d_bases, 0, ln_.prefix.p, prod, BK, grid);
     else k_tree_fwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(meta, pin, yin, ln_.prefix.p, prod, BK, grid);
     CKL(); MARK(T_TREE_FWD);
@@ -346,6 +353,15 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, uin
       const size_t smem = (size_t)(5 * (C::N / 4)) * BA_THREADS * 16;          // 2 points + 1 field element per thread
       if (r == 0) k_tree_bwd_staged<C, true><<<pgrid, BA_THREADS, smem, s>>>(meta, d_bases, 0, ln_.prefix.p, prod, pout, yout, BK, grid);
       else k_tree_bwd_staged<C, false><<<pgrid, BA_THREADS, smem, s>>>(meta, pin, yin, ln_.prefix.p, prod, pout, yout, BK, grid);
+    } else
+#endif
+#if defined(B200_EXPERIMENTS)
+    if (C::EXT == 1 && ctx->opt_bwd_lean) {
+      if constexpr (C::EXT == 1) {
+        const uint32_t lgrid = (ctx->opt_persist > 0 && overlapped) ? std::min<uint32_t>(grid, (uint32_t)ctx->opt_persist * B200_BWD_LEAN_CTAS / 4) : grid;
+        if (r == 0) k_tree_bwd_lean<C, true><<<lgrid, BA_THREADS, 0, s>>>(meta, d_bases, 0, ln_.prefix.p, prod, pout, yout, BK, grid);
+        else k_tree_bwd_lean<C, false><<<lgrid, BA_THREADS, 0, s>>>(meta, pin, yin, ln_.prefix.p, prod, pout, yout, BK, grid);
+      }
     } else
 #endif
     if (r == 0) k_tree_bwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(meta, d_bases, 0, ln_.prefix.p, prod, pout, yout, BK, grid);
@@ -384,6 +400,102 @@ int fold_slots(b200msm_ctx* ctx, cudaStream_t s, void* buckets_g, uint32_t slots
   return B200MSM_OK;
 }
 
+// ---- ordinary MSM with the sort pipelined per window group --------------------------------------------------------------------------
+// The window slots are cut into groups BEFORE sorting (equal numbers of windows; scalars are taken to populate the windows evenly -- an
+// empty group is skipped, an over-full one only takes longer).  Group g is counted, scanned and scattered on ITS lane's stream and its
+// tree follows in stream order, so lane 0's accumulation starts after a quarter of the sort instead of all of it and the lanes' latency-bound
+// tails (fold, read-back, host combination) come staggered instead of together.  Groups are issued from the TOP windows down (the host
+// combination consumes them in that order); the last-issued group is the smallest, because its tail is the one nothing else overlaps.
+// Region of group g in sorted[]: [n * w0, n * w1) -- a scalar has at most one pair per window (the extra slot shares the top window's).
+template <class C>
+int run_grouped(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, const MsmPlan& pl, void* d_out) {
+  cudaStream_t s = ctx->stream;
+  const uint32_t n = pl.n, tb = 256, gb = (n + tb - 1) / tb;
+  const uint32_t lanes = (uint32_t)std::max(1, std::min(ctx->opt_lanes, (int)MAX_LANES));
+  const double per_pair = 8.0 * C::N * 0.75 + 4.0 * C::N * 0.75 + 6;
+  const uint64_t budget_pairs = ctx->opt_group_pairs > 0 ? (uint64_t)ctx->opt_group_pairs : (uint64_t)std::max(1.0, 0.45 * (double)ctx->total_mem / per_pair / lanes);
+  uint32_t ngroups = std::max<uint32_t>(lanes, (uint32_t)(((uint64_t)n * pl.Wd + budget_pairs - 1) / budget_pairs));
+  ngroups = std::min(ngroups, pl.Wd);
+  // window boundaries, bottom up: cut[0] = 0 .. cut[ngroups] = Wd; group ngroups-1 (top) is issued first, group 0 (bottom) last and is the smallest
+  std::vector<uint32_t> cut(ngroups + 1, 0); cut[ngroups] = pl.Wd;
+  { const double small = ngroups > 1 ? 0.7 : 1.0, unit = (double)pl.Wd / ((double)ngroups - 1.0 + small);
+    double acc = small * unit;
+    for (uint32_t g = 1; g < ngroups; g++) { cut[g] = std::min(std::max<uint32_t>((uint32_t)(acc + 0.5), cut[g - 1] + 1), pl.Wd - (ngroups - g)); acc += unit; } }
+  const uint32_t per = pl.logB + 1, npts = pl.W * per;
+  const size_t fbytes = (size_t)npts * 16 * C::N;
+  CK(ctx->wsum.ensure(fbytes));
+  if (ctx->h_folded_cap < fbytes + 4096) { if (ctx->h_folded) cudaFreeHost(ctx->h_folded); ctx->h_folded = nullptr; ctx->h_folded_cap = 0;
+    CK(cudaMallocHost(&ctx->h_folded, fbytes + 4096)); ctx->h_folded_cap = fbytes + 4096; }
+  while (ctx->gev.size() < 2 * (size_t)ngroups) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->gev.push_back(e); }
+  CK(ctx->buckets.ensure((size_t)pl.W * pl.B * 16 * C::N));
+  CK(ctx->misc.ensure(512 * 4));
+  CK(cudaMemsetAsync(ctx->misc.p, 0, 512 * 4, s));
+  CK(cudaEventRecord(ctx->ev_sorted, s));                      // inputs staged, scratch zeroed: the lanes may start
+  int rc;
+  for (uint32_t l = 0; l < lanes; l++) { rc = lane_init(ctx, ctx->lane[l]); if (rc) return rc; CK(cudaStreamWaitEvent(ctx->lane[l].stream, ctx->ev_sorted, 0)); }
+  // ---- phase 1: every group's sort on its lane (all issued up front; the lanes run them concurrently)
+  struct Grp { uint32_t w0, w1, s1, b0, nbg; uint32_t* offs; };
+  std::vector<Grp> grp(ngroups);
+  for (uint32_t gi = 0; gi < ngroups; gi++) {
+    const uint32_t g = ngroups - 1 - gi;
+    TreeLane& ln = ctx->lane[gi % lanes]; cudaStream_t ls = ln.stream;
+    Grp& G = grp[gi];
+    G.w0 = cut[g]; G.w1 = cut[g + 1]; G.s1 = (G.w1 == pl.Wd) ? pl.W : G.w1;           // slots [w0, s1): the top group owns the extra slot
+    G.b0 = G.w0 * pl.B; G.nbg = (G.s1 - G.w0) * pl.B;
+    G.offs = ctx->offsets.as<uint32_t>() + g;                                           // group g's nbg + 1 offsets live at [b0 + g, b0 + g + nbg] (g counted bottom-up): indexable by GLOBAL bucket id, no overlap between groups
+    uint32_t* cnt = ctx->counts.as<uint32_t>() + G.b0;
+    CK(cudaMemsetAsync(cnt, 0, (size_t)G.nbg * 4, ls));
+    k_digits<false><<<gb, tb, 0, ls>>>(d_scal, pl, ctx->counts.as<uint32_t>(), nullptr, ctx->ranks.as<uint32_t>(), nullptr, G.w0, G.w1); CKL();
+    { const uint32_t ntiles = (G.nbg + SCAN_TILE - 1) / SCAN_TILE;
+      CK(ln.tiles.ensure((size_t)(ntiles + 1) * 64 * 4)); }                              // (also serves the tree's multi-round scan, which sizes it again)
+    rc = exclusive_scan(ctx, ls, ln.tiles, cnt, G.offs + G.b0, G.nbg, n * G.w0); if (rc) return rc;
+    { dim3 gd((pl.B + 255) / 256, G.s1 - G.w0); k_window_max<<<gd, 256, 0, ls>>>(cnt, pl.B, ctx->misc.as<uint32_t>() + G.w0); CKL(); }
+    CK(cudaMemcpyAsync(ctx->h_pinned + G.w0, ctx->misc.as<uint32_t>() + G.w0, (G.s1 - G.w0) * 4, cudaMemcpyDeviceToHost, ls));
+    CK(cudaMemcpyAsync(ctx->h_pinned + 512 + gi, G.offs + G.b0 + G.nbg, 4, cudaMemcpyDeviceToHost, ls));      // base + pairs of the group
+    CK(cudaEventRecord(ctx->gev[ngroups + gi], ls));
+    k_digits<true><<<gb, tb, 0, ls>>>(d_scal, pl, nullptr, G.offs, ctx->ranks.as<uint32_t>(), ctx->sorted.as<uint32_t>(), G.w0, G.w1); CKL();
+    if (ctx->bases_pending) CK(cudaStreamWaitEvent(ls, ctx->ev_bases, 0));
+  }
+  // ---- phase 2: as each group's counts arrive, its tree, fold and read-back follow on the same lane
+  uint32_t rounds = 0; uint64_t adds = 0;
+  ctx->adds_r0 = 0; ctx->adds_exact = 0; ctx->cur_n = n; ctx->fused_groups = 0;
+  std::vector<char> live(ngroups, 0);
+  for (uint32_t gi = 0; gi < ngroups; gi++) {
+    const Grp& G = grp[gi];
+    TreeLane& ln = ctx->lane[gi % lanes]; cudaStream_t ls = ln.stream;
+    CK(cudaEventSynchronize(ctx->gev[ngroups + gi]));
+    uint32_t mc = 0; for (uint32_t w = G.w0; w < G.s1; w++) mc = std::max(mc, ctx->h_pinned[w]);
+    const uint64_t m0 = (uint64_t)ctx->h_pinned[512 + gi] - (uint64_t)n * G.w0;
+    const size_t o = (size_t)G.w0 * per * 16 * C::N; const uint32_t np = (G.s1 - G.w0) * per;
+    if (m0 == 0) { memset(reinterpret_cast<char*>(ctx->h_folded) + o, 0, (size_t)np * 16 * C::N); continue; }      // every digit of these windows is zero: all their folded entries are infinity (zz = 0)
+    live[gi] = 1;
+    char* bg = ctx->buckets.as<char>() + (size_t)G.b0 * 16 * C::N;
+    rc = accumulate_batch_affine<C>(ctx, ln, ls, lanes, d_bases, G.offs + G.b0, ctx->counts.as<uint32_t>() + G.b0, G.nbg, m0, mc, bg, &rounds, &adds);
+    if (!rc) rc = fold_slots<C>(ctx, ls, bg, G.s1 - G.w0, pl.B);
+    if (rc) return rc;
+    k_gather_folded<C><<<(np + 127) / 128, 128, 0, ls>>>(bg, G.s1 - G.w0, pl.B, pl.logB, ctx->wsum.as<char>() + o); CKL();
+    CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->h_folded) + o, ctx->wsum.as<char>() + o, (size_t)np * 16 * C::N, cudaMemcpyDeviceToHost, ls));
+    CK(cudaEventRecord(ctx->gev[gi], ls));
+  }
+  // ---- window combination on the host, group by group from the top (host_ec.h)
+  using HF = typename HostField<C>::type; const HF f = HostField<C>::make();
+  b200host::Combiner<HF> cb; cb.begin(f, pl.W, pl.Wd, pl.c0, pl.rem, pl.logB);
+  float host_ms = 0;
+  for (uint32_t gi = 0; gi < ngroups; gi++) {
+    if (live[gi]) CK(cudaEventSynchronize(ctx->gev[gi]));
+    auto t0 = std::chrono::steady_clock::now();
+    cb.feed(reinterpret_cast<const b200host::XYZZ<HF::W>*>(ctx->h_folded), grp[gi].w0, grp[gi].s1);
+    host_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  uint64_t* res = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ctx->h_folded) + fbytes);
+  cb.finish(res);
+  ctx->host_combine_ms = host_ms + std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  for (uint32_t l = 0; l < lanes; l++) { CK(cudaEventRecord(ctx->lane[l].done, ctx->lane[l].stream)); CK(cudaStreamWaitEvent(s, ctx->lane[l].done, 0)); }
+  CK(cudaMemcpyAsync(d_out, res, 12 * C::N, cudaMemcpyHostToDevice, s));
+  return B200MSM_OK;
+}
+
 // Core pipeline: d_bases (affine Montgomery, device), d_scal (canonical 8-word scalars, device), result -> d_out (device, 3*n8 bytes)
 template <class C>
 int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, uint64_t n64, uint32_t nbits, void* d_out, b200msm_stats* st, const Precomp* pre) {
@@ -406,13 +518,16 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   if (pl.W > 400) { ctx->err = "too many windows"; return B200MSM_E_UNSUPPORTED; }
 
   if (st) CK(cudaEventRecord(ctx->ev[1], s));
-  CK(ctx->counts.ensure((size_t)nb * 4)); CK(ctx->offsets.ensure((size_t)(nb + 1) * 4));
+  CK(ctx->counts.ensure((size_t)nb * 4)); CK(ctx->offsets.ensure((size_t)(nb + 1 + 512) * 4));
   CK(ctx->sorted.ensure((size_t)n * std::max(pl.W, pl.Wd) * 4 + 16));
   CK(cudaMemsetAsync(ctx->counts.p, 0, (size_t)nb * 4, s));
   const uint32_t tb = 256, gb = (n + tb - 1) / tb;
   CK(ctx->ranks.ensure((size_t)n * pl.Wd * 4 + 16));
-  k_digits<false><<<gb, tb, 0, s>>>(d_scal, pl, ctx->counts.as<uint32_t>(), nullptr, ctx->ranks.as<uint32_t>(), nullptr); CKL();
-  int rc = exclusive_scan(ctx, ctx->counts.as<uint32_t>(), ctx->offsets.as<uint32_t>(), nb, nullptr);
+  // ---- pipelined form (large ordinary MSMs, several lanes): every window group is sorted on its own lane's stream, see run_grouped
+  if (!pre && !ctx->prof && ctx->opt_sort_groups && ctx->opt_accumulate != 1 && ctx->opt_combine == 0 && ctx->opt_lanes > 1 && n >= (1u << 18))
+    return run_grouped<C>(ctx, d_bases, d_scal, pl, d_out);
+  k_digits<false><<<gb, tb, 0, s>>>(d_scal, pl, ctx->counts.as<uint32_t>(), nullptr, ctx->ranks.as<uint32_t>(), nullptr, 0u, pl.Wd); CKL();
+  int rc = exclusive_scan(ctx, s, ctx->tiles, ctx->counts.as<uint32_t>(), ctx->offsets.as<uint32_t>(), nb, 0u);
   if (rc) return rc;
   // ---- per-slot pair counts and largest bucket populations go back to the host while the scatter runs
   CK(ctx->misc.ensure(512 * 4));
@@ -432,7 +547,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   CK(cudaMemcpyAsync(ctx->h_pinned, ctx->misc.p, G * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpy2DAsync(ctx->h_pinned + 512, 4, ctx->offsets.as<uint32_t>(), (size_t)Bg * 4, 4, G + 1, cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(ctx->ev_plan, s));
-  k_digits<true><<<gb, tb, 0, s>>>(d_scal, pl, nullptr, ctx->offsets.as<uint32_t>(), ctx->ranks.as<uint32_t>(), ctx->sorted.as<uint32_t>()); CKL();
+  k_digits<true><<<gb, tb, 0, s>>>(d_scal, pl, nullptr, ctx->offsets.as<uint32_t>(), ctx->ranks.as<uint32_t>(), ctx->sorted.as<uint32_t>(), 0u, pl.Wd); CKL();
   if (st) CK(cudaEventRecord(ctx->ev[2], s));
   CK(cudaEventRecord(ctx->ev_sorted, s));
   CK(cudaEventSynchronize(ctx->ev_plan));
@@ -923,10 +1038,12 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "pt_k")) { if (v < 2 || v > 64) return B200MSM_E_ARG; ctx->opt_pt_k = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "probe_sqr")) { ctx->probe_sqr = v != 0; return B200MSM_OK; }
 #if defined(B200_EXPERIMENTS)
+  if (!strcmp(key, "bwd_lean")) { ctx->opt_bwd_lean = v != 0; return B200MSM_OK; }
+  if (!strcmp(key, "fused")) { ctx->opt_fused = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "probe29")) { ctx->probe29 = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "bwd_staged")) { ctx->opt_bwd_staged = v != 0; return B200MSM_OK; }
 #endif
-  if (!strcmp(key, "fused")) { ctx->opt_fused = v != 0; return B200MSM_OK; }
+  if (!strcmp(key, "sort_groups")) { ctx->opt_sort_groups = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "lanes")) { if (v < 1 || v > MAX_LANES) return B200MSM_E_ARG; ctx->opt_lanes = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "probe_smem")) { if (v < 0 || v > 200 * 1024) return B200MSM_E_ARG; ctx->opt_probe_smem = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "batch_workers")) { if (v < 1 || v > 16) return B200MSM_E_ARG; ctx->opt_batch_workers = (int)v; return B200MSM_OK; }

@@ -76,9 +76,12 @@ __global__ void k_canon_scalars(const uint8_t* __restrict__ in, uint32_t scalar_
 //   COUNT   : histogram of (window, |digit|); the value each atomicAdd returns is the pair's RANK inside its bucket and is kept
 //             (ranks[w * n + i], coalesced per window), so that
 //   SCATTER : needs no second round of atomics: position = offsets[bucket] + rank, one L2-resident table lookup per pair.
+// [wlo, whi): the windows whose pairs this launch emits (the recoding still walks the windows below wlo for the carry).  The window
+// slots are sorted group by group on the lanes' own streams, so that a lane's tree starts as soon as ITS windows are sorted.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ counters,
-                                                const uint32_t* __restrict__ offsets, uint32_t* __restrict__ ranks, uint32_t* __restrict__ sorted) {
+                                                const uint32_t* __restrict__ offsets, uint32_t* __restrict__ ranks, uint32_t* __restrict__ sorted,
+                                                uint32_t wlo, uint32_t whi) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pl.n) return;
   const uint32_t* s = scalars + (uint64_t)i * 8;
@@ -86,7 +89,8 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
   { const uint4 a = __ldg(reinterpret_cast<const uint4*>(s)), b = __ldg(reinterpret_cast<const uint4*>(s) + 1);
     sw[0] = a.x; sw[1] = a.y; sw[2] = a.z; sw[3] = a.w; sw[4] = b.x; sw[5] = b.y; sw[6] = b.z; sw[7] = b.w; }
   uint32_t carry = 0;
-  for (uint32_t w0 = 0; w0 < pl.Wd; w0 += 8) {
+  const uint32_t wend = min(pl.Wd, whi);
+  for (uint32_t w0 = 0; w0 < wend; w0 += 8) {
     uint32_t gb[8], val[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) {
@@ -102,11 +106,12 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
         const uint32_t d = raw + carry;
         const uint32_t slot0 = pl.pre_stride ? 0u : w * pl.B;
         if (pl.pre_stride) val[u] = i + w * pl.pre_stride;
-        if (w + 1 == pl.Wd) { if (d) gb[u] = slot0 + d - 1; }
+        const bool emit = w >= wlo && w < whi;
+        if (w + 1 == pl.Wd) { if (d && emit) gb[u] = slot0 + d - 1; }
         else {
           carry = d > (1u << (cw - 1));
           const uint32_t mag = carry ? ((1u << cw) - d) : d;
-          if (mag) { gb[u] = slot0 + mag - 1; val[u] |= carry << 31; }
+          if (mag && emit) { gb[u] = slot0 + mag - 1; val[u] |= carry << 31; }
         }
       }
     }
@@ -162,9 +167,9 @@ __global__ void k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restri
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 // single block: scan tile sums in place (exclusive), total appended at tile_sums[ntiles]
-__global__ void k_scan_sums(uint32_t* __restrict__ tile_sums, uint32_t ntiles) {
+__global__ void k_scan_sums(uint32_t* __restrict__ tile_sums, uint32_t ntiles, uint32_t base) {      // base: position of the first element's segment (a group's region of sorted[])
   __shared__ uint32_t carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
+  if (threadIdx.x == 0) carry_s = base;
   __syncthreads();
   for (uint32_t base = 0; base < ntiles; base += blockDim.x) {
     uint32_t i = base + threadIdx.x;
