@@ -333,19 +333,17 @@ def kernel_roofline(eng, handle, scal, n, cid, cname, a, out_dev):
     hbm_peak, hbm_src = measured_peaks()
     lp = LIMB_PRODUCTS_PER_FQMUL[cname]
     adds = st["affine_adds"]
-    fused = cid < 2          # prime fields: the whole tree round (forward pass, product tree, inversion, backward pass) is ONE kernel, k_tree_round
-    # dominant kernel: the tree round 0 launch.  Fused form: all 6 field multiplications of every batch-affine addition of that round;
-    # G2 (separate kernels): k_tree_bwd of round 0, 5 of the 6.
-    mults = 6 if fused else 5
+    # dominant kernel: k_tree_bwd of tree round 0 (the batch-affine backward pass): 5 of the 6 field multiplications of every addition of that round
+    # (the sixth is the forward pass's running product, k_tree_fwd).  A single-launch form of the whole round was measured slower and is not shipped.
+    mults = 5
     r0_ms = st["ms_k_tree_bwd_round0"]; adds0 = st["affine_adds_round0"]
     alg_lp = adds0 * mults * lp                               # algorithmic limb products of that launch
     achieved = alg_lp / (r0_ms * 1e-3) if r0_ms > 0 else 0.0
     # algorithmic HBM bytes of that launch per addition: forward pass 2 x-coordinates + prefix product written; backward pass 2 points + prefix + result
-    bytes_per_add = (2 * n8 + n8) + (2 * 2 * n8 + n8 + 2 * n8) if fused else 2 * 2 * n8 + n8 + n8 / 8 + 2 * n8
-    kname = "k_tree_round<FIRST=1>" if fused else "k_tree_bwd<FIRST=1>"
+    bytes_per_add = 2 * 2 * n8 + n8 + 8 + 2 * n8           # 2 operand points + prefix product + operand record read, 1 point written
+    kname = "k_tree_bwd<FIRST=1>"
     traffic = profile_traffic("%s|%s|2^%d" % (kname, cname, a.log2n))
-    roof = {"bound": "imad", "kernel": kname + (" (tree round 0 as one persistent launch: forward pass + in-kernel batch inversion + backward pass; one launch per window group per step)" if fused
-                                                else " (batch-affine backward pass, tree round 0)"),
+    roof = {"bound": "imad", "kernel": kname + " (batch-affine backward pass, tree round 0; one launch per window group per step)",
             "achieved": achieved / 1e12, "peak": imad / 1e12, "unit": "T limb-products/s (32x32+64 IMAD.WIDE.U32)",
             "frac": (achieved / imad) if imad else None, "traffic": traffic,
             "avg_launch_ms": r0_ms, "algorithmic_units_per_launch": alg_lp, "additions_per_launch": adds0, "field_multiplications_per_addition": mults,
@@ -354,7 +352,7 @@ def kernel_roofline(eng, handle, scal, n, cid, cname, a, out_dev):
             "hbm": {"achieved": adds0 * bytes_per_add / (r0_ms * 1e-3) / 1e9 if r0_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
                     "frac": (adds0 * bytes_per_add / (r0_ms * 1e-3) / 1e9 / hbm_peak) if r0_ms > 0 else None,
                     "algorithmic_bytes_per_launch": adds0 * bytes_per_add, "peak_source": hbm_src},
-            "all_rounds": {"kernel_group": ("k_tree_round" if fused else "k_tree_bwd") + ", all rounds", "limb_products": adds * mults * lp, "ms": st["ms_k_tree_bwd"],
+            "all_rounds": {"kernel_group": "k_tree_bwd, all rounds", "limb_products": adds * mults * lp, "ms": st["ms_k_tree_bwd"],
                            "frac_of_imad_peak": (adds * mults * lp / (st["ms_k_tree_bwd"] * 1e-3) / imad) if imad and st["ms_k_tree_bwd"] > 0 else None},
             "whole_accumulate": {"limb_products": adds * FQMUL_PER_AFFINE_ADD * lp, "ms": st["ms_accumulate"],
                                  "frac_of_imad_peak": (adds * FQMUL_PER_AFFINE_ADD * lp / (st["ms_accumulate"] * 1e-3) / imad) if imad and st["ms_accumulate"] > 0 else None},

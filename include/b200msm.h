@@ -171,9 +171,24 @@ int b200msm_g1_generate_bases(b200msm_ctx* ctx, int curve, uint64_t seed, uint64
  *     6 f1m_fromMontgomery  7 f1m_neg  8 f1m_inverse by Fermat (cross-check)       (src/build_f1m.js:71-105, 466-777, 779-1076, 1089-1122) */
 int b200msm_fq_op(b200msm_ctx* ctx, int curve, int op, const void* a, const void* b, void* r, uint64_t count);
 
+/* ---- f1m_batchInverse (src/build_batchinverse.js:4-140; f2m_batchInverse for the G2 ids): out[i] = 1 / in[i] on Montgomery elements of the
+ * curve's coordinate field, zeros stay zero like in the reference.  One field inversion for the whole array: the grid-wide product tree the
+ * batch-affine rounds of the MSM use (k_prod_fwd / k_inv_root / k_prod_bwd).  Host or device pointers; in == out is allowed. */
+int b200msm_fq_batch_inverse(b200msm_ctx* ctx, int curve, const void* in, uint64_t count, void* out);
+
+/* ---- test hook: the digit / sort phase alone -- computeSchedule + organizeBuckets (src/build_multiexp_opt.js:175-347, 364-633) as the engine
+ * runs them (k_digits<count>, scan, k_digits<scatter>).  plan_out = {Wd windows, W bucket slots, B buckets per slot, c0, rem, nbits}: windows
+ * 0 .. rem-1 are c0+1 bits wide, the others c0 bits; windows 0 .. Wd-2 use signed digits in [-B, B] (|digit| - 1 = bucket, sign in bit 31 of the
+ * entry), the last window is unsigned (digits above B live in slot Wd when there is one).  offsets_out (HOST, W*B + 1 words, slot-major) and
+ * sorted_out (HOST, offsets[W*B] words: point index | sign << 31, bucket by bucket; the order inside a bucket is unspecified).
+ * window_bits = 0: the engine's own choice for n.  offsets_out == NULL: only the plan is written. */
+int b200msm_debug_schedule(b200msm_ctx* ctx, const void* scalars, uint32_t scalar_size, uint64_t n, uint32_t window_bits, uint32_t plan_out[6],
+                           uint32_t* offsets_out, uint64_t offsets_cap, uint32_t* sorted_out, uint64_t sorted_cap);
+
 /* ---- tuning knobs (never change results).  key: "window_bits" (0 = auto), "accumulate" (0 = auto, 1 = serial, 2 = batch-affine),
  * "tree_rounds" (-1 = auto), "combine" (0 = serial tail on the host (default), 1 = device chain k_window_sums + k_horner),
- * "lanes" (1..8 overlapping accumulate streams), "batch_workers", "multi_min_points", "multi_replicate" (multi-device contexts, see
+ * "lanes" (1..8 overlapping accumulate streams), "issue_threads" (1 = one issuing host thread per lane, 0 = the calling
+ * thread issues every lane (default; measured equal, profiles/README.md r2)), "sort_groups" (1 = the sort is pipelined per window group on the lanes' streams (default)), "batch_workers", "multi_min_points", "multi_replicate" (multi-device contexts, see
  * b200msm_create_multi).
  * On a multi-device context an option applies to every device. */
 int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t value);

@@ -246,3 +246,129 @@ def test_sharded_msm_two_ranks_nccl(eng):
     sc = torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device="cuda", generator=g)
     exp = known_answer(cv, seed, 0, n, sc)
     assert got[0] == exp and got[1] == exp
+
+
+# ---------------------------------------------------------------- f1m_batchInverse as its own entry point (build_batchinverse.js:4-140)
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+@pytest.mark.parametrize("n", [1, 2, 5, 1000, 1025, 140000, 300001])
+def test_batch_inverse_direct(eng, cname, n):
+    """the grid-wide product tree (k_prod_fwd / k_inv_root / k_prod_bwd) on plain arrays: every level shape (root only, one warp-assisted
+    level, plain K-ary levels above it), zeros in place like the reference (it skips them), Montgomery semantics out = R^2 / in"""
+    cv = curve(cname); rnd = random.Random(n)
+    xs = [rnd.randrange(cv.q) for _ in range(n)]
+    for k in range(0, n, 7): xs[k] = 0 if (k // 7) % 3 == 0 else xs[k]
+    if n > 2: xs[1] = 1; xs[2] = cv.q - 1
+    a = b"".join(pyref.fe_bytes(cv, x) for x in xs)
+    got = eng.fq_batch_inverse(cv.cid, a)
+    if n <= 1025:
+        exp = b"".join(pyref.fe_bytes(cv, (cv.R * cv.R * pow(x, -1, cv.q)) % cv.q if x else 0) for x in xs)
+    else:
+        exp = eng.fq_op(cv.cid, 4, a)          # elementwise f1m_inverse on the device (pinned against big integers in test_device_inverse_edges)
+    assert got == exp
+
+
+def test_batch_inverse_fq2(eng):
+    """f2m_batchInverse: the same tree over Fq2 (G2 curve ids), against the elementwise f2m_inverse the G2 tests pin to the reference module"""
+    rnd = random.Random(77)
+    for cid, n8 in ((2, 96), (3, 64)):
+        cv = curve("bls12381" if cid == 2 else "bn128"); n = 3000
+        a = b"".join(pyref.fe_bytes(cv, rnd.randrange(cv.q)) + pyref.fe_bytes(cv, rnd.randrange(cv.q)) for _ in range(n))
+        a = bytes(n8) + a[n8:]                  # element 0 = zero
+        got = eng.fq_batch_inverse(cid, a)
+        assert got == eng.fq_op(cid, 4, a) and got[:n8] == bytes(n8)
+
+
+# ---------------------------------------------------------------- the digit / sort kernels against the reference's schedule KATs
+def _expected_buckets(scalars, plan):
+    """the engine's schedule convention restated with Python integers (include/b200msm.h, b200msm_debug_schedule): per-window digits by
+    pyref.get_chunk (pinned by the reference's getChunk KAT), signed recoding with carry, bucket = |digit| - 1"""
+    Wd, B, c0, rem = plan["Wd"], plan["B"], plan["c0"], plan["rem"]
+    out = {}
+    nbytes = (plan["nbits"] + 7) // 8
+    for i, s in enumerate(scalars):
+        carry = 0; sb = s.to_bytes(nbytes, "little")
+        for w in range(Wd):
+            cw = c0 + (1 if w < rem else 0); bit = w * c0 + min(w, rem)
+            d = pyref.get_chunk(sb, nbytes, bit, cw) + carry
+            if w == Wd - 1:
+                if d: out.setdefault(w * B + d - 1, []).append(i)
+            else:
+                carry = 1 if d > (1 << (cw - 1)) else 0
+                mag = (1 << cw) - d if carry else d
+                if mag: out.setdefault(w * B + mag - 1, []).append(i | (carry << 31))
+    return out
+
+
+def _check_schedule(eng, scalars, scalar_size, window_bits):
+    n = len(scalars)
+    sb = b"".join(s.to_bytes(scalar_size, "little") for s in scalars)
+    plan, offs, srt = eng.debug_schedule(sb, scalar_size, n, window_bits)
+    exp = _expected_buckets(scalars, plan)
+    nb = plan["W"] * plan["B"]
+    assert len(offs) == nb + 1 and offs[0] == 0 and all(offs[k] <= offs[k + 1] for k in range(nb))
+    for b in range(nb):
+        assert sorted(srt[offs[b]:offs[b + 1]]) == sorted(exp.get(b, [])), "bucket %d" % b
+    # the schedule is a recoding of the scalars: sum of signed digits * 2^(window offset) gives every scalar back
+    back = [0] * n
+    for b in range(nb):
+        w, mag = divmod(b, plan["B"]); mag += 1
+        wd = min(w, plan["Wd"] - 1)                   # the extra slot continues the last window (digits above B)
+        if w > wd: mag += plan["B"]
+        bit = wd * plan["c0"] + min(wd, plan["rem"])
+        for e in srt[offs[b]:offs[b + 1]]:
+            back[e & 0x7FFFFFFF] += (-mag if e >> 31 else mag) << bit
+    assert back == list(scalars)
+    return plan, offs, srt
+
+
+def test_schedule_kernels_against_reference_kats(eng):
+    """k_digits<count> + scan + k_digits<scatter> on the inputs of the reference's computeSchedule / organizeBuckets KATs (test/batchAffine.js:43-258).
+    The engine recodes to signed digits and equalises window widths, so the comparison is (a) bucket by bucket against the documented convention
+    computed from pyref.get_chunk, (b) reconstruction of every scalar, which the reference's own expected schedule satisfies too, and (c) where the
+    engine's windows coincide with the reference's chunks, bucket membership derived from the reference's expected organizeBuckets output."""
+    import json
+    BA = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "batchAffine.json")))["tests"]
+    ints = lambda v: [ints(x) for x in v] if isinstance(v, list) else int(v, 16)
+    v = {k: ints(x) for k, x in BA["computeSchedule is correct."]["values"].items()}
+    scalars = v["inputScalars"]; c = v["chunkSize"]; n = v["numPoints"]
+    # the reference's expected schedule reconstructs the same scalars (unsigned digits, chunk k at bit k*c)
+    back = [0] * n
+    for k, row in enumerate(v["expectedOutputPointSchedules"]):
+        for wd in row:
+            if wd != pyref.SENTINEL: back[wd >> 32] += (wd & 0x7FFFFFFF) << (k * c)
+    assert back == scalars
+    for wb in (c, 4, 8, 0): _check_schedule(eng, scalars, v["scalarSize"], wb)
+    # organizeBuckets KAT: 7 points, 2 chunks of 3 bits.  As one-byte scalars (digit0 + 8*digit1) with window_bits = 3 the engine's windows 0 and 1 ARE the
+    # reference's chunks (3 + 3 + 2 bits), so its buckets follow from the reference's expected output by the signed recoding alone.
+    v = {k: ints(x) for k, x in BA["organizeBuckets is correct."]["values"].items()}
+    n, W, B = v["numPoints"], v["numChunks"], v["numBuckets"]
+    dig = [[0] * W for _ in range(n)]
+    for k in range(W):
+        for wd in v["inputs"][k * n:(k + 1) * n]:
+            if wd != pyref.SENTINEL: dig[wd >> 32][k] = wd & 0x7FFFFFFF
+    scalars = [d[0] + 8 * d[1] for d in dig]
+    plan, offs, srt = _check_schedule(eng, scalars, 1, 3)
+    assert (plan["Wd"], plan["c0"], plan["rem"], plan["B"]) == (3, 2, 2, 4)
+    exp = {}
+    for k in range(W):                                  # the reference's sorted output, chunk by chunk, recoded
+        live = [wd for wd in v["expectedOutput"][k * n:(k + 1) * n] if wd != pyref.SENTINEL]
+        assert [wd & 0x7FFFFFFF for wd in live] == sorted(wd & 0x7FFFFFFF for wd in live)      # the KAT's own order: by digit
+    for i, d in enumerate(dig):
+        carry = 0
+        for k in range(3):
+            x = (d[k] if k < W else 0) + carry
+            if k == 2:
+                if x: exp.setdefault(2 * 4 + x - 1, []).append(i)
+            else:
+                carry = 1 if x > 4 else 0; mag = 8 - x if carry else x
+                if mag: exp.setdefault(k * 4 + mag - 1, []).append(i | (carry << 31))
+    for b in range(plan["W"] * plan["B"]):
+        assert sorted(srt[offs[b]:offs[b + 1]]) == sorted(exp.get(b, []))
+
+
+@pytest.mark.parametrize("ssz,wb,n", [(32, 0, 5000), (32, 16, 3000), (32, 13, 777), (16, 0, 1000), (4, 1, 50), (32, 24, 100)])
+def test_schedule_kernels_random(eng, ssz, wb, n):
+    rnd = random.Random(ssz * 100 + wb)
+    sc = [rnd.getrandbits(8 * ssz) for _ in range(n)]
+    sc[0] = 0; sc[1] = (1 << (8 * ssz)) - 1; sc[2] = 1 << (8 * ssz - 1)
+    _check_schedule(eng, sc, ssz, wb)

@@ -1,0 +1,8 @@
+set -x
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "msm_random or window_widths or edge_cases or groups_and_lanes or full_size or g2" 2>&1 | tail -4 > gpurun_out/r2j_pytest_core.log; cat gpurun_out/r2j_pytest_core.log
+timeout 600 python tools/exp_r2.py --sizes 16,18,20,22 --configs "base;lanes=1" --phases --tag dense > gpurun_out/r2j_exp_dense.jsonl 2>gpurun_out/r2j_exp.err
+timeout 600 python tools/exp_r2.py --curve bn128 --sizes 18,20 --configs "base" --tag dense_bn > gpurun_out/r2j_exp_dense_bn.jsonl 2>>gpurun_out/r2j_exp.err
+timeout 600 python tools/exp_r2.py --sizes 18,20 --windowed 0 --configs "base" --tag dense_win > gpurun_out/r2j_exp_dense_win.jsonl 2>>gpurun_out/r2j_exp.err
+tail -3 gpurun_out/r2j_exp.err
+timeout 300 python tools/trace_msm.py --log2n 16 --configs "base;fold_cluster=0" --dump > gpurun_out/r2j_trace_2p16.txt 2>gpurun_out/r2j_trace.err
+timeout 300 python tools/trace_msm.py --log2n 20 --configs "base" --dump > gpurun_out/r2j_trace_2p20.txt 2>>gpurun_out/r2j_trace.err

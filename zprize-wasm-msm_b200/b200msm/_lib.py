@@ -20,6 +20,7 @@ EXPORTS = [  # every symbol include/b200msm.h and include/b200msm_probes.h decla
     "b200msm_g1_sum", "b200msm_g1_generate_bases", "b200msm_fq_op", "b200msm_probe_imad", "b200msm_probe_imad32", "b200msm_probe_fqmul",
     "b200msm_set_option", "b200msm_constants", "b200msm_get_counter", "b200msm_g1_batch_convert",
     "b200msm_glv_decompose_scalars", "b200msm_g1_glv_preprocess", "b200msm_upload_bases_windowed", "b200msm_g1_multiexp_batch", "b200msm_fr_fft", "b200msm_fr_fft_last_phases",
+    "b200msm_fq_batch_inverse", "b200msm_debug_schedule",
 ]
 EXPERIMENT_EXPORTS = ["b200msm_probe_dfma", "b200msm_probe_dualpipe"]      # only in -DB200_EXPERIMENTS builds (include/b200msm_probes.h)
 
@@ -76,6 +77,8 @@ lib.b200msm_g1_normalize.argtypes = [_vp, _i, _vp, _u64, _vp]
 lib.b200msm_g1_sum.argtypes = [_vp, _i, _vp, _u64, _vp]
 lib.b200msm_g1_generate_bases.argtypes = [_vp, _i, _u64, _u64, _u64, _vp]
 lib.b200msm_fq_op.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _u64]
+lib.b200msm_fq_batch_inverse.argtypes = [_vp, _i, _vp, _u64, _vp]
+lib.b200msm_debug_schedule.argtypes = [_vp, _vp, _u32, _u64, _u32, ctypes.POINTER(_u32), _vp, _u64, _vp, _u64]
 lib.b200msm_probe_imad.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
 lib.b200msm_probe_imad32.argtypes = [_vp, ctypes.POINTER(ctypes.c_double)]
 lib.b200msm_probe_fqmul.argtypes = [_vp, _i, ctypes.POINTER(ctypes.c_double)]

@@ -163,6 +163,22 @@ class Engine:
         o = ctypes.create_string_buffer(max(1, len(a)))
         self._ck(lib.b200msm_fq_op(self._ctx, curve, op, pa, pb_, o, n)); return o.raw[:len(a)]
 
+    def fq_batch_inverse(self, curve, a):
+        """f1m_batchInverse on Montgomery elements (zeros stay zero)"""
+        n = len(a) // N8[curve]
+        pa, ka = _ptr(a); o = ctypes.create_string_buffer(max(1, len(a)))
+        self._ck(lib.b200msm_fq_batch_inverse(self._ctx, curve, pa, n, o)); return o.raw[:len(a)]
+
+    def debug_schedule(self, scalars, scalar_size, n, window_bits=0):
+        """the engine's digit / sort phase alone: (plan dict, offsets list, sorted entries list)"""
+        plan = (ctypes.c_uint32 * 6)(); ps, ks = _ptr(scalars)
+        self._ck(lib.b200msm_debug_schedule(self._ctx, ps, scalar_size, n, window_bits, plan, None, 0, None, 0))
+        Wd, W, B, c0, rem, nbits = list(plan)
+        offs = (ctypes.c_uint32 * (W * B + 1))(); srt = (ctypes.c_uint32 * max(1, n * W))()
+        self._ck(lib.b200msm_debug_schedule(self._ctx, ps, scalar_size, n, window_bits, plan, offs, W * B + 1, srt, n * W))
+        offs = list(offs)
+        return {"Wd": Wd, "W": W, "B": B, "c0": c0, "rem": rem, "nbits": nbits}, offs, list(srt)[:offs[-1]]
+
     def counter(self, key):
         v = ctypes.c_uint64(); self._ck(lib.b200msm_get_counter(self._ctx, key.encode(), ctypes.byref(v))); return v.value
 

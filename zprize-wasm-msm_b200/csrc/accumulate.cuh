@@ -110,23 +110,27 @@ B200_DI bool tree_slot(const TreeRound& tr, uint32_t j, uint32_t& in0, bool& has
   return true;
 }
 
-// Per-slot operand table of a round, written once by k_tree_meta and read (coalesced) by the forward and the backward pass:
-// meta[j] = (a, b): operand references of output slot j -- round 0: the sorted entries (point index | sign << 31), later rounds:
-// positions in the previous round's output; b = NONE: the slot only carries its single input over; a = NONE: padding slot.
-// This takes the dependent lookups (bid -> offsets -> sorted entry) out of the arithmetic kernels, whose gathers then depend
-// on ONE coalesced load that is issued an iteration ahead; the table covers whole tiles, so those kernels need no bounds checks.
-constexpr uint32_t META_NONE = 0xffffffffu;
+// Operand table of a round: one ITEM per ADDITION, written once by k_tree_meta and read (coalesced) by the forward and the backward pass.
+// item[e] = (a, b, j, -): operand references -- round 0: the sorted entries (point index | sign << 31), later rounds: positions in the
+// previous round's output -- and the output position j.  Slots that only carry a bucket's odd last point over are NOT items: about every
+// second bucket has one per round, which is 3 % of the slots in round 0 but 20-33 % in the last rounds (2-4 points per bucket), and a carried
+// slot idles its lane for the five multiplications of the warp's additions.  k_tree_meta copies those points itself, so the arithmetic
+// kernels run dense: lane utilisation is 32/32 everywhere but in the last warp.  Where an addition's item goes needs no extra scan:
+// the additions of the buckets below b number sum (n_r - n_(r+1)) = (off_in[b] - off_in[0]) - off_out[b].
+// The table takes the dependent lookups (bid -> offsets -> sorted entry) out of the arithmetic kernels, whose gathers then depend on ONE
+// coalesced 16-byte load that is issued an iteration ahead.
+// Carried points: carries[k] = (operand reference, output position), k = number of carrying buckets below b = 2*off_out[b] - (off_in[b] - off_in[0]);
+// the backward pass copies them after its additions (its CTAs are multiplier-bound, the copies ride along for free; copied by k_tree_meta
+// itself they cost 0.2 ms per 2^20-point MSM, latency-bound).
 template <bool FIRST>
-__global__ void __launch_bounds__(256) k_tree_meta(TreeRound tr, const uint32_t* __restrict__ sorted, uint2* __restrict__ meta, uint32_t nslots) {
+__global__ void __launch_bounds__(256) k_tree_meta(TreeRound tr, const uint32_t* __restrict__ sorted, uint4* __restrict__ items, uint2* __restrict__ carries) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nslots) return;
-  uint32_t in0; bool has2;
-  uint2 m = make_uint2(META_NONE, META_NONE);
-  if (tree_slot(tr, j, in0, has2, true)) {
-    if (FIRST) { m.x = __ldg(sorted + in0); if (has2) m.y = __ldg(sorted + in0 + 1); }
-    else { m.x = in0; if (has2) m.y = in0 + 1; }
-  }
-  meta[j] = m;
+  uint32_t in0 = 0; bool has2 = false;
+  if (!tree_slot(tr, j, in0, has2, true)) return;
+  const uint32_t b = tr.bid[j], oo = tr.off_out[b], adds_below = tr.off_in[b] - tr.off_in[0] - oo;      // off_in may start at the group's position in sorted[]; off_out starts at 0
+  const uint32_t ra = FIRST ? __ldg(sorted + in0) : in0;
+  if (has2) items[adds_below + (j - oo)] = make_uint4(ra, FIRST ? __ldg(sorted + in0 + 1) : in0 + 1, j, 0u);
+  else carries[oo - adds_below] = make_uint2(ra, j);
 }
 
 // Round 0 reads the caller's bases (x || y records, 2*n8 bytes apart).  The rounds' own outputs are stored as TWO arrays, all x
@@ -146,24 +150,28 @@ B200_DI void soa_store_point(void* __restrict__ dst, uint64_t yoff, uint32_t j, 
   char* b = reinterpret_cast<char*>(dst) + (uint64_t)j * (4 * C::N); fe_store<C>(b, p.x); fe_store<C>(b + yoff, p.y);
 }
 
-// forward: denominators, per-slot prefix products, per-thread products.
-// The kernel is gather-bound (two scattered 96-byte points per slot in round 0), so the x coordinates of slot i+1 are requested
-// before the multiplication of slot i and the operand references of slot i+2 before that (only the x coordinates are needed;
+// forward: denominators, per-item prefix products, per-thread products.
+// The kernel is gather-bound (two scattered 96-byte points per addition in round 0), so the x coordinates of item i+1 are requested
+// before the multiplication of item i and the operand references of item i+2 before that (only the x coordinates are needed;
 // the y coordinates are fetched in the rare equal-x / zero-x cases).
-// One tile (K * BA_THREADS consecutive slots, thread t owns slots t, t + 128, ...): returns the thread's running product in p.
+// One tile (K * BA_THREADS consecutive items, thread t owns items t, t + 128, ...): returns the thread's running product in p.
+// nadd = number of items of the round (read from the scan totals on the device: the host only knows an upper bound).
 template <class C, bool FIRST>
-B200_DI void tree_fwd_tile(Fe<C::N>& p, const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff, void* __restrict__ prefix, int K, uint32_t tb) {
+B200_DI void tree_fwd_tile(Fe<C::N>& p, const uint4* __restrict__ items, uint32_t nadd, const void* __restrict__ src, uint64_t yoff, void* __restrict__ prefix, int K, uint32_t tb) {
   const uint32_t tile = tb * (K * BA_THREADS) + threadIdx.x;
   fe_set_one<C>(p);
   Fe<C::N> x1, x2, nx1, nx2;
-  uint2 mc = meta[tile], mn = K > 1 ? meta[tile + BA_THREADS] : make_uint2(META_NONE, META_NONE);
-  if (mc.y != META_NONE) { meta_load_x<C, FIRST>(x1, src, mc.x); meta_load_x<C, FIRST>(x2, src, mc.y); }
+  uint4 mc = make_uint4(0, 0, 0, 0), mn = mc;
+  if (tile < nadd) mc = items[tile];
+  if (K > 1 && tile + BA_THREADS < nadd) mn = items[tile + BA_THREADS];
+  if (tile < nadd) { meta_load_x<C, FIRST>(x1, src, mc.x); meta_load_x<C, FIRST>(x2, src, mc.y); }
 #pragma unroll 1
   for (int i = 0; i < K; i++) {
-    uint2 mn2 = make_uint2(META_NONE, META_NONE);
-    if (i + 2 < K) mn2 = meta[tile + (i + 2) * BA_THREADS];
-    if (i + 1 < K && mn.y != META_NONE) { meta_load_x<C, FIRST>(nx1, src, mn.x); meta_load_x<C, FIRST>(nx2, src, mn.y); }
-    if (mc.y != META_NONE) {
+    const uint32_t e = tile + i * BA_THREADS;
+    uint4 mn2 = make_uint4(0, 0, 0, 0);
+    if (i + 2 < K && e + 2 * BA_THREADS < nadd) mn2 = items[e + 2 * BA_THREADS];
+    if (i + 1 < K && e + BA_THREADS < nadd) { meta_load_x<C, FIRST>(nx1, src, mn.x); meta_load_x<C, FIRST>(nx2, src, mn.y); }
+    if (e < nadd) {
       Fe<C::N> d; int kind = 0;
       fe_sub<C>(d, x2, x1);
       if (fe_is_zero<C>(d) || fe_is_zero<C>(x1) || fe_is_zero<C>(x2)) {        // rare: decide with the full points
@@ -173,7 +181,7 @@ B200_DI void tree_fwd_tile(Fe<C::N>& p, const uint2* __restrict__ meta, const vo
         kind = affine_add_denominator<C>(d, p1, p2);
       }
       if (kind <= 1) {
-        fe_store<C>(reinterpret_cast<char*>(prefix) + (uint64_t)(tile + i * BA_THREADS) * 4 * C::N, p);
+        fe_store<C>(reinterpret_cast<char*>(prefix) + (uint64_t)e * 4 * C::N, p);
         fe_mul<C>(p, p, d);
       }
     }
@@ -181,386 +189,68 @@ B200_DI void tree_fwd_tile(Fe<C::N>& p, const uint2* __restrict__ meta, const vo
   }
 }
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 3 : 6) k_tree_fwd(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
-                                                            void* __restrict__ prefix, void* __restrict__ prod, int K, uint32_t ntiles) {
+__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 3 : 6) k_tree_fwd(const uint4* __restrict__ items, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t nb,
+                                                            const void* __restrict__ src, uint64_t yoff, void* __restrict__ prefix, void* __restrict__ prod, int K, uint32_t ntiles) {
+ const uint32_t nadd = off_in[nb] - off_in[0] - off_out[nb];      // additions of this round = inputs - outputs
  // persistent form: gridDim.x may be smaller than ntiles (leaves SM room for the other lane's latency-bound kernels)
  for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
   Fe<C::N> p;
-  tree_fwd_tile<C, FIRST>(p, meta, src, yoff, prefix, K, tb);
+  tree_fwd_tile<C, FIRST>(p, items, nadd, src, yoff, prefix, K, tb);
   fe_store<C>(reinterpret_cast<char*>(prod) + (uint64_t)(tb * BA_THREADS + threadIdx.x) * 4 * C::N, p);
  }
 }
 
 // backward: consume the inverse q of the thread's product, finish every addition, write the round's output points
 template <class C, bool FIRST>
-B200_DI void tree_bwd_tile(Fe<C::N>& q, const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff, const void* __restrict__ prefix,
+B200_DI void tree_bwd_tile(Fe<C::N>& q, const uint4* __restrict__ items, uint32_t nadd, const void* __restrict__ src, uint64_t yoff, const void* __restrict__ prefix,
                            void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t tb) {
   const uint32_t tile = tb * (K * BA_THREADS) + threadIdx.x;
-  uint2 mn = meta[tile + (K - 1) * BA_THREADS];
+  uint4 mn = make_uint4(0, 0, 0, 0);
+  if (tile + (K - 1) * BA_THREADS < nadd) mn = items[tile + (K - 1) * BA_THREADS];
 #pragma unroll 1
   for (int i = K - 1; i >= 0; i--) {
-    const uint2 m = mn;
-    if (i > 0) mn = meta[tile + (i - 1) * BA_THREADS];
-    if (m.x == META_NONE) continue;
-    const uint32_t j = tile + i * BA_THREADS;
+    const uint4 m = mn;
+    const uint32_t e = tile + i * BA_THREADS;
+    if (i > 0 && e - BA_THREADS < nadd) mn = items[e - BA_THREADS];
+    if (e >= nadd) continue;
     Affine<C> p1, p2, r;
     meta_load_point<C, FIRST>(p1, src, yoff, m.x);
-    if (m.y == META_NONE) { soa_store_point<C>(pout, yoff_out, j, p1); continue; }
     meta_load_point<C, FIRST>(p2, src, yoff, m.y);
     Fe<C::N> d, dinv;
     int kind = affine_add_denominator<C>(d, p1, p2);
     if (kind <= 1) {
-      Fe<C::N> pre; fe_load_cg<C>(pre, reinterpret_cast<const char*>(prefix) + (uint64_t)j * 4 * C::N);
+      Fe<C::N> pre; fe_load_cg<C>(pre, reinterpret_cast<const char*>(prefix) + (uint64_t)e * 4 * C::N);
       // the two multiplications of the inverse-sharing step are independent: their rows are interleaved (fe_mul2), which doubles the
       // work between dependent carry-chain instructions (measured: k_tree_bwd 3.46 -> 3.39 ms at 2^20, profiles/README.md r2)
       if constexpr (C::EXT == 1) { Fe<C::N> qn; fe_mul2<C>(dinv, q, pre, qn, q, d); q = qn; }
       else { fe_mul<C>(dinv, q, pre); fe_mul<C>(q, q, d); }
     }
     affine_add_finish<C>(r, p1, p2, dinv, kind);
-    soa_store_point<C>(pout, yoff_out, j, r);
+    soa_store_point<C>(pout, yoff_out, m.z, r);
   }
 }
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_bwd(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
+__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_bwd(const uint4* __restrict__ items, const uint2* __restrict__ carries, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t nb,
+                                                         const void* __restrict__ src, uint64_t yoff,
                                                          const void* __restrict__ prefix, const void* __restrict__ inv,
                                                          void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles) {
+ const uint32_t nadd = off_in[nb] - off_in[0] - off_out[nb];      // additions of this round = inputs - outputs
  for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
   Fe<C::N> q;
   fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)(tb * BA_THREADS + threadIdx.x) * 4 * C::N);
-  tree_bwd_tile<C, FIRST>(q, meta, src, yoff, prefix, pout, yoff_out, K, tb);
+  tree_bwd_tile<C, FIRST>(q, items, nadd, src, yoff, prefix, pout, yoff_out, K, tb);
+ }
+ // the round's carried points (a bucket's odd last input): plain copies into their output slots (round 0: with the digit's sign applied)
+ const uint32_t ncar = off_out[nb] - nadd;
+ for (uint32_t c = blockIdx.x * BA_THREADS + threadIdx.x; c < ncar; c += gridDim.x * BA_THREADS) {
+  const uint2 cr = carries[c];
+  Affine<C> p; meta_load_point<C, FIRST>(p, src, yoff, cr.x); soa_store_point<C>(pout, yoff_out, cr.y, p);
  }
 }
 
-#if defined(B200_EXPERIMENTS)      // round-2 measured alternatives (profiles/README.md r2): a register-lean backward pass and a single-launch tree round -- both slower, not shipped
-// ---- backward pass, register-lean form ------------------------------------------------------------------------------------------
-// The multiplier runs at the IMAD.WIDE peak from 8 warps per SM upwards, but a batch-affine addition is more than its five multiplications:
-// gathers, carry chains of additions, stores.  While a warp is in those parts another must feed the pipe, and at 128 registers only four warps
-// per scheduler are resident.  This form keeps NO operand alive across a multiplication: x1, x2 are loaded for the denominator and dropped,
-// y1, y2 for the slope's numerator and dropped, and x1, x2, y1 are loaded AGAIN (L1 hits: the lines were touched moments ago) for x3 and y3.
-// Live across the multiplications: q and the multiplication's own operands.  The rare cases (an operand at infinity, P + P, P + (-P)) go
-// through the general code out of line.
-template <class C, bool FIRST>
-__device__ __noinline__ void bwd_slot_general(Fe<C::N>& q, uint2 m, const void* __restrict__ src, uint64_t yoff, const void* __restrict__ prefix,
-                                              void* __restrict__ pout, uint64_t yoff_out, uint32_t j) {
-  Affine<C> p1, p2, r;
-  meta_load_point<C, FIRST>(p1, src, yoff, m.x);
-  meta_load_point<C, FIRST>(p2, src, yoff, m.y);
-  Fe<C::N> d, dinv;
-  int kind = affine_add_denominator<C>(d, p1, p2);
-  if (kind <= 1) {
-    Fe<C::N> pre; fe_load_cg<C>(pre, reinterpret_cast<const char*>(prefix) + (uint64_t)j * 4 * C::N);
-    fe_mul<C>(dinv, q, pre); fe_mul<C>(q, q, d);
-  }
-  affine_add_finish<C>(r, p1, p2, dinv, kind);
-  soa_store_point<C>(pout, yoff_out, j, r);
-}
-template <class C, bool FIRST>
-B200_DI void meta_load_y(Fe<C::N>& y, const void* __restrict__ src, uint64_t yoff, uint32_t ref) {
-  if (FIRST) { fe_load<C>(y, reinterpret_cast<const char*>(src) + (uint64_t)(ref & 0x7fffffffu) * (8 * C::N) + 4 * C::N); if (ref >> 31) fe_neg<C>(y, y); }
-  else fe_load_cg<C>(y, reinterpret_cast<const char*>(src) + (uint64_t)ref * (4 * C::N) + yoff);
-}
-B200_DI void reg_fence() { asm volatile("" ::: "memory"); }       // keeps the compiler from hoisting the later loads above the multiplications
-
-template <class C, bool FIRST>
-B200_DI void tree_bwd_tile_lean(Fe<C::N>& q, const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff, const void* __restrict__ prefix,
-                                void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t tb) {
-  const uint32_t tile = tb * (K * BA_THREADS) + threadIdx.x;
-  uint2 mn = meta[tile + (K - 1) * BA_THREADS];
-#pragma unroll 1
-  for (int i = K - 1; i >= 0; i--) {
-    const uint2 m = mn;
-    if (i > 0) mn = meta[tile + (i - 1) * BA_THREADS];
-    if (m.x == META_NONE) continue;
-    const uint32_t j = tile + i * BA_THREADS;
-    char* ox = reinterpret_cast<char*>(pout) + (uint64_t)j * (4 * C::N);
-    if (m.y == META_NONE) { Affine<C> p1; meta_load_point<C, FIRST>(p1, src, yoff, m.x); soa_store_point<C>(pout, yoff_out, j, p1); continue; }
-    Fe<C::N> d, t;
-    { Fe<C::N> x1, x2; meta_load_x<C, FIRST>(x1, src, m.x); meta_load_x<C, FIRST>(x2, src, m.y);
-      fe_sub<C>(d, x2, x1);
-      if (fe_is_zero<C>(d) || fe_is_zero<C>(x1) || fe_is_zero<C>(x2)) { bwd_slot_general<C, FIRST>(q, m, src, yoff, prefix, pout, yoff_out, j); continue; } }
-    { Fe<C::N> pre; fe_load_cg<C>(pre, reinterpret_cast<const char*>(prefix) + (uint64_t)j * 4 * C::N);
-      fe_mul<C>(t, q, pre); }                        // t = 1 / d
-    fe_mul<C>(q, q, d);
-    reg_fence();
-    { Fe<C::N> y1, y2; meta_load_y<C, FIRST>(y1, src, yoff, m.x); meta_load_y<C, FIRST>(y2, src, yoff, m.y);
-      fe_sub<C>(d, y2, y1); }
-    fe_mul<C>(t, d, t);                              // lambda
-    fe_sqr<C>(d, t);
-    reg_fence();
-    { Fe<C::N> x1, x2; meta_load_x<C, FIRST>(x1, src, m.x); meta_load_x<C, FIRST>(x2, src, m.y);
-      fe_sub<C>(d, d, x1); fe_sub<C>(d, d, x2);      // x3
-      fe_store<C>(ox, d);
-      fe_sub<C>(d, x1, d); }
-    fe_mul<C>(t, t, d);
-    reg_fence();
-    { Fe<C::N> y1; meta_load_y<C, FIRST>(y1, src, yoff, m.x); fe_sub<C>(t, t, y1); }
-    fe_store<C>(ox + yoff_out, t);
-  }
-}
-#ifndef B200_BWD_LEAN_CTAS
-#define B200_BWD_LEAN_CTAS 5
-#endif
-template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, B200_BWD_LEAN_CTAS) k_tree_bwd_lean(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
-                                                         const void* __restrict__ prefix, const void* __restrict__ inv,
-                                                         void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles) {
- for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
-  Fe<C::N> q;
-  fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)(tb * BA_THREADS + threadIdx.x) * 4 * C::N);
-  tree_bwd_tile_lean<C, FIRST>(q, meta, src, yoff, prefix, pout, yoff_out, K, tb);
- }
-}
-
-// ---- one tree round in ONE persistent launch ------------------------------------------------------------------------------------
-// k_tree_fwd, the product-tree levels, the root inversion and k_tree_bwd of a round as a single kernel of G co-resident CTAs.
-// CTA c owns the tiles c, c + G, c + 2G, ... ("wave" w = the G tiles w*G .. w*G + G - 1).  Every wave is one batch inversion
-// (f1m_batchInverse, build_batchinverse.js:4-140) of its own: a thread's running product goes up a 128-leaf tree in shared memory,
-// the CTA's product goes to global memory, and one extra CTA (the "root CTA", which owns no tiles) multiplies the <= G CTA products of a
-// wave together as soon as all of them are there (one chain per thread + the same shared-memory tree), inverts the single root (bingcd.h),
-// walks back down and releases the wave.  (A first version let the LAST-arriving worker run the root: that worker then fell one root behind
-// per wave and every wave waited for it -- 3.8 instead of 2.1 ms for round 0 at 2^20.)
-// The waves are software-pipelined: a CTA runs the forward passes of waves w+1 and w+2 BEFORE it waits for the inverse of wave w, so the
-// latency of a wave's root (tree + one inversion, ~70 us) is covered by forward work and by the other CTAs of
-// the SM, which drift out of phase -- gather-bound forward tiles and multiplier-bound backward tiles then share an SM, instead of
-// running as separate kernels one after the other.  Launched cooperatively (all G CTAs resident: the waits below cannot starve), with
-// a clock-bounded spin as a backstop that raises sy.error instead of hanging the device.
-struct RoundSync {
-  uint32_t* arrive;      // [waves]      CTAs that have published their product of wave w
-  uint32_t* ready;       // [waves]      1 once cta_inv[w][*] is complete
-  void* cta_prod;        // [waves][G]   CTA products
-  void* cta_inv;         // [waves][G]   their inverses (scratch for the prefix products of the root's chains before that)
-  uint32_t* error;       // [1]          a spin wait timed out (results invalid)
-};
-constexpr long long ROUND_SPIN_LIMIT = 4000000000ll;      // ~2 s at 1.9 GHz
-
-B200_DI uint32_t ld_volatile_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-
-// 128-leaf product tree in shared memory, heap order (node 1 = root, leaves at [T, 2T)); all threads of the CTA call these
-template <class C> B200_DI void cta_tree_up(uint32_t* __restrict__ tree, const Fe<C::N>& leaf) {
-  constexpr int N = C::N; const uint32_t t = threadIdx.x;
-#pragma unroll
-  for (int k = 0; k < N; k++) tree[(BA_THREADS + t) * N + k] = leaf.l[k];
-  __syncthreads();
-#pragma unroll 1
-  for (uint32_t width = BA_THREADS / 2; width >= 1; width >>= 1) {
-    if (t < width) {
-      Fe<N> a, b, c; const uint32_t node = width + t;
-#pragma unroll
-      for (int k = 0; k < N; k++) { a.l[k] = tree[(2 * node) * N + k]; b.l[k] = tree[(2 * node + 1) * N + k]; }
-      fe_mul<C>(c, a, b);
-#pragma unroll
-      for (int k = 0; k < N; k++) tree[node * N + k] = c.l[k];
-    }
-    __syncthreads();
-  }
-}
-// node 1 holds the inverse of the root on entry; on exit q = inverse of this thread's leaf
-template <class C> B200_DI void cta_tree_down(uint32_t* __restrict__ tree, Fe<C::N>& q) {
-  constexpr int N = C::N; const uint32_t t = threadIdx.x;
-#pragma unroll 1
-  for (uint32_t width = 1; width < BA_THREADS; width <<= 1) {
-    if (t < width) {
-      Fe<N> a, b, ip, ia, ib; const uint32_t node = width + t;
-#pragma unroll
-      for (int k = 0; k < N; k++) { ip.l[k] = tree[node * N + k]; a.l[k] = tree[(2 * node) * N + k]; b.l[k] = tree[(2 * node + 1) * N + k]; }
-      fe_mul<C>(ia, ip, b); fe_mul<C>(ib, ip, a);
-#pragma unroll
-      for (int k = 0; k < N; k++) { tree[(2 * node) * N + k] = ia.l[k]; tree[(2 * node + 1) * N + k] = ib.l[k]; }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int k = 0; k < N; k++) q.l[k] = tree[(BA_THREADS + t) * N + k];
-}
-// the wave's root, run by the whole CTA that arrived last: cnt CTA products -> their inverses
-template <class C> __device__ __noinline__ void round_root(uint32_t* __restrict__ tree, const void* __restrict__ prods, void* __restrict__ invs, uint32_t cnt) {
-  constexpr int N = C::N; const uint32_t t = threadIdx.x;
-  Fe<N> p; fe_set_one<C>(p);
-#pragma unroll 1
-  for (uint32_t e = t; e < cnt; e += BA_THREADS) {       // chain of this thread; its prefix products wait in invs[]
-    Fe<N> v; fe_load_l2<C>(v, reinterpret_cast<const char*>(prods) + (uint64_t)e * 4 * N);
-    fe_store<C>(reinterpret_cast<char*>(invs) + (uint64_t)e * 4 * N, p);
-    fe_mul<C>(p, p, v);
-  }
-  cta_tree_up<C>(tree, p);
-  if (t == 0) {
-    Fe<N> r, ri;
-#pragma unroll
-    for (int k = 0; k < N; k++) r.l[k] = tree[1 * N + k];
-    fe_inv_fast<C>(ri, r);
-#pragma unroll
-    for (int k = 0; k < N; k++) tree[1 * N + k] = ri.l[k];
-  }
-  __syncthreads();
-  Fe<N> q; cta_tree_down<C>(tree, q);
-  if (cnt > 0) {
-    const uint32_t last = t + ((cnt - 1 - t) / BA_THREADS) * BA_THREADS;      // largest e = t (mod 128) below cnt (t < cnt)
-    if (t < cnt) {
-#pragma unroll 1
-      for (int64_t e = last; e >= (int64_t)t; e -= BA_THREADS) {
-        Fe<N> v, pre, r;
-        fe_load_l2<C>(v, reinterpret_cast<const char*>(prods) + (uint64_t)e * 4 * N);
-        fe_load_l2<C>(pre, reinterpret_cast<const char*>(invs) + (uint64_t)e * 4 * N);
-        fe_mul<C>(r, q, pre); fe_mul<C>(q, q, v);
-        fe_store<C>(reinterpret_cast<char*>(invs) + (uint64_t)e * 4 * N, r);
-      }
-    }
-  }
-}
-
-constexpr uint32_t ROUND_DEPTH = 2;       // waves whose forward pass runs ahead of the backward pass (tree buffers: ROUND_DEPTH + 1)
-
-// gridDim.x = G + 1: CTAs 0..G-1 are the workers, the last CTA only runs the waves' roots (so that no worker falls behind by a root per wave)
-template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, 4) k_tree_round(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff, void* __restrict__ prefix,
-                                                              void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles, RoundSync sy) {
-  constexpr int N = C::N;
-  __shared__ uint32_t trees[ROUND_DEPTH + 1][2 * BA_THREADS * N];       // the trees of the waves in flight (the root CTA uses the first)
-  __shared__ uint32_t s_stop;
-  const uint32_t G = gridDim.x - 1, c = blockIdx.x, t = threadIdx.x;
-  const uint32_t nw = (ntiles + G - 1) / G;
-  auto spin_until = [&](const uint32_t* flag, uint32_t want) {          // thread 0 only; false = gave up (error raised by this or another CTA)
-    const long long t0 = clock64();
-    while (ld_volatile_u32(flag) < want) {
-      __nanosleep(64);
-      if (ld_volatile_u32(sy.error) != 0u) return false;
-      if (clock64() - t0 > ROUND_SPIN_LIMIT) { atomicExch(sy.error, 1u); return false; }
-    }
-    return true;
-  };
-  if (c == G) {
-    // ---- root CTA: wave after wave, wait until all its CTAs have published, invert, release
-#pragma unroll 1
-    for (uint32_t w = 0; w < nw; w++) {
-      const uint32_t cnt = min(G, ntiles - w * G);
-      if (t == 0) { s_stop = spin_until(sy.arrive + w, cnt) ? 0u : 1u; __threadfence(); }
-      __syncthreads();
-      if (s_stop) return;
-      round_root<C>(trees[0], reinterpret_cast<const char*>(sy.cta_prod) + (uint64_t)w * G * 4 * N, reinterpret_cast<char*>(sy.cta_inv) + (uint64_t)w * G * 4 * N, cnt);
-      __threadfence();
-      __syncthreads();
-      if (t == 0) atomicExch(sy.ready + w, 1u);
-    }
-    return;
-  }
-  if (c >= ntiles) return;
-  const uint32_t mine = (ntiles - c + G - 1) / G;          // waves this CTA takes part in (>= 1)
-#pragma unroll 1
-  for (uint32_t it = 0; it < mine + ROUND_DEPTH; it++) {   // iteration `it`: forward pass of wave `it`, then wait + backward pass of wave `it - ROUND_DEPTH`
-    if (it < mine) {
-      Fe<N> p;
-      tree_fwd_tile<C, FIRST>(p, meta, src, yoff, prefix, K, it * G + c);
-      uint32_t* tr = trees[it % (ROUND_DEPTH + 1)];
-      cta_tree_up<C>(tr, p);
-      if (t == 0) {
-        Fe<N> r;
-#pragma unroll
-        for (int k = 0; k < N; k++) r.l[k] = tr[1 * N + k];
-        fe_store<C>(reinterpret_cast<char*>(sy.cta_prod) + ((uint64_t)it * G + c) * 4 * N, r);
-        __threadfence();
-        atomicAdd(sy.arrive + it, 1u);
-      }
-    }
-    if (it < ROUND_DEPTH) continue;
-    const uint32_t w = it - ROUND_DEPTH;
-    uint32_t* tr = trees[w % (ROUND_DEPTH + 1)];
-    if (t == 0) {
-      spin_until(sy.ready + w, 1u);
-      __threadfence();
-      Fe<N> r; fe_load_l2<C>(r, reinterpret_cast<const char*>(sy.cta_inv) + ((uint64_t)w * G + c) * 4 * N);
-#pragma unroll
-      for (int k = 0; k < N; k++) tr[1 * N + k] = r.l[k];
-    }
-    __syncthreads();
-    Fe<N> q; cta_tree_down<C>(tr, q);
-    tree_bwd_tile<C, FIRST>(q, meta, src, yoff, prefix, pout, yoff_out, K, w * G + c);
-    __syncthreads();                                       // the tree buffer of wave w is free for wave w + ROUND_DEPTH + 1
-  }
-}
-
-#endif  // B200_EXPERIMENTS
-
-#if defined(B200_EXPERIMENTS)      // measured 0-8 % slower than k_tree_bwd (profiles/README.md): not in the shipped library
-// backward pass with operand staging: the 2 points + prefix product of the NEXT slot are copied global -> shared with cp.async
-// while the current slot's five multiplications run, so the arithmetic never waits on a gather (the plain kernel above shows
-// 2.3 of its 4 warps per scheduler stalled on the scoreboard).  Each thread stages only its own operands (chunk-major layout:
-// 16-byte chunk c of thread t at sm[c * BA_THREADS + t], conflict-free), so no CTA barrier is involved: cp.async.wait_group
-// orders a thread's own copies, and the next copy is issued only after the registers read from the buffer have been consumed.
-B200_DI void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-B200_DI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-B200_DI void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <class C, bool FIRST>
-B200_DI void bwd_stage(uint4* sm, uint2 m, const void* __restrict__ src, uint64_t yoff, const void* __restrict__ prefix, uint32_t j) {
-  constexpr int FC = C::N / 4, PC = 2 * FC;       // 16-byte chunks per field element / per point
-  if (m.x != META_NONE) {
-    const char* b1 = reinterpret_cast<const char*>(src) + (FIRST ? (uint64_t)(m.x & 0x7fffffffu) * (8 * C::N) : (uint64_t)m.x * (4 * C::N));
-#pragma unroll
-    for (int c = 0; c < PC; c++) cp_async16(sm + c * BA_THREADS + threadIdx.x, (FIRST || c < FC) ? b1 + 16 * c : b1 + yoff + 16 * (c - FC));
-    if (m.y != META_NONE) {
-      const char* b2 = reinterpret_cast<const char*>(src) + (FIRST ? (uint64_t)(m.y & 0x7fffffffu) * (8 * C::N) : (uint64_t)m.y * (4 * C::N));
-      const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(prefix) + (uint64_t)j * (4 * C::N));
-#pragma unroll
-      for (int c = 0; c < PC; c++) cp_async16(sm + (PC + c) * BA_THREADS + threadIdx.x, (FIRST || c < FC) ? b2 + 16 * c : b2 + yoff + 16 * (c - FC));
-#pragma unroll
-      for (int c = 0; c < FC; c++) cp_async16(sm + (2 * PC + c) * BA_THREADS + threadIdx.x, gp + c);
-    }
-  }
-  cp_async_commit();
-}
-template <class C> B200_DI void sm_read_fe(Fe<C::N>& r, const uint4* sm, int chunk0) {
-#pragma unroll
-  for (int c = 0; c < C::N / 4; c++) { const uint4 v = sm[(chunk0 + c) * BA_THREADS + threadIdx.x]; r.l[4 * c] = v.x; r.l[4 * c + 1] = v.y; r.l[4 * c + 2] = v.z; r.l[4 * c + 3] = v.w; }
-}
-
-template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_bwd_staged(const uint2* __restrict__ meta, const void* __restrict__ src, uint64_t yoff,
-                                                                const void* __restrict__ prefix, const void* __restrict__ inv,
-                                                                void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles) {
- extern __shared__ uint4 sm[];
- constexpr int FC = C::N / 4, PC = 2 * FC;
- for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
-  const uint32_t tile = tb * (K * BA_THREADS) + threadIdx.x;
-  uint2 mn = meta[tile + (K - 1) * BA_THREADS];
-  bwd_stage<C, FIRST>(sm, mn, src, yoff, prefix, tile + (K - 1) * BA_THREADS);
-  Fe<C::N> q;
-  fe_load_cg<C>(q, reinterpret_cast<const char*>(inv) + (uint64_t)(tb * BA_THREADS + threadIdx.x) * 4 * C::N);
-#pragma unroll 1
-  for (int i = K - 1; i >= 0; i--) {
-    const uint2 m = mn;
-    mn = make_uint2(META_NONE, META_NONE);
-    if (i > 0) mn = meta[tile + (i - 1) * BA_THREADS];
-    const uint32_t j = tile + i * BA_THREADS;
-    cp_async_wait_all();
-    if (m.x == META_NONE) { bwd_stage<C, FIRST>(sm, mn, src, yoff, prefix, j - BA_THREADS); continue; }
-    Affine<C> p1, p2, r;
-    sm_read_fe<C>(p1.x, sm, 0); sm_read_fe<C>(p1.y, sm, FC);
-    if (FIRST && (m.x >> 31)) fe_neg<C>(p1.y, p1.y);
-    if (m.y == META_NONE) {
-      soa_store_point<C>(pout, yoff_out, j, p1);       // the store consumes the registers read from the buffer
-      bwd_stage<C, FIRST>(sm, mn, src, yoff, prefix, j - BA_THREADS);
-      continue;
-    }
-    sm_read_fe<C>(p2.x, sm, PC); sm_read_fe<C>(p2.y, sm, PC + FC);
-    if (FIRST && (m.y >> 31)) fe_neg<C>(p2.y, p2.y);
-    Fe<C::N> d, dinv, pre;
-    sm_read_fe<C>(pre, sm, 2 * PC);
-    int kind = affine_add_denominator<C>(d, p1, p2);
-    if (kind <= 1) {
-      fe_mul<C>(dinv, q, pre);
-      fe_mul<C>(q, q, d);
-    }
-    bwd_stage<C, FIRST>(sm, mn, src, yoff, prefix, j - BA_THREADS);     // p1, p2, pre are in registers (consumed above): the buffer is free
-    affine_add_finish<C>(r, p1, p2, dinv, kind);
-    soa_store_point<C>(pout, yoff_out, j, r);
-  }
-  cp_async_wait_all();
- }
-}
-
-#endif  // B200_EXPERIMENTS
+// Measured alternatives that are no longer in the tree (profiles/README.md has their numbers): a backward pass that stages the next slot's operands
+// in shared memory with cp.async (0-8 % slower), a register-lean backward pass that reloads operands instead of keeping them (5 CTAs/SM: equal
+// or slower), and the whole round as ONE cooperative launch with in-kernel wave-wise batch inversion (2^20: 8.2-10.6 ms against 6.5).
 
 // ---- product tree, levels >= 1: plain arrays of field elements -----------------------------------------
 // A level reduces n values by K per thread (serial running product, prefixes stored) and, when WARP is set, by a further

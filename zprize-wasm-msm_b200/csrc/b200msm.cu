@@ -28,6 +28,12 @@
 #include "internal.h"
 #include <chrono>
 #include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <atomic>
+#include <memory>
 
 using namespace b200;
 
@@ -64,9 +70,47 @@ struct MultiResident { int curve; uint64_t n; bool replicated; std::vector<uint6
 // one accumulate lane: a stream with its own tree scratch (see accumulate_batch_affine)
 struct TreeLane {
   cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
-  DevBuf offs, tiles, bid, pa, pb, prefix, prod, lvlprefix, others, meta, sync;      // sync: wave counters / flags / CTA products of the fused round kernel
+  DevBuf offs, tiles, bid, pa, pb, prefix, prod, lvlprefix, others, meta, carry;
 };
 constexpr int MAX_LANES = 8;
+
+// ---- issue threads: one host thread per lane -----------------------------------------------------------------------------------------
+// A window group is ~40-200 kernel launches (rounds x {operand table, forward pass, product-tree levels, root, backward pass}, fold levels).
+// Issued from ONE host thread the lanes start one after the other, each ~0.1 ms (its launches) behind the previous one; below ~2^19 points
+// that stagger would be a tenth of the whole MSM.  With one issuing thread per lane all lanes start together.  MEASURED (profiles/README.md r2): the
+// stagger seen in a CUPTI trace is the tracer's own per-launch cost; untraced, a launch costs ~2 us and the option changes nothing
+// (2^16: 1.53 / 1.58 ms, 2^18: 2.63 / 2.64, 2^20: 6.57 / 6.56 with 0 / 1) -- kept as the option "issue_threads", off by default.
+// The threads only enqueue work on their lane's stream; everything shared is read-only while they run.
+struct IssuePool {
+  struct Worker { std::thread th; std::mutex m; std::condition_variable cv; std::deque<std::function<void()>> q; std::atomic<int> pending{0}; bool quit = false; };
+  std::vector<std::unique_ptr<Worker>> w;
+  void ensure(int n, int device) {
+    while ((int)w.size() < n) {
+      w.emplace_back(new Worker()); Worker* W = w.back().get();
+      W->th = std::thread([W, device] {
+        cudaSetDevice(device);
+        for (;;) {
+          for (int spin = 0; spin < 4000 && W->pending.load(std::memory_order_acquire) == 0; spin++) { }      // a job usually follows within microseconds of the previous one
+          std::function<void()> f;
+          { std::unique_lock<std::mutex> lk(W->m);
+            W->cv.wait(lk, [&] { return W->quit || !W->q.empty(); });
+            if (W->q.empty()) return;
+            f = std::move(W->q.front()); W->q.pop_front(); W->pending.fetch_sub(1, std::memory_order_relaxed); }
+          f();
+        }
+      });
+    }
+  }
+  void submit(int lane, std::function<void()> f) {
+    Worker* W = w[lane].get();
+    { std::lock_guard<std::mutex> lk(W->m); W->q.push_back(std::move(f)); W->pending.fetch_add(1, std::memory_order_release); }
+    W->cv.notify_one();
+  }
+  ~IssuePool() {
+    for (auto& p : w) { { std::lock_guard<std::mutex> lk(p->m); p->quit = true; } p->cv.notify_one(); }
+    for (auto& p : w) if (p->th.joinable()) p->th.join();
+  }
+};
 constexpr uint64_t WARP_LEVEL_MAX = 131072;     // product-tree levels with at most this many values use the warp-assisted kernel (only one such level can occur: 131072 / 128 <= BA_ROOT_MAX)
 
 }  // namespace
@@ -79,9 +123,7 @@ struct b200msm_ctx {
   DevBuf bases, scalars, canon, counts, offsets, ranks, tiles, sorted, buckets, wsum, out, misc, acc_a, acc_b, acc_c, acc_d, acc_e, jac_in, jac_affine;
   TreeLane lane[MAX_LANES];                                                   // batch-affine tree lanes
   int opt_sort_groups = 1;                                // sort the window slots group by group on the lanes' streams (run_grouped)
-  int opt_bwd_lean = 0;                                   // register-lean backward pass (k_tree_bwd_lean)
-  int opt_fused = 0, round_slots[4] = {0, 0, 0, 0};      // fused round kernel (k_tree_round): on for the prime fields; co-resident CTAs per device for each curve (0 = not queried yet)
-  int opt_lanes = 4, opt_ba_k = 0, opt_pt_k = 8, opt_persist = 592, opt_subslots = 0, opt_bwd_staged = 0, opt_probe_smem = 0;
+  int opt_lanes = 4, opt_ba_k = 0, opt_pt_k = 8, opt_persist = 592, opt_subslots = 0, opt_probe_smem = 0;
   bool probe29 = false, probe_sqr = false; int64_t opt_group_pairs = 0;
   cudaEvent_t ev_plan = nullptr, ev_sorted = nullptr, ev_bases = nullptr, ev_done = nullptr;
   cudaStream_t copy_stream = nullptr; bool bases_pending = false;
@@ -94,7 +136,8 @@ struct b200msm_ctx {
   cudaEvent_t ev[8] = {};
   // fine-grained phase profiler (active only while a stats struct is being filled)
   std::vector<cudaEvent_t> pev; std::vector<int> ptag; size_t pused = 0; bool prof = false;
-  uint64_t launches = 0, adds_r0 = 0, adds_exact = 0, cur_n = 0; uint32_t fused_groups = 0;
+  std::atomic<uint64_t> launches{0}; uint64_t adds_r0 = 0, adds_exact = 0, cur_n = 0;
+  IssuePool* pool = nullptr; int opt_issue_threads = 0, opt_fold_cluster = 1; std::mutex err_mu;      // one issuing host thread per lane (IssuePool); err is written under err_mu
   size_t total_mem = 0;
   // multi-device context (b200msm_create_multi): devs[0] == this, devs[g] = the single-device context of device g; mres = handles of sharded / replicated base sets
   std::vector<b200msm_ctx*> devs; std::map<uint64_t, MultiResident> mres; int64_t opt_multi_min = 1 << 15; int opt_multi_replicate = 0;
@@ -103,7 +146,7 @@ struct b200msm_ctx {
 
 namespace {
 
-#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); \
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { { std::lock_guard<std::mutex> lk_(ctx->err_mu); ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); } \
   return e_ == cudaErrorMemoryAllocation ? B200MSM_E_NOMEM : B200MSM_E_CUDA; } } while (0)
 #define CKL() do { ctx->launches++; CK(cudaGetLastError()); } while (0)
 enum { T_SORT = 0, T_PLAN, T_TREE_FWD, T_INV_TREE, T_TREE_BWD, T_FINISH, T_FOLD, T_WSUM, T_HORNER, T_TREE_BWD0, T_NTAGS };
@@ -112,8 +155,33 @@ enum { T_SORT = 0, T_PLAN, T_TREE_FWD, T_INV_TREE, T_TREE_BWD, T_FINISH, T_FOLD,
 void copy_options(b200msm_ctx* w, const b200msm_ctx* ctx) {
   w->opt_window_bits = ctx->opt_window_bits; w->opt_accumulate = ctx->opt_accumulate; w->opt_tree_rounds = ctx->opt_tree_rounds; w->opt_lanes = ctx->opt_lanes;
   w->opt_ba_k = ctx->opt_ba_k; w->opt_pt_k = ctx->opt_pt_k; w->opt_persist = ctx->opt_persist; w->opt_subslots = ctx->opt_subslots; w->opt_combine = ctx->opt_combine;
-  w->opt_group_pairs = ctx->opt_group_pairs; w->opt_fused = ctx->opt_fused; w->opt_bwd_lean = ctx->opt_bwd_lean; w->opt_sort_groups = ctx->opt_sort_groups; w->opt_batch_workers = ctx->opt_batch_workers;
+  w->opt_group_pairs = ctx->opt_group_pairs; w->opt_sort_groups = ctx->opt_sort_groups; w->opt_fold_cluster = ctx->opt_fold_cluster; w->opt_batch_workers = ctx->opt_batch_workers;
+  w->opt_issue_threads = 0;      // the batch workers already overlap whole MSMs
 }
+
+// The groups of one MSM: job gi runs on lane gi % lanes -- inline (single issuing thread) or on that lane's issue thread.  wait(gi) blocks until
+// job gi has been ISSUED (its kernels are enqueued, its completion event recorded) and returns its status; the destructor waits for every job,
+// so the jobs may refer to the caller's locals.
+struct GroupIssue {
+  b200msm_ctx* ctx; uint32_t n; bool threaded; std::unique_ptr<std::atomic<int>[]> st; std::vector<int> rc;
+  GroupIssue(b200msm_ctx* c, uint32_t ngroups, uint32_t lanes) : ctx(c), n(ngroups), st(new std::atomic<int>[ngroups]), rc(ngroups, 0) {
+    for (uint32_t i = 0; i < n; i++) st[i].store(2);       // 2 = not submitted
+    threaded = c->opt_issue_threads != 0 && lanes > 1 && ngroups > 1 && !c->prof;
+    if (threaded) { if (!c->pool) c->pool = new IssuePool(); c->pool->ensure((int)lanes, c->device); }
+  }
+  template <class F> int run(uint32_t gi, uint32_t lane, F f) {
+    if (!threaded) { rc[gi] = f(); st[gi].store(1); return rc[gi]; }
+    st[gi].store(0);
+    ctx->pool->submit((int)lane, [this, gi, f] { rc[gi] = f(); st[gi].store(1, std::memory_order_release); });
+    return 0;
+  }
+  int wait(uint32_t gi) {
+    for (int spin = 0; st[gi].load(std::memory_order_acquire) == 0; spin++) if (spin > 2000) std::this_thread::yield();
+    return rc[gi];
+  }
+  int wait_all() { int r = 0; for (uint32_t i = 0; i < n; i++) { int x = wait(i); if (x && !r) r = x; } return r; }
+  ~GroupIssue() { wait_all(); }
+};
 
 int lane_init(b200msm_ctx* ctx, TreeLane& ln) {
   if (!ln.stream) {
@@ -204,6 +272,38 @@ int exclusive_scan(b200msm_ctx* ctx, cudaStream_t s, DevBuf& tiles, const uint32
   return B200MSM_OK;
 }
 
+// vals[0 .. n) <- 1 / vals[e], in place, through the grid-wide product tree (f1m_batchInverse, build_batchinverse.js:4-140, for values that are
+// all non-zero): plain K-ary levels while the level is large, one warp-assisted level (arity 32*4) once it is small, one block for the last
+// <= BA_ROOT_MAX values (a single field inversion), and the same levels back down.  Levels above `vals` are appended behind it (vals must have room
+// for 2*n + 4096 elements); lpre = prefix scratch of the same size; ln_.others serves the warp-assisted level.
+template <class C>
+int product_tree_invert(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, char* vals, char* lpre, uint64_t n, int PK) {
+  const size_t fe = 4 * C::N;
+  struct Lvl { uint64_t n; char* v; char* p; bool warp; int K; };
+  std::vector<Lvl> lv;
+  char* cur = vals; char* curp = lpre;
+  while (n > BA_ROOT_MAX) {
+    const bool warp = n <= WARP_LEVEL_MAX;
+    const int K = warp ? 4 : PK;
+    const uint32_t g2 = (uint32_t)((n + (uint64_t)K * BA_THREADS - 1) / ((uint64_t)K * BA_THREADS));
+    char* nxt = cur + n * fe;
+    if (warp) k_prod_fwd<C, true><<<g2, BA_THREADS, 0, s>>>(cur, (uint32_t)n, curp, nxt, ln_.others.p, K);
+    else k_prod_fwd<C, false><<<g2, BA_THREADS, 0, s>>>(cur, (uint32_t)n, curp, nxt, nullptr, K);
+    CKL();
+    lv.push_back(Lvl{n, cur, curp, warp, K});
+    curp += n * fe; cur = nxt; n = warp ? (uint64_t)g2 * (BA_THREADS / 32) : (uint64_t)g2 * BA_THREADS;
+  }
+  k_inv_root<C><<<1, RootCfg<C>::THREADS, 0, s>>>(cur, (uint32_t)n); CKL();
+  for (int l = (int)lv.size() - 1; l >= 0; l--) {
+    const Lvl& L = lv[l];
+    const uint32_t g2 = (uint32_t)((L.n + (uint64_t)L.K * BA_THREADS - 1) / ((uint64_t)L.K * BA_THREADS));
+    if (L.warp) k_prod_bwd<C, true><<<g2, BA_THREADS, 0, s>>>(L.v, (uint32_t)L.n, L.p, L.v + L.n * fe, ln_.others.p, L.K);
+    else k_prod_bwd<C, false><<<g2, BA_THREADS, 0, s>>>(L.v, (uint32_t)L.n, L.p, L.v + L.n * fe, nullptr, L.K);
+    CKL();
+  }
+  return B200MSM_OK;
+}
+
 // ---- batch-affine tree over a bucket range (a group of whole window slots), issued on one lane ----------------
 // A lane = one CUDA stream + its own scratch.  Consecutive groups alternate between lanes so that the latency-bound
 // tail of one group's round (product tree, root inversion) overlaps the throughput-bound kernels of the other group.
@@ -258,114 +358,38 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, uin
   k_fill_bid<<<(nbg + 255) / 256, 256, 0, s>>>(off[1], nbg, bid[1]); CKL();
   MARK(T_PLAN);
   const size_t fe = 4 * C::N, pt = 8 * C::N;
-  bool fused = false;
-#if defined(B200_EXPERIMENTS)
-  if constexpr (C::EXT == 1) {
-    fused = ctx->opt_fused != 0;
-    if (fused && ctx->round_slots[C::ID & 3] == 0) {      // co-resident CTAs of the round kernel on this device (once per context and curve)
-      cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, ctx->device));
-      // shared-memory carve-out: exactly what 4 CTAs need (3 product trees each); the rest of the 228 KB stays L1 for the 16-byte gathers
-      cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_tree_round<C, true>));
-      const int carve = std::min<int>(100, (int)((4 * (fa.sharedSizeBytes + 1024) * 100) / (228 * 1024)) + 2);
-      CK(cudaFuncSetAttribute(k_tree_round<C, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-      CK(cudaFuncSetAttribute(k_tree_round<C, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-      int o1 = 0, o2 = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_tree_round<C, true>, BA_THREADS, 0));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_tree_round<C, false>, BA_THREADS, 0));
-      ctx->round_slots[C::ID & 3] = std::max(1, std::min(o1, o2)) * prop.multiProcessorCount;
-      if (!prop.cooperativeLaunch) { ctx->round_slots[C::ID & 3] = 0; fused = false; ctx->opt_fused = 0; }
-    }
-  }
-#endif
   const int BK = ctx->opt_ba_k > 0 ? ctx->opt_ba_k : (m0 >= (1u << 22) ? 16 : 8), PK = ctx->opt_pt_k;     // chain length per thread: measured 2^20: 8 -> 6.84, 12 -> 6.76, 16 -> 6.70 ms; 2^18: 2.70 / 2.69 / 2.80
   const uint64_t BA_TILE = (uint64_t)BK * BA_THREADS;
   CK(ln_.pa.ensure(U[1] * pt + 1024)); if (R > 1) CK(ln_.pb.ensure(U[2] * pt + 1024));
-  CK(ln_.prefix.ensure((U[1] + BA_TILE) * fe + 16));
-  CK(ln_.meta.ensure((U[1] + BA_TILE) * 8 + 16));
+  // additions of round r: sum floor(n_r / 2) <= U[r] / 2 -- the arithmetic kernels run over these (dense) items, not over the output slots
+  const uint64_t A0 = U[0] / 2;
+  CK(ln_.prefix.ensure((A0 + BA_TILE) * fe + 16));
+  CK(ln_.meta.ensure((A0 + BA_TILE) * 16 + 16)); CK(ln_.carry.ensure(((size_t)std::min<uint64_t>(nbg, U[1]) + 1) * 8));
   // product-tree level sizes for the largest round
-  { uint64_t n1 = ((U[1] + BA_TILE - 1) / BA_TILE) * BA_THREADS;       // every level above is at least 4x smaller: 2*n1 bounds the sum
+  { uint64_t n1 = ((A0 + BA_TILE - 1) / BA_TILE + 1) * BA_THREADS;       // every level above is at least 4x smaller: 2*n1 bounds the sum
     CK(ln_.prod.ensure((2 * n1 + 4096) * fe)); CK(ln_.lvlprefix.ensure((2 * n1 + 4096) * fe)); CK(ln_.others.ensure((WARP_LEVEL_MAX / 4 + 4096) * fe)); }
   void* pin = nullptr; uint64_t yin = 0;
   const uint64_t ya = ((U[1] * fe + 255) / 256) * 256, yb = R > 1 ? ((U[2] * fe + 255) / 256) * 256 : 0;      // x array, then y array (see meta_load_point)
   for (uint32_t r = 0; r < R; r++) {
     void* pout = (r & 1) ? ln_.pb.p : ln_.pa.p; const uint64_t yout = (r & 1) ? yb : ya;
     TreeRound tr{off[r], off[r + 1], (r + 2 <= R) ? off[r + 2] : nullptr, bid[r + 1], (r + 2 <= R) ? bid[r + 2] : nullptr, nbg};
-    uint32_t grid = (uint32_t)((U[r + 1] + BA_TILE - 1) / BA_TILE);
+    uint32_t grid = (uint32_t)((U[r] / 2 + BA_TILE - 1) / BA_TILE);
     if (grid == 0) grid = 1;
     char* prod = ln_.prod.as<char>(); char* lpre = ln_.lvlprefix.as<char>();
     const uint32_t pgrid = (ctx->opt_persist > 0 && overlapped) ? std::min<uint32_t>(grid, (uint32_t)ctx->opt_persist) : grid;   // persistent grid only when lanes overlap
-    const uint32_t nslots = grid * (uint32_t)BA_TILE;
-    uint2* meta = ln_.meta.as<uint2>();
-    if (r == 0) k_tree_meta<true><<<(nslots + 255) / 256, 256, 0, s>>>(tr, sorted, meta, nslots);
-    else k_tree_meta<false><<<(nslots + 255) / 256, 256, 0, s>>>(tr, nullptr, meta, nslots);
+    const uint32_t nslots = (uint32_t)std::max<uint64_t>(U[r + 1], 1);
+    uint4* items = ln_.meta.as<uint4>();
+    uint2* carries = ln_.carry.as<uint2>();
+    if (r == 0) k_tree_meta<true><<<(nslots + 255) / 256, 256, 0, s>>>(tr, sorted, items, carries);
+    else k_tree_meta<false><<<(nslots + 255) / 256, 256, 0, s>>>(tr, nullptr, items, carries);
     CKL();
-#if defined(B200_EXPERIMENTS)
-    if constexpr (C::EXT == 1) if (fused) {
-      // ---- the whole round (forward pass, product tree, root inversion, backward pass) as ONE cooperative launch of G co-resident CTAs
-      const uint32_t slots = (uint32_t)ctx->round_slots[C::ID & 3] / std::max<uint32_t>(1, share);        // co-resident CTAs this lane may use; one of them is the root CTA
-      const uint32_t G = std::max<uint32_t>(1, std::min<uint32_t>(grid, slots > 1 ? slots - 1 : 1));
-      const uint32_t nw = (grid + G - 1) / G;
-      const size_t ctr = (((size_t)2 * nw * 4 + 255) / 256) * 256, arr = (size_t)nw * G * fe;
-      CK(ln_.sync.ensure(256 + ctr + 2 * arr + 256));
-      char* sb = ln_.sync.as<char>();
-      if (r == 0) CK(cudaMemsetAsync(sb, 0, 256 + ctr, s)); else CK(cudaMemsetAsync(sb + 256, 0, ctr, s));      // the error word survives the rounds of a group
-      RoundSync sy{reinterpret_cast<uint32_t*>(sb + 256), reinterpret_cast<uint32_t*>(sb + 256) + nw, sb + 256 + ctr, sb + 256 + ctr + arr, reinterpret_cast<uint32_t*>(sb)};
-      const void* a_src = r == 0 ? d_bases : pin; uint64_t a_yin = r == 0 ? 0 : yin; void* a_prefix = ln_.prefix.p; int a_K = BK; uint32_t a_nt = grid; uint64_t a_yout = yout; void* a_pout = pout;
-      void* args[] = {&meta, &a_src, &a_yin, &a_prefix, &a_pout, &a_yout, &a_K, &a_nt, &sy};
-      const void* fn = r == 0 ? (const void*)k_tree_round<C, true> : (const void*)k_tree_round<C, false>;
-      CK(cudaLaunchCooperativeKernel(fn, dim3(G + 1), dim3(BA_THREADS), args, 0, s));
-      CKL(); MARK(r == 0 ? T_TREE_BWD0 : T_TREE_BWD);
-      pin = pout; yin = yout;
-      *adds_out += U[r] - U[r + 1];
-      continue;
-    }
-#endif
-    if (r == 0) k_tree_fwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(meta, d_bases, 0, ln_.prefix.p, prod, BK, grid);
-    else k_tree_fwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(meta, pin, yin, ln_.prefix.p, prod, BK, grid);
+    if (r == 0) k_tree_fwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(items, off[r], off[r + 1], nbg, d_bases, 0, ln_.prefix.p, prod, BK, grid);
+    else k_tree_fwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(items, off[r], off[r + 1], nbg, pin, yin, ln_.prefix.p, prod, BK, grid);
     CKL(); MARK(T_TREE_FWD);
-    // up the product tree: plain K-ary levels while the level is large, one warp-assisted level (arity 32*4) once it is small
-    struct Lvl { uint64_t n; char* v; char* p; bool warp; int K; };
-    std::vector<Lvl> lv;
-    uint64_t n = (uint64_t)grid * BA_THREADS; char* cur = prod; char* curp = lpre;
-    while (n > BA_ROOT_MAX) {
-      const bool warp = n <= WARP_LEVEL_MAX;
-      const int K = warp ? 4 : PK;
-      const uint32_t g2 = (uint32_t)((n + (uint64_t)K * BA_THREADS - 1) / ((uint64_t)K * BA_THREADS));
-      char* nxt = cur + n * fe;
-      if (warp) k_prod_fwd<C, true><<<g2, BA_THREADS, 0, s>>>(cur, (uint32_t)n, curp, nxt, ln_.others.p, K);
-      else k_prod_fwd<C, false><<<g2, BA_THREADS, 0, s>>>(cur, (uint32_t)n, curp, nxt, nullptr, K);
-      CKL();
-      lv.push_back(Lvl{n, cur, curp, warp, K});
-      curp += n * fe; cur = nxt; n = warp ? (uint64_t)g2 * (BA_THREADS / 32) : (uint64_t)g2 * BA_THREADS;
-    }
-    k_inv_root<C><<<1, RootCfg<C>::THREADS, 0, s>>>(cur, (uint32_t)n); CKL();
-    // back down
-    for (int l = (int)lv.size() - 1; l >= 0; l--) {
-      const Lvl& L = lv[l];
-      const uint32_t g2 = (uint32_t)((L.n + (uint64_t)L.K * BA_THREADS - 1) / ((uint64_t)L.K * BA_THREADS));
-      if (L.warp) k_prod_bwd<C, true><<<g2, BA_THREADS, 0, s>>>(L.v, (uint32_t)L.n, L.p, L.v + L.n * fe, ln_.others.p, L.K);
-      else k_prod_bwd<C, false><<<g2, BA_THREADS, 0, s>>>(L.v, (uint32_t)L.n, L.p, L.v + L.n * fe, nullptr, L.K);
-      CKL();
-    }
+    { int rc_ = product_tree_invert<C>(ctx, ln_, s, prod, lpre, (uint64_t)grid * BA_THREADS, PK); if (rc_) return rc_; }
     MARK(T_INV_TREE);
-#if defined(B200_EXPERIMENTS)
-    if (ctx->opt_bwd_staged) {
-      const size_t smem = (size_t)(5 * (C::N / 4)) * BA_THREADS * 16;          // 2 points + 1 field element per thread
-      if (r == 0) k_tree_bwd_staged<C, true><<<pgrid, BA_THREADS, smem, s>>>(meta, d_bases, 0, ln_.prefix.p, prod, pout, yout, BK, grid);
-      else k_tree_bwd_staged<C, false><<<pgrid, BA_THREADS, smem, s>>>(meta, pin, yin, ln_.prefix.p, prod, pout, yout, BK, grid);
-    } else
-#endif
-#if defined(B200_EXPERIMENTS)
-    if (C::EXT == 1 && ctx->opt_bwd_lean) {
-      if constexpr (C::EXT == 1) {
-        const uint32_t lgrid = (ctx->opt_persist > 0 && overlapped) ? std::min<uint32_t>(grid, (uint32_t)ctx->opt_persist * B200_BWD_LEAN_CTAS / 4) : grid;
-        if (r == 0) k_tree_bwd_lean<C, true><<<lgrid, BA_THREADS, 0, s>>>(meta, d_bases, 0, ln_.prefix.p, prod, pout, yout, BK, grid);
-        else k_tree_bwd_lean<C, false><<<lgrid, BA_THREADS, 0, s>>>(meta, pin, yin, ln_.prefix.p, prod, pout, yout, BK, grid);
-      }
-    } else
-#endif
-    if (r == 0) k_tree_bwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(meta, d_bases, 0, ln_.prefix.p, prod, pout, yout, BK, grid);
-    else k_tree_bwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(meta, pin, yin, ln_.prefix.p, prod, pout, yout, BK, grid);
+    if (r == 0) k_tree_bwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(items, carries, off[r], off[r + 1], nbg, d_bases, 0, ln_.prefix.p, prod, pout, yout, BK, grid);
+    else k_tree_bwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(items, carries, off[r], off[r + 1], nbg, pin, yin, ln_.prefix.p, prod, pout, yout, BK, grid);
     CKL(); MARK(r == 0 ? T_TREE_BWD0 : T_TREE_BWD);
     pin = pout; yin = yout;
     *adds_out += U[r] - U[r + 1];
@@ -377,7 +401,6 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, uin
     for (uint32_t r = 1; r <= R; r++) { uint64_t cur = ctx->h_pinned[1024 + r]; exact += prev - cur; if (r == 1) ctx->adds_r0 += prev - cur; prev = cur; }
     *adds_out -= 0; ctx->adds_exact += exact;
   }
-  if (fused) CK(cudaMemcpyAsync(ctx->h_pinned + 1900 + (ctx->fused_groups++ & 63), ln_.sync.p, 4, cudaMemcpyDeviceToHost, s));      // wave-wait time-outs of this group (checked with the result)
   k_accum_finish<C, false><<<(nbg + 127) / 128, 128, 0, s>>>(nullptr, nullptr, pin, yin, off[R], nbg, buckets_g); CKL();
   MARK(T_FINISH);
   return B200MSM_OK;
@@ -395,7 +418,12 @@ int fold_slots(b200msm_ctx* ctx, cudaStream_t s, void* buckets_g, uint32_t slots
   }
   if (tail >= 2) {                        // remaining levels of every live block of `tail` buckets: one launch
     uint32_t nblk = B / tail, live = 1; for (uint32_t k = 1; k < nblk; k <<= 1) live++;
-    k_fold_tail<C><<<slots * live, 256, 0, s>>>(buckets_g, B, tail, live); CKL();
+    if (ctx->opt_fold_cluster) {          // one cluster of 8 CTAs per live block (k_fold_tail_cluster)
+      cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3(slots * live * FOLD_CLUSTER); cfg.blockDim = dim3(FOLD_CLUSTER_THREADS); cfg.stream = s;
+      cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = FOLD_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&cfg, k_fold_tail_cluster<C>, buckets_g, B, tail, live)); CKL();
+    } else { k_fold_tail<C><<<slots * live, 256, 0, s>>>(buckets_g, B, tail, live); CKL(); }
   }
   return B200MSM_OK;
 }
@@ -456,32 +484,37 @@ int run_grouped(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, c
     k_digits<true><<<gb, tb, 0, ls>>>(d_scal, pl, nullptr, G.offs, ctx->ranks.as<uint32_t>(), ctx->sorted.as<uint32_t>(), G.w0, G.w1); CKL();
     if (ctx->bases_pending) CK(cudaStreamWaitEvent(ls, ctx->ev_bases, 0));
   }
-  // ---- phase 2: as each group's counts arrive, its tree, fold and read-back follow on the same lane
-  uint32_t rounds = 0; uint64_t adds = 0;
-  ctx->adds_r0 = 0; ctx->adds_exact = 0; ctx->cur_n = n; ctx->fused_groups = 0;
-  std::vector<char> live(ngroups, 0);
+  // ---- phase 2: as each group's counts arrive, its tree, fold and read-back follow on the same lane (one issuing thread per lane)
+  ctx->adds_r0 = 0; ctx->adds_exact = 0; ctx->cur_n = n;
+  std::vector<char> live(ngroups, 0); std::vector<uint32_t> g_rounds(ngroups, 0); std::vector<uint64_t> g_adds(ngroups, 0);
+  GroupIssue gi_(ctx, ngroups, lanes);
   for (uint32_t gi = 0; gi < ngroups; gi++) {
-    const Grp& G = grp[gi];
-    TreeLane& ln = ctx->lane[gi % lanes]; cudaStream_t ls = ln.stream;
-    CK(cudaEventSynchronize(ctx->gev[ngroups + gi]));
-    uint32_t mc = 0; for (uint32_t w = G.w0; w < G.s1; w++) mc = std::max(mc, ctx->h_pinned[w]);
-    const uint64_t m0 = (uint64_t)ctx->h_pinned[512 + gi] - (uint64_t)n * G.w0;
-    const size_t o = (size_t)G.w0 * per * 16 * C::N; const uint32_t np = (G.s1 - G.w0) * per;
-    if (m0 == 0) { memset(reinterpret_cast<char*>(ctx->h_folded) + o, 0, (size_t)np * 16 * C::N); continue; }      // every digit of these windows is zero: all their folded entries are infinity (zz = 0)
-    live[gi] = 1;
-    char* bg = ctx->buckets.as<char>() + (size_t)G.b0 * 16 * C::N;
-    rc = accumulate_batch_affine<C>(ctx, ln, ls, lanes, d_bases, G.offs + G.b0, ctx->counts.as<uint32_t>() + G.b0, G.nbg, m0, mc, bg, &rounds, &adds);
-    if (!rc) rc = fold_slots<C>(ctx, ls, bg, G.s1 - G.w0, pl.B);
-    if (rc) return rc;
-    k_gather_folded<C><<<(np + 127) / 128, 128, 0, ls>>>(bg, G.s1 - G.w0, pl.B, pl.logB, ctx->wsum.as<char>() + o); CKL();
-    CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->h_folded) + o, ctx->wsum.as<char>() + o, (size_t)np * 16 * C::N, cudaMemcpyDeviceToHost, ls));
-    CK(cudaEventRecord(ctx->gev[gi], ls));
+    auto job = [&, gi]() -> int {
+      const Grp& G = grp[gi];
+      TreeLane& ln = ctx->lane[gi % lanes]; cudaStream_t ls = ln.stream;
+      CK(cudaEventSynchronize(ctx->gev[ngroups + gi]));
+      uint32_t mc = 0; for (uint32_t w = G.w0; w < G.s1; w++) mc = std::max(mc, ctx->h_pinned[w]);
+      const uint64_t m0 = (uint64_t)ctx->h_pinned[512 + gi] - (uint64_t)n * G.w0;
+      const size_t o = (size_t)G.w0 * per * 16 * C::N; const uint32_t np = (G.s1 - G.w0) * per;
+      if (m0 == 0) { memset(reinterpret_cast<char*>(ctx->h_folded) + o, 0, (size_t)np * 16 * C::N); return B200MSM_OK; }      // every digit of these windows is zero: all their folded entries are infinity (zz = 0)
+      live[gi] = 1;
+      char* bg = ctx->buckets.as<char>() + (size_t)G.b0 * 16 * C::N;
+      int rc2 = accumulate_batch_affine<C>(ctx, ln, ls, lanes, d_bases, G.offs + G.b0, ctx->counts.as<uint32_t>() + G.b0, G.nbg, m0, mc, bg, &g_rounds[gi], &g_adds[gi]);
+      if (!rc2) rc2 = fold_slots<C>(ctx, ls, bg, G.s1 - G.w0, pl.B);
+      if (rc2) return rc2;
+      k_gather_folded<C><<<(np + 127) / 128, 128, 0, ls>>>(bg, G.s1 - G.w0, pl.B, pl.logB, ctx->wsum.as<char>() + o); CKL();
+      CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->h_folded) + o, ctx->wsum.as<char>() + o, (size_t)np * 16 * C::N, cudaMemcpyDeviceToHost, ls));
+      CK(cudaEventRecord(ctx->gev[gi], ls));
+      return B200MSM_OK;
+    };
+    rc = gi_.run(gi, gi % lanes, job); if (rc) return rc;
   }
   // ---- window combination on the host, group by group from the top (host_ec.h)
   using HF = typename HostField<C>::type; const HF f = HostField<C>::make();
   b200host::Combiner<HF> cb; cb.begin(f, pl.W, pl.Wd, pl.c0, pl.rem, pl.logB);
   float host_ms = 0;
   for (uint32_t gi = 0; gi < ngroups; gi++) {
+    rc = gi_.wait(gi); if (rc) return rc;
     if (live[gi]) CK(cudaEventSynchronize(ctx->gev[gi]));
     auto t0 = std::chrono::steady_clock::now();
     cb.feed(reinterpret_cast<const b200host::XYZZ<HF::W>*>(ctx->h_folded), grp[gi].w0, grp[gi].s1);
@@ -558,7 +591,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   int mode = ctx->opt_accumulate;
   if (mode == 0) mode = 2;
   uint32_t rounds = 0; uint64_t adds = 0;
-  ctx->adds_r0 = 0; ctx->adds_exact = 0; ctx->cur_n = n; ctx->fused_groups = 0;
+  ctx->adds_r0 = 0; ctx->adds_exact = 0; ctx->cur_n = n;
   if (pre) {
     // ---- window-table form: the single bucket array is cut into S sub-slots of Bs = Bg buckets (a power of two).  Each sub-slot is a
     // group: its tree runs on one lane, then it is folded on its own (k_fold sees it as a slot of Bs buckets) while the other lanes still
@@ -594,33 +627,41 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
     { uint32_t w = 0; for (uint32_t g = 1; g < ngroups; g++) { uint64_t target = mtot * g / ngroups;
         while (w < G && ctx->h_pinned[512 + w] < target) w++;
         cut[g] = std::min(std::max(w, cut[g - 1] + 1), G - (ngroups - g)); } }
+    std::vector<uint32_t> g_rounds(ngroups, 0); std::vector<uint64_t> g_adds(ngroups, 0);
+    GroupIssue gi_(ctx, ngroups, lanes);
     for (uint32_t g = 0; g < ngroups; g++) {
-      TreeLane& ln = ctx->lane[g % lanes];
-      const uint32_t g0 = cut[g], g1 = cut[g + 1];
-      uint32_t mc = 0; for (uint32_t k = g0; k < g1; k++) mc = std::max(mc, ctx->h_pinned[k]);
-      const uint64_t m0 = ctx->h_pinned[512 + g1] - ctx->h_pinned[512 + g0];
-      const uint32_t b0 = g0 * Bg, nbg = (g1 - g0) * Bg;
-      cudaStream_t ls = lanes == 1 ? s : ln.stream;
-      char* bg = ctx->buckets.as<char>() + (size_t)b0 * 16 * C::N;
-      rc = accumulate_batch_affine<C>(ctx, ln, ls, lanes, d_bases, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc, bg, &rounds, &adds);
-      if (!rc && host_tail) {
-        if (st && g + 1 == ngroups) CK(cudaEventRecord(ctx->ev[3], s));
-        rc = fold_slots<C>(ctx, ls, bg, g1 - g0, Bg);
-        if (!rc) {
-          const uint32_t np = (g1 - g0) * per; const size_t o = (size_t)g0 * per * 16 * C::N;
-          k_gather_folded<C><<<(np + 127) / 128, 128, 0, ls>>>(bg, g1 - g0, Bg, logBs, ctx->wsum.as<char>() + o); CKL();
-          CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->h_folded) + o, ctx->wsum.as<char>() + o, (size_t)np * 16 * C::N, cudaMemcpyDeviceToHost, ls));
-          CK(cudaEventRecord(ctx->gev[g], ls));
+      auto job = [&, g]() -> int {
+        TreeLane& ln = ctx->lane[g % lanes];
+        const uint32_t g0 = cut[g], g1 = cut[g + 1];
+        uint32_t mc = 0; for (uint32_t k = g0; k < g1; k++) mc = std::max(mc, ctx->h_pinned[k]);
+        const uint64_t m0 = ctx->h_pinned[512 + g1] - ctx->h_pinned[512 + g0];
+        const uint32_t b0 = g0 * Bg, nbg = (g1 - g0) * Bg;
+        cudaStream_t ls = lanes == 1 ? s : ln.stream;
+        char* bg = ctx->buckets.as<char>() + (size_t)b0 * 16 * C::N;
+        int rc2 = accumulate_batch_affine<C>(ctx, ln, ls, lanes, d_bases, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc, bg, &g_rounds[g], &g_adds[g]);
+        if (!rc2 && host_tail) {
+          if (st && g + 1 == ngroups) CK(cudaEventRecord(ctx->ev[3], s));
+          rc2 = fold_slots<C>(ctx, ls, bg, g1 - g0, Bg);
+          if (!rc2) {
+            const uint32_t np = (g1 - g0) * per; const size_t o = (size_t)g0 * per * 16 * C::N;
+            k_gather_folded<C><<<(np + 127) / 128, 128, 0, ls>>>(bg, g1 - g0, Bg, logBs, ctx->wsum.as<char>() + o); CKL();
+            CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->h_folded) + o, ctx->wsum.as<char>() + o, (size_t)np * 16 * C::N, cudaMemcpyDeviceToHost, ls));
+            CK(cudaEventRecord(ctx->gev[g], ls));
+          }
         }
-      }
-      if (rc) return rc;
+        return rc2;
+      };
+      rc = gi_.run(g, g % lanes, job); if (rc) return rc;
     }
+    if (!host_tail) { rc = gi_.wait_all(); if (rc) return rc; }
+    auto merge_stats = [&]() { for (uint32_t g = 0; g < ngroups; g++) { rounds = std::max(rounds, g_rounds[g]); adds += g_adds[g]; } };
     if (host_tail) {
       if (st) { MARK(T_FOLD); CK(cudaEventRecord(ctx->ev[4], s)); }
       using HF = typename HostField<C>::type; const HF f = HostField<C>::make();
       b200host::SubslotCombiner<HF> cb; cb.begin(f, G, logBs);
       float host_ms = 0;
       for (uint32_t g = 0; g < ngroups; g++) {          // each group's sub-slots are reduced as soon as they arrive, while the other lanes still run
+        rc = gi_.wait(g); if (rc) return rc;
         CK(cudaEventSynchronize(ctx->gev[g]));
         auto t0 = std::chrono::steady_clock::now();
         cb.feed(reinterpret_cast<const b200host::XYZZ<HF::W>*>(ctx->h_folded), cut[g], cut[g + 1]);
@@ -628,12 +669,12 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
       }
       uint64_t* res = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ctx->h_folded) + fbytes);
       cb.finish(res);
-      for (uint32_t k = 0; k < std::min<uint32_t>(ctx->fused_groups, 64u); k++) if (ctx->h_pinned[1900 + k]) { ctx->err = "k_tree_round: a wave wait timed out (CTAs not co-resident?)"; return B200MSM_E_CUDA; }
-      ctx->host_combine_ms = host_ms;
+      ctx->host_combine_ms = host_ms; merge_stats();
       if (lanes > 1) for (uint32_t l = 0; l < lanes; l++) { CK(cudaEventRecord(ctx->lane[l].done, ctx->lane[l].stream)); CK(cudaStreamWaitEvent(s, ctx->lane[l].done, 0)); }
       CK(cudaMemcpyAsync(d_out, res, 12 * C::N, cudaMemcpyHostToDevice, s));
       MARK(T_HORNER);
     } else {   // device chain (cross-check form): fold the whole array as pl.W slots of B buckets
+      merge_stats();
       if (lanes > 1) for (uint32_t l = 0; l < lanes; l++) { CK(cudaEventRecord(ctx->lane[l].done, ctx->lane[l].stream)); CK(cudaStreamWaitEvent(s, ctx->lane[l].done, 0)); }
       if (st) CK(cudaEventRecord(ctx->ev[3], s));
       rc = fold_slots<C>(ctx, s, ctx->buckets.p, pl.W, pl.B); if (rc) return rc;
@@ -683,27 +724,34 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
     }
     // groups are issued from the TOP windows down: lane 0 (highest priority) owns the top group, so its folded points
     // reach the host first and the serial window combination runs while the GPU is still busy with the lower windows
+    std::vector<uint32_t> g_rounds(ngroups, 0); std::vector<uint64_t> g_adds(ngroups, 0);
+    GroupIssue gi_(ctx, ngroups, lanes);
     for (uint32_t gi = 0; gi < ngroups; gi++) {
-      const uint32_t g = ngroups - 1 - gi;
-      TreeLane& ln = ctx->lane[gi % lanes];
-      uint32_t w0 = cut[g], w1 = cut[g + 1];
-      uint32_t mc = 0; for (uint32_t w = w0; w < w1; w++) mc = std::max(mc, ctx->h_pinned[w]);
-      uint64_t m0 = ctx->h_pinned[512 + w1] - ctx->h_pinned[512 + w0];
-      uint32_t b0 = w0 * pl.B, nbg = (w1 - w0) * pl.B;
-      cudaStream_t ls = lanes == 1 ? s : ln.stream;
-      char* bg = ctx->buckets.as<char>() + (size_t)b0 * 16 * C::N;
-      rc = accumulate_batch_affine<C>(ctx, ln, ls, lanes, d_bases, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc, bg, &rounds, &adds);
-      if (!rc && (lanes > 1 || host_tail)) {
-        if (st && gi + 1 == ngroups) CK(cudaEventRecord(ctx->ev[3], s));          // stats mode is single-lane: accumulate ends here
-        rc = fold_slots<C>(ctx, ls, bg, w1 - w0, pl.B); }
-      if (!rc && host_tail) {
-        const uint32_t np = (w1 - w0) * per; const size_t o = (size_t)w0 * per * 16 * C::N;
-        k_gather_folded<C><<<(np + 127) / 128, 128, 0, ls>>>(bg, w1 - w0, pl.B, pl.logB, ctx->wsum.as<char>() + o); CKL();
-        CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->h_folded) + o, ctx->wsum.as<char>() + o, (size_t)np * 16 * C::N, cudaMemcpyDeviceToHost, ls));
-        CK(cudaEventRecord(ctx->gev[gi], ls));
-      }
-      if (rc) return rc;
+      auto job = [&, gi]() -> int {
+        const uint32_t g = ngroups - 1 - gi;
+        TreeLane& ln = ctx->lane[gi % lanes];
+        uint32_t w0 = cut[g], w1 = cut[g + 1];
+        uint32_t mc = 0; for (uint32_t w = w0; w < w1; w++) mc = std::max(mc, ctx->h_pinned[w]);
+        uint64_t m0 = ctx->h_pinned[512 + w1] - ctx->h_pinned[512 + w0];
+        uint32_t b0 = w0 * pl.B, nbg = (w1 - w0) * pl.B;
+        cudaStream_t ls = lanes == 1 ? s : ln.stream;
+        char* bg = ctx->buckets.as<char>() + (size_t)b0 * 16 * C::N;
+        int rc2 = accumulate_batch_affine<C>(ctx, ln, ls, lanes, d_bases, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc, bg, &g_rounds[gi], &g_adds[gi]);
+        if (!rc2 && (lanes > 1 || host_tail)) {
+          if (st && gi + 1 == ngroups) CK(cudaEventRecord(ctx->ev[3], s));          // stats mode is single-lane: accumulate ends here
+          rc2 = fold_slots<C>(ctx, ls, bg, w1 - w0, pl.B); }
+        if (!rc2 && host_tail) {
+          const uint32_t np = (w1 - w0) * per; const size_t o = (size_t)w0 * per * 16 * C::N;
+          k_gather_folded<C><<<(np + 127) / 128, 128, 0, ls>>>(bg, w1 - w0, pl.B, pl.logB, ctx->wsum.as<char>() + o); CKL();
+          CK(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->h_folded) + o, ctx->wsum.as<char>() + o, (size_t)np * 16 * C::N, cudaMemcpyDeviceToHost, ls));
+          CK(cudaEventRecord(ctx->gev[gi], ls));
+        }
+        return rc2;
+      };
+      rc = gi_.run(gi, gi % lanes, job); if (rc) return rc;
     }
+    if (!host_tail || st) { rc = gi_.wait_all(); if (rc) return rc; }
+    auto merge_stats = [&]() { for (uint32_t g = 0; g < ngroups; g++) { rounds = std::max(rounds, g_rounds[g]); adds += g_adds[g]; } };
     if (st) { if (!host_tail) CK(cudaEventRecord(ctx->ev[3], s)); else { MARK(T_FOLD); } CK(cudaEventRecord(ctx->ev[4], s)); }
     if (host_tail) {
       using HF = typename HostField<C>::type; const HF f = HostField<C>::make();
@@ -711,6 +759,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
       float host_ms = 0;
       for (uint32_t gi = 0; gi < ngroups; gi++) {
         const uint32_t g = ngroups - 1 - gi;
+        rc = gi_.wait(gi); if (rc) return rc;
         CK(cudaEventSynchronize(ctx->gev[gi]));
         auto t0 = std::chrono::steady_clock::now();
         cb.feed(reinterpret_cast<const b200host::XYZZ<HF::W>*>(ctx->h_folded), cut[g], cut[g + 1]);
@@ -719,12 +768,13 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
       auto t0 = std::chrono::steady_clock::now();
       uint64_t* res = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(ctx->h_folded) + fbytes);   // 3*n8 bytes in the pinned tail
       cb.finish(res);
-      for (uint32_t k = 0; k < std::min<uint32_t>(ctx->fused_groups, 64u); k++) if (ctx->h_pinned[1900 + k]) { ctx->err = "k_tree_round: a wave wait timed out (CTAs not co-resident?)"; return B200MSM_E_CUDA; }
       ctx->host_combine_ms = host_ms + std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      merge_stats();
       if (lanes > 1) for (uint32_t l = 0; l < lanes; l++) { CK(cudaEventRecord(ctx->lane[l].done, ctx->lane[l].stream)); CK(cudaStreamWaitEvent(s, ctx->lane[l].done, 0)); }
       CK(cudaMemcpyAsync(d_out, res, 12 * C::N, cudaMemcpyHostToDevice, s));
       MARK(T_HORNER);
     } else {
+      merge_stats();
       if (lanes > 1) for (uint32_t l = 0; l < lanes; l++) { CK(cudaEventRecord(ctx->lane[l].done, ctx->lane[l].stream)); CK(cudaStreamWaitEvent(s, ctx->lane[l].done, 0)); }
       if (Wuse < pl.W) CK(cudaMemsetAsync(ctx->buckets.as<char>() + (size_t)Wuse * pl.B * 16 * C::N, 0, (size_t)(pl.W - Wuse) * pl.B * 16 * C::N, s));   // skipped slots = infinity (zz = 0)
       if (lanes == 1) { rc = fold_slots<C>(ctx, s, ctx->buckets.p, pl.W, pl.B); if (rc) return rc; }
@@ -985,12 +1035,13 @@ void b200msm_destroy(b200msm_ctx* ctx) {
   b200ntt_release(ctx);
   for (b200msm_ctx* w : ctx->workers) b200msm_destroy(w);
   ctx->workers.clear();
+  delete ctx->pool; ctx->pool = nullptr;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->bases, &ctx->scalars, &ctx->canon, &ctx->counts, &ctx->offsets, &ctx->ranks, &ctx->tiles, &ctx->sorted, &ctx->buckets,
                     &ctx->wsum, &ctx->out, &ctx->misc, &ctx->acc_a, &ctx->acc_b, &ctx->acc_c, &ctx->acc_d, &ctx->acc_e, &ctx->jac_in, &ctx->jac_affine}) b->release();
   for (auto& ln : ctx->lane) {
-    for (DevBuf* b : {&ln.offs, &ln.tiles, &ln.bid, &ln.pa, &ln.pb, &ln.prefix, &ln.prod, &ln.lvlprefix, &ln.others, &ln.meta, &ln.sync}) b->release();
+    for (DevBuf* b : {&ln.offs, &ln.tiles, &ln.bid, &ln.pa, &ln.pb, &ln.prefix, &ln.prod, &ln.lvlprefix, &ln.others, &ln.meta, &ln.carry}) b->release();
     if (ln.done) cudaEventDestroy(ln.done);
     if (ln.stream) cudaStreamDestroy(ln.stream);
   }
@@ -1038,11 +1089,10 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "pt_k")) { if (v < 2 || v > 64) return B200MSM_E_ARG; ctx->opt_pt_k = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "probe_sqr")) { ctx->probe_sqr = v != 0; return B200MSM_OK; }
 #if defined(B200_EXPERIMENTS)
-  if (!strcmp(key, "bwd_lean")) { ctx->opt_bwd_lean = v != 0; return B200MSM_OK; }
-  if (!strcmp(key, "fused")) { ctx->opt_fused = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "probe29")) { ctx->probe29 = v != 0; return B200MSM_OK; }
-  if (!strcmp(key, "bwd_staged")) { ctx->opt_bwd_staged = v != 0; return B200MSM_OK; }
 #endif
+  if (!strcmp(key, "fold_cluster")) { ctx->opt_fold_cluster = v != 0; return B200MSM_OK; }
+  if (!strcmp(key, "issue_threads")) { ctx->opt_issue_threads = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "sort_groups")) { ctx->opt_sort_groups = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "lanes")) { if (v < 1 || v > MAX_LANES) return B200MSM_E_ARG; ctx->opt_lanes = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "probe_smem")) { if (v < 0 || v > 200 * 1024) return B200MSM_E_ARG; ctx->opt_probe_smem = (int)v; return B200MSM_OK; }
@@ -1498,6 +1548,76 @@ int b200msm_g1_glv_preprocess(b200msm_ctx* ctx, int curve, const void* points, c
   k_glv_points<<<g, 128, 0, ctx->stream>>>(d_p, ctx->acc_d.as<uint32_t>(), (uint32_t)n, d_po); CKL();
   if (!so_dev) { rc = deliver(ctx, d_so, out_scalars, n * 64); if (rc) return rc; }
   if (!po_dev) { rc = deliver(ctx, d_po, out_points, n * 192); if (rc) return rc; }
+  return B200MSM_OK;
+}
+
+// f1m_batchInverse (build_batchinverse.js:4-140): out[i] = 1 / in[i], zeros stay zero (the reference skips them the same way), through the
+// product tree the batch-affine rounds use.  Elements are Montgomery residues of the curve's coordinate field (Fq, or Fq2 for the G2 ids).
+extern "C++" {
+namespace {
+template <class C> __global__ void k_binv_prepare(const void* __restrict__ in, void* __restrict__ vals, uint8_t* __restrict__ zero, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  Fe<C::N> v; fe_load_cg<C>(v, reinterpret_cast<const char*>(in) + (uint64_t)i * 4 * C::N);
+  const bool z = fe_is_zero<C>(v); zero[i] = z;
+  if (z) fe_set_one<C>(v);
+  fe_store<C>(reinterpret_cast<char*>(vals) + (uint64_t)i * 4 * C::N, v);
+}
+template <class C> __global__ void k_binv_finish(void* __restrict__ vals, const uint8_t* __restrict__ zero, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n || !zero[i]) return;
+  Fe<C::N> v; fe_set_zero<C>(v); fe_store<C>(reinterpret_cast<char*>(vals) + (uint64_t)i * 4 * C::N, v);
+}
+}
+}
+int b200msm_fq_batch_inverse(b200msm_ctx* ctx, int curve, const void* in, uint64_t count, void* out) {
+  if (!ctx || !curve_ok(curve) || !in || !out) return B200MSM_E_ARG;
+  if (count == 0) return B200MSM_OK;
+  if (count >= (1ull << 31)) { ctx->err = "count must be < 2^31"; return B200MSM_E_UNSUPPORTED; }
+  CK(cudaSetDevice(ctx->device));
+  const size_t n8 = (size_t)n8_of(curve), bytes = (size_t)count * n8;
+  const void* din; int rc = stage(ctx, in, bytes, ctx->acc_a, &din); if (rc) return rc;
+  TreeLane& ln = ctx->lane[0];
+  CK(ln.prod.ensure((2 * count + 4096) * n8)); CK(ln.lvlprefix.ensure((2 * count + 4096) * n8)); CK(ln.others.ensure((WARP_LEVEL_MAX / 4 + 4096) * n8));
+  CK(ctx->misc.ensure(std::max<size_t>(count, 2048)));
+  const uint32_t g = (uint32_t)((count + 255) / 256);
+  B200_CURVE_SWITCH(curve,
+    k_binv_prepare<C><<<g, 256, 0, ctx->stream>>>(din, ln.prod.p, ctx->misc.as<uint8_t>(), (uint32_t)count); CKL();
+    rc = product_tree_invert<C>(ctx, ln, ctx->stream, ln.prod.as<char>(), ln.lvlprefix.as<char>(), count, ctx->opt_pt_k);
+    if (!rc) { k_binv_finish<C><<<g, 256, 0, ctx->stream>>>(ln.prod.p, ctx->misc.as<uint8_t>(), (uint32_t)count); CKL(); })
+  if (rc) return rc;
+  return deliver(ctx, ln.prod.p, out, bytes);
+}
+
+// Test hook: the digit / sort phase alone -- signed-digit recoding + histogram (k_digits<count>), exclusive scan, scatter (k_digits<scatter>)
+// (computeSchedule + organizeBuckets, build_multiexp_opt.js:175-633).  plan_out = {Wd windows, W bucket slots, B buckets per slot, c0, rem, nbits}:
+// windows 0 .. Wd-1 are c0 + 1 bits wide for the first `rem` of them and c0 bits after that; offsets_out (host, W*B + 1 words) = segment starts of
+// every bucket (slot-major), sorted_out (host, >= offsets[W*B] words) = point index | sign << 31 of every pair, bucket by bucket.
+int b200msm_debug_schedule(b200msm_ctx* ctx, const void* scalars, uint32_t scalar_size, uint64_t n64, uint32_t window_bits, uint32_t plan_out[6],
+                           uint32_t* offsets_out, uint64_t offsets_cap, uint32_t* sorted_out, uint64_t sorted_cap) {
+  if (!ctx || !scalars || !plan_out || scalar_size == 0 || scalar_size > 32 || n64 == 0 || n64 >= (1ull << 31)) return B200MSM_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream; const uint32_t n = (uint32_t)n64, nbits = 8 * scalar_size;
+  const void* d_sraw; int rc = stage(ctx, scalars, (size_t)n * scalar_size, ctx->scalars, &d_sraw); if (rc) return rc;
+  CK(ctx->canon.ensure((size_t)n * 32));
+  k_canon_scalars<<<(n + 255) / 256, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d_sraw), scalar_size, n, 0, nbits, ctx->canon.as<uint32_t>()); CKL();
+  MsmPlan pl; pl.n = n; pl.nbits = nbits; pl.pre_stride = 0;
+  const uint32_t ct = window_bits > 0 ? std::min<uint32_t>(window_bits, std::min<uint32_t>(nbits, 24)) : auto_window_bits(n, nbits);
+  pl.Wd = (nbits + ct - 1) / ct; pl.c0 = nbits / pl.Wd; pl.rem = nbits - pl.c0 * pl.Wd;
+  pl.c = pl.c0 + (pl.rem ? 1 : 0); pl.B = 1u << (pl.c - 1); pl.logB = pl.c - 1; pl.W = pl.Wd + (pl.rem == 0 ? 1 : 0);
+  const uint64_t nb = (uint64_t)pl.W * pl.B;
+  if (nb > (1ull << 28) || (uint64_t)n * pl.W >= (1ull << 32)) { ctx->err = "schedule too large for the test hook"; return B200MSM_E_UNSUPPORTED; }
+  plan_out[0] = pl.Wd; plan_out[1] = pl.W; plan_out[2] = pl.B; plan_out[3] = pl.c0; plan_out[4] = pl.rem; plan_out[5] = nbits;
+  if (!offsets_out || offsets_cap < nb + 1) return offsets_out ? B200MSM_E_ARG : B200MSM_OK;       // plan only
+  CK(ctx->counts.ensure(nb * 4)); CK(ctx->offsets.ensure((nb + 1 + 512) * 4)); CK(ctx->sorted.ensure((size_t)n * pl.W * 4 + 16)); CK(ctx->ranks.ensure((size_t)n * pl.Wd * 4 + 16));
+  CK(cudaMemsetAsync(ctx->counts.p, 0, nb * 4, s));
+  const uint32_t tb = 256, gb = (n + tb - 1) / tb;
+  k_digits<false><<<gb, tb, 0, s>>>(ctx->canon.as<uint32_t>(), pl, ctx->counts.as<uint32_t>(), nullptr, ctx->ranks.as<uint32_t>(), nullptr, 0u, pl.Wd); CKL();
+  rc = exclusive_scan(ctx, s, ctx->tiles, ctx->counts.as<uint32_t>(), ctx->offsets.as<uint32_t>(), (uint32_t)nb, 0u); if (rc) return rc;
+  k_digits<true><<<gb, tb, 0, s>>>(ctx->canon.as<uint32_t>(), pl, nullptr, ctx->offsets.as<uint32_t>(), ctx->ranks.as<uint32_t>(), ctx->sorted.as<uint32_t>(), 0u, pl.Wd); CKL();
+  CK(cudaMemcpyAsync(offsets_out, ctx->offsets.p, (nb + 1) * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const uint64_t pairs = offsets_out[nb];
+  if (sorted_out) { if (sorted_cap < pairs) { ctx->err = "sorted_out too small"; return B200MSM_E_ARG; }
+    CK(cudaMemcpyAsync(sorted_out, ctx->sorted.p, pairs * 4, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); }
   return B200MSM_OK;
 }
 

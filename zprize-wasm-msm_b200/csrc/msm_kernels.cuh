@@ -250,6 +250,46 @@ __global__ void __launch_bounds__(256) k_fold_tail(void* __restrict__ buckets, u
   }
 }
 
+// The same levels spread over a thread-block CLUSTER (8 CTAs of 64 threads on 8 SMs, one live block of `tail` buckets per cluster).
+// One CTA of 256 threads puts 2 warps on every scheduler of ONE SM and the rest of the GPU idles: a level is one XYZZ addition deep
+// (14 multiplications = 4200 dependent IMAD.WIDE), i.e. bound by that SM's multiplier pipe at 2 warps per scheduler, and the first three
+// levels hold two additions per thread (measured: 235 us for the ten levels of a 1024-bucket block, of which the last groups' are the
+// unoverlapped end of every MSM).  Across a cluster every level is one addition per thread at less than one warp per scheduler; the
+// barrier between levels is the hardware cluster barrier, operands are read through L2 (another SM wrote them).
+constexpr uint32_t FOLD_CLUSTER = 8, FOLD_CLUSTER_THREADS = 64;
+template <class C> B200_DI void xyzz_load_l2(XYZZ<C>& p, const void* base, uint64_t idx) {
+  const char* s = reinterpret_cast<const char*>(base) + idx * (uint64_t)(16 * C::N);
+  fe_load_l2<C>(p.x, s); fe_load_l2<C>(p.y, s + 4 * C::N); fe_load_l2<C>(p.zz, s + 8 * C::N); fe_load_l2<C>(p.zzz, s + 12 * C::N);
+}
+B200_DI uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+B200_DI void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <class C>
+__global__ void __launch_bounds__(FOLD_CLUSTER_THREADS) k_fold_tail_cluster(void* __restrict__ buckets, uint32_t B, uint32_t tail, uint32_t live_blocks) {
+  const uint32_t cl = blockIdx.x / FOLD_CLUSTER;                      // cluster = FOLD_CLUSTER consecutive CTAs of the 1-D grid
+  const uint32_t w = cl / live_blocks, lb0 = cl % live_blocks;
+  const uint32_t blk0 = lb0 == 0 ? 0 : (1u << (lb0 - 1));
+  const uint64_t base = (uint64_t)w * B + (uint64_t)blk0 * tail;
+  const uint32_t tid = cluster_ctarank() * FOLD_CLUSTER_THREADS + threadIdx.x, nthr = FOLD_CLUSTER * FOLD_CLUSTER_THREADS;
+  uint32_t live = 1;
+  for (uint32_t sz = tail; sz >= 2; sz >>= 1, live++) {
+    const uint32_t half = sz >> 1, work = live * half;
+    for (uint32_t r = tid; r < work; r += nthr) {
+      const uint32_t lb = r / half, i = r % half;
+      const uint32_t blk = lb == 0 ? 0 : (1u << (lb - 1));
+      const uint64_t lo = base + (uint64_t)blk * sz + i;
+      XYZZ<C> a, b;
+      xyzz_load_l2<C>(a, buckets, lo); xyzz_load_l2<C>(b, buckets, lo + half);
+      xyzz_add<C>(a, b);
+      xyzz_store<C>(buckets, lo, a);
+    }
+    __threadfence();
+    cluster_barrier();
+  }
+}
+
 // One thread per slot: R_w = T[0] + sum_j 2^j T[2^j] by Horner over j (logB doublings).  The extra slot (index Wd,
 // present when W == Wd + 1) holds buckets B+1 .. 2B of the last window: its value is the same expression + B * T[0].
 template <class C>
