@@ -137,7 +137,7 @@ struct b200msm_ctx {
   // fine-grained phase profiler (active only while a stats struct is being filled)
   std::vector<cudaEvent_t> pev; std::vector<int> ptag; size_t pused = 0; bool prof = false;
   std::atomic<uint64_t> launches{0}; uint64_t adds_r0 = 0, adds_exact = 0, cur_n = 0;
-  IssuePool* pool = nullptr; int opt_issue_threads = 0, opt_fold_cluster = 1; std::mutex err_mu;      // one issuing host thread per lane (IssuePool); err is written under err_mu
+  IssuePool* pool = nullptr; int opt_issue_threads = 0, opt_fold_cluster = 1, opt_groups = 0, opt_group_small = 70; std::mutex err_mu;      // one issuing host thread per lane (IssuePool); err is written under err_mu
   size_t total_mem = 0;
   // multi-device context (b200msm_create_multi): devs[0] == this, devs[g] = the single-device context of device g; mres = handles of sharded / replicated base sets
   std::vector<b200msm_ctx*> devs; std::map<uint64_t, MultiResident> mres; int64_t opt_multi_min = 1 << 15; int opt_multi_replicate = 0;
@@ -442,11 +442,11 @@ int run_grouped(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, c
   const uint32_t lanes = (uint32_t)std::max(1, std::min(ctx->opt_lanes, (int)MAX_LANES));
   const double per_pair = 8.0 * C::N * 0.75 + 4.0 * C::N * 0.75 + 6;
   const uint64_t budget_pairs = ctx->opt_group_pairs > 0 ? (uint64_t)ctx->opt_group_pairs : (uint64_t)std::max(1.0, 0.45 * (double)ctx->total_mem / per_pair / lanes);
-  uint32_t ngroups = std::max<uint32_t>(lanes, (uint32_t)(((uint64_t)n * pl.Wd + budget_pairs - 1) / budget_pairs));
+  uint32_t ngroups = std::max<uint32_t>(ctx->opt_groups > 0 ? (uint32_t)ctx->opt_groups : lanes, (uint32_t)(((uint64_t)n * pl.Wd + budget_pairs - 1) / budget_pairs));
   ngroups = std::min(ngroups, pl.Wd);
   // window boundaries, bottom up: cut[0] = 0 .. cut[ngroups] = Wd; group ngroups-1 (top) is issued first, group 0 (bottom) last and is the smallest
   std::vector<uint32_t> cut(ngroups + 1, 0); cut[ngroups] = pl.Wd;
-  { const double small = ngroups > 1 ? 0.7 : 1.0, unit = (double)pl.Wd / ((double)ngroups - 1.0 + small);
+  { const double small = ngroups > 1 ? ctx->opt_group_small / 100.0 : 1.0, unit = (double)pl.Wd / ((double)ngroups - 1.0 + small);
     double acc = small * unit;
     for (uint32_t g = 1; g < ngroups; g++) { cut[g] = std::min(std::max<uint32_t>((uint32_t)(acc + 0.5), cut[g - 1] + 1), pl.Wd - (ngroups - g)); acc += unit; } }
   const uint32_t per = pl.logB + 1, npts = pl.W * per;
@@ -1091,6 +1091,8 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
 #if defined(B200_EXPERIMENTS)
   if (!strcmp(key, "probe29")) { ctx->probe29 = v != 0; return B200MSM_OK; }
 #endif
+  if (!strcmp(key, "groups")) { if (v < 0 || v > 64) return B200MSM_E_ARG; ctx->opt_groups = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "group_small")) { if (v < 5 || v > 100) return B200MSM_E_ARG; ctx->opt_group_small = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "fold_cluster")) { ctx->opt_fold_cluster = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "issue_threads")) { ctx->opt_issue_threads = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "sort_groups")) { ctx->opt_sort_groups = v != 0; return B200MSM_OK; }
