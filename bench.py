@@ -396,7 +396,8 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     cpu_group = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))      # a mismatched collective fails in minutes, not after the default 10
         cpu_group = dist.new_group(backend="gloo")            # host-side barriers / object exchange (an NCCL barrier would spin on the GPUs while rank 0 measures alone)
     cname = a.curve; cid = CURVE_ID[cname]; n8 = b200msm.N8[cid]
     strong = a.log2n_total > 0
@@ -500,8 +501,8 @@ def run_ours(a):
 
     e2e_ms = T.run(step_host, max(3, min(a.steps, 10)), 2, wall=True)
     e2e_ok = None
+    step_host(0)                      # every rank: the step holds a collective when N > 1
     if rank == 0:
-        step_host(0)
         e2e_ok = eng.normalize(cid, bytes(hout.numpy())) == expect
         assert e2e_ok, "e2e (host buffers) result fails the known-answer identity"
     T.sync_all()

@@ -137,7 +137,7 @@ struct b200msm_ctx {
   // fine-grained phase profiler (active only while a stats struct is being filled)
   std::vector<cudaEvent_t> pev; std::vector<int> ptag; size_t pused = 0; bool prof = false;
   std::atomic<uint64_t> launches{0}; uint64_t adds_r0 = 0, adds_exact = 0, cur_n = 0;
-  IssuePool* pool = nullptr; int opt_issue_threads = 0, opt_fold_cluster = 1, opt_groups = 0, opt_group_small = 70; std::mutex err_mu;      // one issuing host thread per lane (IssuePool); err is written under err_mu
+  IssuePool* pool = nullptr; int opt_issue_threads = 0, opt_fold_cluster = 1, opt_groups = 0, opt_group_small = 70, opt_persist_fwd = 0, opt_ba_k0 = 0; std::mutex err_mu;      // one issuing host thread per lane (IssuePool); err is written under err_mu
   size_t total_mem = 0;
   // multi-device context (b200msm_create_multi): devs[0] == this, devs[g] = the single-device context of device g; mres = handles of sharded / replicated base sets
   std::vector<b200msm_ctx*> devs; std::map<uint64_t, MultiResident> mres; int64_t opt_multi_min = 1 << 15; int opt_multi_replicate = 0;
@@ -327,7 +327,7 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, uin
     uint32_t full = 0, need16 = 0, mc = maxcnt;
     while (mc > 3) { if (mc > 16) need16++; mc = (mc + 1) >> 1; full++; }
     const uint64_t npts = ctx->cur_n;
-    const uint32_t pref = npts < (1u << 16) ? 0u : npts < (1u << 17) ? 1u : npts <= (1u << 18) ? 3u : npts <= (1u << 19) ? 4u : 99u;
+    const uint32_t pref = npts < (1u << 16) ? 0u : npts < (1u << 17) ? 2u : npts <= (1u << 18) ? 3u : npts <= (1u << 19) ? 4u : 99u;
     R = std::min(full, std::max(pref, need16));
   }
   if (m0 < 2) R = 0;
@@ -383,8 +383,9 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, uin
     if (r == 0) k_tree_meta<true><<<(nslots + 255) / 256, 256, 0, s>>>(tr, sorted, items, carries);
     else k_tree_meta<false><<<(nslots + 255) / 256, 256, 0, s>>>(tr, nullptr, items, carries);
     CKL();
-    if (r == 0) k_tree_fwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(items, off[r], off[r + 1], nbg, d_bases, 0, ln_.prefix.p, prod, BK, grid);
-    else k_tree_fwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(items, off[r], off[r + 1], nbg, pin, yin, ln_.prefix.p, prod, BK, grid);
+    const uint32_t fgrid = (ctx->opt_persist > 0 && overlapped) ? std::min<uint32_t>(grid, (uint32_t)(ctx->opt_persist_fwd > 0 ? ctx->opt_persist_fwd : ctx->opt_persist)) : grid;
+    if (r == 0) k_tree_fwd<C, true><<<fgrid, BA_THREADS, 0, s>>>(items, off[r], off[r + 1], nbg, d_bases, 0, ln_.prefix.p, prod, BK, grid);
+    else k_tree_fwd<C, false><<<fgrid, BA_THREADS, 0, s>>>(items, off[r], off[r + 1], nbg, pin, yin, ln_.prefix.p, prod, BK, grid);
     CKL(); MARK(T_TREE_FWD);
     { int rc_ = product_tree_invert<C>(ctx, ln_, s, prod, lpre, (uint64_t)grid * BA_THREADS, PK); if (rc_) return rc_; }
     MARK(T_INV_TREE);
@@ -1091,6 +1092,7 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
 #if defined(B200_EXPERIMENTS)
   if (!strcmp(key, "probe29")) { ctx->probe29 = v != 0; return B200MSM_OK; }
 #endif
+  if (!strcmp(key, "persist_fwd")) { if (v < 0 || v > 4096) return B200MSM_E_ARG; ctx->opt_persist_fwd = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "groups")) { if (v < 0 || v > 64) return B200MSM_E_ARG; ctx->opt_groups = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "group_small")) { if (v < 5 || v > 100) return B200MSM_E_ARG; ctx->opt_group_small = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "fold_cluster")) { ctx->opt_fold_cluster = v != 0; return B200MSM_OK; }

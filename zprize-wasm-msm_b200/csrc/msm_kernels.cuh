@@ -384,12 +384,15 @@ __global__ void k_normalize(const void* __restrict__ jac, void* __restrict__ xy,
   fe_store<C>(d, X); fe_store<C>(d + 4 * C::N, Y);
 }
 
-// out = sum of n Jacobian points (g1m_add chain) -- combines per-GPU partial results.
+// out = sum of n Jacobian points (g1m_add) -- combines per-GPU partial results.  One warp: lane t adds up points t, t + 32, ...,
+// then a shared-memory tree over the lanes; the dependent chain is ceil(n / 32) + log2(min(n, 32)) additions instead of n (8 partial
+// results: 3 deep instead of 8 -- the chain is pure latency, ~17 us per XYZZ addition on one thread, and sits inside every multi-GPU step).
 template <class C>
-__global__ void k_sum_jacobian(const void* __restrict__ pts, uint32_t n, void* __restrict__ out_jac) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+__global__ void __launch_bounds__(32) k_sum_jacobian(const void* __restrict__ pts, uint32_t n, void* __restrict__ out_jac) {
+  __shared__ uint32_t sh[16 * 16 * C::N];      // lanes w .. 2w-1 hand their partial sums to lanes 0 .. w-1 (slot = lane - w)
+  const uint32_t t = threadIdx.x;
   XYZZ<C> acc; xyzz_set_inf<C>(acc);
-  for (uint32_t i = 0; i < n; i++) {
+  for (uint32_t i = t; i < n; i += 32) {
     const char* s = reinterpret_cast<const char*>(pts) + (uint64_t)i * 12 * C::N;
     Fe<C::N> X, Y, Z; fe_load_cg<C>(X, s); fe_load_cg<C>(Y, s + 4 * C::N); fe_load_cg<C>(Z, s + 8 * C::N);
     XYZZ<C> p;
@@ -397,6 +400,21 @@ __global__ void k_sum_jacobian(const void* __restrict__ pts, uint32_t n, void* _
     else { p.x = X; p.y = Y; fe_sqr<C>(p.zz, Z); fe_mul<C>(p.zzz, p.zz, Z); }
     xyzz_add<C>(acc, p);
   }
+  for (uint32_t w = 16; w >= 1; w >>= 1) {
+    if (t >= w && t < 2 * w) {
+#pragma unroll
+      for (int k = 0; k < C::N; k++) { sh[((t - w) * 4 + 0) * C::N + k] = acc.x.l[k]; sh[((t - w) * 4 + 1) * C::N + k] = acc.y.l[k]; sh[((t - w) * 4 + 2) * C::N + k] = acc.zz.l[k]; sh[((t - w) * 4 + 3) * C::N + k] = acc.zzz.l[k]; }
+    }
+    __syncwarp();
+    if (t < w && t + w < n) {
+      XYZZ<C> q;
+#pragma unroll
+      for (int k = 0; k < C::N; k++) { q.x.l[k] = sh[(t * 4 + 0) * C::N + k]; q.y.l[k] = sh[(t * 4 + 1) * C::N + k]; q.zz.l[k] = sh[(t * 4 + 2) * C::N + k]; q.zzz.l[k] = sh[(t * 4 + 3) * C::N + k]; }
+      xyzz_add<C>(acc, q);
+    }
+    __syncwarp();
+  }
+  if (t != 0) return;
   Fe<C::N> X, Y, Z; xyzz_to_jacobian<C>(X, Y, Z, acc);
   char* o = reinterpret_cast<char*>(out_jac);
   fe_store<C>(o, X); fe_store<C>(o + 4 * C::N, Y); fe_store<C>(o + 8 * C::N, Z);
