@@ -641,6 +641,9 @@ def abi_multi_block(a, torch, dist, b200msm, cpu_group, rank, world, cid, n8, hb
     return res
 
 
+BATCH_WORKERS = 8          # the engine's default for b200msm_g1_multiexp_batch (option "batch_workers"): one lane per worker
+
+
 def run_batched(a):
     """BASELINE config 5: a.batch independent MSMs of 2^log2n points over the same bases, MSM j on rank j % world (replicas, no collective
     on the data path; one barrier brackets the step).  value = points of the whole batch / second, scalars resident in HBM;
@@ -701,10 +704,10 @@ def run_batched(a):
                 "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "u32 limbs (Montgomery Fq, 32x32->64 IMAD)", "data": "synthetic",
                 "config": {"workload": "batched: %d independent %s G1 MSMs of 2^%d points per step over one resident base set, MSM j on GPU j %% %d, %d worker contexts per GPU; uniform 256-bit scalars"
-                                       % (a.batch, CURVE_LABEL[cname].replace(" G1", ""), a.log2n, world, 4),
+                                       % (a.batch, CURVE_LABEL[cname].replace(" G1", ""), a.log2n, world, BATCH_WORKERS),
                            "curve": cname, "log2n_per_msm": a.log2n, "batch": a.batch, "parallelism": "replicas (independent MSMs), no collective",
                            "window_bits": int(st["window_bits"]), "windows": int(st["windows"]),
-                           "cache": "no L2 flush: each MSM's working set (bases %d MiB + sort/tree scratch) exceeds the 126 MB L2 and %d MSMs run concurrently" % (n * 2 * n8 >> 20, 4)},
+                           "cache": "no L2 flush: each MSM's working set (bases %d MiB + sort/tree scratch) exceeds the 126 MB L2 and %d MSMs run concurrently" % (n * 2 * n8 >> 20, BATCH_WORKERS)},
                 "msm_per_s": a.batch / (ms * 1e-3), "ms_per_msm": ms / a.batch,
                 "clocks": clocks,
                 "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": a.batch * n * 32, "d2h_bytes_per_step": a.batch * 3 * n8,

@@ -118,7 +118,7 @@ int b200msm_upload_bases_windowed(b200msm_ctx* ctx, int curve, const void* bases
 
 /* ---- count independent MSMs of n points each over the same resident bases (a stream of proofs over one proving key; the
  *      reference runs one WASM instance per worker for this, SURVEY.md 8b "Threading").  scalars: count * n * scalar_size bytes,
- *      MSM j uses the j-th block; out: count * 3*n8 bytes.  Internally spread over `batch_workers` (option, default 4) sub-contexts
+ *      MSM j uses the j-th block; out: count * 3*n8 bytes.  Internally spread over `batch_workers` (option, default 8; each runs its MSMs on one lane, "batch_lanes") sub-contexts
  *      with their own streams, scratch and host threads.  Returns when all results are in `out`. */
 int b200msm_g1_multiexp_batch(b200msm_ctx* ctx, uint64_t handle, const void* scalars, uint32_t scalar_size, uint64_t n,
                               uint32_t count, void* out);

@@ -138,10 +138,10 @@ struct b200msm_ctx {
   std::vector<cudaEvent_t> pev; std::vector<int> ptag; size_t pused = 0; bool prof = false;
   std::atomic<uint64_t> launches{0}; uint64_t adds_r0 = 0, adds_exact = 0, cur_n = 0;
   IssuePool* pool = nullptr; int opt_issue_threads = 0, opt_fold_cluster = 1, opt_groups = 0, opt_group_small = 70, opt_persist_fwd = 0, opt_ba_k0 = 0; std::mutex err_mu;      // one issuing host thread per lane (IssuePool); err is written under err_mu
-  size_t total_mem = 0;
+  size_t total_mem = 0; double mem_share = 1.0;      // fraction of the device memory budget this context may plan with (batch workers: 1 / workers)
   // multi-device context (b200msm_create_multi): devs[0] == this, devs[g] = the single-device context of device g; mres = handles of sharded / replicated base sets
   std::vector<b200msm_ctx*> devs; std::map<uint64_t, MultiResident> mres; int64_t opt_multi_min = 1 << 15; int opt_multi_replicate = 0;
-  std::vector<b200msm_ctx*> workers; int opt_batch_workers = 4;            // sub-contexts (own stream + scratch) that run the MSMs of a batch concurrently
+  std::vector<b200msm_ctx*> workers; int opt_batch_workers = 8, opt_batch_lanes = 1;            // sub-contexts (own stream + scratch) that run the MSMs of a batch concurrently
 };
 
 namespace {
@@ -153,10 +153,15 @@ enum { T_SORT = 0, T_PLAN, T_TREE_FWD, T_INV_TREE, T_TREE_BWD, T_FINISH, T_FOLD,
 #define MARK(tag) do { if (ctx->prof) { int rc_ = prof_mark(ctx, tag); if (rc_) return rc_; } } while (0)
 
 void copy_options(b200msm_ctx* w, const b200msm_ctx* ctx) {
-  w->opt_window_bits = ctx->opt_window_bits; w->opt_accumulate = ctx->opt_accumulate; w->opt_tree_rounds = ctx->opt_tree_rounds; w->opt_lanes = ctx->opt_lanes;
+  w->opt_window_bits = ctx->opt_window_bits; w->opt_accumulate = ctx->opt_accumulate; w->opt_tree_rounds = ctx->opt_tree_rounds;
   w->opt_ba_k = ctx->opt_ba_k; w->opt_pt_k = ctx->opt_pt_k; w->opt_persist = ctx->opt_persist; w->opt_subslots = ctx->opt_subslots; w->opt_combine = ctx->opt_combine;
-  w->opt_group_pairs = ctx->opt_group_pairs; w->opt_sort_groups = ctx->opt_sort_groups; w->opt_fold_cluster = ctx->opt_fold_cluster; w->opt_batch_workers = ctx->opt_batch_workers;
-  w->opt_issue_threads = 0;      // the batch workers already overlap whole MSMs
+  w->opt_group_pairs = ctx->opt_group_pairs; w->opt_sort_groups = ctx->opt_sort_groups; w->opt_batch_workers = ctx->opt_batch_workers;
+  // A batch worker runs whole MSMs next to other workers' MSMs: the workers are in DIFFERENT phases at any moment (one sorting, one in a
+  // multiplier-bound backward pass, one in its latency-bound fold), which overlaps better than the lanes of one MSM, whose rounds run in
+  // step.  So a worker uses ONE lane with full (non-persistent) grids and the plain fold tail (a cluster launch waits for 8 free SMs of one GPC).
+  // Measured, 64 MSMs of 2^18 points on one B200: 4 workers x 4 lanes 133.7 ms, 8 workers x 1 lane 108.7 ms (1.70 ms per MSM); 16 x 2^20:
+  // 94.0 -> 82.9 ms (5.18 ms per MSM); 64 x 2^16: 54.2 -> 44.4 ms (profiles/README.md r2).
+  w->opt_lanes = ctx->opt_batch_lanes; w->opt_fold_cluster = 0; w->opt_issue_threads = 0;
 }
 
 // The groups of one MSM: job gi runs on lane gi % lanes -- inline (single issuing thread) or on that lane's issue thread.  wait(gi) blocks until
@@ -442,7 +447,7 @@ int run_grouped(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, c
   const uint32_t n = pl.n, tb = 256, gb = (n + tb - 1) / tb;
   const uint32_t lanes = (uint32_t)std::max(1, std::min(ctx->opt_lanes, (int)MAX_LANES));
   const double per_pair = 8.0 * C::N * 0.75 + 4.0 * C::N * 0.75 + 6;
-  const uint64_t budget_pairs = ctx->opt_group_pairs > 0 ? (uint64_t)ctx->opt_group_pairs : (uint64_t)std::max(1.0, 0.45 * (double)ctx->total_mem / per_pair / lanes);
+  const uint64_t budget_pairs = ctx->opt_group_pairs > 0 ? (uint64_t)ctx->opt_group_pairs : (uint64_t)std::max(1.0, 0.45 * ctx->mem_share * (double)ctx->total_mem / per_pair / lanes);
   uint32_t ngroups = std::max<uint32_t>(ctx->opt_groups > 0 ? (uint32_t)ctx->opt_groups : lanes, (uint32_t)(((uint64_t)n * pl.Wd + budget_pairs - 1) / budget_pairs));
   ngroups = std::min(ngroups, pl.Wd);
   // window boundaries, bottom up: cut[0] = 0 .. cut[ngroups] = Wd; group ngroups-1 (top) is issued first, group 0 (bottom) last and is the smallest
@@ -570,7 +575,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   uint32_t Bg = pl.B;
   if (pre) {   // sub-slots (see the accumulate block): 8 per slot by default, more when a sub-slot's tree scratch would exceed the memory budget
     const double per_pair = 8.0 * C::N * 0.75 + 4.0 * C::N * 0.75 + 6;
-    const double budget = ctx->opt_group_pairs > 0 ? (double)ctx->opt_group_pairs : 0.45 * (double)ctx->total_mem / per_pair / MAX_LANES;
+    const double budget = ctx->opt_group_pairs > 0 ? (double)ctx->opt_group_pairs : 0.45 * ctx->mem_share * (double)ctx->total_mem / per_pair / MAX_LANES;
     uint32_t S = ctx->opt_subslots > 0 ? (uint32_t)ctx->opt_subslots : 4;      // measured at 2^20, c = 20: 4 -> 5.86 ms, 8 -> 5.97, 16 -> 5.96, 32 -> 6.23
     while (S < 256 && (double)n * pl.Wd / S > budget) S *= 2;
     while (S > 1 && pl.B / S < 64) S /= 2;
@@ -622,7 +627,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
     for (uint32_t l = 0; l < lanes; l++) { rc = lane_init(ctx, ctx->lane[l]); if (rc) return rc; if (lanes > 1) CK(cudaStreamWaitEvent(ctx->lane[l].stream, ctx->ev_sorted, 0)); }
     // groups = contiguous runs of sub-slots with (nearly) equal pair counts, one tree each; at least one per lane
     const double per_pair = 8.0 * C::N * 0.75 + 4.0 * C::N * 0.75 + 6;
-    const uint64_t budget_pairs = ctx->opt_group_pairs > 0 ? (uint64_t)ctx->opt_group_pairs : (uint64_t)std::max(1.0, 0.45 * (double)ctx->total_mem / per_pair / lanes);
+    const uint64_t budget_pairs = ctx->opt_group_pairs > 0 ? (uint64_t)ctx->opt_group_pairs : (uint64_t)std::max(1.0, 0.45 * ctx->mem_share * (double)ctx->total_mem / per_pair / lanes);
     uint32_t ngroups = std::min<uint32_t>(G, std::max<uint32_t>(lanes, (uint32_t)((mtot + budget_pairs - 1) / budget_pairs)));
     std::vector<uint32_t> cut(ngroups + 1, 0); cut[ngroups] = G;
     { uint32_t w = 0; for (uint32_t g = 1; g < ngroups; g++) { uint64_t target = mtot * g / ngroups;
@@ -693,7 +698,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
     uint32_t lanes = ctx->prof ? 1u : (uint32_t)std::max(1, std::min(ctx->opt_lanes, (int)MAX_LANES));
     if (mtot < (1u << 16)) lanes = 1;
     const double per_pair = 8.0 * C::N * 0.75 + 4.0 * C::N * 0.75 + 6;      // points (pa+pb) + prefix/products + bid, per input pair
-    const uint64_t budget_pairs = ctx->opt_group_pairs > 0 ? (uint64_t)ctx->opt_group_pairs : (uint64_t)std::max(1.0, 0.45 * (double)ctx->total_mem / per_pair / lanes);
+    const uint64_t budget_pairs = ctx->opt_group_pairs > 0 ? (uint64_t)ctx->opt_group_pairs : (uint64_t)std::max(1.0, 0.45 * ctx->mem_share * (double)ctx->total_mem / per_pair / lanes);
     uint32_t ngroups = std::max<uint32_t>(lanes, (uint32_t)((mtot + budget_pairs - 1) / budget_pairs));
     // slots above the highest non-empty one are skipped altogether (short scalars in wide containers, e.g. GLV halves)
     uint32_t Wuse = pl.W; while (Wuse > 0 && ctx->h_pinned[512 + Wuse] == ctx->h_pinned[512 + Wuse - 1]) Wuse--;
@@ -1100,6 +1105,7 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "sort_groups")) { ctx->opt_sort_groups = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "lanes")) { if (v < 1 || v > MAX_LANES) return B200MSM_E_ARG; ctx->opt_lanes = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "probe_smem")) { if (v < 0 || v > 200 * 1024) return B200MSM_E_ARG; ctx->opt_probe_smem = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "batch_lanes")) { if (v < 1 || v > MAX_LANES) return B200MSM_E_ARG; ctx->opt_batch_lanes = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "batch_workers")) { if (v < 1 || v > 16) return B200MSM_E_ARG; ctx->opt_batch_workers = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "subslots")) { if (v < 0 || v > 256 || (v & (v - 1))) return B200MSM_E_ARG; ctx->opt_subslots = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "combine")) { if (v < 0 || v > 1) return B200MSM_E_ARG; ctx->opt_combine = (int)v; return B200MSM_OK; }
@@ -1199,7 +1205,7 @@ static int single_batch(b200msm_ctx* ctx, uint64_t handle, const void* scalars, 
     if (rc) { ctx->err = "cannot create a batch worker context"; return rc; }
     ctx->workers.push_back(w);
   }
-  for (uint32_t k = 0; k < K; k++) copy_options(ctx->workers[k], ctx);      // workers inherit the tuning options of the parent
+  for (uint32_t k = 0; k < K; k++) { copy_options(ctx->workers[k], ctx); ctx->workers[k]->mem_share = 1.0 / K; }      // workers inherit the tuning options of the parent and share its memory budget
   CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream));       // inputs produced on the caller's stream are complete
   Precomp pre{(uint32_t)r.n, r.t_nbits, r.t_c0, r.t_rem, r.t_Wd};
   const uint32_t nbits = 8 * scalar_size;
