@@ -188,7 +188,8 @@ int b200msm_debug_schedule(b200msm_ctx* ctx, const void* scalars, uint32_t scala
 /* ---- tuning knobs (never change results).  key: "window_bits" (0 = auto), "accumulate" (0 = auto, 1 = serial, 2 = batch-affine),
  * "tree_rounds" (-1 = auto), "combine" (0 = serial tail on the host (default), 1 = device chain k_window_sums + k_horner),
  * "lanes" (1..8 overlapping accumulate streams), "issue_threads" (1 = one issuing host thread per lane, 0 = the calling
- * thread issues every lane (default; measured equal, profiles/README.md r2)), "sort_groups" (1 = the sort is pipelined per window group on the lanes' streams (default)), "batch_workers", "multi_min_points", "multi_replicate" (multi-device contexts, see
+ * thread issues every lane (default; measured equal, profiles/README.md r2)), "sort_groups" (1 = the sort is pipelined per window group on the lanes' streams (default)), "batch_workers" (8), "batch_lanes" (1), "batch_blocking" (1 = the batch workers sleep in their host waits instead of spinning: set it before the first batch when the
+ * workers of several processes outnumber the host cores), "fold_cluster", "multi_min_points", "multi_replicate" (multi-device contexts, see
  * b200msm_create_multi).
  * On a multi-device context an option applies to every device. */
 int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t value);

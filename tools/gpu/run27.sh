@@ -1,0 +1,4 @@
+set -x
+nvidia-smi -L | wc -l
+( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r2A_bench_8gpu.json 2> gpurun_out/r2A_bench_8gpu.err ) 2> gpurun_out/r2A_time.txt; tail -3 gpurun_out/r2A_bench_8gpu.err; cat gpurun_out/r2A_time.txt
+( time timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 8 --workload batched --no-cpu-baseline > gpurun_out/r2A_bench_batched_8gpu.json 2> gpurun_out/r2A_bench_batched_8gpu.err ) 2>> gpurun_out/r2A_time.txt; tail -2 gpurun_out/r2A_bench_batched_8gpu.err

@@ -138,10 +138,11 @@ struct b200msm_ctx {
   std::vector<cudaEvent_t> pev; std::vector<int> ptag; size_t pused = 0; bool prof = false;
   std::atomic<uint64_t> launches{0}; uint64_t adds_r0 = 0, adds_exact = 0, cur_n = 0;
   IssuePool* pool = nullptr; int opt_issue_threads = 0, opt_fold_cluster = 1, opt_groups = 0, opt_group_small = 70, opt_persist_fwd = 0, opt_ba_k0 = 0; std::mutex err_mu;      // one issuing host thread per lane (IssuePool); err is written under err_mu
+  bool blocking_waits = false;      // batch workers: host waits sleep instead of spinning (8 workers per GPU x 8 ranks would spin on more threads than the host has cores)
   size_t total_mem = 0; double mem_share = 1.0;      // fraction of the device memory budget this context may plan with (batch workers: 1 / workers)
   // multi-device context (b200msm_create_multi): devs[0] == this, devs[g] = the single-device context of device g; mres = handles of sharded / replicated base sets
   std::vector<b200msm_ctx*> devs; std::map<uint64_t, MultiResident> mres; int64_t opt_multi_min = 1 << 15; int opt_multi_replicate = 0;
-  std::vector<b200msm_ctx*> workers; int opt_batch_workers = 8, opt_batch_lanes = 1;            // sub-contexts (own stream + scratch) that run the MSMs of a batch concurrently
+  std::vector<b200msm_ctx*> workers; int opt_batch_workers = 8, opt_batch_lanes = 1, opt_batch_blocking = 0;            // sub-contexts (own stream + scratch) that run the MSMs of a batch concurrently
 };
 
 namespace {
@@ -460,7 +461,7 @@ int run_grouped(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, c
   CK(ctx->wsum.ensure(fbytes));
   if (ctx->h_folded_cap < fbytes + 4096) { if (ctx->h_folded) cudaFreeHost(ctx->h_folded); ctx->h_folded = nullptr; ctx->h_folded_cap = 0;
     CK(cudaMallocHost(&ctx->h_folded, fbytes + 4096)); ctx->h_folded_cap = fbytes + 4096; }
-  while (ctx->gev.size() < 2 * (size_t)ngroups) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->gev.push_back(e); }
+  while (ctx->gev.size() < 2 * (size_t)ngroups) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (ctx->blocking_waits ? cudaEventBlockingSync : 0))); ctx->gev.push_back(e); }
   CK(ctx->buckets.ensure((size_t)pl.W * pl.B * 16 * C::N));
   CK(ctx->misc.ensure(512 * 4));
   CK(cudaMemsetAsync(ctx->misc.p, 0, 512 * 4, s));
@@ -622,7 +623,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
       CK(ctx->wsum.ensure(fbytes));
       if (ctx->h_folded_cap < fbytes + 4096) { if (ctx->h_folded) cudaFreeHost(ctx->h_folded); ctx->h_folded = nullptr; ctx->h_folded_cap = 0;
         CK(cudaMallocHost(&ctx->h_folded, fbytes + 4096)); ctx->h_folded_cap = fbytes + 4096; }
-      while (ctx->gev.size() < G) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->gev.push_back(e); }
+      while (ctx->gev.size() < G) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (ctx->blocking_waits ? cudaEventBlockingSync : 0))); ctx->gev.push_back(e); }
     }
     for (uint32_t l = 0; l < lanes; l++) { rc = lane_init(ctx, ctx->lane[l]); if (rc) return rc; if (lanes > 1) CK(cudaStreamWaitEvent(ctx->lane[l].stream, ctx->ev_sorted, 0)); }
     // groups = contiguous runs of sub-slots with (nearly) equal pair counts, one tree each; at least one per lane
@@ -726,7 +727,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
       CK(ctx->wsum.ensure(fbytes));
       if (ctx->h_folded_cap < fbytes + 4096) { if (ctx->h_folded) cudaFreeHost(ctx->h_folded); ctx->h_folded = nullptr; ctx->h_folded_cap = 0;
         CK(cudaMallocHost(&ctx->h_folded, fbytes + 4096)); ctx->h_folded_cap = fbytes + 4096; }
-      while (ctx->gev.size() < ngroups) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->gev.push_back(e); }
+      while (ctx->gev.size() < ngroups) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (ctx->blocking_waits ? cudaEventBlockingSync : 0))); ctx->gev.push_back(e); }
     }
     // groups are issued from the TOP windows down: lane 0 (highest priority) owns the top group, so its folded points
     // reach the host first and the serial window combination runs while the GPU is still busy with the lower windows
@@ -1105,6 +1106,7 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "sort_groups")) { ctx->opt_sort_groups = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "lanes")) { if (v < 1 || v > MAX_LANES) return B200MSM_E_ARG; ctx->opt_lanes = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "probe_smem")) { if (v < 0 || v > 200 * 1024) return B200MSM_E_ARG; ctx->opt_probe_smem = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "batch_blocking")) { ctx->opt_batch_blocking = v != 0; return B200MSM_OK; }      // takes effect for workers created afterwards
   if (!strcmp(key, "batch_lanes")) { if (v < 1 || v > MAX_LANES) return B200MSM_E_ARG; ctx->opt_batch_lanes = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "batch_workers")) { if (v < 1 || v > 16) return B200MSM_E_ARG; ctx->opt_batch_workers = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "subslots")) { if (v < 0 || v > 256 || (v & (v - 1))) return B200MSM_E_ARG; ctx->opt_subslots = (int)v; return B200MSM_OK; }
@@ -1203,6 +1205,11 @@ static int single_batch(b200msm_ctx* ctx, uint64_t handle, const void* scalars, 
   while (ctx->workers.size() < K) {
     b200msm_ctx* w = nullptr; int rc = b200msm_create(&w, ctx->device);
     if (rc) { ctx->err = "cannot create a batch worker context"; return rc; }
+    if (ctx->opt_batch_blocking) {      // host waits sleep instead of spinning: for hosts where the workers of several processes outnumber the cores (measured: one process, 16 cores: 4 % slower)
+      w->blocking_waits = true;
+      cudaEventDestroy(w->ev_plan); w->ev_plan = nullptr;
+      if (cudaEventCreateWithFlags(&w->ev_plan, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) { b200msm_destroy(w); ctx->err = "cannot create a batch worker context"; return B200MSM_E_CUDA; }
+    }
     ctx->workers.push_back(w);
   }
   for (uint32_t k = 0; k < K; k++) { copy_options(ctx->workers[k], ctx); ctx->workers[k]->mem_share = 1.0 / K; }      // workers inherit the tuning options of the parent and share its memory budget
