@@ -372,3 +372,70 @@ def test_schedule_kernels_random(eng, ssz, wb, n):
     sc = [rnd.getrandbits(8 * ssz) for _ in range(n)]
     sc[0] = 0; sc[1] = (1 << (8 * ssz)) - 1; sc[2] = 1 << (8 * ssz - 1)
     _check_schedule(eng, sc, ssz, wb)
+
+
+# ---------------------------------------------------------------- round-2 kernels against each other and against the oracle
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+def test_sum_points_warp_tree(eng, cname):
+    """b200msm_g1_sum (k_sum_jacobian: strided per-lane sums + shared-memory tree) for counts below, at and above one warp, with infinities mixed in:
+    count copies of P sum to (count * s) P"""
+    cv = curve(cname); n = 200
+    bases = make_bases(cv, n, 71); sc = make_scalars(n, 72, "u256")
+    one = eng.multiexp_affine(cv.cid, bases, sc, 32, n)
+    zero = eng.multiexp_affine(cv.cid, bases, bytes(32 * n), 32, n)
+    for cnt in (1, 2, 3, 8, 31, 32, 33, 70):
+        scaled = b"".join(((int.from_bytes(sc[32 * i:32 * i + 32], "little") * cnt) % cv.r).to_bytes(32, "little") for i in range(n))
+        exp = oracle_msm(cv, bases, scaled, 32, n)
+        assert _norm(eng, cv, eng.sum_points(cv.cid, one * cnt, cnt)) == exp
+        mixed = b"".join(one if k % 2 == 0 else zero for k in range(2 * cnt))            # every second entry is the point at infinity
+        assert _norm(eng, cv, eng.sum_points(cv.cid, mixed, 2 * cnt)) == exp
+    assert _norm(eng, cv, eng.sum_points(cv.cid, zero * 5, 5)) == bytes(2 * cv.n8)
+
+
+@pytest.mark.parametrize("lg", [16, 18])
+def test_lane_and_tail_variants_agree(eng, lg):
+    """the same MSM through every scheduling variant of round 2: grouped sort on/off, 1-4 lanes, cluster / single-CTA fold tail, issuing threads,
+    forced tree rounds -- one group element, and the known answer"""
+    import torch
+    cv = curve("bls12381"); n = 1 << lg
+    d = torch.empty(n * 96, dtype=torch.uint8, device="cuda"); eng.generate_bases(0, 0xB2000000 + lg, 0, n, d)
+    g = torch.Generator(device="cuda"); g.manual_seed(lg)
+    sd = torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device="cuda", generator=g)
+    ref = _norm(eng, cv, eng.multiexp_affine(0, d, sd, 32, n))
+    assert any(ref)
+    try:
+        for opts in ({"lanes": 1}, {"lanes": 2}, {"lanes": 3}, {"sort_groups": 0}, {"fold_cluster": 0}, {"issue_threads": 1}, {"tree_rounds": 5}, {"tree_rounds": 1},
+                     {"lanes": 4, "groups": 6}, {"persist": 0}):
+            for k, v in opts.items(): eng.set_option(k, v)
+            assert _norm(eng, cv, eng.multiexp_affine(0, d, sd, 32, n)) == ref, opts
+            for k in opts: eng.set_option(k, {"lanes": 4, "sort_groups": 1, "fold_cluster": 1, "issue_threads": 0, "tree_rounds": -1, "groups": 0, "persist": 592}[k])
+    finally:
+        for k, v in {"lanes": 4, "sort_groups": 1, "fold_cluster": 1, "issue_threads": 0, "tree_rounds": -1, "groups": 0, "persist": 592}.items(): eng.set_option(k, v)
+
+
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+def test_skewed_scalars_dense_items(eng, cname):
+    """half of 2^16 scalars are EQUAL (every window has one bucket of 32768 points: 14+ tree rounds, long carry chains of odd remainders) and the rest
+    random; the batch-affine tree (dense addition items, carried points copied by the backward pass) must give the serial one-thread-per-bucket result"""
+    import torch
+    cv = curve(cname); n = 1 << 16
+    d = torch.empty(n * 2 * cv.n8, dtype=torch.uint8, device="cuda"); eng.generate_bases(cv.cid, 99, 0, n, d)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    sd = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g)
+    sd[::2] = sd[0]                                    # every second scalar equals scalar 0
+    sd[1:n:1024] = 0                                   # a few zero scalars
+    sd = sd.reshape(-1).contiguous()
+    got = _norm(eng, cv, eng.multiexp_affine(cv.cid, d, sd, 32, n))
+    try:
+        eng.set_option("accumulate", 1)
+        ser = _norm(eng, cv, eng.multiexp_affine(cv.cid, d, sd, 32, n))
+    finally:
+        eng.set_option("accumulate", 0)
+    assert got == ser and any(got)
+    try:
+        eng.set_option("lanes", 1); assert _norm(eng, cv, eng.multiexp_affine(cv.cid, d, sd, 32, n)) == ser
+    finally:
+        eng.set_option("lanes", 4)
+    h = eng.upload_bases_windowed(cv.cid, d, n, 32, 0)
+    try: assert _norm(eng, cv, eng.multiexp_resident(h, sd, 32, n, cv.cid)) == ser
+    finally: eng.free_bases(h)

@@ -43,4 +43,24 @@ for cid in (0, 1):
         x = torch.randint(0, 256, (32 << lg,), dtype=torch.uint8, device="cuda"); x.view(-1, 32)[:, 31] &= 0x0F
         y = torch.empty_like(x); eng.fr_fft(cid, x, lg, out=y); eng.fr_fft(cid, y, lg, inverse=True, out=y); eng.synchronize()
         assert torch.equal(x, y), (cid, lg)
+# round 2: the grouped-sort path with dense addition items and the cluster fold tail (2^18 points), forced tree rounds on a small input, the warp-tree
+# sum of partial points, f1m_batchInverse and the schedule hook
+cv = pyref.BLS12_381
+n = 1 << 18
+d = torch.empty(n * 96, dtype=torch.uint8, device="cuda"); eng.generate_bases(0, 21, 0, n, d)
+sd = torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device="cuda")
+a = eng.normalize(0, eng.multiexp_affine(0, d, sd, 32, n))
+eng.set_option("lanes", 1); assert eng.normalize(0, eng.multiexp_affine(0, d, sd, 32, n)) == a; eng.set_option("lanes", 4)
+eng.set_option("fold_cluster", 0); assert eng.normalize(0, eng.multiexp_affine(0, d, sd, 32, n)) == a; eng.set_option("fold_cluster", 1)
+bases = make_bases(cv, 3000, 7); sc = make_scalars(3000, 8, "u256"); exp = oracle_msm(cv, bases, sc, 32, 3000)
+eng.set_option("tree_rounds", 4); eng.set_option("window_bits", 7)
+assert eng.normalize(0, eng.multiexp_affine(0, bases, sc, 32, 3000)) == exp
+eng.set_option("tree_rounds", -1); eng.set_option("window_bits", 0)
+one = eng.multiexp_affine(0, bases, sc, 32, 3000)
+for cnt in (1, 2, 8, 33, 70):
+    tot = eng.normalize(0, eng.sum_points(0, one * cnt, cnt))
+    assert tot == eng.normalize(0, eng.multiexp_affine(0, bases, b"".join(((int.from_bytes(sc[32 * i:32 * i + 32], "little") * cnt) % cv.r).to_bytes(32, "little") for i in range(3000)), 32, 3000)), cnt
+xs = b"".join(pyref.fe_bytes(cv, (i * 7919 + 1) % cv.q if i % 11 else 0) for i in range(3000))
+assert eng.fq_batch_inverse(0, xs) == eng.fq_op(0, 4, xs)
+plan, offs, srt = eng.debug_schedule(sc[:32 * 500], 32, 500, 9); assert offs[-1] == len(srt)
 print("sanitizer case ok")
