@@ -137,7 +137,8 @@ int b200msm_g1_sum(b200msm_ctx* ctx, int curve, const void* jac_points, uint64_t
  * (src/build_curve_jacobian_a0.js:1166-1328,1413-1416), 4 == g1m_batchToAffine (:1040-1125), 5 == g1m_batchToJacobian (:1418).
  * Element sizes in -> out (bytes): 0: 2n8 -> 2n8, 1: 2n8 -> n8, 2: 2n8 -> 2n8, 3: n8 -> 2n8, 4: 3n8 -> 2n8, 5: 2n8 -> 3n8.
  * "LEM" = little-endian Montgomery affine (the MSM's input format); "U"/"C" = big-endian plain uncompressed/compressed,
- * first byte 0x40 = infinity, 0x80 (compressed only) = y is the greater of the two roots. */
+ * first byte 0x40 = infinity, 0x80 (compressed only) = y is the greater of the two roots.  The G2 curve ids give g2m_batch* (elements Fq2 = c0 || c1,
+ * n8 = 96 / 64; the byte reversal covers the whole element, the sign is f2m_sign, the root f2m_sqrt). */
 int b200msm_g1_batch_convert(b200msm_ctx* ctx, int curve, int op, const void* in, uint64_t n, void* out);
 
 /* ---- GLV pre-pass, BLS12-381 only like the reference (src/build_glv.js:3; other curves: B200MSM_E_UNSUPPORTED).

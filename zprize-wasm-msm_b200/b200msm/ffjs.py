@@ -68,7 +68,7 @@ class G1:
 
 class G2(G1):
     """curve.G2 of ffjavascript: the same multiexp surface over the G2 exports (g2m_multiexpAffine / g2m_multiexp); elements are
-    Fq2 = c0 || c1, so n8 here is 96 / 64 bytes.  The wire codecs (batchLEMtoU ...) exist for G1 only in this engine."""
+    Fq2 = c0 || c1, so n8 here is 96 / 64 bytes.  The wire codecs (batchLEMtoU ...) are the g2m_batch* exports: the same kernels over Fq2."""
 
     def __init__(self, engine, curve):
         self.engine = engine
@@ -82,5 +82,3 @@ class G2(G1):
         h = self.n8 // 2
         return bytes(self.n8) + one.to_bytes(h, "little") + bytes(h) + bytes(self.n8)
 
-    def _conv(self, op, buff, in_sz): raise NotImplementedError("point codecs are built for G1")
-    def toAffine(self, p): raise NotImplementedError("use Engine.normalize for G2")

@@ -1512,7 +1512,6 @@ int b200msm_g1_generate_bases(b200msm_ctx* ctx, int curve, uint64_t seed, uint64
 
 int b200msm_g1_batch_convert(b200msm_ctx* ctx, int curve, int op, const void* in, uint64_t n, void* out) {
   if (!ctx || !curve_ok(curve) || op < 0 || op > 5 || (n && (!in || !out)) || n >= (1ull << 31)) return B200MSM_E_ARG;
-  if (!curve_g1(curve)) { ctx->err = "the point codecs are built for G1"; return B200MSM_E_UNSUPPORTED; }
   if (n == 0) return B200MSM_OK;
   CK(cudaSetDevice(ctx->device));
   const size_t n8 = n8_of(curve);
@@ -1523,10 +1522,8 @@ int b200msm_g1_batch_convert(b200msm_ctx* ctx, int curve, int op, const void* in
   if (op == CODEC_TO_AFFINE) {
     constexpr int GROUP = 8;
     const uint32_t g2 = (uint32_t)(((n + GROUP - 1) / GROUP + 127) / 128);
-    if (curve == 0) k_jacobian_to_affine<BLS12_381, GROUP><<<g2, 128, 0, ctx->stream>>>((const uint8_t*)d_in, (uint32_t)n, ctx->acc_c.as<uint8_t>());
-    else k_jacobian_to_affine<BN254, GROUP><<<g2, 128, 0, ctx->stream>>>((const uint8_t*)d_in, (uint32_t)n, ctx->acc_c.as<uint8_t>());
-  } else if (curve == 0) k_codec<BLS12_381><<<g, 128, 0, ctx->stream>>>(op, (const uint8_t*)d_in, (uint32_t)n, ctx->acc_c.as<uint8_t>(), 4u);
-  else k_codec<BN254><<<g, 128, 0, ctx->stream>>>(op, (const uint8_t*)d_in, (uint32_t)n, ctx->acc_c.as<uint8_t>(), 3u);
+    B200_CURVE_SWITCH(curve, k_jacobian_to_affine<C, GROUP><<<g2, 128, 0, ctx->stream>>>((const uint8_t*)d_in, (uint32_t)n, ctx->acc_c.as<uint8_t>()))
+  } else { B200_CURVE_SWITCH(curve, k_codec<C><<<g, 128, 0, ctx->stream>>>(op, (const uint8_t*)d_in, (uint32_t)n, ctx->acc_c.as<uint8_t>())) }
   CKL();
   return deliver(ctx, ctx->acc_c.p, out, n * out_sz[op]);
 }
