@@ -20,7 +20,7 @@ import torch, b200msm
 
 cid = {"bls12381": 0, "bn128": 1, "bls12381_g2": 2, "bn128_g2": 3}[a.curve]; n8 = b200msm.N8[cid]
 dev = torch.device("cuda", 0)
-DEFAULTS = {"lanes": 4, "sort_groups": 1, "window_bits": 0, "tree_rounds": -1, "ba_k": 0, "pt_k": 8, "persist": 592, "combine": 0, "accumulate": 0, "subslots": 0, "group_pairs": 0}
+DEFAULTS = {"lanes": 4, "sort_groups": 1, "window_bits": 0, "tree_rounds": -1, "ba_k": 0, "pt_k": 8, "persist": 592, "combine": 0, "accumulate": 0, "subslots": 0, "group_pairs": 0, "xonly": 1, "fused_tiles": 592, "fused_kmax": 16}
 
 
 def parse_cfg(c):
@@ -40,7 +40,9 @@ for lg in [int(x) for x in a.sizes.split(",")]:
     ref = None
     for cfg in a.configs.split(";"):
         opts = parse_cfg(cfg)
-        for k, v in DEFAULTS.items(): eng.set_option(k, v)
+        for k, v in DEFAULTS.items():
+            try: eng.set_option(k, v)
+            except Exception: pass      # an older build of the library may not know a newer key
         try:
             for k, v in opts.items(): eng.set_option(k, v)
         except Exception as ex:

@@ -29,7 +29,7 @@ constexpr uint32_t BA_ROOT_MAX = 1024;   // = BA_ROOT_THREADS * ROOT_PER   // th
 
 // All rounds' segment offsets in one three-phase scan: off[r][b] = exclusive scan over b of ceil(n_0[b] / 2^r), r = 1..R.
 // offs: R arrays of (n + 1) words; tile_sums: R arrays of (ntiles + 1) words.
-__global__ void __launch_bounds__(SCAN_THREADS) k_mscan_tiles(const uint32_t* __restrict__ cnt0, uint32_t n, uint32_t R,
+B200_KERNEL void __launch_bounds__(SCAN_THREADS) k_mscan_tiles(const uint32_t* __restrict__ cnt0, uint32_t n, uint32_t R,
                                                               uint32_t* __restrict__ offs, uint32_t* __restrict__ tile_sums, uint32_t ntiles) {
   uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   uint32_t v0[SCAN_ITEMS];
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_mscan_tiles(const uint32_t* __
     if (threadIdx.x == 0) tile_sums[(size_t)(r - 1) * (ntiles + 1) + blockIdx.x] = total;
   }
 }
-__global__ void k_mscan_sums(uint32_t* __restrict__ tile_sums, uint32_t ntiles) {      // one block per round
+B200_KERNEL void k_mscan_sums(uint32_t* __restrict__ tile_sums, uint32_t ntiles) {      // one block per round
   uint32_t* ts = tile_sums + (size_t)blockIdx.x * (ntiles + 1);
   __shared__ uint32_t carry_s;
   if (threadIdx.x == 0) carry_s = 0;
@@ -64,7 +64,7 @@ __global__ void k_mscan_sums(uint32_t* __restrict__ tile_sums, uint32_t ntiles) 
   }
   if (threadIdx.x == 0) ts[ntiles] = carry_s;
 }
-__global__ void k_mscan_apply(uint32_t* __restrict__ offs, uint32_t n, const uint32_t* __restrict__ tile_sums, uint32_t ntiles) {   // grid.y = round
+B200_KERNEL void k_mscan_apply(uint32_t* __restrict__ offs, uint32_t n, const uint32_t* __restrict__ tile_sums, uint32_t ntiles) {   // grid.y = round
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t* out = offs + (size_t)blockIdx.y * (n + 1);
   const uint32_t* ts = tile_sums + (size_t)blockIdx.y * (ntiles + 1);
@@ -75,7 +75,7 @@ __global__ void k_mscan_apply(uint32_t* __restrict__ offs, uint32_t n, const uin
 // bid1[j] = bucket owning output slot j of round 0.  One warp per 32 buckets: each lane fetches the slot range of its
 // bucket, then the warp writes the 32 ranges one after the other with coalesced stores (a range is ~16 slots for
 // uniform scalars; a heavy bucket's range is simply more iterations of the whole warp -- no per-slot binary search).
-__global__ void __launch_bounds__(256) k_fill_bid(const uint32_t* __restrict__ off1, uint32_t nb, uint32_t* __restrict__ bid1) {
+B200_KERNEL void __launch_bounds__(256) k_fill_bid(const uint32_t* __restrict__ off1, uint32_t nb, uint32_t* __restrict__ bid1) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t b = warp * 32 + lane;
@@ -140,10 +140,21 @@ B200_DI void meta_load_point(Affine<C>& p, const void* __restrict__ src, uint64_
   if (FIRST) { affine_load<C>(p, src, ref & 0x7fffffffu); if (ref >> 31) fe_neg<C>(p.y, p.y); }
   else { const char* b = reinterpret_cast<const char*>(src) + (uint64_t)ref * (4 * C::N); fe_load_cg<C>(p.x, b); fe_load_cg<C>(p.y, b + yoff); }
 }
+// xs (round 0 only, may be null): a copy of the bases' x coordinates alone (k_extract_x), n8 bytes apart.  Every base is gathered once per
+// window by the forward pass; 2 * n8 bytes apart the 2^20 x coordinates of BLS12-381 spread over 96 MiB and every gather goes to HBM, n8
+// bytes apart they are 48 MiB, which the 126 MB L2 keeps between the windows (no persisting set-aside: carving it out of L2 slowed every other kernel, 2^20: 6.3 -> 8.1 ms).
 template <class C, bool FIRST>
-B200_DI void meta_load_x(Fe<C::N>& x, const void* __restrict__ src, uint32_t ref) {
-  if (FIRST) fe_load<C>(x, reinterpret_cast<const char*>(src) + (uint64_t)(ref & 0x7fffffffu) * (8 * C::N));
+B200_DI void meta_load_x(Fe<C::N>& x, const void* __restrict__ src, const void* __restrict__ xs, uint32_t ref) {
+  if (FIRST) { if (xs) fe_load<C>(x, reinterpret_cast<const char*>(xs) + (uint64_t)(ref & 0x7fffffffu) * (4 * C::N));
+               else fe_load<C>(x, reinterpret_cast<const char*>(src) + (uint64_t)(ref & 0x7fffffffu) * (8 * C::N)); }
   else fe_load_cg<C>(x, reinterpret_cast<const char*>(src) + (uint64_t)ref * (4 * C::N));
+}
+template <class C>
+__global__ void __launch_bounds__(256) k_extract_x(const void* __restrict__ bases, uint32_t n, void* __restrict__ xs) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<C::N> x; fe_load<C>(x, reinterpret_cast<const char*>(bases) + (uint64_t)i * (8 * C::N));
+  fe_store<C>(reinterpret_cast<char*>(xs) + (uint64_t)i * (4 * C::N), x);
 }
 template <class C>
 B200_DI void soa_store_point(void* __restrict__ dst, uint64_t yoff, uint32_t j, const Affine<C>& p) {
@@ -157,20 +168,20 @@ B200_DI void soa_store_point(void* __restrict__ dst, uint64_t yoff, uint32_t j, 
 // One tile (K * BA_THREADS consecutive items, thread t owns items t, t + 128, ...): returns the thread's running product in p.
 // nadd = number of items of the round (read from the scan totals on the device: the host only knows an upper bound).
 template <class C, bool FIRST>
-B200_DI void tree_fwd_tile(Fe<C::N>& p, const uint4* __restrict__ items, uint32_t nadd, const void* __restrict__ src, uint64_t yoff, void* __restrict__ prefix, int K, uint32_t tb) {
+B200_DI void tree_fwd_tile(Fe<C::N>& p, const uint4* __restrict__ items, uint32_t nadd, const void* __restrict__ src, const void* __restrict__ xs, uint64_t yoff, void* __restrict__ prefix, int K, uint32_t tb) {
   const uint32_t tile = tb * (K * BA_THREADS) + threadIdx.x;
   fe_set_one<C>(p);
   Fe<C::N> x1, x2, nx1, nx2;
   uint4 mc = make_uint4(0, 0, 0, 0), mn = mc;
   if (tile < nadd) mc = items[tile];
   if (K > 1 && tile + BA_THREADS < nadd) mn = items[tile + BA_THREADS];
-  if (tile < nadd) { meta_load_x<C, FIRST>(x1, src, mc.x); meta_load_x<C, FIRST>(x2, src, mc.y); }
+  if (tile < nadd) { meta_load_x<C, FIRST>(x1, src, xs, mc.x); meta_load_x<C, FIRST>(x2, src, xs, mc.y); }
 #pragma unroll 1
   for (int i = 0; i < K; i++) {
     const uint32_t e = tile + i * BA_THREADS;
     uint4 mn2 = make_uint4(0, 0, 0, 0);
     if (i + 2 < K && e + 2 * BA_THREADS < nadd) mn2 = items[e + 2 * BA_THREADS];
-    if (i + 1 < K && e + BA_THREADS < nadd) { meta_load_x<C, FIRST>(nx1, src, mn.x); meta_load_x<C, FIRST>(nx2, src, mn.y); }
+    if (i + 1 < K && e + BA_THREADS < nadd) { meta_load_x<C, FIRST>(nx1, src, xs, mn.x); meta_load_x<C, FIRST>(nx2, src, xs, mn.y); }
     if (e < nadd) {
       Fe<C::N> d; int kind = 0;
       fe_sub<C>(d, x2, x1);
@@ -190,12 +201,12 @@ B200_DI void tree_fwd_tile(Fe<C::N>& p, const uint4* __restrict__ items, uint32_
 }
 template <class C, bool FIRST>
 __global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 3 : 6) k_tree_fwd(const uint4* __restrict__ items, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t nb,
-                                                            const void* __restrict__ src, uint64_t yoff, void* __restrict__ prefix, void* __restrict__ prod, int K, uint32_t ntiles) {
+                                                            const void* __restrict__ src, const void* __restrict__ xs, uint64_t yoff, void* __restrict__ prefix, void* __restrict__ prod, int K, uint32_t ntiles) {
  const uint32_t nadd = off_in[nb] - off_in[0] - off_out[nb];      // additions of this round = inputs - outputs
  // persistent form: gridDim.x may be smaller than ntiles (leaves SM room for the other lane's latency-bound kernels)
  for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
   Fe<C::N> p;
-  tree_fwd_tile<C, FIRST>(p, items, nadd, src, yoff, prefix, K, tb);
+  tree_fwd_tile<C, FIRST>(p, items, nadd, src, xs, yoff, prefix, K, tb);
   fe_store<C>(reinterpret_cast<char*>(prod) + (uint64_t)(tb * BA_THREADS + threadIdx.x) * 4 * C::N, p);
  }
 }
@@ -248,9 +259,214 @@ __global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_bwd(cons
  }
 }
 
+// ---- one tree round as ONE kernel: every CTA inverts the product of ITS OWN tile ------------------------------------------------------
+// MEASURED AND NOT ADOPTED (round 2, profiles/README.md "r2 late"): 2^20 BLS12-381 8.2-9.8 ms against 6.29 (four lanes), 64 x 2^18 in a batch 2.24 ms per MSM
+// against 1.70, BN254 2^20 4.17 against 3.44 -- the CTAs of a launch run in step (all in their memory-bound forward phase, then all waiting for
+// their inverting thread, then all in the multiplier-bound backward phase), so the phases add up instead of overlapping, which separate
+// forward / backward launches on several lanes avoid.  Kept for -DB200_EXPERIMENTS builds only (option "fused_round").
+#if defined(B200_EXPERIMENTS)
+// f1m_batchInverse (build_batchinverse.js:4-140) needs one field inversion per batch, and the reference runs one batch per level of its
+// addition chains.  The grid-wide form above does the same -- one inversion per round -- and pays for it with a chain of launches
+// (forward pass, product-tree levels, root, levels back down, backward pass) whose latency-bound middle is ~0.2 ms per round per lane.
+// Here the batch is a TILE (K * BA_THREADS additions): a CTA runs the forward pass of its tile, reduces the 128 per-thread products by a
+// binary tree in shared memory, thread 0 inverts the tile's root (Pornin's binary GCD, ~50 us on one thread, ~1 % of the tile's instructions),
+// the tree is walked back down and the backward pass follows -- no grid-wide dependency, no product-tree launches, one launch per round.
+// The other CTAs resident on the SM (different phases of their own tiles) keep the multiplier busy while one thread inverts.
+// Cost per addition: the same 6 multiplications + 3 / K for the block tree (the grid-wide product tree's first level costs the same 3 / K).
+// ---- block-level product tree (the first level of the round's batch inversion lives INSIDE the tree kernels) ---------------------------
+// MEASURED AND NOT ADOPTED (round 2; k_tree_fwd_bt / k_tree_bwd_bt, -DB200_EXPERIMENTS builds only, option "block_tree"): 2^16 1.476 -> 1.457 ms,
+// 2^18 2.63 -> 2.61, but 2^20 6.25 -> 6.55 and 2^22 20.5 -> 21.6, batches 1.70 -> 1.77 ms per MSM: the down-sweep at the head of every backward tile is a
+// latency-bound phase that all CTAs of the launch enter together (k_tree_bwd round 0: 1.53 -> 1.75 ms), which costs more than the product-tree launches it removes.
+// The 128 per-thread products of a tile are reduced by a binary tree in shared memory at the end of the forward pass, so ONE value per
+// tile goes up to the grid-wide product tree (a round of 2 M additions then needs no product-tree launch at all: <= 1024 tile roots go
+// straight to k_inv_root); the tree's nodes are kept (256 elements per tile) and the backward pass walks them down from the tile root's
+// inverse before its additions.  Same multiplications as a K-ary level of the grid-wide tree (3 per value), two to four launches and
+// their latency-bound tails fewer per round.  Heap order: node 1 = root, leaves at [BA_THREADS, 2 * BA_THREADS).
+template <class C>
+B200_DI void block_upsweep(const Fe<C::N>& p, uint32_t* __restrict__ tree, void* __restrict__ gtree) {      // gtree: this tile's 2 * BA_THREADS elements in global memory
+  constexpr int N = C::N;
+  const uint32_t t = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < N; k++) tree[(BA_THREADS + t) * N + k] = p.l[k];
+  fe_store<C>(reinterpret_cast<char*>(gtree) + (uint64_t)(BA_THREADS + t) * 4 * N, p);
+  __syncthreads();
+#pragma unroll 1
+  for (uint32_t width = BA_THREADS / 2; width >= 1; width >>= 1) {
+    if (t < width) {
+      Fe<N> a, b, c; const uint32_t node = width + t;
+#pragma unroll
+      for (int k = 0; k < N; k++) { a.l[k] = tree[(2 * node) * N + k]; b.l[k] = tree[(2 * node + 1) * N + k]; }
+      fe_mul<C>(c, a, b);
+#pragma unroll
+      for (int k = 0; k < N; k++) tree[node * N + k] = c.l[k];
+      fe_store<C>(reinterpret_cast<char*>(gtree) + (uint64_t)node * 4 * N, c);
+    }
+    __syncthreads();
+  }
+}
+// tree[1] holds the inverse of the root on entry (written before the call, barrier included here); on exit q = inverse of the thread's own product
+template <class C>
+B200_DI void block_downsweep(Fe<C::N>& q, uint32_t* __restrict__ tree) {
+  constexpr int N = C::N;
+  const uint32_t t = threadIdx.x;
+  __syncthreads();
+#pragma unroll 1
+  for (uint32_t width = 1; width < BA_THREADS; width <<= 1) {          // one thread per CHILD: inv(child) = inv(parent) * sibling
+    Fe<N> ip, sib, r; const uint32_t child = 2 * width + t;
+    if (t < 2 * width) {
+#pragma unroll
+      for (int k = 0; k < N; k++) { ip.l[k] = tree[(child >> 1) * N + k]; sib.l[k] = tree[(child ^ 1) * N + k]; }
+    }
+    __syncthreads();
+    if (t < 2 * width) {
+      fe_mul<C>(r, ip, sib);
+#pragma unroll
+      for (int k = 0; k < N; k++) tree[child * N + k] = r.l[k];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < N; k++) q.l[k] = tree[(BA_THREADS + t) * N + k];
+}
+
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 3 : 6) k_tree_fwd_bt(const uint4* __restrict__ items, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t nb,
+                                                            const void* __restrict__ src, const void* __restrict__ xs, uint64_t yoff, void* __restrict__ prefix, void* __restrict__ prod, int K, uint32_t ntiles, void* __restrict__ gtree) {
+ __shared__ __align__(16) uint32_t tree[2 * BA_THREADS * C::N];
+ const uint32_t nadd = off_in[nb] - off_in[0] - off_out[nb];      // additions of this round = inputs - outputs
+ // persistent form: gridDim.x may be smaller than ntiles (leaves SM room for the other lane's latency-bound kernels)
+ for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
+  Fe<C::N> p;
+  tree_fwd_tile<C, FIRST>(p, items, nadd, src, xs, yoff, prefix, K, tb);
+  {      // one value per TILE goes up (tiles beyond the round's additions contribute 1)
+    block_upsweep<C>(p, tree, reinterpret_cast<char*>(gtree) + (uint64_t)tb * (2 * BA_THREADS) * 4 * C::N);
+    if (threadIdx.x == 0) { Fe<C::N> r;
+#pragma unroll
+      for (int k = 0; k < C::N; k++) r.l[k] = tree[C::N + k];
+      fe_store<C>(reinterpret_cast<char*>(prod) + (uint64_t)tb * 4 * C::N, r); }
+  }
+ }
+}
+
+
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_bwd_bt(const uint4* __restrict__ items, const uint2* __restrict__ carries, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t nb,
+                                                         const void* __restrict__ src, uint64_t yoff,
+                                                         const void* __restrict__ prefix, const void* __restrict__ inv,
+                                                         void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles, const void* __restrict__ gtree) {
+ __shared__ __align__(16) uint32_t tree[2 * BA_THREADS * C::N];
+ const uint32_t nadd = off_in[nb] - off_in[0] - off_out[nb];      // additions of this round = inputs - outputs
+ for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
+  Fe<C::N> q;
+  {      // the tile's tree (written by the forward pass) with the root replaced by its inverse, walked down to the threads
+    const char* gt = reinterpret_cast<const char*>(gtree) + (uint64_t)tb * (2 * BA_THREADS) * 4 * C::N;
+    const uint32_t t = threadIdx.x;
+    Fe<C::N> a, b;
+    fe_load_cg<C>(a, t <= 1 ? reinterpret_cast<const char*>(inv) + (uint64_t)tb * 4 * C::N : gt + (uint64_t)t * 4 * C::N);      // node 0 is unused; node 1 <- inverse of the root
+    fe_load_cg<C>(b, gt + (uint64_t)(BA_THREADS + t) * 4 * C::N);
+    __syncthreads();                                                        // the previous tile's down-sweep has been read by every thread
+#pragma unroll
+    for (int k = 0; k < C::N; k++) { tree[t * C::N + k] = a.l[k]; tree[(BA_THREADS + t) * C::N + k] = b.l[k]; }
+    block_downsweep<C>(q, tree);
+  }
+  tree_bwd_tile<C, FIRST>(q, items, nadd, src, yoff, prefix, pout, yoff_out, K, tb);
+ }
+ // the round's carried points (a bucket's odd last input): plain copies into their output slots (round 0: with the digit's sign applied)
+ const uint32_t ncar = off_out[nb] - nadd;
+ for (uint32_t c = blockIdx.x * BA_THREADS + threadIdx.x; c < ncar; c += gridDim.x * BA_THREADS) {
+  const uint2 cr = carries[c];
+  Affine<C> p; meta_load_point<C, FIRST>(p, src, yoff, cr.x); soa_store_point<C>(pout, yoff_out, cr.y, p);
+ }
+}
+
+
+template <class C>
+B200_DI void block_invert(Fe<C::N>& q, const Fe<C::N>& p, uint32_t* __restrict__ tree) {     // tree: 2 * BA_THREADS elements, heap order, leaves at [BA_THREADS, 2 * BA_THREADS)
+  constexpr int N = C::N;
+  const uint32_t t = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < N; k++) tree[(BA_THREADS + t) * N + k] = p.l[k];
+  __syncthreads();
+#pragma unroll 1
+  for (uint32_t width = BA_THREADS / 2; width >= 1; width >>= 1) {     // up-sweep: node = left * right
+    if (t < width) {
+      Fe<N> a, b, c; const uint32_t node = width + t;
+#pragma unroll
+      for (int k = 0; k < N; k++) { a.l[k] = tree[(2 * node) * N + k]; b.l[k] = tree[(2 * node + 1) * N + k]; }
+      fe_mul<C>(c, a, b);
+#pragma unroll
+      for (int k = 0; k < N; k++) tree[node * N + k] = c.l[k];
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    Fe<N> r, ri;
+#pragma unroll
+    for (int k = 0; k < N; k++) r.l[k] = tree[N + k];
+    fe_inv_fast<C>(ri, r);
+#pragma unroll
+    for (int k = 0; k < N; k++) tree[N + k] = ri.l[k];
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (uint32_t width = 1; width < BA_THREADS; width <<= 1) {          // down-sweep, one thread per CHILD: inv(child) = inv(node) * sibling
+    Fe<N> ip, sib, r; const uint32_t child = 2 * width + t;
+    if (t < 2 * width) {
+#pragma unroll
+      for (int k = 0; k < N; k++) { ip.l[k] = tree[(child >> 1) * N + k]; sib.l[k] = tree[(child ^ 1) * N + k]; }
+    }
+    __syncthreads();
+    if (t < 2 * width) {
+      fe_mul<C>(r, ip, sib);
+#pragma unroll
+      for (int k = 0; k < N; k++) tree[child * N + k] = r.l[k];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < N; k++) q.l[k] = tree[(BA_THREADS + t) * N + k];
+}
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_round(const uint4* __restrict__ items, const uint2* __restrict__ carries, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t nb,
+                                                           const void* __restrict__ src, uint64_t yoff, void* __restrict__ prefix,
+                                                           void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles) {
+ __shared__ __align__(16) uint32_t tree[2 * BA_THREADS * C::N];
+ const uint32_t nadd = off_in[nb] - off_in[0] - off_out[nb];      // additions of this round = inputs - outputs
+ for (uint32_t tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
+  if (tb * (uint32_t)(K * BA_THREADS) >= nadd) break;             // ntiles comes from the host's upper bound of nadd
+  Fe<C::N> p, q;
+  tree_fwd_tile<C, FIRST>(p, items, nadd, src, nullptr, yoff, prefix, K, tb);
+  block_invert<C>(q, p, tree);
+  tree_bwd_tile<C, FIRST>(q, items, nadd, src, yoff, prefix, pout, yoff_out, K, tb);
+ }
+ const uint32_t ncar = off_out[nb] - nadd;
+ for (uint32_t c = blockIdx.x * BA_THREADS + threadIdx.x; c < ncar; c += gridDim.x * BA_THREADS) {
+  const uint2 cr = carries[c];
+  Affine<C> p; meta_load_point<C, FIRST>(p, src, yoff, cr.x); soa_store_point<C>(pout, yoff_out, cr.y, p);
+ }
+}
+
+#endif  // B200_EXPERIMENTS
+
 // Measured alternatives that are no longer in the tree (profiles/README.md has their numbers): a backward pass that stages the next slot's operands
 // in shared memory with cp.async (0-8 % slower), a register-lean backward pass that reloads operands instead of keeping them (5 CTAs/SM: equal
 // or slower), and the whole round as ONE cooperative launch with in-kernel wave-wise batch inversion (2^20: 8.2-10.6 ms against 6.5).
+
+// Explicit instantiations of the two hot kernels live in tree.cu (one object per curve, compiled without -split-compile: see there);
+// every other translation unit sees them as `extern template`.
+#define B200_TREE_INSTANTIATE(KW, C) \
+  KW __global__ void k_tree_fwd<C, true>(const uint4* __restrict__, const uint32_t* __restrict__, const uint32_t* __restrict__, uint32_t, const void* __restrict__, const void* __restrict__, uint64_t, void* __restrict__, void* __restrict__, int, uint32_t); \
+  KW __global__ void k_tree_fwd<C, false>(const uint4* __restrict__, const uint32_t* __restrict__, const uint32_t* __restrict__, uint32_t, const void* __restrict__, const void* __restrict__, uint64_t, void* __restrict__, void* __restrict__, int, uint32_t); \
+  KW __global__ void k_tree_bwd<C, true>(const uint4* __restrict__, const uint2* __restrict__, const uint32_t* __restrict__, const uint32_t* __restrict__, uint32_t, const void* __restrict__, uint64_t, const void* __restrict__, const void* __restrict__, void* __restrict__, uint64_t, int, uint32_t); \
+  KW __global__ void k_tree_bwd<C, false>(const uint4* __restrict__, const uint2* __restrict__, const uint32_t* __restrict__, const uint32_t* __restrict__, uint32_t, const void* __restrict__, uint64_t, const void* __restrict__, const void* __restrict__, void* __restrict__, uint64_t, int, uint32_t);
+#if !defined(TREE_CURVE)
+B200_TREE_INSTANTIATE(extern template, BLS12_381)
+B200_TREE_INSTANTIATE(extern template, BN254)
+#if !defined(B200_NO_G2)
+B200_TREE_INSTANTIATE(extern template, Fq2<BLS12_381>)
+B200_TREE_INSTANTIATE(extern template, Fq2<BN254>)
+#endif
+#endif
 
 // ---- product tree, levels >= 1: plain arrays of field elements -----------------------------------------
 // A level reduces n values by K per thread (serial running product, prefixes stored) and, when WARP is set, by a further

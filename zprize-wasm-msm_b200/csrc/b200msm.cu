@@ -60,7 +60,8 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct Resident { int curve; uint64_t n; void* d;                // d: n affine points; with a window table: Wd rows of n points, row 0 = the bases
+struct Resident { int curve; uint64_t n; void* d; void* dx = nullptr;      // dx: the x coordinates alone (built at upload for sets of >= 2^19 points, see k_extract_x)
+                                 // d: n affine points; with a window table: Wd rows of n points, row 0 = the bases
                   uint32_t t_nbits = 0, t_c0 = 0, t_rem = 0, t_Wd = 0; };   // window plan the table was built for (t_Wd == 0: no table)
 struct Precomp { uint32_t stride, nbits, c0, rem, Wd; };
 // one base set spread over the devices of a multi context: device g holds points [lo[g], lo[g] + cnt[g]) under its own handle h[g]
@@ -70,7 +71,7 @@ struct MultiResident { int curve; uint64_t n; bool replicated; std::vector<uint6
 // one accumulate lane: a stream with its own tree scratch (see accumulate_batch_affine)
 struct TreeLane {
   cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
-  DevBuf offs, tiles, bid, pa, pb, prefix, prod, lvlprefix, others, meta, carry;
+  DevBuf offs, tiles, bid, pa, pb, prefix, prod, lvlprefix, others, meta, carry, btree;
 };
 constexpr int MAX_LANES = 8;
 
@@ -127,6 +128,7 @@ struct b200msm_ctx {
   bool probe29 = false, probe_sqr = false; int64_t opt_group_pairs = 0;
   cudaEvent_t ev_plan = nullptr, ev_sorted = nullptr, ev_bases = nullptr, ev_done = nullptr;
   cudaStream_t copy_stream = nullptr; bool bases_pending = false;
+  DevBuf xonly; const void* xs_hint = nullptr; const void* cur_xs = nullptr; uint64_t cur_xs_bytes = 0; int opt_xonly = 1; bool prof_noxs = false;      // x coordinates of the bases alone (k_extract_x) for the forward pass of round 0
   std::vector<cudaEvent_t> gev;                                               // one event per window group (folded points on the host)
   uint32_t* h_pinned = nullptr;
   void* h_folded = nullptr; size_t h_folded_cap = 0;                         // pinned staging of the folded bucket entries
@@ -137,7 +139,8 @@ struct b200msm_ctx {
   // fine-grained phase profiler (active only while a stats struct is being filled)
   std::vector<cudaEvent_t> pev; std::vector<int> ptag; size_t pused = 0; bool prof = false;
   std::atomic<uint64_t> launches{0}; uint64_t adds_r0 = 0, adds_exact = 0, cur_n = 0;
-  IssuePool* pool = nullptr; int opt_issue_threads = 0, opt_fold_cluster = 1, opt_groups = 0, opt_group_small = 70, opt_persist_fwd = 0, opt_ba_k0 = 0; std::mutex err_mu;      // one issuing host thread per lane (IssuePool); err is written under err_mu
+  IssuePool* pool = nullptr; int opt_issue_threads = 0, opt_fold_cluster = 1, opt_groups = 0, opt_group_small = 70, opt_persist_fwd = 0, opt_ba_k0 = 0, opt_fused = 0, opt_fused_tiles = 592, opt_fused_kmax = 16, opt_block_tree = 0, opt_meta_upfront = 0;      // measured alternatives, -DB200_EXPERIMENTS builds only (accumulate.cuh)
+  int64_t opt_group_plan = 0; std::mutex err_mu;      // one issuing host thread per lane (IssuePool); err is written under err_mu
   bool blocking_waits = false;      // batch workers: host waits sleep instead of spinning (8 workers per GPU x 8 ranks would spin on more threads than the host has cores)
   size_t total_mem = 0; double mem_share = 1.0;      // fraction of the device memory budget this context may plan with (batch workers: 1 / workers)
   // multi-device context (b200msm_create_multi): devs[0] == this, devs[g] = the single-device context of device g; mres = handles of sharded / replicated base sets
@@ -156,6 +159,7 @@ enum { T_SORT = 0, T_PLAN, T_TREE_FWD, T_INV_TREE, T_TREE_BWD, T_FINISH, T_FOLD,
 void copy_options(b200msm_ctx* w, const b200msm_ctx* ctx) {
   w->opt_window_bits = ctx->opt_window_bits; w->opt_accumulate = ctx->opt_accumulate; w->opt_tree_rounds = ctx->opt_tree_rounds;
   w->opt_ba_k = ctx->opt_ba_k; w->opt_pt_k = ctx->opt_pt_k; w->opt_persist = ctx->opt_persist; w->opt_subslots = ctx->opt_subslots; w->opt_combine = ctx->opt_combine;
+  w->opt_xonly = ctx->opt_xonly; w->opt_meta_upfront = ctx->opt_meta_upfront; w->opt_block_tree = ctx->opt_block_tree; w->opt_fused = ctx->opt_fused; w->opt_fused_tiles = ctx->opt_fused_tiles; w->opt_fused_kmax = ctx->opt_fused_kmax;
   w->opt_group_pairs = ctx->opt_group_pairs; w->opt_sort_groups = ctx->opt_sort_groups; w->opt_batch_workers = ctx->opt_batch_workers;
   // A batch worker runs whole MSMs next to other workers' MSMs: the workers are in DIFFERENT phases at any moment (one sorting, one in a
   // multiplier-bound backward pass, one in its latency-bound fold), which overlaps better than the lanes of one MSM, whose rounds run in
@@ -316,7 +320,7 @@ int product_tree_invert(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, char* v
 // off0 = sort offsets (absolute positions in sorted[]), cnt0 = bucket counts of the range,
 // m0 = pairs in the range, maxcnt = largest bucket population in the range.  Writes buckets_g[0 .. nbg) as XYZZ.
 template <class C>
-int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, uint32_t share, const void* d_bases, const uint32_t* off0, const uint32_t* cnt0, uint32_t nbg, uint64_t m0,
+int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, uint32_t share, const void* d_bases, const void* xs, const uint32_t* off0, const uint32_t* cnt0, uint32_t nbg, uint64_t m0,
                             uint32_t maxcnt, void* buckets_g, uint32_t* rounds_out, uint64_t* adds_out) {
   const bool overlapped = share > 1;
   // s = the stream this group is issued on: the lane's own stream when several lanes overlap, the context's stream otherwise
@@ -370,34 +374,87 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, uin
   // additions of round r: sum floor(n_r / 2) <= U[r] / 2 -- the arithmetic kernels run over these (dense) items, not over the output slots
   const uint64_t A0 = U[0] / 2;
   CK(ln_.prefix.ensure((A0 + BA_TILE) * fe + 16));
-  CK(ln_.meta.ensure((A0 + BA_TILE) * 16 + 16)); CK(ln_.carry.ensure(((size_t)std::min<uint64_t>(nbg, U[1]) + 1) * 8));
+  // operand tables: one per round when they are all written up front (option "meta_upfront", off: measured 2^20 6.33 vs 6.25 ms, 2^18 2.61 vs 2.58 -- the later rounds' tables delay the first forward pass; a round's table depends only on the segment
+  // offsets and the slot -> bucket maps, not on the points, so no k_tree_meta sits between a backward pass and the next forward pass), else one, reused
+  const bool upfront = ctx->opt_meta_upfront != 0 && !ctx->prof;
+  std::vector<uint64_t> ioff(R + 1, 0), coff(R + 1, 0);
+  for (uint32_t r = 0; r < R; r++) { ioff[r + 1] = upfront ? ioff[r] + U[r] / 2 + 8 : 0; coff[r + 1] = upfront ? coff[r] + std::min<uint64_t>(nbg, U[r + 1]) + 8 : 0; }
+  CK(ln_.meta.ensure((std::max<uint64_t>(ioff[R], A0) + BA_TILE) * 16 + 16)); CK(ln_.carry.ensure(((size_t)std::max<uint64_t>(coff[R], std::min<uint64_t>(nbg, U[1])) + 1) * 8));
   // product-tree level sizes for the largest round
   { uint64_t n1 = ((A0 + BA_TILE - 1) / BA_TILE + 1) * BA_THREADS;       // every level above is at least 4x smaller: 2*n1 bounds the sum
     CK(ln_.prod.ensure((2 * n1 + 4096) * fe)); CK(ln_.lvlprefix.ensure((2 * n1 + 4096) * fe)); CK(ln_.others.ensure((WARP_LEVEL_MAX / 4 + 4096) * fe)); }
+#if defined(B200_EXPERIMENTS)
+  const bool bt = ctx->opt_block_tree != 0 && !ctx->opt_fused;
+#else
+  const bool bt = false;
+#endif
+  if (bt) CK(ln_.btree.ensure(((A0 + BA_TILE - 1) / BA_TILE + 2) * (2 * BA_THREADS) * fe));      // 256 tree nodes per tile (tiles never outnumber round 0's at the shortest chain length)
   void* pin = nullptr; uint64_t yin = 0;
   const uint64_t ya = ((U[1] * fe + 255) / 256) * 256, yb = R > 1 ? ((U[2] * fe + 255) / 256) * 256 : 0;      // x array, then y array (see meta_load_point)
-  for (uint32_t r = 0; r < R; r++) {
-    void* pout = (r & 1) ? ln_.pb.p : ln_.pa.p; const uint64_t yout = (r & 1) ? yb : ya;
+  auto launch_meta = [&](uint32_t r) -> int {
     TreeRound tr{off[r], off[r + 1], (r + 2 <= R) ? off[r + 2] : nullptr, bid[r + 1], (r + 2 <= R) ? bid[r + 2] : nullptr, nbg};
-    uint32_t grid = (uint32_t)((U[r] / 2 + BA_TILE - 1) / BA_TILE);
-    if (grid == 0) grid = 1;
-    char* prod = ln_.prod.as<char>(); char* lpre = ln_.lvlprefix.as<char>();
-    const uint32_t pgrid = (ctx->opt_persist > 0 && overlapped) ? std::min<uint32_t>(grid, (uint32_t)ctx->opt_persist) : grid;   // persistent grid only when lanes overlap
     const uint32_t nslots = (uint32_t)std::max<uint64_t>(U[r + 1], 1);
-    uint4* items = ln_.meta.as<uint4>();
-    uint2* carries = ln_.carry.as<uint2>();
+    uint4* items = ln_.meta.as<uint4>() + ioff[r]; uint2* carries = ln_.carry.as<uint2>() + coff[r];
     if (r == 0) k_tree_meta<true><<<(nslots + 255) / 256, 256, 0, s>>>(tr, sorted, items, carries);
     else k_tree_meta<false><<<(nslots + 255) / 256, 256, 0, s>>>(tr, nullptr, items, carries);
     CKL();
+    return B200MSM_OK;
+  };
+  if (upfront) for (uint32_t r = 0; r < R; r++) { int rc_ = launch_meta(r); if (rc_) return rc_; }
+  for (uint32_t r = 0; r < R; r++) {
+    void* pout = (r & 1) ? ln_.pb.p : ln_.pa.p; const uint64_t yout = (r & 1) ? yb : ya;
+    // chain length of this round: with the block-level tree a round whose tiles number <= BA_ROOT_MAX needs no product-tree launch at all,
+    // so the chains are lengthened (up to 16) until they do
+    int RK = BK;
+    if (bt && ctx->opt_ba_k == 0) while (RK < 16 && (U[r] / 2 + (uint64_t)RK * BA_THREADS - 1) / ((uint64_t)RK * BA_THREADS) > BA_ROOT_MAX) RK *= 2;
+    const uint64_t R_TILE = (uint64_t)RK * BA_THREADS;
+    uint32_t grid = (uint32_t)((U[r] / 2 + R_TILE - 1) / R_TILE);
+    if (grid == 0) grid = 1;
+    char* prod = ln_.prod.as<char>(); char* lpre = ln_.lvlprefix.as<char>();
+    const uint32_t pgrid = (ctx->opt_persist > 0 && overlapped) ? std::min<uint32_t>(grid, (uint32_t)ctx->opt_persist) : grid;   // persistent grid only when lanes overlap
+    uint4* items = ln_.meta.as<uint4>() + ioff[r];
+    uint2* carries = ln_.carry.as<uint2>() + coff[r];
+    if (!upfront) { int rc_ = launch_meta(r); if (rc_) return rc_; }
+#if defined(B200_EXPERIMENTS)
+    if (ctx->opt_fused) {
+      // the whole round in one launch, every CTA inverting its own tile's product (k_tree_round).  Small rounds use shorter chains so that the
+      // round still spreads over the SMs (a tile is then cheaper than its inversion's latency, which is all such a round costs).
+      MARK(T_TREE_FWD);
+      int FK = BK;
+      if (ctx->opt_ba_k == 0) { const uint64_t want = (U[r] / 2 + (uint64_t)BA_THREADS * ctx->opt_fused_tiles - 1) / ((uint64_t)BA_THREADS * ctx->opt_fused_tiles); FK = (int)std::min<uint64_t>(ctx->opt_fused_kmax, std::max<uint64_t>(2, want)); }
+      uint32_t fg = (uint32_t)((U[r] / 2 + (uint64_t)FK * BA_THREADS - 1) / ((uint64_t)FK * BA_THREADS)); if (fg == 0) fg = 1;
+      const uint32_t fpg = (ctx->opt_persist > 0 && overlapped) ? std::min<uint32_t>(fg, (uint32_t)ctx->opt_persist) : fg;
+      if (r == 0) k_tree_round<C, true><<<fpg, BA_THREADS, 0, s>>>(items, carries, off[r], off[r + 1], nbg, d_bases, 0, ln_.prefix.p, pout, yout, FK, fg);
+      else k_tree_round<C, false><<<fpg, BA_THREADS, 0, s>>>(items, carries, off[r], off[r + 1], nbg, pin, yin, ln_.prefix.p, pout, yout, FK, fg);
+      CKL(); MARK(r == 0 ? T_TREE_BWD0 : T_TREE_BWD);
+    } else
+#endif
+    {
     const uint32_t fgrid = (ctx->opt_persist > 0 && overlapped) ? std::min<uint32_t>(grid, (uint32_t)(ctx->opt_persist_fwd > 0 ? ctx->opt_persist_fwd : ctx->opt_persist)) : grid;
-    if (r == 0) k_tree_fwd<C, true><<<fgrid, BA_THREADS, 0, s>>>(items, off[r], off[r + 1], nbg, d_bases, 0, ln_.prefix.p, prod, BK, grid);
-    else k_tree_fwd<C, false><<<fgrid, BA_THREADS, 0, s>>>(items, off[r], off[r + 1], nbg, pin, yin, ln_.prefix.p, prod, BK, grid);
+#if defined(B200_EXPERIMENTS)
+    if (bt) {      // first product-tree level inside the tree kernels: one value per tile goes up (block_upsweep / block_downsweep)
+      void* gt = ln_.btree.p;
+      if (r == 0) k_tree_fwd_bt<C, true><<<fgrid, BA_THREADS, 0, s>>>(items, off[r], off[r + 1], nbg, d_bases, xs, 0, ln_.prefix.p, prod, RK, grid, gt);
+      else k_tree_fwd_bt<C, false><<<fgrid, BA_THREADS, 0, s>>>(items, off[r], off[r + 1], nbg, pin, nullptr, yin, ln_.prefix.p, prod, RK, grid, gt);
+      CKL(); MARK(T_TREE_FWD);
+      { int rc_ = product_tree_invert<C>(ctx, ln_, s, prod, lpre, (uint64_t)grid, PK); if (rc_) return rc_; }
+      MARK(T_INV_TREE);
+      if (r == 0) k_tree_bwd_bt<C, true><<<pgrid, BA_THREADS, 0, s>>>(items, carries, off[r], off[r + 1], nbg, d_bases, 0, ln_.prefix.p, prod, pout, yout, RK, grid, gt);
+      else k_tree_bwd_bt<C, false><<<pgrid, BA_THREADS, 0, s>>>(items, carries, off[r], off[r + 1], nbg, pin, yin, ln_.prefix.p, prod, pout, yout, RK, grid, gt);
+      CKL(); MARK(r == 0 ? T_TREE_BWD0 : T_TREE_BWD);
+    } else
+#endif
+    {
+    if (r == 0) k_tree_fwd<C, true><<<fgrid, BA_THREADS, 0, s>>>(items, off[r], off[r + 1], nbg, d_bases, xs, 0, ln_.prefix.p, prod, BK, grid);
+    else k_tree_fwd<C, false><<<fgrid, BA_THREADS, 0, s>>>(items, off[r], off[r + 1], nbg, pin, nullptr, yin, ln_.prefix.p, prod, BK, grid);
     CKL(); MARK(T_TREE_FWD);
     { int rc_ = product_tree_invert<C>(ctx, ln_, s, prod, lpre, (uint64_t)grid * BA_THREADS, PK); if (rc_) return rc_; }
     MARK(T_INV_TREE);
     if (r == 0) k_tree_bwd<C, true><<<pgrid, BA_THREADS, 0, s>>>(items, carries, off[r], off[r + 1], nbg, d_bases, 0, ln_.prefix.p, prod, pout, yout, BK, grid);
     else k_tree_bwd<C, false><<<pgrid, BA_THREADS, 0, s>>>(items, carries, off[r], off[r + 1], nbg, pin, yin, ln_.prefix.p, prod, pout, yout, BK, grid);
     CKL(); MARK(r == 0 ? T_TREE_BWD0 : T_TREE_BWD);
+    }
+    }
     pin = pout; yin = yout;
     *adds_out += U[r] - U[r + 1];
   }
@@ -443,7 +500,7 @@ int fold_slots(b200msm_ctx* ctx, cudaStream_t s, void* buckets_g, uint32_t slots
 // combination consumes them in that order); the last-issued group is the smallest, because its tail is the one nothing else overlaps.
 // Region of group g in sorted[]: [n * w0, n * w1) -- a scalar has at most one pair per window (the extra slot shares the top window's).
 template <class C>
-int run_grouped(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, const MsmPlan& pl, void* d_out) {
+int run_grouped(b200msm_ctx* ctx, const void* d_bases, const void* xs, const uint32_t* d_scal, const MsmPlan& pl, void* d_out) {
   cudaStream_t s = ctx->stream;
   const uint32_t n = pl.n, tb = 256, gb = (n + tb - 1) / tb;
   const uint32_t lanes = (uint32_t)std::max(1, std::min(ctx->opt_lanes, (int)MAX_LANES));
@@ -451,9 +508,14 @@ int run_grouped(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, c
   const uint64_t budget_pairs = ctx->opt_group_pairs > 0 ? (uint64_t)ctx->opt_group_pairs : (uint64_t)std::max(1.0, 0.45 * ctx->mem_share * (double)ctx->total_mem / per_pair / lanes);
   uint32_t ngroups = std::max<uint32_t>(ctx->opt_groups > 0 ? (uint32_t)ctx->opt_groups : lanes, (uint32_t)(((uint64_t)n * pl.Wd + budget_pairs - 1) / budget_pairs));
   ngroups = std::min(ngroups, pl.Wd);
+  // explicit plan (option "group_plan", tuning): window counts of the groups in ISSUE order (top group first), 5 bits each; used when they sum to Wd
+  std::vector<uint32_t> plan;
+  if (ctx->opt_group_plan > 0) { uint32_t sum = 0; for (int64_t v = ctx->opt_group_plan; v; v >>= 5) { plan.push_back((uint32_t)(v & 31)); sum += (uint32_t)(v & 31); }
+    if (sum != pl.Wd || std::find(plan.begin(), plan.end(), 0u) != plan.end() || (uint64_t)n * pl.Wd > budget_pairs * plan.size()) plan.clear(); else ngroups = (uint32_t)plan.size(); }
   // window boundaries, bottom up: cut[0] = 0 .. cut[ngroups] = Wd; group ngroups-1 (top) is issued first, group 0 (bottom) last and is the smallest
   std::vector<uint32_t> cut(ngroups + 1, 0); cut[ngroups] = pl.Wd;
-  { const double small = ngroups > 1 ? ctx->opt_group_small / 100.0 : 1.0, unit = (double)pl.Wd / ((double)ngroups - 1.0 + small);
+  if (!plan.empty()) { for (uint32_t g = ngroups; g-- > 1; ) cut[g] = cut[g + 1] - plan[ngroups - 1 - g]; }
+  else { const double small = ngroups > 1 ? ctx->opt_group_small / 100.0 : 1.0, unit = (double)pl.Wd / ((double)ngroups - 1.0 + small);
     double acc = small * unit;
     for (uint32_t g = 1; g < ngroups; g++) { cut[g] = std::min(std::max<uint32_t>((uint32_t)(acc + 0.5), cut[g - 1] + 1), pl.Wd - (ngroups - g)); acc += unit; } }
   const uint32_t per = pl.logB + 1, npts = pl.W * per;
@@ -506,7 +568,7 @@ int run_grouped(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, c
       if (m0 == 0) { memset(reinterpret_cast<char*>(ctx->h_folded) + o, 0, (size_t)np * 16 * C::N); return B200MSM_OK; }      // every digit of these windows is zero: all their folded entries are infinity (zz = 0)
       live[gi] = 1;
       char* bg = ctx->buckets.as<char>() + (size_t)G.b0 * 16 * C::N;
-      int rc2 = accumulate_batch_affine<C>(ctx, ln, ls, lanes, d_bases, G.offs + G.b0, ctx->counts.as<uint32_t>() + G.b0, G.nbg, m0, mc, bg, &g_rounds[gi], &g_adds[gi]);
+      int rc2 = accumulate_batch_affine<C>(ctx, ln, ls, lanes, d_bases, xs, G.offs + G.b0, ctx->counts.as<uint32_t>() + G.b0, G.nbg, m0, mc, bg, &g_rounds[gi], &g_adds[gi]);
       if (!rc2) rc2 = fold_slots<C>(ctx, ls, bg, G.s1 - G.w0, pl.B);
       if (rc2) return rc2;
       k_gather_folded<C><<<(np + 127) / 128, 128, 0, ls>>>(bg, G.s1 - G.w0, pl.B, pl.logB, ctx->wsum.as<char>() + o); CKL();
@@ -553,6 +615,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
     pl.c = pl.c0 + (pl.rem ? 1 : 0); pl.B = 1u << (pl.c - 1); pl.logB = pl.c - 1;
     pl.W = pl.Wd + (pl.rem == 0 ? 1 : 0); }
   const uint32_t nb = pl.W * pl.B;
+  const void* xs = pre ? nullptr : ctx->cur_xs;
   if (pre && (uint64_t)pre->stride * pl.Wd >= (1ull << 31)) { ctx->err = "window table too large for 31-bit point indices"; return B200MSM_E_UNSUPPORTED; }
   if ((uint64_t)pl.W * pl.B > (1ull << 31) || (uint64_t)n * std::max(pl.W, pl.Wd) >= (1ull << 32)) { ctx->err = "problem too large for 32-bit pair indices"; return B200MSM_E_UNSUPPORTED; }
   if (pl.W > 400) { ctx->err = "too many windows"; return B200MSM_E_UNSUPPORTED; }
@@ -565,7 +628,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
   CK(ctx->ranks.ensure((size_t)n * pl.Wd * 4 + 16));
   // ---- pipelined form (large ordinary MSMs, several lanes): every window group is sorted on its own lane's stream, see run_grouped
   if (!pre && !ctx->prof && ctx->opt_sort_groups && ctx->opt_accumulate != 1 && ctx->opt_combine == 0 && ctx->opt_lanes > 1 && n >= (1u << 18))
-    return run_grouped<C>(ctx, d_bases, d_scal, pl, d_out);
+    return run_grouped<C>(ctx, d_bases, xs, d_scal, pl, d_out);
   k_digits<false><<<gb, tb, 0, s>>>(d_scal, pl, ctx->counts.as<uint32_t>(), nullptr, ctx->ranks.as<uint32_t>(), nullptr, 0u, pl.Wd); CKL();
   int rc = exclusive_scan(ctx, s, ctx->tiles, ctx->counts.as<uint32_t>(), ctx->offsets.as<uint32_t>(), nb, 0u);
   if (rc) return rc;
@@ -645,7 +708,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
         const uint32_t b0 = g0 * Bg, nbg = (g1 - g0) * Bg;
         cudaStream_t ls = lanes == 1 ? s : ln.stream;
         char* bg = ctx->buckets.as<char>() + (size_t)b0 * 16 * C::N;
-        int rc2 = accumulate_batch_affine<C>(ctx, ln, ls, lanes, d_bases, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc, bg, &g_rounds[g], &g_adds[g]);
+        int rc2 = accumulate_batch_affine<C>(ctx, ln, ls, lanes, d_bases, nullptr, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc, bg, &g_rounds[g], &g_adds[g]);
         if (!rc2 && host_tail) {
           if (st && g + 1 == ngroups) CK(cudaEventRecord(ctx->ev[3], s));
           rc2 = fold_slots<C>(ctx, ls, bg, g1 - g0, Bg);
@@ -743,7 +806,7 @@ int run_pipeline(b200msm_ctx* ctx, const void* d_bases, const uint32_t* d_scal, 
         uint32_t b0 = w0 * pl.B, nbg = (w1 - w0) * pl.B;
         cudaStream_t ls = lanes == 1 ? s : ln.stream;
         char* bg = ctx->buckets.as<char>() + (size_t)b0 * 16 * C::N;
-        int rc2 = accumulate_batch_affine<C>(ctx, ln, ls, lanes, d_bases, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc, bg, &g_rounds[gi], &g_adds[gi]);
+        int rc2 = accumulate_batch_affine<C>(ctx, ln, ls, lanes, d_bases, xs, ctx->offsets.as<uint32_t>() + b0, ctx->counts.as<uint32_t>() + b0, nbg, m0, mc, bg, &g_rounds[gi], &g_adds[gi]);
         if (!rc2 && (lanes > 1 || host_tail)) {
           if (st && gi + 1 == ngroups) CK(cudaEventRecord(ctx->ev[3], s));          // stats mode is single-lane: accumulate ends here
           rc2 = fold_slots<C>(ctx, ls, bg, w1 - w0, pl.B); }
@@ -870,10 +933,24 @@ int msm_entry_impl(b200msm_ctx* ctx, int curve, const void* bases, bool bases_re
       CK(cudaEventRecord(ctx->ev_done, ctx->stream));                       // everything issued so far (previous calls may still read ctx->bases)
       CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0));
       CK(cudaMemcpyAsync(ctx->bases.p, bases, bytes, cudaMemcpyDefault, ctx->copy_stream));
-      CK(cudaEventRecord(ctx->ev_bases, ctx->copy_stream));
       ctx->bases_pending = true; d_bases = ctx->bases.p;
     }
   }
+  // x coordinates alone for the forward pass of round 0 (meta_load_x): a resident set brings its copy (built at upload), otherwise it is
+  // extracted per call -- behind the transfer on the copy stream when the bases come from the host.  Below 2^19 points the bases fit in L2 as they are.
+  const void* xs_res = ctx->xs_hint; ctx->xs_hint = nullptr; ctx->cur_xs = nullptr;
+  if (ctx->opt_xonly && !pre && n >= (1u << 19) && !ctx->prof_noxs) {
+    if (xs_res) ctx->cur_xs = xs_res;
+    else {
+      CK(ctx->xonly.ensure((size_t)n * n8 + 16));
+      cudaStream_t xst = ctx->bases_pending ? ctx->copy_stream : ctx->stream;
+      B200_CURVE_SWITCH(curve, k_extract_x<C><<<(uint32_t)((n + 255) / 256), 256, 0, xst>>>(d_bases, (uint32_t)n, ctx->xonly.p))
+      CKL();
+      ctx->cur_xs = ctx->xonly.p;
+    }
+    ctx->cur_xs_bytes = (uint64_t)n * n8;
+  }
+  if (ctx->bases_pending) CK(cudaEventRecord(ctx->ev_bases, ctx->copy_stream));
   const uint32_t* d_scal;
   if (scalar_size == 32 && bit0 == 0 && nbits == 256) d_scal = reinterpret_cast<const uint32_t*>(d_sraw);
   else {
@@ -1046,9 +1123,9 @@ void b200msm_destroy(b200msm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (DevBuf* b : {&ctx->bases, &ctx->scalars, &ctx->canon, &ctx->counts, &ctx->offsets, &ctx->ranks, &ctx->tiles, &ctx->sorted, &ctx->buckets,
-                    &ctx->wsum, &ctx->out, &ctx->misc, &ctx->acc_a, &ctx->acc_b, &ctx->acc_c, &ctx->acc_d, &ctx->acc_e, &ctx->jac_in, &ctx->jac_affine}) b->release();
+                    &ctx->wsum, &ctx->out, &ctx->misc, &ctx->acc_a, &ctx->acc_b, &ctx->acc_c, &ctx->acc_d, &ctx->acc_e, &ctx->jac_in, &ctx->jac_affine, &ctx->xonly}) b->release();
   for (auto& ln : ctx->lane) {
-    for (DevBuf* b : {&ln.offs, &ln.tiles, &ln.bid, &ln.pa, &ln.pb, &ln.prefix, &ln.prod, &ln.lvlprefix, &ln.others, &ln.meta, &ln.carry}) b->release();
+    for (DevBuf* b : {&ln.offs, &ln.tiles, &ln.bid, &ln.pa, &ln.pb, &ln.prefix, &ln.prod, &ln.lvlprefix, &ln.others, &ln.meta, &ln.carry, &ln.btree}) b->release();
     if (ln.done) cudaEventDestroy(ln.done);
     if (ln.stream) cudaStreamDestroy(ln.stream);
   }
@@ -1060,7 +1137,7 @@ void b200msm_destroy(b200msm_ctx* ctx) {
   for (auto& e : ctx->gev) cudaEventDestroy(e);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->h_folded) cudaFreeHost(ctx->h_folded);
-  for (auto& kv : ctx->residents) cudaFree(kv.second.d);
+  for (auto& kv : ctx->residents) { cudaFree(kv.second.d); if (kv.second.dx) cudaFree(kv.second.dx); }
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   for (auto& e : ctx->pev) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1098,6 +1175,13 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
 #if defined(B200_EXPERIMENTS)
   if (!strcmp(key, "probe29")) { ctx->probe29 = v != 0; return B200MSM_OK; }
 #endif
+  if (!strcmp(key, "meta_upfront")) { ctx->opt_meta_upfront = v != 0; return B200MSM_OK; }
+  if (!strcmp(key, "xonly")) { ctx->opt_xonly = v != 0; return B200MSM_OK; }
+  if (!strcmp(key, "group_plan")) { if (v < 0) return B200MSM_E_ARG; ctx->opt_group_plan = v; return B200MSM_OK; }
+  if (!strcmp(key, "block_tree")) { ctx->opt_block_tree = v != 0; return B200MSM_OK; }
+  if (!strcmp(key, "fused_round")) { ctx->opt_fused = v != 0; return B200MSM_OK; }
+  if (!strcmp(key, "fused_tiles")) { if (v < 1 || v > 65536) return B200MSM_E_ARG; ctx->opt_fused_tiles = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "fused_kmax")) { if (v < 1 || v > 64) return B200MSM_E_ARG; ctx->opt_fused_kmax = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "persist_fwd")) { if (v < 0 || v > 4096) return B200MSM_E_ARG; ctx->opt_persist_fwd = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "groups")) { if (v < 0 || v > 64) return B200MSM_E_ARG; ctx->opt_groups = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "group_small")) { if (v < 5 || v > 100) return B200MSM_E_ARG; ctx->opt_group_small = (int)v; return B200MSM_OK; }
@@ -1143,8 +1227,17 @@ static int single_upload(b200msm_ctx* ctx, int curve, const void* bases, uint64_
   cudaError_t e = cudaMemcpyAsync(d, bases, bytes, cudaMemcpyDefault, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { cudaFree(d); ctx->err = cudaGetErrorString(e); return B200MSM_E_CUDA; }
+  void* dx = nullptr;
+  if (n >= (1u << 19) && n < (1ull << 31)) {      // x coordinates alone for the forward pass of round 0 (a failed allocation just leaves the per-call copy in charge)
+    if (cudaMalloc(&dx, (size_t)n * n8_of(curve) + 16) == cudaSuccess) {
+      B200_CURVE_SWITCH(curve, k_extract_x<C><<<(uint32_t)((n + 255) / 256), 256, 0, ctx->stream>>>(d, (uint32_t)n, dx))
+      ctx->launches++;
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); cudaFree(dx); dx = nullptr; }
+    } else { cudaGetLastError(); dx = nullptr; }
+  }
   uint64_t h = ctx->next_handle++;
-  ctx->residents[h] = Resident{curve, n, d};
+  Resident r{curve, n, d}; r.dx = dx;
+  ctx->residents[h] = r;
   *handle = h;
   return B200MSM_OK;
 }
@@ -1178,7 +1271,7 @@ static int single_free(b200msm_ctx* ctx, uint64_t handle) {
   if (it == ctx->residents.end()) return B200MSM_E_ARG;
   cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
   for (b200msm_ctx* w : ctx->workers) cudaStreamSynchronize(w->stream);
-  cudaFree(it->second.d); ctx->residents.erase(it);
+  cudaFree(it->second.d); if (it->second.dx) cudaFree(it->second.dx); ctx->residents.erase(it);
   return B200MSM_OK;
 }
 // MSM over the resident points [first, first + n) of a handle (first > 0: one device's share of a replicated base set)
@@ -1188,6 +1281,7 @@ static int single_resident(b200msm_ctx* ctx, uint64_t handle, uint64_t first, co
   const Resident& r = it->second;
   Precomp pre{(uint32_t)r.n, r.t_nbits, r.t_c0, r.t_rem, r.t_Wd};          // a table row is r.n points long whatever the offset
   const char* d = reinterpret_cast<const char*>(r.d) + first * 2 * (size_t)n8_of(r.curve);
+  ctx->xs_hint = r.dx ? reinterpret_cast<const char*>(r.dx) + first * (size_t)n8_of(r.curve) : nullptr;
   return msm_entry(ctx, r.curve, d, true, scalars, scalar_size, n, 0, 8 * scalar_size, out, stats, r.t_Wd ? &pre : nullptr);
 }
 
@@ -1224,6 +1318,7 @@ static int single_batch(b200msm_ctx* ctx, uint64_t handle, const void* scalars, 
       const uint64_t j = first + (uint64_t)t * stride;
       const char* sc = reinterpret_cast<const char*>(scalars) + (size_t)j * n * scalar_size;
       char* o = reinterpret_cast<char*>(out) + (size_t)j * 3 * n8;
+      w->xs_hint = r.dx;
       int rc = msm_entry(w, r.curve, r.d, true, sc, scalar_size, n, 0, nbits, o, nullptr, r.t_Wd ? &pre : nullptr);
       if (rc) { rcs[k] = rc; return; }
     }

@@ -33,6 +33,12 @@ template <class B> struct Fq2 {
 };
 
 template <int N> struct alignas(16) Fe { uint32_t l[N]; };
+// non-template kernels defined in headers: internal linkage in the translation units that only borrow the headers for their templates (tree.cu)
+#if defined(TREE_CURVE)
+#define B200_KERNEL static __global__
+#else
+#define B200_KERNEL __global__
+#endif
 #ifndef B200_DI
 #define B200_DI __device__ __forceinline__
 #endif

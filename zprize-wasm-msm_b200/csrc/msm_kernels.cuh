@@ -38,7 +38,7 @@ struct MsmPlan {
 // Canonical scalar layout inside the engine: 8 u32 words (256 bit) little-endian per scalar, already
 // shifted so that bit 0 is the first processed bit and masked to nbits.  For the common case
 // (scalar_size == 32, bit0 == 0, nbits == 256) the caller's buffer is used in place.
-__global__ void k_canon_scalars(const uint8_t* __restrict__ in, uint32_t scalar_size, uint32_t n,
+B200_KERNEL void k_canon_scalars(const uint8_t* __restrict__ in, uint32_t scalar_size, uint32_t n,
                                 uint32_t bit0, uint32_t nbits, uint32_t* __restrict__ out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -155,7 +155,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
   return base + x - v;
 }
 
-__global__ void k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, uint32_t* __restrict__ tile_sums) {
+B200_KERNEL void k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, uint32_t* __restrict__ tile_sums) {
   uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   uint32_t v[SCAN_ITEMS], sum = 0;
 #pragma unroll
@@ -167,7 +167,7 @@ __global__ void k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restri
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 // single block: scan tile sums in place (exclusive), total appended at tile_sums[ntiles]
-__global__ void k_scan_sums(uint32_t* __restrict__ tile_sums, uint32_t ntiles, uint32_t base) {      // base: position of the first element's segment (a group's region of sorted[])
+B200_KERNEL void k_scan_sums(uint32_t* __restrict__ tile_sums, uint32_t ntiles, uint32_t base) {      // base: position of the first element's segment (a group's region of sorted[])
   __shared__ uint32_t carry_s;
   if (threadIdx.x == 0) carry_s = base;
   __syncthreads();
@@ -184,7 +184,7 @@ __global__ void k_scan_sums(uint32_t* __restrict__ tile_sums, uint32_t ntiles, u
   if (threadIdx.x == 0) tile_sums[ntiles] = carry_s;
 }
 // add tile offsets; writes offsets[n] = grand total; optionally copies the offsets into a cursor array
-__global__ void k_scan_apply(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tile_sums, uint32_t ntiles,
+B200_KERNEL void k_scan_apply(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tile_sums, uint32_t ntiles,
                              uint32_t* __restrict__ cursors) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { uint32_t v = out[i] + tile_sums[i / SCAN_TILE]; out[i] = v; if (cursors) cursors[i] = v; }
@@ -192,7 +192,7 @@ __global__ void k_scan_apply(uint32_t* __restrict__ out, uint32_t n, const uint3
 }
 
 // per-window maximum bucket population (decides the number of tree rounds); out[w] must be zeroed
-__global__ void k_window_max(const uint32_t* __restrict__ counts, uint32_t B, uint32_t* __restrict__ out) {
+B200_KERNEL void k_window_max(const uint32_t* __restrict__ counts, uint32_t B, uint32_t* __restrict__ out) {
   uint32_t w = blockIdx.y;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t v = (i < B) ? counts[(uint64_t)w * B + i] : 0;
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(256) k_imad_probe(uint32_t iters, uint32_t see
   if (s == 0x1234567u) sink[0] = s;
 }
 // IMAD.WIDE.U32 with carry in/out: 4 independent carry chains of 4 wide multiply-adds each (16 per inner iteration).
-__global__ void __launch_bounds__(256) k_imadx_probe(uint32_t iters, uint32_t seed, uint32_t* __restrict__ sink) {
+B200_KERNEL void __launch_bounds__(256) k_imadx_probe(uint32_t iters, uint32_t seed, uint32_t* __restrict__ sink) {
   uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
   uint32_t r[32];
 #pragma unroll
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(256) k_imadx_probe(uint32_t iters, uint32_t se
 // Field-multiply throughput probe: ITER dependent Montgomery multiplications per thread (2N^2+N limb products each).
 #if defined(B200_EXPERIMENTS)
 // FP64 pipe probe: 8 independent DFMA chains per thread (the pipe an FP64-based multiplier would run on, beside the integer pipe)
-__global__ void __launch_bounds__(256) k_dfma_probe(uint32_t iters, double seed, double* __restrict__ sink) {
+B200_KERNEL void __launch_bounds__(256) k_dfma_probe(uint32_t iters, double seed, double* __restrict__ sink) {
   double a[8], b = seed * 1.0000001, c = seed * 0.5;
 #pragma unroll
   for (int k = 0; k < 8; k++) a[k] = seed + k;
