@@ -414,6 +414,47 @@ def test_lane_and_tail_variants_agree(eng, lg):
 
 
 @pytest.mark.parametrize("cname", ["bls12381", "bn128"])
+def test_x_only_copy_of_the_bases(eng, cname):
+    """round 0's forward pass gathers from a copy of the x coordinates alone (k_extract_x) from 2^19 points on: the same group element with the copy
+    switched off, through every way the bases can arrive -- device pointer (copy made per call), host buffer (copy made behind the transfer on the
+    copy stream), resident handle (copy made at upload; also a prefix of the set and a batch) -- with infinities, repeated points and P / -P among
+    the bases (the rare equal-x / zero-x cases re-read the full points), and the known answer of the plain generator stream"""
+    import torch
+    cv = curve(cname); lg = 19; n = 1 << lg; seed = 0xB2000000 + lg; pt = 2 * cv.n8
+    d = torch.empty(n * pt, dtype=torch.uint8, device="cuda"); eng.generate_bases(cv.cid, seed, 0, n, d)
+    g = torch.Generator(device="cuda"); g.manual_seed(77)
+    sc = torch.randint(0, 256, (n * 32,), dtype=torch.uint8, device="cuda", generator=g)
+    ref = _norm(eng, cv, eng.multiexp_affine(cv.cid, d, sc, 32, n))
+    assert ref == known_answer(cv, seed, 0, n, sc)
+    # special points: infinity (zeros), a point repeated, a point and its negative -- all forced into the same buckets by equal scalars
+    v = d.view(n, pt).clone()
+    v[5].zero_(); v[6].zero_(); v[11] = v[10]; v[12] = v[10]
+    neg = bytes(v[20].cpu().numpy().tobytes()); y = int.from_bytes(neg[cv.n8:], "little")
+    v[21] = torch.frombuffer(bytearray(neg[:cv.n8] + ((cv.q - y) % cv.q).to_bytes(cv.n8, "little")), dtype=torch.uint8).cuda()
+    s2 = sc.view(n, 32).clone(); s2[6] = s2[5]; s2[11] = s2[10]; s2[12] = s2[10]; s2[21] = s2[20]
+    d2 = v.reshape(-1).contiguous(); sc2 = s2.reshape(-1).contiguous()
+    try:
+        eng.set_option("xonly", 0)
+        want = {"plain": _norm(eng, cv, eng.multiexp_affine(cv.cid, d, sc, 32, n)), "special": _norm(eng, cv, eng.multiexp_affine(cv.cid, d2, sc2, 32, n))}
+        assert want["plain"] == ref
+        eng.set_option("xonly", 1)
+        for name, (db, ds) in {"plain": (d, sc), "special": (d2, sc2)}.items():
+            assert _norm(eng, cv, eng.multiexp_affine(cv.cid, db, ds, 32, n)) == want[name], name                       # device pointers
+            hb = bytes(db.cpu().numpy().tobytes()); hs = bytes(ds.cpu().numpy().tobytes())
+            assert _norm(eng, cv, eng.multiexp_affine(cv.cid, hb, hs, 32, n)) == want[name], name                       # host buffers
+            h = eng.upload_bases(cv.cid, db, n)
+            try:
+                assert _norm(eng, cv, eng.multiexp_resident(h, ds, 32, n, cv.cid)) == want[name], name                  # resident
+                outs = eng.multiexp_batch(h, torch.cat([ds, ds]), 32, n, 2, cv.cid)
+                assert all(_norm(eng, cv, outs[j * 3 * cv.n8:(j + 1) * 3 * cv.n8]) == want[name] for j in range(2)), name
+            finally:
+                eng.free_bases(h)
+    finally:
+        eng.set_option("xonly", 1)
+    del d, d2, sc, sc2, v, s2; torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("cname", ["bls12381", "bn128"])
 def test_skewed_scalars_dense_items(eng, cname):
     """half of 2^16 scalars are EQUAL (every window has one bucket of 32768 points: 14+ tree rounds, long carry chains of odd remainders) and the rest
     random; the batch-affine tree (dense addition items, carried points copied by the backward pass) must give the serial one-thread-per-bucket result"""

@@ -13,7 +13,7 @@ import argparse, collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ap = argparse.ArgumentParser()
 ap.add_argument("--lib", default=os.path.join(ROOT, "zprize-wasm-msm_b200", "b200msm", "libb200msm.so"))
-ap.add_argument("--kernels", default="k_tree_bwd,k_tree_fwd,k_tree_meta,k_fold,k_accum_finish,k_digits,k_inv_root,k_prod_fwd,k_prod_bwd,k_probe_fqmul,k_ntt")
+ap.add_argument("--kernels", default="k_tree_bwd,k_tree_fwd,k_tree_meta,k_fold,k_accum_finish,k_digits,k_inv_root,k_prod_fwd,k_prod_bwd,k_fpmul_probe,k_ntt")
 ap.add_argument("--curves", default="BLS12_381,BN254", help="substrings of the mangled template arguments to keep (G2 = Fq2 instantiations are skipped unless named)")
 ap.add_argument("--out", default="")
 a = ap.parse_args()
