@@ -446,6 +446,98 @@ __global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_round(co
  }
 }
 
+// ---- the same round, software-pipelined inside the CTA (option fused_round = 2) ----------------------------------------------------------
+// Four compute warps + ONE inverting warp per CTA, two product-tree buffers: the compute warps run the forward phase of tile i+1, hand its
+// root to the inverting warp and go on to the backward phase of tile i, whose root the inverting warp finished meanwhile -- the 50 us of
+// the inversion sit under ~100-250 us of multiplications instead of stalling the CTA.  Named barriers: 1 = the compute warps among
+// themselves, 2 + b = "root of buffer b is ready" (compute arrives, inverter waits), 4 + b = "its inverse is ready" (the other way round).
+B200_DI void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+B200_DI void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+constexpr int RP_THREADS = BA_THREADS + 32;
+template <class C>
+B200_DI void pipe_upsweep(const Fe<C::N>& p, uint32_t* __restrict__ tree) {
+  constexpr int N = C::N;
+  const uint32_t t = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < N; k++) tree[(BA_THREADS + t) * N + k] = p.l[k];
+  bar_sync_n(1, BA_THREADS);
+#pragma unroll 1
+  for (uint32_t width = BA_THREADS / 2; width >= 1; width >>= 1) {
+    if (t < width) {
+      Fe<N> a, b, c; const uint32_t node = width + t;
+#pragma unroll
+      for (int k = 0; k < N; k++) { a.l[k] = tree[(2 * node) * N + k]; b.l[k] = tree[(2 * node + 1) * N + k]; }
+      fe_mul<C>(c, a, b);
+#pragma unroll
+      for (int k = 0; k < N; k++) tree[node * N + k] = c.l[k];
+    }
+    bar_sync_n(1, BA_THREADS);
+  }
+}
+template <class C>
+B200_DI void pipe_downsweep(Fe<C::N>& q, uint32_t* __restrict__ tree) {
+  constexpr int N = C::N;
+  const uint32_t t = threadIdx.x;
+#pragma unroll 1
+  for (uint32_t width = 1; width < BA_THREADS; width <<= 1) {
+    Fe<N> ip, sib, r; const uint32_t child = 2 * width + t;
+    if (t < 2 * width) {
+#pragma unroll
+      for (int k = 0; k < N; k++) { ip.l[k] = tree[(child >> 1) * N + k]; sib.l[k] = tree[(child ^ 1) * N + k]; }
+    }
+    bar_sync_n(1, BA_THREADS);
+    if (t < 2 * width) {
+      fe_mul<C>(r, ip, sib);
+#pragma unroll
+      for (int k = 0; k < N; k++) tree[child * N + k] = r.l[k];
+    }
+    bar_sync_n(1, BA_THREADS);
+  }
+#pragma unroll
+  for (int k = 0; k < N; k++) q.l[k] = tree[(BA_THREADS + t) * N + k];
+}
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(RP_THREADS, 3) k_tree_round_pipe(const uint4* __restrict__ items, const uint2* __restrict__ carries, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t nb,
+                                                           const void* __restrict__ src, const void* __restrict__ xs, uint64_t yoff, void* __restrict__ prefix,
+                                                           void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles) {
+ constexpr int N = C::N;
+ __shared__ __align__(16) uint32_t tree[2][2 * BA_THREADS * N];
+ const uint32_t nadd = off_in[nb] - off_in[0] - off_out[nb];
+ const uint32_t tile_sz = (uint32_t)K * BA_THREADS;
+ const uint32_t nt = min(ntiles, (nadd + tile_sz - 1) / tile_sz);
+ const uint32_t T = blockIdx.x < nt ? (nt - 1 - blockIdx.x) / gridDim.x + 1 : 0;      // tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+ if (threadIdx.x >= BA_THREADS) {                                                     // the inverting warp
+  for (uint32_t k = 0; k < T; k++) {
+   const uint32_t b = k & 1;
+   bar_sync_n(2 + b, RP_THREADS);
+   if (threadIdx.x == BA_THREADS) {
+    Fe<N> r, ri;
+#pragma unroll
+    for (int j = 0; j < N; j++) r.l[j] = tree[b][N + j];
+    fe_inv_fast<C>(ri, r);
+#pragma unroll
+    for (int j = 0; j < N; j++) tree[b][N + j] = ri.l[j];
+   }
+   __syncwarp();
+   bar_arrive_n(4 + b, RP_THREADS);
+  }
+  return;
+ }
+ if (T) { Fe<N> p; tree_fwd_tile<C, FIRST>(p, items, nadd, src, xs, yoff, prefix, K, blockIdx.x); pipe_upsweep<C>(p, tree[0]); bar_arrive_n(2, RP_THREADS); }
+ for (uint32_t k = 0; k < T; k++) {
+  const uint32_t b = k & 1, tb = blockIdx.x + k * gridDim.x;
+  if (k + 1 < T) { Fe<N> p; tree_fwd_tile<C, FIRST>(p, items, nadd, src, xs, yoff, prefix, K, tb + gridDim.x); pipe_upsweep<C>(p, tree[b ^ 1]); bar_arrive_n(2 + (b ^ 1), RP_THREADS); }
+  bar_sync_n(4 + b, RP_THREADS);
+  Fe<N> q;
+  pipe_downsweep<C>(q, tree[b]);
+  tree_bwd_tile<C, FIRST>(q, items, nadd, src, yoff, prefix, pout, yoff_out, K, tb);
+ }
+ const uint32_t ncar = off_out[nb] - nadd;
+ for (uint32_t c = blockIdx.x * BA_THREADS + threadIdx.x; c < ncar; c += gridDim.x * BA_THREADS) {
+  const uint2 cr = carries[c];
+  Affine<C> p; meta_load_point<C, FIRST>(p, src, yoff, cr.x); soa_store_point<C>(pout, yoff_out, cr.y, p);
+ }
+}
 #endif  // B200_EXPERIMENTS
 
 // Measured alternatives that are no longer in the tree (profiles/README.md has their numbers): a backward pass that stages the next slot's operands

@@ -139,7 +139,7 @@ struct b200msm_ctx {
   // fine-grained phase profiler (active only while a stats struct is being filled)
   std::vector<cudaEvent_t> pev; std::vector<int> ptag; size_t pused = 0; bool prof = false;
   std::atomic<uint64_t> launches{0}; uint64_t adds_r0 = 0, adds_exact = 0, cur_n = 0;
-  IssuePool* pool = nullptr; int opt_issue_threads = 0, opt_fold_cluster = 1, opt_groups = 0, opt_group_small = 70, opt_persist_fwd = 0, opt_ba_k0 = 0, opt_fused = 0, opt_fused_tiles = 592, opt_fused_kmax = 16, opt_block_tree = 0, opt_meta_upfront = 0;      // measured alternatives, -DB200_EXPERIMENTS builds only (accumulate.cuh)
+  IssuePool* pool = nullptr; int opt_issue_threads = 0, opt_fold_cluster = 1, opt_groups = 0, opt_group_small = 70, opt_persist_fwd = 0, opt_ba_k0 = 0, opt_fused = 0, opt_fused_grid = 444, opt_fused_tiles = 592, opt_fused_kmax = 16, opt_block_tree = 0, opt_meta_upfront = 0;      // measured alternatives, -DB200_EXPERIMENTS builds only (accumulate.cuh)
   int64_t opt_group_plan = 0; std::mutex err_mu;      // one issuing host thread per lane (IssuePool); err is written under err_mu
   bool blocking_waits = false;      // batch workers: host waits sleep instead of spinning (8 workers per GPU x 8 ranks would spin on more threads than the host has cores)
   size_t total_mem = 0; double mem_share = 1.0;      // fraction of the device memory budget this context may plan with (batch workers: 1 / workers)
@@ -159,7 +159,7 @@ enum { T_SORT = 0, T_PLAN, T_TREE_FWD, T_INV_TREE, T_TREE_BWD, T_FINISH, T_FOLD,
 void copy_options(b200msm_ctx* w, const b200msm_ctx* ctx) {
   w->opt_window_bits = ctx->opt_window_bits; w->opt_accumulate = ctx->opt_accumulate; w->opt_tree_rounds = ctx->opt_tree_rounds;
   w->opt_ba_k = ctx->opt_ba_k; w->opt_pt_k = ctx->opt_pt_k; w->opt_persist = ctx->opt_persist; w->opt_subslots = ctx->opt_subslots; w->opt_combine = ctx->opt_combine;
-  w->opt_xonly = ctx->opt_xonly; w->opt_meta_upfront = ctx->opt_meta_upfront; w->opt_block_tree = ctx->opt_block_tree; w->opt_fused = ctx->opt_fused; w->opt_fused_tiles = ctx->opt_fused_tiles; w->opt_fused_kmax = ctx->opt_fused_kmax;
+  w->opt_xonly = ctx->opt_xonly; w->opt_meta_upfront = ctx->opt_meta_upfront; w->opt_block_tree = ctx->opt_block_tree; w->opt_fused = ctx->opt_fused; w->opt_fused_grid = ctx->opt_fused_grid; w->opt_fused_tiles = ctx->opt_fused_tiles; w->opt_fused_kmax = ctx->opt_fused_kmax;
   w->opt_group_pairs = ctx->opt_group_pairs; w->opt_sort_groups = ctx->opt_sort_groups; w->opt_batch_workers = ctx->opt_batch_workers;
   // A batch worker runs whole MSMs next to other workers' MSMs: the workers are in DIFFERENT phases at any moment (one sorting, one in a
   // multiplier-bound backward pass, one in its latency-bound fold), which overlaps better than the lanes of one MSM, whose rounds run in
@@ -424,8 +424,16 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, uin
       if (ctx->opt_ba_k == 0) { const uint64_t want = (U[r] / 2 + (uint64_t)BA_THREADS * ctx->opt_fused_tiles - 1) / ((uint64_t)BA_THREADS * ctx->opt_fused_tiles); FK = (int)std::min<uint64_t>(ctx->opt_fused_kmax, std::max<uint64_t>(2, want)); }
       uint32_t fg = (uint32_t)((U[r] / 2 + (uint64_t)FK * BA_THREADS - 1) / ((uint64_t)FK * BA_THREADS)); if (fg == 0) fg = 1;
       const uint32_t fpg = (ctx->opt_persist > 0 && overlapped) ? std::min<uint32_t>(fg, (uint32_t)ctx->opt_persist) : fg;
+      bool piped = false;
+      if constexpr (C::EXT == 1) { if (ctx->opt_fused == 2) {      // software-pipelined form: 4 compute warps + 1 inverting warp, 3 CTAs per SM
+        const uint32_t ppg = std::min<uint32_t>(fg, (uint32_t)ctx->opt_fused_grid);
+        if (r == 0) k_tree_round_pipe<C, true><<<ppg, RP_THREADS, 0, s>>>(items, carries, off[r], off[r + 1], nbg, d_bases, xs, 0, ln_.prefix.p, pout, yout, FK, fg);
+        else k_tree_round_pipe<C, false><<<ppg, RP_THREADS, 0, s>>>(items, carries, off[r], off[r + 1], nbg, pin, nullptr, yin, ln_.prefix.p, pout, yout, FK, fg);
+        piped = true; } }
+      if (!piped) {
       if (r == 0) k_tree_round<C, true><<<fpg, BA_THREADS, 0, s>>>(items, carries, off[r], off[r + 1], nbg, d_bases, 0, ln_.prefix.p, pout, yout, FK, fg);
       else k_tree_round<C, false><<<fpg, BA_THREADS, 0, s>>>(items, carries, off[r], off[r + 1], nbg, pin, yin, ln_.prefix.p, pout, yout, FK, fg);
+      }
       CKL(); MARK(r == 0 ? T_TREE_BWD0 : T_TREE_BWD);
     } else
 #endif
@@ -1179,7 +1187,8 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "xonly")) { ctx->opt_xonly = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "group_plan")) { if (v < 0) return B200MSM_E_ARG; ctx->opt_group_plan = v; return B200MSM_OK; }
   if (!strcmp(key, "block_tree")) { ctx->opt_block_tree = v != 0; return B200MSM_OK; }
-  if (!strcmp(key, "fused_round")) { ctx->opt_fused = v != 0; return B200MSM_OK; }
+  if (!strcmp(key, "fused_round")) { if (v < 0 || v > 2) return B200MSM_E_ARG; ctx->opt_fused = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "fused_grid")) { if (v < 1 || v > 65536) return B200MSM_E_ARG; ctx->opt_fused_grid = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "fused_tiles")) { if (v < 1 || v > 65536) return B200MSM_E_ARG; ctx->opt_fused_tiles = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "fused_kmax")) { if (v < 1 || v > 64) return B200MSM_E_ARG; ctx->opt_fused_kmax = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "persist_fwd")) { if (v < 0 || v > 4096) return B200MSM_E_ARG; ctx->opt_persist_fwd = (int)v; return B200MSM_OK; }
