@@ -191,7 +191,9 @@ int b200msm_debug_schedule(b200msm_ctx* ctx, const void* scalars, uint32_t scala
  * "lanes" (1..8 overlapping accumulate streams), "issue_threads" (1 = one issuing host thread per lane, 0 = the calling
  * thread issues every lane (default; measured equal, profiles/README.md r2)), "sort_groups" (1 = the sort is pipelined per window group on the lanes' streams (default)), "batch_workers" (8), "batch_lanes" (1), "batch_blocking" (1 = the batch workers sleep in their host waits instead of spinning: set it before the first batch when the
  * workers of several processes outnumber the host cores), "fold_cluster", "multi_min_points", "multi_replicate" (multi-device contexts, see
- * b200msm_create_multi).
+ * b200msm_create_multi), "xonly" (1 = from 2^19 points on, round 0's forward pass gathers from a copy of the bases' x coordinates alone (default), 0 = from the
+ * bases themselves), "group_plan" / "meta_upfront" / "ba_k" / "pt_k" / "persist" / "groups" / "group_small" / "subslots" / "group_pairs" (scheduling shapes measured in
+ * profiles/README.md; the defaults are the measured optima).
  * On a multi-device context an option applies to every device. */
 int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t value);
 
