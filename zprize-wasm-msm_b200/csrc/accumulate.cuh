@@ -451,6 +451,67 @@ __global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_round(co
 // root to the inverting warp and go on to the backward phase of tile i, whose root the inverting warp finished meanwhile -- the 50 us of
 // the inversion sit under ~100-250 us of multiplications instead of stalling the CTA.  Named barriers: 1 = the compute warps among
 // themselves, 2 + b = "root of buffer b is ready" (compute arrives, inverter waits), 4 + b = "its inverse is ready" (the other way round).
+// (copies of tree_fwd_tile / tree_bwd_tile that take the index of the tile's first item: the de-phased form below cuts a CTA's first tile in two)
+template <class C, bool FIRST>
+B200_DI void tree_fwd_tile_b(Fe<C::N>& p, const uint4* __restrict__ items, uint32_t nadd, const void* __restrict__ src, const void* __restrict__ xs, uint64_t yoff, void* __restrict__ prefix, int K, uint32_t tb) {
+  const uint32_t tile = tb + threadIdx.x;      // tb = index of the tile's first item
+  fe_set_one<C>(p);
+  Fe<C::N> x1, x2, nx1, nx2;
+  uint4 mc = make_uint4(0, 0, 0, 0), mn = mc;
+  if (tile < nadd) mc = items[tile];
+  if (K > 1 && tile + BA_THREADS < nadd) mn = items[tile + BA_THREADS];
+  if (tile < nadd) { meta_load_x<C, FIRST>(x1, src, xs, mc.x); meta_load_x<C, FIRST>(x2, src, xs, mc.y); }
+#pragma unroll 1
+  for (int i = 0; i < K; i++) {
+    const uint32_t e = tile + i * BA_THREADS;
+    uint4 mn2 = make_uint4(0, 0, 0, 0);
+    if (i + 2 < K && e + 2 * BA_THREADS < nadd) mn2 = items[e + 2 * BA_THREADS];
+    if (i + 1 < K && e + BA_THREADS < nadd) { meta_load_x<C, FIRST>(nx1, src, xs, mn.x); meta_load_x<C, FIRST>(nx2, src, xs, mn.y); }
+    if (e < nadd) {
+      Fe<C::N> d; int kind = 0;
+      fe_sub<C>(d, x2, x1);
+      if (fe_is_zero<C>(d) || fe_is_zero<C>(x1) || fe_is_zero<C>(x2)) {        // rare: decide with the full points
+        Affine<C> p1, p2;
+        meta_load_point<C, FIRST>(p1, src, yoff, mc.x);
+        meta_load_point<C, FIRST>(p2, src, yoff, mc.y);
+        kind = affine_add_denominator<C>(d, p1, p2);
+      }
+      if (kind <= 1) {
+        fe_store<C>(reinterpret_cast<char*>(prefix) + (uint64_t)e * 4 * C::N, p);
+        fe_mul<C>(p, p, d);
+      }
+    }
+    mc = mn; mn = mn2; x1 = nx1; x2 = nx2;
+  }
+}
+template <class C, bool FIRST>
+B200_DI void tree_bwd_tile_b(Fe<C::N>& q, const uint4* __restrict__ items, uint32_t nadd, const void* __restrict__ src, uint64_t yoff, const void* __restrict__ prefix,
+                           void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t tb) {
+  const uint32_t tile = tb + threadIdx.x;      // tb = index of the tile's first item
+  uint4 mn = make_uint4(0, 0, 0, 0);
+  if (tile + (K - 1) * BA_THREADS < nadd) mn = items[tile + (K - 1) * BA_THREADS];
+#pragma unroll 1
+  for (int i = K - 1; i >= 0; i--) {
+    const uint4 m = mn;
+    const uint32_t e = tile + i * BA_THREADS;
+    if (i > 0 && e - BA_THREADS < nadd) mn = items[e - BA_THREADS];
+    if (e >= nadd) continue;
+    Affine<C> p1, p2, r;
+    meta_load_point<C, FIRST>(p1, src, yoff, m.x);
+    meta_load_point<C, FIRST>(p2, src, yoff, m.y);
+    Fe<C::N> d, dinv;
+    int kind = affine_add_denominator<C>(d, p1, p2);
+    if (kind <= 1) {
+      Fe<C::N> pre; fe_load_cg<C>(pre, reinterpret_cast<const char*>(prefix) + (uint64_t)e * 4 * C::N);
+      // the two multiplications of the inverse-sharing step are independent: their rows are interleaved (fe_mul2), which doubles the
+      // work between dependent carry-chain instructions (measured: k_tree_bwd 3.46 -> 3.39 ms at 2^20, profiles/README.md r2)
+      if constexpr (C::EXT == 1) { Fe<C::N> qn; fe_mul2<C>(dinv, q, pre, qn, q, d); q = qn; }
+      else { fe_mul<C>(dinv, q, pre); fe_mul<C>(q, q, d); }
+    }
+    affine_add_finish<C>(r, p1, p2, dinv, kind);
+    soa_store_point<C>(pout, yoff_out, m.z, r);
+  }
+}
 B200_DI void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 B200_DI void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 constexpr int RP_THREADS = BA_THREADS + 32;
@@ -531,6 +592,61 @@ __global__ void __launch_bounds__(RP_THREADS, 3) k_tree_round_pipe(const uint4* 
   Fe<N> q;
   pipe_downsweep<C>(q, tree[b]);
   tree_bwd_tile<C, FIRST>(q, items, nadd, src, yoff, prefix, pout, yoff_out, K, tb);
+ }
+ const uint32_t ncar = off_out[nb] - nadd;
+ for (uint32_t c = blockIdx.x * BA_THREADS + threadIdx.x; c < ncar; c += gridDim.x * BA_THREADS) {
+  const uint2 cr = carries[c];
+  Affine<C> p; meta_load_point<C, FIRST>(p, src, yoff, cr.x); soa_store_point<C>(pout, yoff_out, cr.y, p);
+ }
+}
+// De-phased form (fused_round = 3): the CTAs that share an SM (blockIdx.x / phase_div = 0, 1, 2 for a grid of three CTAs per SM) cut their FIRST tile
+// in two pieces of j/3 and (3 - j)/3 of its length, so that from then on they sit a third of a tile period apart: while one gathers (forward
+// phase), the others multiply.
+template <class C, bool FIRST>
+__global__ void __launch_bounds__(RP_THREADS, 3) k_tree_round_pipe3(const uint4* __restrict__ items, const uint2* __restrict__ carries, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t nb,
+                                                           const void* __restrict__ src, const void* __restrict__ xs, uint64_t yoff, void* __restrict__ prefix,
+                                                           void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles, uint32_t phase_div) {
+ constexpr int N = C::N;
+ __shared__ __align__(16) uint32_t tree[2][2 * BA_THREADS * N];
+ const uint32_t nadd = off_in[nb] - off_in[0] - off_out[nb];
+ const uint32_t tile_sz = (uint32_t)K * BA_THREADS;
+ const uint32_t nt = min(ntiles, (nadd + tile_sz - 1) / tile_sz);
+ const uint32_t T = blockIdx.x < nt ? (nt - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+ const uint32_t j = (blockIdx.x / phase_div) % 3, K0 = (uint32_t)K * j / 3;                 // first piece: K0 items per thread (0: the tile is not cut)
+ const uint32_t U = T + ((K0 && T) ? 1 : 0);                                                // units = tiles + 1 when the first tile is cut
+ auto unit = [&](uint32_t u, uint32_t& base, int& Ku) {
+  if (K0 == 0) { base = (blockIdx.x + u * gridDim.x) * tile_sz; Ku = K; return; }
+  if (u == 0) { base = blockIdx.x * tile_sz; Ku = (int)K0; return; }
+  if (u == 1) { base = blockIdx.x * tile_sz + K0 * BA_THREADS; Ku = K - (int)K0; return; }
+  base = (blockIdx.x + (u - 1) * gridDim.x) * tile_sz; Ku = K;
+ };
+ if (threadIdx.x >= BA_THREADS) {
+  for (uint32_t k = 0; k < U; k++) {
+   const uint32_t b = k & 1;
+   bar_sync_n(2 + b, RP_THREADS);
+   if (threadIdx.x == BA_THREADS) {
+    Fe<N> r, ri;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.l[i] = tree[b][N + i];
+    fe_inv_fast<C>(ri, r);
+#pragma unroll
+    for (int i = 0; i < N; i++) tree[b][N + i] = ri.l[i];
+   }
+   __syncwarp();
+   bar_arrive_n(4 + b, RP_THREADS);
+  }
+  return;
+ }
+ uint32_t base; int Ku;
+ if (U) { Fe<N> p; unit(0, base, Ku); tree_fwd_tile_b<C, FIRST>(p, items, nadd, src, xs, yoff, prefix, Ku, base); pipe_upsweep<C>(p, tree[0]); bar_arrive_n(2, RP_THREADS); }
+ for (uint32_t k = 0; k < U; k++) {
+  const uint32_t b = k & 1;
+  if (k + 1 < U) { Fe<N> p; unit(k + 1, base, Ku); tree_fwd_tile_b<C, FIRST>(p, items, nadd, src, xs, yoff, prefix, Ku, base); pipe_upsweep<C>(p, tree[b ^ 1]); bar_arrive_n(2 + (b ^ 1), RP_THREADS); }
+  bar_sync_n(4 + b, RP_THREADS);
+  Fe<N> q;
+  pipe_downsweep<C>(q, tree[b]);
+  unit(k, base, Ku);
+  tree_bwd_tile_b<C, FIRST>(q, items, nadd, src, yoff, prefix, pout, yoff_out, Ku, base);
  }
  const uint32_t ncar = off_out[nb] - nadd;
  for (uint32_t c = blockIdx.x * BA_THREADS + threadIdx.x; c < ncar; c += gridDim.x * BA_THREADS) {

@@ -425,6 +425,11 @@ int accumulate_batch_affine(b200msm_ctx* ctx, TreeLane& ln_, cudaStream_t s, uin
       uint32_t fg = (uint32_t)((U[r] / 2 + (uint64_t)FK * BA_THREADS - 1) / ((uint64_t)FK * BA_THREADS)); if (fg == 0) fg = 1;
       const uint32_t fpg = (ctx->opt_persist > 0 && overlapped) ? std::min<uint32_t>(fg, (uint32_t)ctx->opt_persist) : fg;
       bool piped = false;
+      if constexpr (C::EXT == 1) { if (ctx->opt_fused == 3) {      // de-phased: CTAs sharing an SM start a third of a tile apart
+        const uint32_t ppg = std::min<uint32_t>(fg, (uint32_t)ctx->opt_fused_grid), pdiv = std::max<uint32_t>(1, (uint32_t)ctx->opt_fused_grid / 3);
+        if (r == 0) k_tree_round_pipe3<C, true><<<ppg, RP_THREADS, 0, s>>>(items, carries, off[r], off[r + 1], nbg, d_bases, xs, 0, ln_.prefix.p, pout, yout, FK, fg, pdiv);
+        else k_tree_round_pipe3<C, false><<<ppg, RP_THREADS, 0, s>>>(items, carries, off[r], off[r + 1], nbg, pin, nullptr, yin, ln_.prefix.p, pout, yout, FK, fg, pdiv);
+        piped = true; } }
       if constexpr (C::EXT == 1) { if (ctx->opt_fused == 2) {      // software-pipelined form: 4 compute warps + 1 inverting warp, 3 CTAs per SM
         const uint32_t ppg = std::min<uint32_t>(fg, (uint32_t)ctx->opt_fused_grid);
         if (r == 0) k_tree_round_pipe<C, true><<<ppg, RP_THREADS, 0, s>>>(items, carries, off[r], off[r + 1], nbg, d_bases, xs, 0, ln_.prefix.p, pout, yout, FK, fg);
@@ -1187,7 +1192,7 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "xonly")) { ctx->opt_xonly = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "group_plan")) { if (v < 0) return B200MSM_E_ARG; ctx->opt_group_plan = v; return B200MSM_OK; }
   if (!strcmp(key, "block_tree")) { ctx->opt_block_tree = v != 0; return B200MSM_OK; }
-  if (!strcmp(key, "fused_round")) { if (v < 0 || v > 2) return B200MSM_E_ARG; ctx->opt_fused = (int)v; return B200MSM_OK; }
+  if (!strcmp(key, "fused_round")) { if (v < 0 || v > 3) return B200MSM_E_ARG; ctx->opt_fused = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "fused_grid")) { if (v < 1 || v > 65536) return B200MSM_E_ARG; ctx->opt_fused_grid = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "fused_tiles")) { if (v < 1 || v > 65536) return B200MSM_E_ARG; ctx->opt_fused_tiles = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "fused_kmax")) { if (v < 1 || v > 64) return B200MSM_E_ARG; ctx->opt_fused_kmax = (int)v; return B200MSM_OK; }
