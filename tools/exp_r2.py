@@ -20,7 +20,7 @@ import torch, b200msm
 
 cid = {"bls12381": 0, "bn128": 1, "bls12381_g2": 2, "bn128_g2": 3}[a.curve]; n8 = b200msm.N8[cid]
 dev = torch.device("cuda", 0)
-DEFAULTS = {"lanes": 4, "sort_groups": 1, "window_bits": 0, "tree_rounds": -1, "ba_k": 0, "pt_k": 8, "persist": 592, "combine": 0, "accumulate": 0, "subslots": 0, "group_pairs": 0, "xonly": 1, "fused_round": 0, "fused_grid": 444, "block_tree": 0, "meta_upfront": 0, "fused_tiles": 592, "fused_kmax": 16}
+DEFAULTS = {"lanes": 4, "sort_groups": 1, "window_bits": 0, "tree_rounds": -1, "ba_k": 0, "pt_k": 8, "persist": 592, "combine": 0, "accumulate": 0, "subslots": 0, "group_pairs": 0, "xonly": 1, "fold_cluster": 1, "fused_round": 0, "fused_grid": 444, "block_tree": 0, "meta_upfront": 0, "fused_tiles": 592, "fused_kmax": 16}
 
 
 def parse_cfg(c):

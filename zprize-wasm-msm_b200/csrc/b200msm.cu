@@ -495,6 +495,18 @@ int fold_slots(b200msm_ctx* ctx, cudaStream_t s, void* buckets_g, uint32_t slots
   }
   if (tail >= 2) {                        // remaining levels of every live block of `tail` buckets: one launch
     uint32_t nblk = B / tail, live = 1; for (uint32_t k = 1; k < nblk; k <<= 1) live++;
+#if defined(B200_EXPERIMENTS)
+    bool quad = false;
+    if constexpr (C::EXT == 1) quad = ctx->opt_fold_cluster == 2;
+    if (quad) {                            // one cluster of 8 CTAs per live block, four lanes per addition (k_fold_tail_quad)
+      if constexpr (C::EXT == 1) {
+      cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3(slots * live * FOLD_CLUSTER); cfg.blockDim = dim3(FOLD_QUAD_THREADS); cfg.stream = s;
+      cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = FOLD_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&cfg, k_fold_tail_quad<C>, buckets_g, B, tail, live)); CKL();
+      }
+    } else
+#endif
     if (ctx->opt_fold_cluster) {          // one cluster of 8 CTAs per live block (k_fold_tail_cluster)
       cudaLaunchConfig_t cfg = {}; cfg.gridDim = dim3(slots * live * FOLD_CLUSTER); cfg.blockDim = dim3(FOLD_CLUSTER_THREADS); cfg.stream = s;
       cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = FOLD_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1199,7 +1211,7 @@ int b200msm_set_option(b200msm_ctx* ctx, const char* key, int64_t v) {
   if (!strcmp(key, "persist_fwd")) { if (v < 0 || v > 4096) return B200MSM_E_ARG; ctx->opt_persist_fwd = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "groups")) { if (v < 0 || v > 64) return B200MSM_E_ARG; ctx->opt_groups = (int)v; return B200MSM_OK; }
   if (!strcmp(key, "group_small")) { if (v < 5 || v > 100) return B200MSM_E_ARG; ctx->opt_group_small = (int)v; return B200MSM_OK; }
-  if (!strcmp(key, "fold_cluster")) { ctx->opt_fold_cluster = v != 0; return B200MSM_OK; }
+  if (!strcmp(key, "fold_cluster")) { if (v < 0 || v > 2) return B200MSM_E_ARG; ctx->opt_fold_cluster = (int)v; return B200MSM_OK; }      // 0 = one CTA per live block, 1 = a cluster per live block, 2 = the same with four lanes per addition
   if (!strcmp(key, "issue_threads")) { ctx->opt_issue_threads = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "sort_groups")) { ctx->opt_sort_groups = v != 0; return B200MSM_OK; }
   if (!strcmp(key, "lanes")) { if (v < 1 || v > MAX_LANES) return B200MSM_E_ARG; ctx->opt_lanes = (int)v; return B200MSM_OK; }

@@ -290,6 +290,86 @@ __global__ void __launch_bounds__(FOLD_CLUSTER_THREADS) k_fold_tail_cluster(void
   }
 }
 
+// ---- the same levels with FOUR LANES PER ADDITION (Fq curves) ---------------------------------------------------------------------------------
+// MEASURED AND NOT ADOPTED (round 2, profiles/README.md r2late; -DB200_EXPERIMENTS builds, option fold_cluster = 2): bit-exact, but the tail kernel takes 212 us
+// instead of 229 at 2^16 (CUPTI, four lanes) and the MSM is unchanged or slower (2^16 1.447 vs 1.451, 2^18 2.58 vs 2.56, 2^20 6.32 vs 6.24 ms): a level is bound by
+// the L2 round trips and the cluster barrier between levels at least as much as by the addition's multiplier chain.
+#if defined(B200_EXPERIMENTS)
+// A level of the tail is one XYZZ addition deep, and one thread's addition is a chain of 14 dependent multiplications (~1.1 us each: the
+// carry chains issue in order) = 16 us per level, 160 us for the ten levels -- the unoverlapped end of every MSM.  The addition's data flow
+// is only FOUR multiplications deep:
+//   depth 1: U1 = X1*ZZ2   U2 = X2*ZZ1   S1 = Y1*ZZZ2   S2 = Y2*ZZZ1          P = U2 - U1, R = S2 - S1
+//   depth 2: PP = P*P      RR = R*R      ZZ12 = ZZ1*ZZ2  ZZZ12 = ZZZ1*ZZZ2
+//   depth 3: Q = U1*PP     PPP = P*PP    ZZ3 = ZZ12*PP                         X3 = RR - PPP - 2Q
+//   depth 4: t = R*(Q-X3)  SP = S1*PPP   ZZZ3 = ZZZ12*PPP                      Y3 = t - SP
+// (g1m_add, build_curve_jacobian_a0.js:541-658, in the XYZZ form of xyzz_add).  The four lanes of a quad hold the same two points, multiply
+// the four operand pairs of a depth at the same time (operands picked by lane role with selects: no divergence) and exchange the products by
+// shuffles inside the quad (12 words per value, ~50 shuffles per depth against ~1600 multiplier instructions).  Same field values as the
+// one-thread addition, bit for bit.  The special cases are decided identically by all four lanes (they hold the same data).
+template <class C> B200_DI void quad_gather(Fe<C::N> (&g)[4], const Fe<C::N>& mine, uint32_t qmask, uint32_t qbase) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+#pragma unroll
+    for (int i = 0; i < C::N; i++) g[k].l[i] = __shfl_sync(qmask, mine.l[i], qbase + k);
+  }
+}
+template <class C> B200_DI void fe_sel4(Fe<C::N>& r, uint32_t role, const Fe<C::N>& a0, const Fe<C::N>& a1, const Fe<C::N>& a2, const Fe<C::N>& a3) {
+#pragma unroll
+  for (int i = 0; i < C::N; i++) r.l[i] = role == 0 ? a0.l[i] : role == 1 ? a1.l[i] : role == 2 ? a2.l[i] : a3.l[i];
+}
+template <class C> B200_DI void xyzz_add_quad(XYZZ<C>& acc, const XYZZ<C>& q, uint32_t role, uint32_t qmask, uint32_t qbase) {
+  if (xyzz_is_inf<C>(q)) return;
+  if (xyzz_is_inf<C>(acc)) { acc = q; return; }
+  Fe<C::N> a, b, m, g[4];
+  fe_sel4<C>(a, role, acc.x, q.x, acc.y, q.y); fe_sel4<C>(b, role, q.zz, acc.zz, q.zzz, acc.zzz);
+  fe_mul<C>(m, a, b); quad_gather<C>(g, m, qmask, qbase);
+  Fe<C::N> U1 = g[0], S1 = g[2], P, R;
+  fe_sub<C>(P, g[1], g[0]); fe_sub<C>(R, g[3], g[2]);
+  if (fe_is_zero<C>(P)) {
+    if (fe_is_zero<C>(R)) { XYZZ<C> d; xyzz_dbl<C>(d, q); acc = d; } else xyzz_set_inf<C>(acc);
+    return;
+  }
+  fe_sel4<C>(a, role, P, R, acc.zz, acc.zzz); fe_sel4<C>(b, role, P, R, q.zz, q.zzz);
+  fe_mul<C>(m, a, b); quad_gather<C>(g, m, qmask, qbase);
+  Fe<C::N> PP = g[0], RR = g[1], ZZ12 = g[2], ZZZ12 = g[3];
+  fe_sel4<C>(a, role, U1, P, ZZ12, U1);
+  fe_mul<C>(m, a, PP); quad_gather<C>(g, m, qmask, qbase);
+  Fe<C::N> Q = g[0], PPP = g[1], X3, t;
+  acc.zz = g[2];
+  fe_sub<C>(X3, RR, PPP); fe_sub<C>(X3, X3, Q); fe_sub<C>(X3, X3, Q);
+  fe_sub<C>(t, Q, X3);
+  fe_sel4<C>(a, role, R, S1, ZZZ12, ZZZ12); fe_sel4<C>(b, role, t, PPP, PPP, PPP);
+  fe_mul<C>(m, a, b); quad_gather<C>(g, m, qmask, qbase);
+  acc.x = X3; fe_sub<C>(acc.y, g[0], g[1]); acc.zzz = g[2];
+}
+constexpr uint32_t FOLD_QUAD_THREADS = 128;      // 8 CTAs x 128 threads = 256 quads per live block
+template <class C>
+__global__ void __launch_bounds__(FOLD_QUAD_THREADS) k_fold_tail_quad(void* __restrict__ buckets, uint32_t B, uint32_t tail, uint32_t live_blocks) {
+  const uint32_t cl = blockIdx.x / FOLD_CLUSTER;
+  const uint32_t w = cl / live_blocks, lb0 = cl % live_blocks;
+  const uint32_t blk0 = lb0 == 0 ? 0 : (1u << (lb0 - 1));
+  const uint64_t base = (uint64_t)w * B + (uint64_t)blk0 * tail;
+  const uint32_t tid = cluster_ctarank() * FOLD_QUAD_THREADS + threadIdx.x, nquads = FOLD_CLUSTER * FOLD_QUAD_THREADS / 4;
+  const uint32_t quad = tid >> 2, role = tid & 3, lane = threadIdx.x & 31, qbase = lane & ~3u, qmask = 0xfu << qbase;
+  uint32_t live = 1;
+  for (uint32_t sz = tail; sz >= 2; sz >>= 1, live++) {
+    const uint32_t half = sz >> 1, work = live * half;
+    for (uint32_t r = quad; r < work; r += nquads) {
+      const uint32_t lb = r / half, i = r % half;
+      const uint32_t blk = lb == 0 ? 0 : (1u << (lb - 1));
+      const uint64_t lo = base + (uint64_t)blk * sz + i;
+      XYZZ<C> a, b;
+      xyzz_load_l2<C>(a, buckets, lo); xyzz_load_l2<C>(b, buckets, lo + half);
+      xyzz_add_quad<C>(a, b, role, qmask, qbase);
+      Fe<C::N> mine; fe_sel4<C>(mine, role, a.x, a.y, a.zz, a.zzz);      // lane r stores coordinate r
+      fe_store<C>(reinterpret_cast<char*>(buckets) + lo * (uint64_t)(16 * C::N) + (uint64_t)role * (4 * C::N), mine);
+    }
+    __threadfence();
+    cluster_barrier();
+  }
+}
+#endif  // B200_EXPERIMENTS
+
 // One thread per slot: R_w = T[0] + sum_j 2^j T[2^j] by Horner over j (logB doublings).  The extra slot (index Wd,
 // present when W == Wd + 1) holds buckets B+1 .. 2B of the last window: its value is the same expression + B * T[0].
 template <class C>
