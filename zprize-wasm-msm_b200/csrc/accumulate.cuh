@@ -790,14 +790,17 @@ __global__ void __launch_bounds__(RootCfg<C>::THREADS) k_inv_root(void* __restri
     for (int k = 0; k < N; k++) tree[1 * N + k] = ri.l[k];
   }
   __syncthreads();
-  for (uint32_t width = 1; width < BA_ROOT_THREADS; width <<= 1) {          // down-sweep: inv(left) = inv(node) * right, inv(right) = inv(node) * left
-    if (t < width) {
-      Fe<N> a, b, ip, ia, ib; uint32_t node = width + t;
+  for (uint32_t width = 1; width < BA_ROOT_THREADS; width <<= 1) {          // down-sweep, one thread per CHILD: inv(child) = inv(parent) * sibling -- one
+    Fe<N> ip, sib, r; const uint32_t child = 2 * width + t;                  // multiplication deep per level instead of two (the kernel is one dependent chain)
+    if (t < 2 * width) {
 #pragma unroll
-      for (int k = 0; k < N; k++) { ip.l[k] = tree[node * N + k]; a.l[k] = tree[(2 * node) * N + k]; b.l[k] = tree[(2 * node + 1) * N + k]; }
-      fe_mul<C>(ia, ip, b); fe_mul<C>(ib, ip, a);
+      for (int k = 0; k < N; k++) { ip.l[k] = tree[(child >> 1) * N + k]; sib.l[k] = tree[(child ^ 1) * N + k]; }
+    }
+    __syncthreads();
+    if (t < 2 * width) {
+      fe_mul<C>(r, ip, sib);
 #pragma unroll
-      for (int k = 0; k < N; k++) { tree[(2 * node) * N + k] = ia.l[k]; tree[(2 * node + 1) * N + k] = ib.l[k]; }
+      for (int k = 0; k < N; k++) tree[child * N + k] = r.l[k];
     }
     __syncthreads();
   }
