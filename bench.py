@@ -811,7 +811,7 @@ def run_ntt(a):
         roof = {"bound": "hbm", "kernel": "k_ntt_stage4 (two radix-2 stages per pass over the array; %d radix-4 + %d radix-2 passes per transform)" % (ph["radix4_passes"], ph["radix2_passes"]),
                 "achieved": alg_bytes / (per_pass_ms * 1e-3) / 1e9 if per_pass_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
                 "frac": (alg_bytes / (per_pass_ms * 1e-3) / 1e9 / hbm_peak) if per_pass_ms > 0 else None,
-                "traffic": 1.02e9 if (cid == 0 and lg == 24) else None,      # profiles/r1b_ncu_full_ntt_2p24_bls_fr.csv: 0.54 GB read + 0.48 GB written per pass
+                "traffic": profile_traffic("k_ntt_stage4|%s|2^%d" % ("bls12381_fr" if cid == 0 else "bn128_fr", lg)),      # from the committed ncu capture (profiles/r2_ncu_traffic.json), None when there is none for this size
                 "avg_launch_ms": per_pass_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": hbm_src,
                 "note": "each pass also performs n/2 (radix-2) or n (radix-4) Fr multiplications: %.1f G multiplications/s in the passes"
                         % ((ph["radix4_passes"] * n + ph["radix2_passes"] * n / 2) / (ph["ms_passes"] * 1e-3) / 1e9 if ph["ms_passes"] > 0 else 0.0)}
