@@ -405,12 +405,13 @@ def test_lane_and_tail_variants_agree(eng, lg):
     assert any(ref)
     try:
         for opts in ({"lanes": 1}, {"lanes": 2}, {"lanes": 3}, {"sort_groups": 0}, {"fold_cluster": 0}, {"issue_threads": 1}, {"tree_rounds": 5}, {"tree_rounds": 1},
-                     {"lanes": 4, "groups": 6}, {"persist": 0}):
+                     {"lanes": 4, "groups": 6}, {"persist": 0}, {"meta_upfront": 1}, {"xonly": 0}, {"ba_k": 5}, {"ba_k": 16, "pt_k": 3},
+                     {"group_plan": 136357}, {"group_plan": 70936235107}):      # window groups 5-5-5-4 and 3-3-3-2-2-2-2-2 (19 windows at 2^18; ignored where they do not sum to the window count)
             for k, v in opts.items(): eng.set_option(k, v)
             assert _norm(eng, cv, eng.multiexp_affine(0, d, sd, 32, n)) == ref, opts
-            for k in opts: eng.set_option(k, {"lanes": 4, "sort_groups": 1, "fold_cluster": 1, "issue_threads": 0, "tree_rounds": -1, "groups": 0, "persist": 592}[k])
+            for k in opts: eng.set_option(k, {"lanes": 4, "sort_groups": 1, "fold_cluster": 1, "issue_threads": 0, "tree_rounds": -1, "groups": 0, "persist": 592, "meta_upfront": 0, "xonly": 1, "ba_k": 0, "pt_k": 8, "group_plan": 0}[k])
     finally:
-        for k, v in {"lanes": 4, "sort_groups": 1, "fold_cluster": 1, "issue_threads": 0, "tree_rounds": -1, "groups": 0, "persist": 592}.items(): eng.set_option(k, v)
+        for k, v in {"lanes": 4, "sort_groups": 1, "fold_cluster": 1, "issue_threads": 0, "tree_rounds": -1, "groups": 0, "persist": 592, "meta_upfront": 0, "xonly": 1, "ba_k": 0, "pt_k": 8, "group_plan": 0}.items(): eng.set_option(k, v)
 
 
 @pytest.mark.parametrize("cname", ["bls12381", "bn128"])
