@@ -23,6 +23,13 @@
 
 namespace b200 {
 
+#ifndef B200_BWD_CTAS_N8
+#define B200_BWD_CTAS_N8 5      // resident CTAs per SM k_tree_bwd is compiled for on the 8-limb field (BN254): 94 registers, no spill; measured against 4 (106 registers):
+                                // k_tree_bwd 1.551 -> 1.510 ms at 2^20, the MSM 3.342 -> 3.294, 2^22 10.97 -> 10.84 (profiles/README.md r2late).  BLS12-381 needs 128 registers: 4.
+#endif
+#ifndef B200_FWD_CTAS_N8
+#define B200_FWD_CTAS_N8 6      // (7 measured equal: 72 registers either way)
+#endif
 constexpr int BA_THREADS = 128;     // threads per block in the tree kernels; a block owns a tile of K * BA_THREADS consecutive slots,
                                     // K = additions per thread per inversion chain (level 0) or product-tree arity (levels >= 1): run-time parameters
 constexpr uint32_t BA_ROOT_MAX = 1024;   // = BA_ROOT_THREADS * ROOT_PER   // the product tree is reduced until at most this many values remain
@@ -200,7 +207,7 @@ B200_DI void tree_fwd_tile(Fe<C::N>& p, const uint4* __restrict__ items, uint32_
   }
 }
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 3 : 6) k_tree_fwd(const uint4* __restrict__ items, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t nb,
+__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 3 : C::N <= 8 ? B200_FWD_CTAS_N8 : 6) k_tree_fwd(const uint4* __restrict__ items, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t nb,
                                                             const void* __restrict__ src, const void* __restrict__ xs, uint64_t yoff, void* __restrict__ prefix, void* __restrict__ prod, int K, uint32_t ntiles) {
  const uint32_t nadd = off_in[nb] - off_in[0] - off_out[nb];      // additions of this round = inputs - outputs
  // persistent form: gridDim.x may be smaller than ntiles (leaves SM room for the other lane's latency-bound kernels)
@@ -241,7 +248,7 @@ B200_DI void tree_bwd_tile(Fe<C::N>& q, const uint4* __restrict__ items, uint32_
   }
 }
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : 4) k_tree_bwd(const uint4* __restrict__ items, const uint2* __restrict__ carries, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t nb,
+__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 2 : C::N <= 8 ? B200_BWD_CTAS_N8 : 4) k_tree_bwd(const uint4* __restrict__ items, const uint2* __restrict__ carries, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t nb,
                                                          const void* __restrict__ src, uint64_t yoff,
                                                          const void* __restrict__ prefix, const void* __restrict__ inv,
                                                          void* __restrict__ pout, uint64_t yoff_out, int K, uint32_t ntiles) {
