@@ -450,6 +450,14 @@ def test_x_only_copy_of_the_bases(eng, cname):
                 assert all(_norm(eng, cv, outs[j * 3 * cv.n8:(j + 1) * 3 * cv.n8]) == want[name] for j in range(2)), name
             finally:
                 eng.free_bases(h)
+        # a resident call that FAILS must not leave its x-only copy behind for the next call (other bases, same size)
+        import b200msm as _m
+        h = eng.upload_bases(cv.cid, d, n)
+        try:
+            with pytest.raises(_m.B200MsmError): eng.multiexp_resident(h, sc, 0, n, cv.cid)
+            assert _norm(eng, cv, eng.multiexp_affine(cv.cid, d2, sc2, 32, n)) == want["special"]
+        finally:
+            eng.free_bases(h)
     finally:
         eng.set_option("xonly", 1)
     del d, d2, sc, sc2, v, s2; torch.cuda.empty_cache()

@@ -927,6 +927,7 @@ int stage(b200msm_ctx* ctx, const void* src, size_t bytes, DevBuf& buf, const vo
 int msm_entry_impl(b200msm_ctx* ctx, int curve, const void* bases, bool bases_resident, const void* scalars, uint32_t scalar_size, uint64_t n,
                    uint32_t bit0, uint32_t nbits, void* out, b200msm_stats* st, const Precomp* pre) {
   if (!ctx) return B200MSM_E_ARG;
+  const void* xs_res = ctx->xs_hint; ctx->xs_hint = nullptr; ctx->cur_xs = nullptr;      // the caller's x-only copy belongs to THIS call only, whatever becomes of it
   if (!curve_ok(curve) || !out || (n && (!bases || !scalars)) || scalar_size == 0) { ctx->err = "bad argument"; return B200MSM_E_ARG; }
   if (n >= (1ull << 31)) { ctx->err = "n must be < 2^31"; return B200MSM_E_UNSUPPORTED; }
   CK(cudaSetDevice(ctx->device));
@@ -963,7 +964,6 @@ int msm_entry_impl(b200msm_ctx* ctx, int curve, const void* bases, bool bases_re
   }
   // x coordinates alone for the forward pass of round 0 (meta_load_x): a resident set brings its copy (built at upload), otherwise it is
   // extracted per call -- behind the transfer on the copy stream when the bases come from the host.  Below 2^19 points the bases fit in L2 as they are.
-  const void* xs_res = ctx->xs_hint; ctx->xs_hint = nullptr; ctx->cur_xs = nullptr;
   if (ctx->opt_xonly && !pre && n >= (1u << 19) && !ctx->prof_noxs) {
     if (xs_res) ctx->cur_xs = xs_res;
     else {
