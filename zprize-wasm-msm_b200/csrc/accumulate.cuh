@@ -27,6 +27,10 @@ namespace b200 {
 #define B200_BWD_CTAS_N8 5      // resident CTAs per SM k_tree_bwd is compiled for on the 8-limb field (BN254): 94 registers, no spill; measured against 4 (106 registers):
                                 // k_tree_bwd 1.551 -> 1.510 ms at 2^20, the MSM 3.342 -> 3.294, 2^22 10.97 -> 10.84 (profiles/README.md r2late).  BLS12-381 needs 128 registers: 4.
 #endif
+#ifndef B200_FWD_CTAS_N12
+#define B200_FWD_CTAS_N12 5     // k_tree_fwd on the 12-limb field (BLS12-381): 96 registers, no spill, against 80 registers + 64-96 bytes of spill at 6 CTAs per SM.  With the
+                                // x-only copy of the bases the pass is issue-bound rather than HBM-bound: 0.997 -> 0.854 ms at 2^20, the MSM 6.25 -> 6.17, 2^22 20.04 -> 19.73 (r2late)
+#endif
 #ifndef B200_FWD_CTAS_N8
 #define B200_FWD_CTAS_N8 6      // (7 measured equal: 72 registers either way)
 #endif
@@ -207,7 +211,7 @@ B200_DI void tree_fwd_tile(Fe<C::N>& p, const uint4* __restrict__ items, uint32_
   }
 }
 template <class C, bool FIRST>
-__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 3 : C::N <= 8 ? B200_FWD_CTAS_N8 : 6) k_tree_fwd(const uint4* __restrict__ items, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t nb,
+__global__ void __launch_bounds__(BA_THREADS, C::N > 12 ? 3 : C::N <= 8 ? B200_FWD_CTAS_N8 : B200_FWD_CTAS_N12) k_tree_fwd(const uint4* __restrict__ items, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out, uint32_t nb,
                                                             const void* __restrict__ src, const void* __restrict__ xs, uint64_t yoff, void* __restrict__ prefix, void* __restrict__ prod, int K, uint32_t ntiles) {
  const uint32_t nadd = off_in[nb] - off_in[0] - off_out[nb];      // additions of this round = inputs - outputs
  // persistent form: gridDim.x may be smaller than ntiles (leaves SM room for the other lane's latency-bound kernels)
